@@ -1,0 +1,176 @@
+/*
+ * lgs.h -- C ABI of the B200-native LEG-SLAM mapping hot path (liblgs.so).
+ *
+ * This is the drop-in boundary *beneath* the reference's raw-pointer interface
+ *   CudaRasterizer::Rasterizer::{forward,backward,markVisible}
+ *   (reference: cuda_rasterizer/rasterizer.h:24-92, impl rasterizer_impl.cu:141-453)
+ * and beneath the libtorch functions
+ *   RasterizeGaussiansCUDA / RasterizeGaussiansBackwardCUDA / markVisible
+ *   (reference: include/rasterize_points.h:19-72, impl src/rasterize_points.cu:37-228).
+ * include/cuda_rasterizer/rasterizer.h and include/rasterize_points.h in this repo
+ * re-declare those two levels with identical signatures; both are thin shims
+ * over the functions below.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless it says "host";
+ *   - nothing here allocates device memory; the caller sizes the three opaque
+ *     work buffers with lgs_*_bytes() (replaces required<GeometryState/ImageState/
+ *     BinningState>(), reference rasterizer_impl.h:66-73);
+ *   - every launch goes to `stream` (a cudaStream_t passed as void*); the
+ *     reference uses the legacy default stream;
+ *   - return value: 0 = LGS_OK, otherwise an lgs_status (no exceptions cross the ABI);
+ *   - a NULL shs / colors_precomp / scales / rotations / cov3D_precomp / lang_feat
+ *     selects the alternative path exactly like the reference's nullptr tests
+ *     (forward.cu:205,241; backward.cu:390,394);
+ *   - matrices are 4x4 column-major as the reference kernels index them
+ *     (auxiliary.h:58-77), i.e. torch row-major of the transposed matrix.
+ *   - LGS_LF_DIM (64) language-feature channels, 3 colour channels, 8x8 tiles
+ *     (reference config.h:15-18, CMakeLists.txt:4).
+ */
+#ifndef LGS_H_INCLUDED
+#define LGS_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGS_LF_DIM 64
+#define LGS_NUM_CHANNELS 3
+#define LGS_TILE 8
+
+typedef enum lgs_status {
+    LGS_OK = 0,
+    LGS_ERR_INVALID_ARG = 1,   /* bad sizes / NULL where a pointer is required        */
+    LGS_ERR_NO_COLOR = 2,      /* neither shs nor colors_precomp (rasterizer_impl.cu:243-245 analogue) */
+    LGS_ERR_NO_COV = 3,        /* neither scales+rotations nor cov3D_precomp           */
+    LGS_ERR_CUDA = 4,          /* a CUDA runtime call failed; see lgs_last_cuda_error  */
+    LGS_ERR_ALIGNMENT = 5,     /* a pointer that must be 16-byte aligned is not        */
+    LGS_ERR_PREFILTERED = 6    /* reserved: prefiltered contract violated              */
+} lgs_status;
+
+const char* lgs_status_string(int status);
+/* cudaError_t value of the most recent failing CUDA call on this host thread (0 if none). */
+int lgs_last_cuda_error(void);
+int lgs_abi_version(void);
+
+/* ---- opaque work-buffer sizes (bytes) -------------------------------------------- */
+size_t lgs_geom_bytes(int P);          /* replaces required<GeometryState>(P)          */
+size_t lgs_image_bytes(int W, int H);  /* replaces required<ImageState>(W*H)           */
+size_t lgs_binning_bytes(int R);       /* replaces required<BinningState>(R)           */
+
+/* ---- forward ---------------------------------------------------------------------
+ * Split in two because the reference sizes the binning buffer from the number of
+ * (Gaussian, tile) instances R = num_rendered, read back once per forward
+ * (rasterizer_impl.cu:281-286).
+ *
+ * stage1 = FORWARD::preprocess + InclusiveSum (rasterizer_impl.cu:248-278):
+ *   writes radii[P] (int32; pass NULL to use an internal array), fills geom_buffer,
+ *   writes *num_rendered_host and synchronises `stream` once (the :282 readback).
+ * stage2 = duplicateWithKeys + 64-bit radix sort on bits [0,32+msb(tiles)) +
+ *   identifyTileRanges + renderCUDA (rasterizer_impl.cu:290-340):
+ *   out_color [3,H,W], out_lang_feat [64,H,W] (written only if include_lang_feat),
+ *   out_depth [1,H,W]. Every pixel of the written outputs is written (no pre-zero
+ *   needed).
+ */
+int lgs_forward_stage1(
+    int P, int D, int M, int W, int H,
+    const float* means3D, const float* shs, const float* colors_precomp,
+    const float* opacities, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+    float tan_fovx, float tan_fovy, int prefiltered,
+    char* geom_buffer, int* radii, int* num_rendered_host, void* stream);
+
+int lgs_forward_stage2(
+    int P, int W, int H, int R,
+    const float* background, const float* lang_feat,
+    char* geom_buffer, char* binning_buffer, char* image_buffer,
+    float* out_color, float* out_lang_feat, float* out_depth,
+    int include_lang_feat, void* stream);
+
+/* ---- backward  (Rasterizer::backward, rasterizer_impl.cu:347-453) -----------------
+ * dL_dmean2D [P,3], dL_dconic [P,2,2] (slots 0,1,3 used), dL_dopacity [P,1],
+ * dL_dcolor [P,3], dL_dlang_feat [P,64], dL_ddepth [P,1] are ACCUMULATED into and must
+ * be zero on entry unless zero_outputs != 0, in which case this call zeroes them
+ * itself (one fused memset kernel).  dL_dmean3D [P,3], dL_dcov3D [P,6],
+ * dL_dsh [P,M,3], dL_dscale [P,3], dL_drot [P,4] are fully overwritten (zeros for
+ * culled Gaussians) when zero_outputs != 0; with zero_outputs == 0 only visible
+ * Gaussians are written, exactly like the reference.
+ * dL_ddepth may be NULL (the reference computes and discards it,
+ * rasterize_points.cu:161,207).
+ */
+int lgs_backward(
+    int P, int D, int M, int R, int W, int H,
+    const float* background,
+    const float* means3D, const float* shs, const float* colors_precomp,
+    const float* lang_feat, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+    float tan_fovx, float tan_fovy, const int* radii,
+    const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
+    const float* dL_dpix, const float* dL_dpix_lf, const float* dL_dpix_depth,
+    float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+    float* dL_dlang_feat, float* dL_ddepth, float* dL_dmean3D, float* dL_dcov3D,
+    float* dL_dsh, float* dL_dscale, float* dL_drot,
+    int include_lang_feat, int zero_outputs, void* stream);
+
+/* ---- markVisible  (rasterizer_impl.cu:54-66,141-153): present[i] = view-z > 0.2 --- */
+int lgs_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, unsigned char* present, void* stream);
+
+/* ---- introspection of the opaque buffers (parity tests: bit-exact keys / order /
+ *      ranges; reference layouts rasterizer_impl.h:33-63).  Returned pointers alias the
+ *      caller's buffers. */
+typedef struct lgs_binning_view {
+    const uint64_t* keys_unsorted;   /* [R] tile<<32 | depth bits, emission order       */
+    const uint32_t* values_unsorted; /* [R] Gaussian index                              */
+    const uint64_t* keys_sorted;     /* [R]                                             */
+    const uint32_t* point_list;      /* [R] sorted Gaussian indices                     */
+} lgs_binning_view;
+typedef struct lgs_image_view {
+    const uint32_t* ranges;          /* [tiles][2] (start,end) into point_list          */
+    const float*    final_T;         /* [H*W]                                           */
+    const uint32_t* n_contrib;       /* [H*W]                                           */
+} lgs_image_view;
+typedef struct lgs_geom_view {
+    const float*    records;         /* [P][12]: x,y,depth,0 | conic a,b,c, opacity | r,g,b,0 */
+    const float*    cov3D;           /* [P][6]                                          */
+    const uint32_t* tiles_touched;   /* [P]                                             */
+    const uint32_t* point_offsets;   /* [P] inclusive scan                              */
+    const int32_t*  internal_radii;  /* [P]                                             */
+    const uint8_t*  clamped;         /* [P] bit c set if colour channel c was clamped   */
+} lgs_geom_view;
+int lgs_view_binning(const char* binning_buffer, int R, lgs_binning_view* out);
+int lgs_view_image(const char* image_buffer, int W, int H, lgs_image_view* out);
+int lgs_view_geom(const char* geom_buffer, int P, lgs_geom_view* out);
+
+/* ---- fused multi-tensor Adam  (torch::optim::Adam, reference
+ *      src/gaussian_model.cpp:483-518, step at src/gaussian_mapper.cpp:793-796) -----
+ * One launch over n <= 16 tensors (host arrays of device pointers).  step is the 1-based
+ * step count AFTER increment, as torch uses it for bias correction.  lr / betas / eps are
+ * double like libtorch's AdamOptions (bias corrections are evaluated in double, then cast).
+ *   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g
+ *   p -= (lr/(1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ */
+int lgs_adam_multi(int n_tensors, float* const* params, const float* const* grads,
+                   float* const* exp_avg, float* const* exp_avg_sq,
+                   const int64_t* numel, const double* lr,
+                   double beta1, double beta2, double eps, int step, void* stream);
+
+/* ---- semantic query (reference eval/find_objects_gaussians.py:160-175) ------------
+ * sim[p,q] = <f_p/|f_p|, t_q/|t_q|> for feats [P,64] and text [Q,64] (both row-major,
+ * un-normalised; eps 1e-12 like F.normalize).  out is [P,Q] row-major.
+ * lgs_minmax_invert turns one similarity column into the reference's score
+ *   1 - (s-min)/(max-min)   (find_objects_gaussians.py:173-175), in place.
+ */
+int lgs_cosine_query(int P, int Q, const float* feats, const float* text, float* out,
+                     void* stream);
+int lgs_minmax_invert(int64_t n, float* scores, float* scratch2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGS_H_INCLUDED */

@@ -1,0 +1,208 @@
+// api.cu -- the extern "C" surface of liblgs.so (declared in include/lgs.h).
+//
+// Host orchestration that replaces CudaRasterizer::Rasterizer::{forward,backward,
+// markVisible} (reference rasterizer_impl.cu:141-153,198-343,347-453).  Nothing here
+// allocates device memory and nothing throws: every failure becomes an lgs_status.
+#include <cstdio>
+#include <cstring>
+#include "common.cuh"
+
+namespace lgs {
+
+static thread_local int g_last_cuda_error = 0;
+void set_last_cuda_error(cudaError_t e) { g_last_cuda_error = (int)e; }
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace lgs
+
+using namespace lgs;
+
+extern "C" {
+
+const char* lgs_status_string(int status) {
+    switch (status) {
+        case LGS_OK: return "ok";
+        case LGS_ERR_INVALID_ARG: return "invalid argument";
+        case LGS_ERR_NO_COLOR: return "neither shs nor colors_precomp given";
+        case LGS_ERR_NO_COV: return "neither scales+rotations nor cov3D_precomp given";
+        case LGS_ERR_CUDA: return "CUDA runtime error (see lgs_last_cuda_error)";
+        case LGS_ERR_ALIGNMENT: return "pointer not 16-byte aligned";
+        case LGS_ERR_PREFILTERED: return "prefiltered contract violated";
+        default: return "unknown status";
+    }
+}
+
+int lgs_last_cuda_error(void) { return g_last_cuda_error; }
+int lgs_abi_version(void) { return 1; }
+
+// ---- buffer sizes ----------------------------------------------------------------------
+// Same trick as the reference's required<T>() (rasterizer_impl.h:66-73): carve from a null
+// base and read how far the cursor moved, plus slack for the base pointer's alignment.
+size_t lgs_geom_bytes(int P) {
+    if (P < 0) return 0;
+    GeomState g = geom_from_chunk(nullptr, P);
+    return (size_t)(reinterpret_cast<uintptr_t>(g.scan_temp) + g.scan_temp_bytes) + 256;
+}
+size_t lgs_image_bytes(int W, int H) {
+    if (W < 0 || H < 0) return 0;
+    ImageState im = image_from_chunk(nullptr, W, H);
+    const size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    return (size_t)(reinterpret_cast<uintptr_t>(im.tile_last + (tiles > 0 ? tiles : 1))) + 256;
+}
+size_t lgs_binning_bytes(int R) {
+    if (R < 0) return 0;
+    BinningState b = binning_from_chunk(nullptr, R);
+    return (size_t)(reinterpret_cast<uintptr_t>(b.sort_temp) + b.sort_temp_bytes) + 256;
+}
+
+// ---- forward ---------------------------------------------------------------------------
+int lgs_forward_stage1(int P, int D, int M, int W, int H, const float* means3D, const float* shs,
+                       const float* colors_precomp, const float* opacities, const float* scales,
+                       float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                       const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                       float tan_fovx, float tan_fovy, int prefiltered, char* geom_buffer, int* radii,
+                       int* num_rendered_host, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!num_rendered_host) return LGS_ERR_INVALID_ARG;
+    *num_rendered_host = 0;
+    if (P < 0 || W <= 0 || H <= 0 || D < 0 || D > 3) return LGS_ERR_INVALID_ARG;
+    if (P == 0) return LGS_OK;
+    if (!means3D || !opacities || !viewmatrix || !projmatrix || !geom_buffer) return LGS_ERR_INVALID_ARG;
+    if (!shs && !colors_precomp) return LGS_ERR_NO_COLOR;
+    if (!colors_precomp && (!cam_pos || M < (D + 1) * (D + 1))) return LGS_ERR_INVALID_ARG;
+    if (!cov3D_precomp && (!scales || !rotations)) return LGS_ERR_NO_COV;
+    if (rotations && !aligned16(rotations)) return LGS_ERR_ALIGNMENT;
+    if (shs && !aligned16(shs)) return LGS_ERR_ALIGNMENT;
+
+    GeomState g = geom_from_chunk(geom_buffer, P);
+    if (!radii) radii = g.internal_radii;
+    int st = launch_preprocess(P, D, M, means3D, shs, colors_precomp, opacities, scales, scale_modifier,
+                               rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, W, H, tan_fovx,
+                               tan_fovy, prefiltered, g, radii, s);
+    if (st != LGS_OK) return st;
+    st = launch_scan(P, g, s);
+    if (st != LGS_OK) return st;
+    // the one readback of the forward (reference rasterizer_impl.cu:281-282)
+    uint32_t R = 0;
+    LGS_CUDA_TRY(cudaMemcpyAsync(&R, g.point_offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    LGS_CUDA_TRY(cudaStreamSynchronize(s));
+    *num_rendered_host = (int)R;
+    return LGS_OK;
+}
+
+int lgs_forward_stage2(int P, int W, int H, int R, const float* background, const float* lang_feat,
+                       char* geom_buffer, char* binning_buffer, char* image_buffer, float* out_color,
+                       float* out_lang_feat, float* out_depth, int include_lang_feat, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P < 0 || W <= 0 || H <= 0 || R < 0) return LGS_ERR_INVALID_ARG;
+    if (!background || !image_buffer || !out_color || !out_depth) return LGS_ERR_INVALID_ARG;
+    if (include_lang_feat && (!lang_feat || !out_lang_feat)) return LGS_ERR_INVALID_ARG;
+    if (include_lang_feat && !aligned16(lang_feat)) return LGS_ERR_ALIGNMENT;
+    if (P > 0 && !geom_buffer) return LGS_ERR_INVALID_ARG;
+    if (R > 0 && !binning_buffer) return LGS_ERR_INVALID_ARG;
+
+    GeomState g = geom_from_chunk(geom_buffer, P);
+    BinningState b = binning_from_chunk(binning_buffer, R);
+    ImageState im = image_from_chunk(image_buffer, W, H);
+    // radii for key emission: the internal copy is always written by stage1 when the
+    // caller passed NULL; otherwise stage1 wrote the caller's array and mirrors it here.
+    int st = launch_binning(P, R, W, H, g, g.internal_radii, b, im, s);
+    if (st != LGS_OK) return st;
+    return launch_render_fwd(W, H, R, g, b, im, background, lang_feat, out_color, out_lang_feat, out_depth,
+                             include_lang_feat != 0, s);
+}
+
+// ---- markVisible -----------------------------------------------------------------------
+int lgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     unsigned char* present, void* stream) {
+    (void)projmatrix;  // the reference computes p_proj and never uses it (auxiliary.h:150-154)
+    if (P < 0) return LGS_ERR_INVALID_ARG;
+    if (P == 0) return LGS_OK;
+    if (!means3D || !viewmatrix || !present) return LGS_ERR_INVALID_ARG;
+    return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+// ---- backward --------------------------------------------------------------------------
+int lgs_backward(int P, int D, int M, int R, int W, int H, const float* background, const float* means3D,
+                 const float* shs, const float* colors_precomp, const float* lang_feat, const float* scales,
+                 float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                 const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                 float tan_fovy, const int* radii, const char* geom_buffer, const char* binning_buffer,
+                 const char* image_buffer, const float* dL_dpix, const float* dL_dpix_lf,
+                 const float* dL_dpix_depth, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                 float* dL_dcolor, float* dL_dlang_feat, float* dL_ddepth, float* dL_dmean3D,
+                 float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, int include_lang_feat,
+                 int zero_outputs, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P < 0 || W <= 0 || H <= 0 || R < 0 || D < 0 || D > 3) return LGS_ERR_INVALID_ARG;
+    if (P == 0) return LGS_OK;
+    if (!background || !means3D || !viewmatrix || !projmatrix || !geom_buffer || !image_buffer)
+        return LGS_ERR_INVALID_ARG;
+    if (R > 0 && !binning_buffer) return LGS_ERR_INVALID_ARG;
+    if (!dL_dpix || !dL_dpix_depth || !dL_dmean2D || !dL_dconic || !dL_dopacity || !dL_dcolor || !dL_dmean3D ||
+        !dL_dcov3D)
+        return LGS_ERR_INVALID_ARG;
+    if (include_lang_feat && (!lang_feat || !dL_dpix_lf || !dL_dlang_feat)) return LGS_ERR_INVALID_ARG;
+    if (shs && (!dL_dsh || !cam_pos)) return LGS_ERR_INVALID_ARG;
+    if (scales && (!rotations || !dL_dscale || !dL_drot)) return LGS_ERR_INVALID_ARG;
+    if (!cov3D_precomp && !scales) return LGS_ERR_NO_COV;
+    if ((rotations && !aligned16(rotations)) || (dL_drot && !aligned16(dL_drot)) || !aligned16(dL_dconic) ||
+        (include_lang_feat && (!aligned16(lang_feat) || !aligned16(dL_dlang_feat))))
+        return LGS_ERR_ALIGNMENT;
+
+    GeomState g = geom_from_chunk(const_cast<char*>(geom_buffer), P);
+    BinningState b = binning_from_chunk(const_cast<char*>(binning_buffer), R);
+    ImageState im = image_from_chunk(const_cast<char*>(image_buffer), W, H);
+    if (!radii) radii = g.internal_radii;
+
+    int st;
+    if (zero_outputs) {
+        st = launch_zero_grads(P, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dlang_feat, dL_ddepth,
+                               include_lang_feat != 0, s);
+        if (st != LGS_OK) return st;
+    }
+    if (R > 0) {
+        st = launch_render_bwd(P, W, H, R, g, b, im, background, lang_feat, dL_dpix, dL_dpix_lf, dL_dpix_depth,
+                               dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dlang_feat, dL_ddepth,
+                               include_lang_feat != 0, s);
+        if (st != LGS_OK) return st;
+    }
+    const float* cov3D = cov3D_precomp ? cov3D_precomp : g.cov3D;
+    return launch_preprocess_bwd(P, D, M, means3D, radii, shs, scales, rotations, scale_modifier, cov3D,
+                                 viewmatrix, projmatrix, cam_pos, W, H, tan_fovx, tan_fovy, g, dL_dmean2D,
+                                 dL_dconic, dL_dmean3D, dL_dcolor, dL_dcov3D, dL_dsh, dL_dscale, dL_drot,
+                                 zero_outputs != 0, s);
+}
+
+// ---- introspection ---------------------------------------------------------------------
+int lgs_view_binning(const char* binning_buffer, int R, lgs_binning_view* out) {
+    if (!out || R < 0) return LGS_ERR_INVALID_ARG;
+    BinningState b = binning_from_chunk(const_cast<char*>(binning_buffer), R);
+    out->keys_unsorted = b.keys_unsorted;
+    out->values_unsorted = b.vals_unsorted;
+    out->keys_sorted = b.keys;
+    out->point_list = b.point_list;
+    return LGS_OK;
+}
+int lgs_view_image(const char* image_buffer, int W, int H, lgs_image_view* out) {
+    if (!out || W <= 0 || H <= 0) return LGS_ERR_INVALID_ARG;
+    ImageState im = image_from_chunk(const_cast<char*>(image_buffer), W, H);
+    out->ranges = reinterpret_cast<const uint32_t*>(im.ranges);
+    out->final_T = im.final_T;
+    out->n_contrib = im.n_contrib;
+    return LGS_OK;
+}
+int lgs_view_geom(const char* geom_buffer, int P, lgs_geom_view* out) {
+    if (!out || P < 0) return LGS_ERR_INVALID_ARG;
+    GeomState g = geom_from_chunk(const_cast<char*>(geom_buffer), P);
+    out->records = reinterpret_cast<const float*>(g.rec);
+    out->cov3D = g.cov3D;
+    out->tiles_touched = g.tiles_touched;
+    out->point_offsets = g.point_offsets;
+    out->internal_radii = g.internal_radii;
+    out->clamped = g.clamped;
+    return LGS_OK;
+}
+
+}  // extern "C"

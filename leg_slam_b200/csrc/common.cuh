@@ -1,0 +1,133 @@
+// common.cuh -- shared definitions for the sm_100a kernels of liblgs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "lgs.h"
+
+namespace lgs {
+
+constexpr int TILE = LGS_TILE;          // 8x8 pixel tiles (reference config.h:17-18)
+constexpr int TILE_PIX = TILE * TILE;   // 64
+constexpr int LF = LGS_LF_DIM;          // 64 language-feature channels
+constexpr int NCH = LGS_NUM_CHANNELS;   // 3 colour channels
+constexpr int REC_FLOATS = 12;          // per-Gaussian render record, 48 B (3 x float4)
+
+// ---- per-Gaussian render record (geometry buffer) --------------------------------
+// One 48-byte record replaces the reference's separate means2D / depths /
+// conic_opacity / rgb arrays (rasterizer_impl.h:33-48): the render kernels move
+// one contiguous 48 B chunk per (tile, Gaussian) instance instead of four gathers.
+//   q0 = (x, y, depth, 0)   q1 = (conic.a, conic.b, conic.c, opacity)   q2 = (r, g, b, 0)
+struct __align__(16) GaussRec {
+    float4 q0, q1, q2;
+};
+static_assert(sizeof(GaussRec) == 48, "record must be 48 bytes");
+
+// ---- carved views of the three opaque buffers ------------------------------------
+struct GeomState {
+    GaussRec* rec;            // [P]
+    float* cov3D;             // [P*6]
+    uint32_t* tiles_touched;  // [P]
+    uint32_t* point_offsets;  // [P]
+    int32_t* internal_radii;  // [P]
+    uint8_t* clamped;         // [P] bit c = colour channel c clamped at 0
+    char* scan_temp;          // CUB scan scratch
+    size_t scan_temp_bytes;
+};
+struct ImageState {
+    uint2* ranges;        // [tiles]
+    float* final_T;       // [H*W]
+    uint32_t* n_contrib;  // [H*W]
+    uint32_t* tile_last;  // [tiles] max n_contrib over the tile's pixels (bwd skips the rest)
+};
+struct BinningState {
+    uint64_t* keys_unsorted;  // [R]
+    uint64_t* keys;           // [R]
+    uint32_t* vals_unsorted;  // [R]
+    uint32_t* point_list;     // [R]
+    char* sort_temp;
+    size_t sort_temp_bytes;
+};
+
+template <typename T>
+static inline void carve(char*& p, T*& out, size_t count, size_t align = 256) {
+    uintptr_t a = (reinterpret_cast<uintptr_t>(p) + align - 1) & ~(uintptr_t)(align - 1);
+    out = reinterpret_cast<T*>(a);
+    p = reinterpret_cast<char*>(out + count);
+}
+
+size_t scan_temp_bytes(int P);
+size_t sort_temp_bytes(int R);
+GeomState geom_from_chunk(char* chunk, int P);
+ImageState image_from_chunk(char* chunk, int W, int H);
+BinningState binning_from_chunk(char* chunk, int R);
+
+// ---- error plumbing ----------------------------------------------------------------
+void set_last_cuda_error(cudaError_t e);
+#define LGS_CUDA_TRY(expr)                                   \
+    do {                                                     \
+        cudaError_t _e = (expr);                             \
+        if (_e != cudaSuccess) {                             \
+            ::lgs::set_last_cuda_error(_e);                  \
+            return LGS_ERR_CUDA;                             \
+        }                                                    \
+    } while (0)
+#define LGS_LAUNCH_CHECK() LGS_CUDA_TRY(cudaGetLastError())
+
+// ---- kernel launchers (one per .cu) ------------------------------------------------
+struct ViewParams {
+    float view[16];
+    float proj[16];
+    float cam[3];
+    float tan_fovx, tan_fovy, focal_x, focal_y;
+    int W, H, tiles_x, tiles_y;
+};
+
+int launch_preprocess(int P, int D, int M, const float* means3D, const float* shs,
+                      const float* colors_precomp, const float* opacities, const float* scales,
+                      float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                      const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                      int W, int H, float tan_fovx, float tan_fovy, int prefiltered,
+                      GeomState& g, int* radii, cudaStream_t s);
+int launch_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                        unsigned char* present, cudaStream_t s);
+int launch_scan(int P, GeomState& g, cudaStream_t s);
+int launch_binning(int P, int R, int W, int H, const GeomState& g, const int* radii,
+                   BinningState& b, ImageState& im, cudaStream_t s);
+int launch_render_fwd(int W, int H, int R, const GeomState& g, const BinningState& b,
+                      ImageState& im, const float* background, const float* lang_feat,
+                      float* out_color, float* out_lang_feat, float* out_depth,
+                      bool include_lf, cudaStream_t s);
+int launch_render_bwd(int P, int W, int H, int R, const GeomState& g, const BinningState& b,
+                      const ImageState& im, const float* background, const float* lang_feat,
+                      const float* dL_dpix, const float* dL_dpix_lf, const float* dL_dpix_depth,
+                      float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                      float* dL_dlang_feat, float* dL_ddepth, bool include_lf, cudaStream_t s);
+int launch_preprocess_bwd(int P, int D, int M, const float* means3D, const int* radii,
+                          const float* shs, const float* scales, const float* rotations,
+                          float scale_modifier, const float* cov3D, const float* viewmatrix,
+                          const float* projmatrix, const float* cam_pos, int W, int H,
+                          float tan_fovx, float tan_fovy, const GeomState& g,
+                          const float* dL_dmean2D, const float* dL_dconic, float* dL_dmean3D,
+                          const float* dL_dcolor, float* dL_dcov3D, float* dL_dsh,
+                          float* dL_dscale, float* dL_drot, bool write_zeros, cudaStream_t s);
+int launch_zero_grads(int P, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                      float* dL_dcolor, float* dL_dlang_feat, float* dL_ddepth, bool include_lf,
+                      cudaStream_t s);
+
+#ifdef __CUDACC__
+// ---- per-fragment falloff shared by the forward and backward blend kernels -----------------
+// power = -0.5*(a*dx*dx + c*dy*dy) - b*dx*dy with the exact association the reference's
+// renderCUDA compiles to on sm_100 (forward.cu:337-341 -> SASS: s = fma(dx, dx*a, dy*(dy*c));
+// power = fma(s, -0.5, -(dy*(dx*b)))), so that the alpha tests, T and n_contrib are decided on
+// bit-identical values.
+__device__ __forceinline__ float eval_power(float gx, float gy, float px, float py, float a, float b, float c,
+                                            float& dx, float& dy) {
+    dx = __fsub_rn(gx, px);
+    dy = __fsub_rn(gy, py);
+    const float s = __fmaf_rn(dx, __fmul_rn(dx, a), __fmul_rn(dy, __fmul_rn(dy, c)));
+    return __fmaf_rn(s, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, b)));
+}
+#endif
+
+}  // namespace lgs

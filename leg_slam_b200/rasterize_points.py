@@ -1,0 +1,138 @@
+"""L1 of the drop-in boundary in Python: the three functions the reference exports from
+`rasterize_points.cu` / pybind `_C`, same names, argument order, return tuples and error
+behaviour, implemented on liblgs.so (include/lgs.h) -- never on torch ops.
+
+  rasterize_gaussians(...)          <- RasterizeGaussiansCUDA          (src/rasterize_points.cu:37-120)
+  rasterize_gaussians_backward(...) <- RasterizeGaussiansBackwardCUDA  (src/rasterize_points.cu:122-209)
+  mark_visible(...)                 <- markVisible                     (src/rasterize_points.cu:211-228)
+
+The C++ twin of this file (csrc/host/rasterize_points.cpp) exports the libtorch signatures
+themselves; both sit on the same C ABI.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr
+
+NUM_CHANNELS = 3
+LF_NUM_CHANNELS = 64
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _f32c(t):
+    """`.contiguous()` as the reference does on every input (float32 is assumed there too)."""
+    if t is None:
+        return None
+    if t.numel() and t.dtype != torch.float32:
+        raise TypeError(f"expected float32 tensor, got {t.dtype}")
+    return t.contiguous()
+
+
+def rasterize_gaussians(background, means3D, colors, lang_feat, opacity, scales, rotations, scale_modifier,
+                        cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width,
+                        sh, degree, campos, prefiltered, include_lang_feat):
+    """-> (num_rendered, out_color[3,H,W], out_lang_feat[64,H,W], out_depth[1,H,W], radii[P] int32,
+           geomBuffer, binningBuffer, imgBuffer)"""
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise ValueError("means3D must have dimensions (num_points, 3)")  # AT_ERROR, rasterize_points.cu:59-61
+    L = _lib.lib()
+    if not means3D.is_cuda:
+        raise _lib.LgsError("leg_slam_b200 has no CPU path: tensors must live on a CUDA device")
+    P, H, W = int(means3D.size(0)), int(image_height), int(image_width)
+    dev = means3D.device
+    fopt = dict(dtype=torch.float32, device=dev)
+    byte = dict(dtype=torch.uint8, device=dev)
+    include_lf = bool(include_lang_feat)
+
+    if P == 0:  # the reference returns its zero-filled outputs untouched
+        return (0, torch.zeros((NUM_CHANNELS, H, W), **fopt), torch.zeros((LF_NUM_CHANNELS, H, W), **fopt),
+                torch.zeros((1, H, W), **fopt), torch.zeros((0,), dtype=torch.int32, device=dev),
+                torch.empty(0, **byte), torch.empty(0, **byte), torch.empty(0, **byte))
+
+    # every pixel of the written outputs is written by the kernel: no memset needed
+    out_color = torch.empty((NUM_CHANNELS, H, W), **fopt)
+    out_depth = torch.empty((1, H, W), **fopt)
+    out_lf = (torch.empty if include_lf else torch.zeros)((LF_NUM_CHANNELS, H, W), **fopt)
+    radii = torch.empty((P,), dtype=torch.int32, device=dev)
+
+    background, means3D, colors, lang_feat, opacity, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, \
+        sh, campos = map(_f32c, (background, means3D, colors, lang_feat, opacity, scales, rotations, cov3D_precomp,
+                                 viewmatrix, projmatrix, sh, campos))
+    M = int(sh.size(1)) if sh is not None and sh.size(0) != 0 else 0
+    s = _stream(means3D)
+
+    geom = torch.empty(L.lgs_geom_bytes(P), **byte)
+    img = torch.empty(L.lgs_image_bytes(W, H), **byte)
+    R = ctypes.c_int(0)
+    with torch.cuda.device(dev):
+        check(L.lgs_forward_stage1(P, int(degree), M, W, H, ptr(means3D), ptr(sh), ptr(colors), ptr(opacity),
+                                   ptr(scales), float(scale_modifier), ptr(rotations), ptr(cov3D_precomp),
+                                   ptr(viewmatrix), ptr(projmatrix), ptr(campos), float(tan_fovx), float(tan_fovy),
+                                   int(bool(prefiltered)), geom.data_ptr(), radii.data_ptr(), ctypes.byref(R), s),
+              "lgs_forward_stage1")
+        binning = torch.empty(L.lgs_binning_bytes(R.value), **byte)
+        check(L.lgs_forward_stage2(P, W, H, R.value, ptr(background), ptr(lang_feat) if include_lf else None,
+                                   geom.data_ptr(), binning.data_ptr(), img.data_ptr(), out_color.data_ptr(),
+                                   out_lf.data_ptr(), out_depth.data_ptr(), int(include_lf), s),
+              "lgs_forward_stage2")
+    return R.value, out_color, out_lf, out_depth, radii, geom, binning, img
+
+
+def rasterize_gaussians_backward(background, means3D, radii, colors, lang_feat, scales, rotations, scale_modifier,
+                                 cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
+                                 dL_dout_lang_feat, dL_dout_depth, sh, degree, campos, geomBuffer, R, binningBuffer,
+                                 imageBuffer, include_lang_feat):
+    """-> (dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dlang_feats[P,64], dL_dopacity[P,1], dL_dmeans3D[P,3],
+           dL_dcov3D[P,6], dL_dsh[P,M,3], dL_dscales[P,3], dL_drotations[P,4])"""
+    L = _lib.lib()
+    P = int(means3D.size(0))
+    H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
+    dev = means3D.device
+    M = int(sh.size(1)) if sh is not None and sh.size(0) != 0 else 0
+    include_lf = bool(include_lang_feat)
+    mk = (lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)) if P else \
+         (lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev))
+    dL_dmeans3D, dL_dmeans2D, dL_dcolors = mk(P, 3), mk(P, 3), mk(P, NUM_CHANNELS)
+    # without language features nothing accumulates into dL_dlang_feats: it must still be zeros
+    dL_dlang = mk(P, LF_NUM_CHANNELS) if include_lf else torch.zeros((P, LF_NUM_CHANNELS), dtype=torch.float32, device=dev)
+    dL_dconic, dL_dopacity, dL_dcov3D = mk(P, 2, 2), mk(P, 1), mk(P, 6)
+    # the kernel fills (or zero-fills) these only on the path that produces them
+    has_sh = M != 0 and sh is not None and sh.numel() != 0
+    has_scales = scales is not None and scales.numel() != 0
+    dL_dsh = mk(P, M, 3) if has_sh else torch.zeros((P, M, 3), dtype=torch.float32, device=dev)
+    dL_dscales = mk(P, 3) if has_scales else torch.zeros((P, 3), dtype=torch.float32, device=dev)
+    dL_drot = mk(P, 4) if has_scales else torch.zeros((P, 4), dtype=torch.float32, device=dev)
+    if P != 0:
+        background, means3D, colors, lang_feat, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, sh, \
+            campos, dL_dout_color, dL_dout_lang_feat, dL_dout_depth = map(
+                _f32c, (background, means3D, colors, lang_feat, scales, rotations, cov3D_precomp, viewmatrix,
+                        projmatrix, sh, campos, dL_dout_color, dL_dout_lang_feat, dL_dout_depth))
+        with torch.cuda.device(dev):
+            check(L.lgs_backward(
+                P, int(degree), M, int(R), W, H, ptr(background), ptr(means3D), ptr(sh), ptr(colors),
+                ptr(lang_feat) if include_lf else None, ptr(scales), float(scale_modifier), ptr(rotations),
+                ptr(cov3D_precomp), ptr(viewmatrix), ptr(projmatrix), ptr(campos), float(tan_fovx), float(tan_fovy),
+                ptr(radii.contiguous()), ptr(geomBuffer), ptr(binningBuffer), ptr(imageBuffer), ptr(dL_dout_color),
+                ptr(dL_dout_lang_feat) if include_lf else None, ptr(dL_dout_depth), dL_dmeans2D.data_ptr(),
+                dL_dconic.data_ptr(), dL_dopacity.data_ptr(), dL_dcolors.data_ptr(), dL_dlang.data_ptr(), None,
+                dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr(), ptr(dL_dsh), ptr(dL_dscales), ptr(dL_drot),
+                int(include_lf), 1, _stream(means3D)), "lgs_backward")
+    return dL_dmeans2D, dL_dcolors, dL_dlang, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drot
+
+
+def mark_visible(means3D, viewmatrix, projmatrix):
+    """-> bool[P], true where the Gaussian's view-space z exceeds 0.2."""
+    L = _lib.lib()
+    P = int(means3D.size(0))
+    present = torch.zeros((P,), dtype=torch.bool, device=means3D.device)
+    if P != 0:
+        means3D, viewmatrix, projmatrix = map(_f32c, (means3D, viewmatrix, projmatrix))
+        with torch.cuda.device(means3D.device):
+            check(L.lgs_mark_visible(P, ptr(means3D), ptr(viewmatrix), ptr(projmatrix), present.data_ptr(),
+                                     _stream(means3D)), "lgs_mark_visible")
+    return present

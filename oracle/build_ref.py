@@ -1,0 +1,104 @@
+#!/usr/bin/env python
+"""Build the UNMODIFIED reference rasterizer for sm_100 into oracle/_ref/.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under leg_slam_b200/ may import or link what
+this script produces; only tests/, __graft_entry__.smoke() and bench.py's
+reference / cpu_baseline legs do.
+
+The reference ships a self-contained copy of its CUDA rasterizer + libtorch
+binding + vendored glm under
+    /root/reference/eval/submodules/diff-gaussian-rasterization-legs-slam/
+(byte-identical to /root/reference/cuda_rasterizer + src/rasterize_points.cu
+except LF_NUM_CHANNELS is hard-coded to 64).  We compile
+those sources *where they lie* (no copy into this repo) with our own short
+recipe -- not the reference's setup.py/CMake:
+
+  nvcc  -gencode arch=compute_100,code=sm_100 -include cstdint   forward.cu backward.cu rasterizer_impl.cu
+  g++   -x c++                                                   rasterize_points.cu ext.cpp   (no kernels in them)
+  g++   -shared  ->  oracle/_ref/ref_rasterizer.so   (python module `ref_rasterizer`)
+
+`-include cstdint` is needed because gcc-13 no longer leaks std::uintptr_t
+through <iostream> (rasterizer_impl.h:24).  No other change.
+
+oracle/_ref/ is git-ignored (binary) but NOT gpurun-ignored: the .so travels to
+the GPU box, where /root/reference does not exist.
+"""
+import os
+import subprocess
+import sys
+import sysconfig
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "_ref")
+REF = "/root/reference/eval/submodules/diff-gaussian-rasterization-legs-slam"
+MODNAME = "ref_rasterizer"
+
+
+def _torch_paths():
+    import torch  # noqa: F401
+    from torch.utils import cpp_extension as ce
+    return ce.include_paths(), ce.library_paths()
+
+
+def build(force=False, verbose=True):
+    so = os.path.join(OUT, MODNAME + ".so")
+    if os.path.exists(so) and not force:
+        return so
+    if not os.path.isdir(REF):
+        raise RuntimeError("reference tree not present (GPU box?) and no prebuilt " + so)
+    os.makedirs(OUT, exist_ok=True)
+    inc, lib = _torch_paths()
+    pyinc = sysconfig.get_paths()["include"]
+    glm = os.path.join(REF, "third_party", "glm")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+
+    nvcc = [os.path.join(cuda, "bin", "nvcc"), "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+            "-gencode", "arch=compute_100,code=sm_100", "-include", "cstdint",
+            "-I" + glm, "-I" + REF, "-c"]
+    cxx = ["g++", "-O2", "-std=c++17", "-fPIC", "-x", "c++",
+           "-DTORCH_EXTENSION_NAME=" + MODNAME, "-DTORCH_API_INCLUDE_EXTENSION_H",
+           "-D_GLIBCXX_USE_CXX11_ABI=1",
+           "-I" + REF, "-I" + os.path.join(cuda, "include"), "-I" + pyinc] + ["-I" + p for p in inc] + ["-c"]
+
+    jobs = []
+    objs = []
+    for f in ("cuda_rasterizer/forward.cu", "cuda_rasterizer/backward.cu", "cuda_rasterizer/rasterizer_impl.cu"):
+        o = os.path.join(OUT, os.path.basename(f) + ".o")
+        objs.append(o)
+        jobs.append(nvcc + [os.path.join(REF, f), "-o", o])
+    for f in ("rasterize_points.cu", "ext.cpp"):
+        o = os.path.join(OUT, os.path.basename(f) + ".o")
+        objs.append(o)
+        jobs.append(cxx + [os.path.join(REF, f), "-o", o])
+
+    def run(cmd):
+        if verbose:
+            print("[build_ref]", " ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+
+    with ThreadPoolExecutor(max_workers=5) as ex:
+        list(ex.map(run, jobs))
+
+    link = ["g++", "-shared", "-o", so] + objs + ["-L" + p for p in lib] + \
+           ["-L" + os.path.join(cuda, "lib64"), "-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python",
+            "-lc10_cuda", "-ltorch_cuda", "-lcudart"] + ["-Wl,-rpath," + p for p in lib]
+    run(link)
+    return so
+
+
+def load():
+    """Import the prebuilt module (after `import torch`)."""
+    import importlib.util
+    import torch  # noqa: F401  (libtorch must be loaded first)
+    so = os.path.join(OUT, MODNAME + ".so")
+    if not os.path.exists(so):
+        raise FileNotFoundError(so + " missing: run `python oracle/build_ref.py` where /root/reference exists")
+    spec = importlib.util.spec_from_file_location(MODNAME, so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))
