@@ -1,0 +1,338 @@
+"""GPU parity tests: the CUDA path (through the reference-shaped API on the C ABI) against
+(1) the CPU oracle on the same seeded inputs, (2) the golden fixtures produced by the
+UNMODIFIED reference (tests/golden/), (3) the compiled reference itself when oracle/_ref was
+shipped.  Gates: keys / sorted order / tile ranges / radii bit-exact;
+images <= 1e-4 relative; gradients <= 1e-3 relative."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+IMG_TOL = 1e-4
+GRAD_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def run_ours(cs):
+    from leg_slam_b200 import rasterize_points as rp, debug
+    R, color, lf, depth, radii, geom, binning, img = rp.rasterize_gaussians(*cases.fwd_args(cs))
+    grads = rp.rasterize_gaussians_backward(*cases.bwd_args(cs, radii, geom, R, binning, img))
+    torch.cuda.synchronize()
+    P, W, H = cs["P"], cs["W"], cs["H"]
+    n = lambda t: t.detach().cpu().numpy()  # noqa: E731
+    gv, bv, iv = debug.geom_view(geom, P), debug.binning_view(binning, R), debug.image_view(img, W, H)
+    out = dict(num_rendered=R, radii=n(radii), out_color=n(color), out_lf=n(lf), out_depth=n(depth),
+               records=n(gv["records"]), cov3D=n(gv["cov3D"]), tiles_touched=n(gv["tiles_touched"]),
+               keys_unsorted=n(bv["keys_unsorted"]), values_unsorted=n(bv["values_unsorted"]),
+               keys_sorted=n(bv["keys_sorted"]), point_list=n(bv["point_list"]), ranges=n(iv["ranges"]),
+               n_contrib=n(iv["n_contrib"]), final_T=n(iv["final_T"]))
+    for name, g in zip(cases.GRAD_NAMES, grads):
+        out[name] = n(g)
+    return out
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_forward_backward_vs_oracle(name, dev, oracle_mod):
+    cs = cases.make_case(name, dev)
+    ours = run_ours(cs)
+    f = cases.oracle_forward(cases.make_case(name), oracle_mod)
+    g = cases.oracle_backward(cases.make_case(name), f, oracle_mod)
+    vis = f["radii"] > 0
+    # ---- integer / bit-exact gates
+    assert ours["num_rendered"] == f["num_rendered"]
+    np.testing.assert_array_equal(ours["radii"], f["radii"])
+    np.testing.assert_array_equal(ours["tiles_touched"].view(np.uint32), f["tiles_touched"])
+    np.testing.assert_array_equal(ours["records"][vis, 2].view(np.uint32), f["depths"][vis].view(np.uint32))
+    np.testing.assert_array_equal(ours["records"][vis, 0:2].copy().view(np.uint32), f["means2D"][vis].view(np.uint32))
+    np.testing.assert_array_equal(ours["keys_unsorted"].view(np.uint64), f["keys_unsorted"])
+    np.testing.assert_array_equal(ours["values_unsorted"].view(np.uint32), f["values_unsorted"])
+    np.testing.assert_array_equal(ours["keys_sorted"].view(np.uint64), f["keys_sorted"])
+    np.testing.assert_array_equal(ours["point_list"].view(np.uint32), f["point_list"])
+    np.testing.assert_array_equal(ours["ranges"].view(np.uint32), f["ranges"])
+    # conic: same float sequence on both sides (division / fma are IEEE on CPU and GPU)
+    np.testing.assert_array_equal(ours["records"][vis, 4:8].copy().view(np.uint32), f["conic_opacity"][vis].view(np.uint32))
+    # ---- images (expf differs by ulps between libm and CUDA: tolerance, and the per-pixel
+    #      contributor count may differ for a vanishing fraction of threshold-straddling fragments)
+    assert cases.rel_err(ours["out_color"], f["out_color"]) <= IMG_TOL
+    assert cases.rel_err(ours["out_depth"], f["out_depth"]) <= IMG_TOL
+    if cs["include_lf"]:
+        assert cases.rel_err(ours["out_lf"], f["out_lf"]) <= IMG_TOL
+    else:
+        assert not ours["out_lf"].any()  # allocated as zeros, like the reference (rasterize_points.cu:71)
+    assert (ours["n_contrib"].view(np.uint32) != f["n_contrib"]).mean() <= 1e-3
+    # ---- gradients
+    for gname in cases.GRAD_NAMES:
+        assert ours[gname].shape == g[gname].shape, gname
+        assert cases.rel_err(ours[gname], g[gname]) <= GRAD_TOL, gname
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_vs_reference_golden(name, dev):
+    gd = golden(name)
+    cs = cases.make_case(name, dev)
+    ours = run_ours(cs)
+    vis = gd["visible"]
+    assert ours["num_rendered"] == int(gd["num_rendered"])
+    for k in ("radii", "tiles_touched", "keys_unsorted", "values_unsorted", "keys_sorted", "point_list", "ranges",
+              "n_contrib"):
+        np.testing.assert_array_equal(ours[k].view(gd[k].dtype), gd[k], err_msg=k)
+    np.testing.assert_array_equal(ours["records"][vis, 2].view(np.uint32), gd["depths"][vis].view(np.uint32))
+    np.testing.assert_array_equal(ours["records"][vis, 0:2].copy().view(np.uint32), gd["means2D"][vis].view(np.uint32))
+    np.testing.assert_array_equal(ours["final_T"].view(np.uint32), gd["final_T"].view(np.uint32))
+    assert cases.rel_err(ours["out_color"], gd["out_color"]) <= IMG_TOL
+    assert cases.rel_err(ours["out_depth"], gd["out_depth"]) <= IMG_TOL
+    assert cases.rel_err(ours["out_lf"][cases.LF_GOLDEN_CH], gd["out_lf_sub"]) <= IMG_TOL
+    for gname in cases.GRAD_NAMES:
+        o = ours[gname][:, cases.LF_GOLDEN_CH] if gname == "dL_dlang_feats" else ours[gname]
+        assert cases.rel_err(o, gd[gname]) <= GRAD_TOL, gname
+
+
+@pytest.mark.parametrize("name", ["sh3_lf", "dense_opaque"])
+def test_vs_compiled_reference_live(name, dev, ref_mod):
+    """Same call, same tensors, reference .so vs ours, side by side on this GPU."""
+    import refbuf
+    from leg_slam_b200 import rasterize_points as rp, debug
+    cs = cases.make_case(name, dev)
+    Rr, cr, lr, dr, radr, gr, br, ir = ref_mod.rasterize_gaussians(*cases.fwd_args(cs))
+    Ro, co, lo, do, rado, go, bo, io = rp.rasterize_gaussians(*cases.fwd_args(cs))
+    assert Rr == Ro
+    assert torch.equal(radr, rado)
+    rb, ob = refbuf.ref_binning_view(br, Rr), debug.binning_view(bo, Ro)
+    assert torch.equal(rb["keys_sorted"], ob["keys_sorted"])
+    assert torch.equal(rb["point_list"], ob["point_list"])
+    ri, oi = refbuf.ref_image_view(ir, cs["W"], cs["H"]), debug.image_view(io, cs["W"], cs["H"])
+    assert torch.equal(ri["ranges"], oi["ranges"])
+    assert torch.equal(ri["n_contrib"], oi["n_contrib"])
+    n = lambda t: t.cpu().numpy()  # noqa: E731
+    assert cases.rel_err(n(co), n(cr)) <= IMG_TOL and cases.rel_err(n(lo), n(lr)) <= IMG_TOL
+    assert cases.rel_err(n(do), n(dr)) <= IMG_TOL
+    gref = ref_mod.rasterize_gaussians_backward(*cases.bwd_args(cs, radr, gr, Rr, br, ir))
+    gour = rp.rasterize_gaussians_backward(*cases.bwd_args(cs, rado, go, Ro, bo, io))
+    for gname, a, b in zip(cases.GRAD_NAMES, gour, gref):
+        assert cases.rel_err(n(a), n(b)) <= GRAD_TOL, gname
+
+
+# ---------------------------------------------------------------------------- edge cases
+def test_empty_and_all_culled(dev):
+    from leg_slam_b200 import rasterize_points as rp
+    cs = cases.make_case("sh3_lf", dev)
+    # P == 0: zero-filled outputs, nothing rendered (rasterize_points.cu:85: `if (P != 0)`)
+    e = dict(cs)
+    for k in ("means3D", "opacities", "lang_feats", "shs", "scales", "rotations"):
+        e[k] = cs[k][:0]
+    R, color, lf, depth, radii, *_ = rp.rasterize_gaussians(*cases.fwd_args(e))
+    assert R == 0 and radii.numel() == 0 and not color.any() and not lf.any() and not depth.any()
+    # everything behind the camera: R == 0, the image is the background, gradients are all zero
+    b = dict(cs)
+    b["means3D"] = cs["means3D"] - 1000.0 * cs["viewmatrix"][:3, 2]  # push along -view_z
+    R, color, lf, depth, radii, geom, binning, img = rp.rasterize_gaussians(*cases.fwd_args(b))
+    assert R == 0 and not radii.any()
+    assert torch.allclose(color, cs["bg"][:, None, None].expand_as(color))
+    assert not lf.any() and not depth.any()
+    grads = rp.rasterize_gaussians_backward(*cases.bwd_args(b, radii, geom, R, binning, img))
+    assert all(not g.any() for g in grads)
+
+
+def test_single_gaussian_and_huge_radius(dev, oracle_mod):
+    """One Gaussian covering the whole image: its rectangle is clamped to the tile grid."""
+    from leg_slam_b200 import rasterize_points as rp
+    cs = cases.make_case("sh3_lf", dev)
+    cpu = cases.make_case("sh3_lf")
+    for d in (cs, cpu):
+        idx = int((cpu["means3D"] @ cpu["viewmatrix"][:3, 2] + cpu["viewmatrix"][3, 2]).argmax())  # farthest in front
+        for k in ("means3D", "opacities", "lang_feats", "shs", "scales", "rotations"):
+            d[k] = d[k][idx:idx + 1].contiguous()
+        d["scales"] = d["scales"] * 0 + 5.0
+        d["P"] = 1
+    R, color, lf, depth, radii, *_ = rp.rasterize_gaussians(*cases.fwd_args(cs))
+    f = cases.oracle_forward(cpu, oracle_mod)
+    assert R == f["num_rendered"] == ((cs["W"] + 7) // 8) * ((cs["H"] + 7) // 8)
+    assert int(radii[0]) == int(f["radii"][0])
+    assert cases.rel_err(color.cpu().numpy(), f["out_color"]) <= IMG_TOL
+
+
+def test_radii_pointer_optional_and_mark_visible(dev, oracle_mod):
+    from leg_slam_b200 import rasterize_points as rp
+    cs = cases.make_case("ragged_sh1", dev)
+    vis = rp.mark_visible(cs["means3D"], cs["viewmatrix"], cs["projmatrix"])
+    ref = oracle_mod.mark_visible(cs["means3D"].cpu().numpy(), cs["viewmatrix"].cpu().numpy())
+    assert vis.dtype == torch.bool and np.array_equal(vis.cpu().numpy(), ref)
+    assert rp.mark_visible(cs["means3D"][:0], cs["viewmatrix"], cs["projmatrix"]).numel() == 0
+
+
+# ---------------------------------------------------------------------------- full-size properties
+@pytest.fixture(scope="module")
+def cfgB(dev):
+    """BASELINE.json configs[1]: 500k Gaussians, 640x480."""
+    from leg_slam_b200 import synthetic, rasterize_points as rp
+    sc = synthetic.make_scene(500_000, seed=2, device=dev)
+    cam = synthetic.make_cameras(1, 640, 480, seed=2)[0].to(dev)
+    a = synthetic.activate(sc)
+    bg = torch.zeros(3, device=dev)
+    e = torch.empty(0, device=dev)
+    args = (bg, a["means3D"], e, a["lang_feats"], a["opacities"], a["scales"], a["rotations"], 1.0, e, cam.viewmatrix,
+            cam.projmatrix, cam.tanfovx, cam.tanfovy, 480, 640, a["shs"], 3, cam.campos, False, True)
+    out = rp.rasterize_gaussians(*args)
+    return dict(a=a, cam=cam, bg=bg, args=args, out=out)
+
+
+def test_fullsize_binning_properties(cfgB, dev):
+    from leg_slam_b200 import debug
+    R, color, lf, depth, radii, geom, binning, img = cfgB["out"]
+    P, W, H = 500_000, 640, 480
+    gv, bv, iv = debug.geom_view(geom, P), debug.binning_view(binning, R), debug.image_view(img, W, H)
+    tt = gv["tiles_touched"].long()
+    assert int(tt.sum()) == R and torch.equal(gv["point_offsets"].long(), tt.cumsum(0))
+    assert torch.equal(tt > 0, radii > 0)
+    ks = bv["keys_sorted"]
+    assert bool((ks[1:] >= ks[:-1]).all())  # sorted (keys are < 2^63, signed compare is fine)
+    # the sorted list is a permutation of the emitted list: checksum of checksums
+    assert int(ks.sum()) == int(bv["keys_unsorted"].sum())
+    assert int(bv["point_list"].long().sum()) == int(bv["values_unsorted"].long().sum())
+    # stability: equal keys keep emission order = ascending Gaussian index
+    same = ks[1:] == ks[:-1]
+    pl = bv["point_list"].long()
+    assert bool((pl[1:][same] > pl[:-1][same]).all())
+    # ranges tile the list: every tile's range holds exactly its tile id, lengths add up to R
+    rg = iv["ranges"].long()
+    lens = rg[:, 1] - rg[:, 0]
+    assert int(lens.sum()) == R
+    tile_of = (ks >> 32)
+    nz = lens > 0
+    assert torch.equal(tile_of[rg[nz, 0]], torch.nonzero(nz).flatten())
+    assert torch.equal(tile_of[rg[nz, 1] - 1], torch.nonzero(nz).flatten())
+    # depth bits in keys equal the stored depths of the listed Gaussians
+    assert torch.equal((ks & 0xffffffff).int(), gv["records"][pl, 2].contiguous().view(torch.int32))
+    assert bool((iv["n_contrib"].view(H, W).long() <= lens.view(H // 8, W // 8).repeat_interleave(8, 0).repeat_interleave(8, 1)).all())
+
+
+def test_fullsize_forward_idempotent_backward_linear(cfgB, dev):
+    from leg_slam_b200 import rasterize_points as rp
+    R, color, lf, depth, radii, geom, binning, img = cfgB["out"]
+    R2, color2, lf2, depth2, radii2, *_ = rp.rasterize_gaussians(*cfgB["args"])
+    assert R2 == R and torch.equal(color, color2) and torch.equal(lf, lf2) and torch.equal(depth, depth2)
+    assert torch.equal(radii, radii2)
+    assert bool(torch.isfinite(color).all() and torch.isfinite(lf).all() and torch.isfinite(depth).all())
+    a, cam, bg = cfgB["a"], cfgB["cam"], cfgB["bg"]
+    e = torch.empty(0, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    dc = (torch.randn(3, 480, 640, generator=g) / 307200).to(dev)
+    dl = (torch.randn(64, 480, 640, generator=g) / 307200).to(dev)
+    dd = (torch.randn(1, 480, 640, generator=g) / 307200).to(dev)
+
+    def bwd(s):
+        return rp.rasterize_gaussians_backward(bg, a["means3D"], radii, e, a["lang_feats"], a["scales"], a["rotations"],
+                                               1.0, e, cam.viewmatrix, cam.projmatrix, cam.tanfovx, cam.tanfovy,
+                                               dc * s, dl * s, dd * s, a["shs"], 3, cam.campos, geom, R, binning, img, True)
+    g1, g2 = bwd(1.0), bwd(-2.0)
+    for name, x, y in zip(cases.GRAD_NAMES, g1, g2):
+        assert bool(torch.isfinite(x).all()), name
+        assert cases.rel_err((y / -2.0).cpu().numpy(), x.cpu().numpy()) <= 1e-4, name  # linear in the upstream gradient
+    # culled Gaussians receive exactly zero gradient
+    inv = radii == 0
+    for x in g1:
+        assert not x[inv].any()
+
+
+def test_autograd_wrapper_matches_direct_call(dev):
+    from leg_slam_b200 import GaussianRasterizationSettings, GaussianRasterizer, rasterize_points as rp
+    cs = cases.make_case("sh3_lf", dev)
+    rs = GaussianRasterizationSettings(cs["H"], cs["W"], cs["tanfovx"], cs["tanfovy"], cs["bg"], 1.0, cs["viewmatrix"],
+                                       cs["projmatrix"], cs["degree"], cs["campos"], False, True)
+    leaves = {k: cs[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "shs", "lang_feats", "scales", "rotations")}
+    means2D = torch.zeros_like(cs["means3D"], requires_grad=True)
+    color, lf, depth, radii = GaussianRasterizer(rs)(leaves["means3D"], means2D, leaves["opacities"], shs=leaves["shs"],
+                                                     lang_feats=leaves["lang_feats"], scales=leaves["scales"],
+                                                     rotations=leaves["rotations"])
+    ((color * cs["dL_dcolor"]).sum() + (lf * cs["dL_dlf"]).sum() + (depth * cs["dL_ddepth"]).sum()).backward()
+    R, c2, l2, d2, rad2, geom, binning, img = rp.rasterize_gaussians(*cases.fwd_args(cs))
+    direct = dict(zip(cases.GRAD_NAMES, rp.rasterize_gaussians_backward(*cases.bwd_args(cs, rad2, geom, R, binning, img))))
+    assert torch.equal(color, c2) and torch.equal(radii, rad2)
+    pairs = [(leaves["means3D"].grad, direct["dL_dmeans3D"]), (means2D.grad, direct["dL_dmeans2D"]),
+             (leaves["shs"].grad, direct["dL_dsh"]), (leaves["lang_feats"].grad, direct["dL_dlang_feats"]),
+             (leaves["opacities"].grad, direct["dL_dopacity"]), (leaves["scales"].grad, direct["dL_dscales"]),
+             (leaves["rotations"].grad, direct["dL_drotations"])]
+    for a, b in pairs:
+        assert cases.rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-4  # atomics reorder between runs
+
+
+# ---------------------------------------------------------------------------- Adam / cosine
+def test_fused_adam_vs_oracle_and_torch_golden(dev, oracle_mod):
+    from leg_slam_b200 import FusedAdam
+    params, grads = cases.adam_case()
+    tp = {k: torch.nn.Parameter(v.clone().to(dev)) for k, v in params.items()}
+    opt = FusedAdam([dict(params=[tp[k]], lr=cases.ADAM_LRS[k], name=k) for k in tp], lr=0.0, eps=1e-15)
+    op = {k: v.clone().numpy() for k, v in params.items()}
+    om = {k: np.zeros_like(v) for k, v in op.items()}
+    ov = {k: np.zeros_like(v) for k, v in op.items()}
+    try:
+        gd = golden("adam")
+    except pytest.skip.Exception:
+        gd = None
+    for step, gr in enumerate(grads):
+        for k in tp:
+            tp[k].grad = gr[k].to(dev)
+            oracle_mod.adam(op[k].reshape(-1), gr[k].numpy().reshape(-1), om[k].reshape(-1), ov[k].reshape(-1),
+                            cases.ADAM_LRS[k], step=step + 1)
+        opt.step()
+        for k in tp:
+            got = tp[k].detach().cpu().numpy()
+            np.testing.assert_array_equal(got.view(np.uint32), op[k].view(np.uint32), err_msg=f"{k} step {step}")  # bit-exact vs oracle
+            if gd is not None:
+                assert cases.rel_err(got, gd[f"p{step}_{k}"]) <= 1e-6, k  # Adam-updated params <= 1e-6 rel
+    if gd is not None:
+        for k in tp:
+            assert cases.rel_err(opt.state[tp[k]]["exp_avg"].cpu().numpy(), gd[f"m_{k}"]) <= 1e-6
+            assert cases.rel_err(opt.state[tp[k]]["exp_avg_sq"].cpu().numpy(), gd[f"v_{k}"]) <= 1e-6
+
+
+def test_adam_odd_sizes_and_unaligned(dev, oracle_mod):
+    """Ragged tails, a tensor smaller than one vector, an unaligned view."""
+    from leg_slam_b200 import FusedAdam
+    g = torch.Generator().manual_seed(3)
+    shapes = [(1,), (3,), (4097,), (8192,), (12291,)]
+    base = [torch.randn(s[0] + 1, generator=g) for s in shapes]
+    ps = [torch.nn.Parameter(b.to(dev)[1:]) for b in base]  # +4 bytes: not 16-byte aligned
+    gs = [torch.randn(s, generator=g) for s in shapes]
+    opt = FusedAdam([dict(params=[p], lr=1e-2) for p in ps], eps=1e-15)
+    for p, gr in zip(ps, gs):
+        p.grad = gr.to(dev)
+    opt.step()
+    for b, p, gr in zip(base, ps, gs):
+        ref = b[1:].clone().numpy()
+        oracle_mod.adam(ref, gr.numpy(), np.zeros_like(ref), np.zeros_like(ref), 1e-2, step=1)
+        np.testing.assert_array_equal(p.detach().cpu().numpy().view(np.uint32), ref.view(np.uint32))
+
+
+def test_cosine_query(dev, oracle_mod):
+    from leg_slam_b200 import cosine_query, relevance_scores
+    feats, text = cases.cosine_case()
+    sim = cosine_query(feats.to(dev), text.to(dev)).cpu().numpy()
+    ref = oracle_mod.cosine(feats.numpy(), text.numpy())
+    assert sim.shape == ref.shape and np.abs(sim - ref).max() <= 2e-6
+    one = cosine_query(feats.to(dev), text[0].to(dev)).cpu().numpy()
+    np.testing.assert_array_equal(one, sim[:, 0])
+    rel = relevance_scores(feats.to(dev), text[0].to(dev)).cpu().numpy()
+    s0 = ref[:, 0].astype(np.float64)
+    np.testing.assert_allclose(rel, 1 - (s0 - s0.min()) / (s0.max() - s0.min()), atol=5e-6)
+    try:
+        gd = golden("cosine")
+    except pytest.skip.Exception:
+        return
+    assert np.abs(sim - gd["sim"]).max() <= 2e-6
+    assert np.abs(rel - gd["relevance0"]).max() <= 5e-6
+    # many queries (one CTA column sweep is 256 wide)
+    g = torch.Generator().manual_seed(9)
+    text2 = torch.randn(300, 64, generator=g)
+    sim2 = cosine_query(feats[:1000].to(dev), text2.to(dev)).cpu().numpy()
+    assert np.abs(sim2 - oracle_mod.cosine(feats[:1000].numpy(), text2.numpy())).max() <= 2e-6

@@ -1,0 +1,105 @@
+"""CPU: host-side logic of the reference-shaped interface (no kernels run)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from leg_slam_b200 import GaussianRasterizationSettings, GaussianRasterizer, synthetic
+from leg_slam_b200 import _lib
+from leg_slam_b200 import rasterize_points as rp
+
+
+def _settings(cs):
+    return GaussianRasterizationSettings(cs["H"], cs["W"], cs["tanfovx"], cs["tanfovy"], cs["bg"], 1.0, cs["viewmatrix"],
+                                         cs["projmatrix"], cs["degree"], cs["campos"], False, True)
+
+
+def test_rasterizer_argument_validation_matches_reference():
+    """GaussianRasterizer::forward throws on ambiguous inputs (src/gaussian_rasterizer.cpp:196-206)."""
+    cs = cases.make_case("sh3_lf")
+    r = GaussianRasterizer(_settings(cs))
+    m2d = torch.zeros_like(cs["means3D"])
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(cs["means3D"], m2d, cs["opacities"], scales=cs["scales"], rotations=cs["rotations"])
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(cs["means3D"], m2d, cs["opacities"], shs=cs["shs"], colors_precomp=cs["means3D"], scales=cs["scales"],
+          rotations=cs["rotations"])
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(cs["means3D"], m2d, cs["opacities"], shs=cs["shs"], scales=cs["scales"])
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(cs["means3D"], m2d, cs["opacities"], shs=cs["shs"], scales=cs["scales"], rotations=cs["rotations"],
+          cov3D_precomp=torch.zeros(cs["P"], 6))
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are refused loudly: the hot path is CUDA only."""
+    cs = cases.make_case("sh3_lf")
+    with pytest.raises(_lib.LgsError, match="no CPU path"):
+        rp.rasterize_gaussians(*cases.fwd_args(cs))
+    with pytest.raises(ValueError, match="num_points, 3"):
+        bad = dict(cs, means3D=cs["means3D"][:, :2])
+        rp.rasterize_gaussians(*cases.fwd_args(bad))
+    from leg_slam_b200 import cosine_query, FusedAdam
+    with pytest.raises(_lib.LgsError):
+        cosine_query(torch.zeros(4, 64), torch.zeros(64))
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.zeros(4)
+    with pytest.raises(_lib.LgsError):
+        FusedAdam([p], lr=1e-3).step()
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "liblgs.so"))
+    with pytest.raises(_lib.LgsError, match="no CPU or PyTorch fallback"):
+        _lib.lib()
+
+
+def test_camera_conventions_match_reference():
+    """viewmatrix = W2C^T, projmatrix = viewmatrix @ P^T, campos = inverse(viewmatrix)[3,:3]
+    (src/gaussian_keyframe.cpp:111-193); the kernels read both column-major."""
+    cam = synthetic.make_cameras(3, 640, 480, seed=5)[1]
+    assert math.isclose(cam.tanfovx, 1.0, rel_tol=1e-6) and math.isclose(cam.tanfovy, 0.75, rel_tol=1e-6)
+    w2c = cam.viewmatrix.t()
+    R = w2c[:3, :3]
+    assert torch.allclose(R @ R.t(), torch.eye(3), atol=1e-5) and torch.det(R) > 0
+    assert torch.allclose(w2c[3], torch.tensor([0.0, 0.0, 0.0, 1.0]))
+    # camera centre maps to the view-space origin
+    c = torch.cat([cam.campos, torch.ones(1)])
+    assert torch.allclose(w2c @ c, torch.tensor([0.0, 0.0, 0.0, 1.0]), atol=1e-5)
+    # a point 2 m straight ahead projects to the image centre with w = z_view
+    fwd = R[2]  # third row of R_w2c = camera z axis in world coordinates
+    pt = torch.cat([cam.campos + 2.0 * fwd, torch.ones(1)])
+    hom = pt @ cam.projmatrix  # row-vector convention of the stored (transposed) matrix
+    assert abs(float(hom[0] / hom[3])) < 1e-5 and abs(float(hom[1] / hom[3])) < 1e-5
+    assert math.isclose(float(hom[3]), 2.0, rel_tol=1e-5)
+    P = synthetic.projection_matrix(0.01, 100.0, 2 * math.atan(1.0), 2 * math.atan(0.75))
+    assert math.isclose(float(P[0, 0]), 1.0, rel_tol=1e-6) and math.isclose(float(P[1, 1]), 1 / 0.75, rel_tol=1e-6)
+    assert float(P[3, 2]) == 1.0 and math.isclose(float(P[2, 2]), 100.0 / 99.99, rel_tol=1e-6)
+
+
+def test_scene_generator_is_deterministic_and_shaped():
+    a = synthetic.make_scene(5000, seed=3)
+    b = synthetic.make_scene(5000, seed=3)
+    c = synthetic.make_scene(5000, seed=4)
+    for k in a:
+        assert torch.equal(a[k], b[k])
+    assert not torch.equal(a["xyz"], c["xyz"])
+    assert a["features_dc"].shape == (5000, 1, 3) and a["features_rest"].shape == (5000, 15, 3)
+    assert a["lang_feat"].shape == (5000, 64) and a["rotation"].shape == (5000, 4)
+    act = synthetic.activate(a)
+    assert act["shs"].shape == (5000, 16, 3)
+    assert torch.allclose(act["rotations"].norm(dim=1), torch.ones(5000), atol=1e-5)
+    assert (act["opacities"] > 0).all() and (act["opacities"] < 1).all() and (act["scales"] > 0).all()
+    assert (a["xyz"].min(0).values > -0.2).all() and (a["xyz"].max(0).values < torch.tensor([6.2, 4.2, 3.0])).all()
+
+
+def test_cov3d_precomp_helper_matches_oracle(oracle_mod):
+    """tests/cases.covariance_from_scale_rot restates forward.cu:118-152; the oracle's cov3D agrees."""
+    cs = cases.make_case("sh3_lf")
+    f = cases.oracle_forward(cs, oracle_mod)
+    vis = f["radii"] > 0
+    cov = cases.covariance_from_scale_rot(cs["scales"], cs["rotations"]).numpy()
+    assert cases.rel_err(cov[vis], f["cov3D"][vis]) <= 1e-5
