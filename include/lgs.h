@@ -147,6 +147,18 @@ int lgs_view_binning(const char* binning_buffer, int R, lgs_binning_view* out);
 int lgs_view_image(const char* image_buffer, int W, int H, lgs_image_view* out);
 int lgs_view_geom(const char* geom_buffer, int P, lgs_geom_view* out);
 
+/* ---- optional per-stage timing (bench.py's roofline): when enabled, CUDA events are recorded
+ *      on the launch stream between the kernels of stage1 / stage2 / backward.  After the caller
+ *      has synchronised, lgs_profile_read fills ms[0..8] = preprocess, scan, emit_keys, sort,
+ *      tile_ranges, render_fwd, zero_grads, render_bwd, preprocess_bwd (milliseconds, -1 if the
+ *      stage did not run).  Not thread-safe; off by default. */
+int lgs_profile_enable(int on);
+int lgs_profile_read(float* ms, int n);
+
+/* FP32 FMA micro-benchmark for bench.py (issues blocks*256*iters*256 flops of dependent FFMA
+ * chains, 8 per thread); not part of the mapping path. */
+int lgs_bench_fma(int blocks, int iters, float* sink, void* stream);
+
 /* ---- fused multi-tensor Adam  (torch::optim::Adam, reference
  *      src/gaussian_model.cpp:483-518, step at src/gaussian_mapper.cpp:793-796) -----
  * One launch over n <= 16 tensors (host arrays of device pointers).  step is the 1-based

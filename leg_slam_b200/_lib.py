@@ -45,6 +45,9 @@ SIGNATURES = {
     "lgs_view_binning": (c_int, [c_void_p, c_int, ctypes.POINTER(BinningView)]),
     "lgs_view_image": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(ImageView)]),
     "lgs_view_geom": (c_int, [c_void_p, c_int, ctypes.POINTER(GeomView)]),
+    "lgs_profile_enable": (c_int, [c_int]),
+    "lgs_profile_read": (c_int, [ctypes.POINTER(c_float), c_int]),
+    "lgs_bench_fma": (c_int, [c_int, c_int, c_void_p, c_void_p]),
     "lgs_adam_multi": (c_int, [c_int] + [c_void_p] * 6 + [c_double, c_double, c_double, c_int, c_void_p]),
     "lgs_cosine_query": (c_int, [c_int, c_int] + [c_void_p] * 4),
     "lgs_minmax_invert": (c_int, [c_int64] + [c_void_p] * 3),

@@ -12,6 +12,20 @@ namespace lgs {
 static thread_local int g_last_cuda_error = 0;
 void set_last_cuda_error(cudaError_t e) { g_last_cuda_error = (int)e; }
 
+static bool g_prof = false;
+static cudaEvent_t g_ev[PM_COUNT];
+static bool g_ev_made = false;
+static bool g_ev_set[PM_COUNT];
+void prof_mark(int id, cudaStream_t s) {
+    if (!g_prof) return;
+    if (!g_ev_made) {
+        for (int i = 0; i < PM_COUNT; ++i) { cudaEventCreate(&g_ev[i]); g_ev_set[i] = false; }
+        g_ev_made = true;
+    }
+    cudaEventRecord(g_ev[id], s);
+    g_ev_set[id] = true;
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace lgs
@@ -77,12 +91,15 @@ int lgs_forward_stage1(int P, int D, int M, int W, int H, const float* means3D, 
 
     GeomState g = geom_from_chunk(geom_buffer, P);
     if (!radii) radii = g.internal_radii;
+    prof_mark(PM_S1_BEGIN, s);
     int st = launch_preprocess(P, D, M, means3D, shs, colors_precomp, opacities, scales, scale_modifier,
                                rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, W, H, tan_fovx,
                                tan_fovy, prefiltered, g, radii, s);
     if (st != LGS_OK) return st;
+    prof_mark(PM_PREPROCESS, s);
     st = launch_scan(P, g, s);
     if (st != LGS_OK) return st;
+    prof_mark(PM_SCAN, s);
     // the one readback of the forward (reference rasterizer_impl.cu:281-282)
     uint32_t R = 0;
     LGS_CUDA_TRY(cudaMemcpyAsync(&R, g.point_offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -107,10 +124,13 @@ int lgs_forward_stage2(int P, int W, int H, int R, const float* background, cons
     ImageState im = image_from_chunk(image_buffer, W, H);
     // radii for key emission: the internal copy is always written by stage1 when the
     // caller passed NULL; otherwise stage1 wrote the caller's array and mirrors it here.
+    prof_mark(PM_S2_BEGIN, s);
     int st = launch_binning(P, R, W, H, g, g.internal_radii, b, im, s);
     if (st != LGS_OK) return st;
-    return launch_render_fwd(W, H, R, g, b, im, background, lang_feat, out_color, out_lang_feat, out_depth,
-                             include_lang_feat != 0, s);
+    st = launch_render_fwd(W, H, R, g, b, im, background, lang_feat, out_color, out_lang_feat, out_depth,
+                           include_lang_feat != 0, s);
+    prof_mark(PM_RENDER_FWD, s);
+    return st;
 }
 
 // ---- markVisible -----------------------------------------------------------------------
@@ -157,22 +177,52 @@ int lgs_backward(int P, int D, int M, int R, int W, int H, const float* backgrou
     if (!radii) radii = g.internal_radii;
 
     int st;
+    prof_mark(PM_BWD_BEGIN, s);
     if (zero_outputs) {
         st = launch_zero_grads(P, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dlang_feat, dL_ddepth,
                                include_lang_feat != 0, s);
         if (st != LGS_OK) return st;
     }
+    prof_mark(PM_ZERO, s);
     if (R > 0) {
         st = launch_render_bwd(P, W, H, R, g, b, im, background, lang_feat, dL_dpix, dL_dpix_lf, dL_dpix_depth,
                                dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dlang_feat, dL_ddepth,
                                include_lang_feat != 0, s);
         if (st != LGS_OK) return st;
     }
+    prof_mark(PM_RENDER_BWD, s);
     const float* cov3D = cov3D_precomp ? cov3D_precomp : g.cov3D;
-    return launch_preprocess_bwd(P, D, M, means3D, radii, shs, scales, rotations, scale_modifier, cov3D,
+    st = launch_preprocess_bwd(P, D, M, means3D, radii, shs, scales, rotations, scale_modifier, cov3D,
                                  viewmatrix, projmatrix, cam_pos, W, H, tan_fovx, tan_fovy, g, dL_dmean2D,
-                                 dL_dconic, dL_dmean3D, dL_dcolor, dL_dcov3D, dL_dsh, dL_dscale, dL_drot,
-                                 zero_outputs != 0, s);
+                               dL_dconic, dL_dmean3D, dL_dcolor, dL_dcov3D, dL_dsh, dL_dscale, dL_drot,
+                               zero_outputs != 0, s);
+    prof_mark(PM_PREPROCESS_BWD, s);
+    return st;
+}
+
+// ---- per-stage timing ------------------------------------------------------------------
+int lgs_profile_enable(int on) {
+    g_prof = on != 0;
+    return LGS_OK;
+}
+int lgs_profile_read(float* ms, int n) {
+    // ms[0..8] = preprocess, scan, emit_keys(+memset), sort, tile_ranges, render_fwd, zero_grads,
+    //            render_bwd, preprocess_bwd of the most recent forward+backward; the caller must have
+    //            synchronised the stream.  Entries whose stage did not run are -1.
+    static const int a[9] = {PM_S1_BEGIN, PM_PREPROCESS, PM_S2_BEGIN, PM_EMIT, PM_SORT, PM_RANGES, PM_BWD_BEGIN,
+                             PM_ZERO, PM_RENDER_BWD};
+    static const int b[9] = {PM_PREPROCESS, PM_SCAN, PM_EMIT, PM_SORT, PM_RANGES, PM_RENDER_FWD, PM_ZERO,
+                             PM_RENDER_BWD, PM_PREPROCESS_BWD};
+    if (!ms || n < 9) return LGS_ERR_INVALID_ARG;
+    for (int i = 0; i < 9; ++i) {
+        ms[i] = -1.f;
+        if (g_ev_made && g_ev_set[a[i]] && g_ev_set[b[i]]) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, g_ev[a[i]], g_ev[b[i]]) == cudaSuccess) ms[i] = t;
+            else (void)cudaGetLastError();
+        }
+    }
+    return LGS_OK;
 }
 
 // ---- introspection ---------------------------------------------------------------------

@@ -136,12 +136,15 @@ int launch_binning(int P, int R, int W, int H, const GeomState& g, const int* ra
     emit_keys_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g.rec, g.point_offsets, radii,
                                                      b.keys_unsorted, b.vals_unsorted, tiles_x, tiles_y);
     LGS_LAUNCH_CHECK();
+    prof_mark(PM_EMIT, s);
     const int end_bit = 32 + key_bits_for_tiles((uint32_t)tiles);
     size_t n = b.sort_temp_bytes;
     LGS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(b.sort_temp, n, b.keys_unsorted, b.keys,
                                                  b.vals_unsorted, b.point_list, R, 0, end_bit, s));
+    prof_mark(PM_SORT, s);
     tile_ranges_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, b.keys, im.ranges);
     LGS_LAUNCH_CHECK();
+    prof_mark(PM_RANGES, s);
     return LGS_OK;
 }
 

@@ -74,6 +74,11 @@ void set_last_cuda_error(cudaError_t e);
     } while (0)
 #define LGS_LAUNCH_CHECK() LGS_CUDA_TRY(cudaGetLastError())
 
+// ---- optional per-stage timing (lgs_profile_enable): CUDA events recorded on the launch stream
+enum ProfMark { PM_S1_BEGIN = 0, PM_PREPROCESS, PM_SCAN, PM_S2_BEGIN, PM_EMIT, PM_SORT, PM_RANGES, PM_RENDER_FWD,
+                PM_BWD_BEGIN, PM_ZERO, PM_RENDER_BWD, PM_PREPROCESS_BWD, PM_COUNT };
+void prof_mark(int id, cudaStream_t s);
+
 // ---- kernel launchers (one per .cu) ------------------------------------------------
 struct ViewParams {
     float view[16];

@@ -1,0 +1,130 @@
+"""One mapping iteration over a window of keyframes, data-parallel over views.
+
+Host-side mirror of the part of GaussianMapper::trainForOneIteration that is on the hot path
+(reference src/gaussian_mapper.cpp:687-796): activations -> GaussianRasterizer (ours) -> loss
+-> backward -> Adam, with the reference's 7 single-tensor Adam groups
+(src/gaussian_model.cpp:483-518).
+
+New relative to the reference (which renders ONE keyframe per iteration on one GPU,
+src/gaussian_mapper.cpp:629): the K views of a window are split over the ranks of a
+torch.distributed process group; every rank renders and back-propagates its views against the
+replicated Gaussian set; gradients accumulate into ONE flat fp32 buffer [123*P] (the 7 .grad
+tensors are views into it), which is summed across ranks with a single NCCL all-reduce over
+NVLink (492 B per Gaussian) before the fused Adam step.  Gradients are
+summed, not averaged.
+"""
+from typing import Callable, NamedTuple, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import loss as loss_mod
+from .optim import FusedAdam
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+from .synthetic import Camera
+
+PARAM_ORDER = ("xyz", "features_dc", "features_rest", "lang_feat", "opacity", "scaling", "rotation")
+# learning rates of the reference's Replica configuration
+DEFAULT_LRS = dict(xyz=3.2e-4, features_dc=2.5e-3, features_rest=2.5e-3 / 20.0, lang_feat=1.5e-3, opacity=0.05,
+                   scaling=5e-3, rotation=1e-3)
+
+
+class Keyframe(NamedTuple):
+    camera: Camera
+    gt_image: torch.Tensor   # [3,H,W]
+    gt_lf: torch.Tensor      # [64,h,w] encoder resolution (37x37 in the reference), resized per iteration
+    gt_depth: torch.Tensor   # [1,H,W]
+    mask: Optional[torch.Tensor] = None  # [3,H,W] undistortion mask (ones when absent)
+
+
+def shard_views(n_views: int, rank: int, world_size: int):
+    """Indices of the window's views this rank renders (round-robin, so any K works)."""
+    return list(range(rank, n_views, world_size))
+
+
+class FlatGrads:
+    """The 7 parameters' .grad tensors as views into one contiguous buffer (one collective,
+    one memset)."""
+
+    def __init__(self, params: dict):
+        n = sum(params[k].numel() for k in PARAM_ORDER)
+        any_p = params[PARAM_ORDER[0]]
+        self.flat = torch.zeros(n, dtype=torch.float32, device=any_p.device)
+        off = 0
+        self.views = {}
+        for k in PARAM_ORDER:
+            p = params[k]
+            self.views[k] = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def attach(self, params: dict):
+        for k in PARAM_ORDER:
+            params[k].grad = self.views[k]
+
+    def zero_(self):
+        self.flat.zero_()
+
+
+class Mapper:
+    """Replicated Gaussian set + fused Adam; `train_step(window)` is one mapping iteration."""
+
+    def __init__(self, params: dict, lrs: Optional[dict] = None, sh_degree: int = 3,
+                 process_group=None, optimizer_factory: Optional[Callable] = None,
+                 render_fn: Optional[Callable] = None, faithful_loss_sign: bool = True):
+        self.params = {k: torch.nn.Parameter(params[k].detach().clone().contiguous()) for k in PARAM_ORDER}
+        lrs = dict(DEFAULT_LRS, **(lrs or {}))
+        groups = [dict(params=[self.params[k]], lr=lrs[k], name=k) for k in PARAM_ORDER]
+        self.optimizer = (optimizer_factory or (lambda g: FusedAdam(g, lr=0.0, eps=1e-15)))(groups)
+        self.grads = FlatGrads(self.params)
+        self.sh_degree = sh_degree
+        self.pg = process_group
+        self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
+        self.render_fn = render_fn or self._render
+        self.faithful_loss_sign = faithful_loss_sign
+        dev = self.params["xyz"].device
+        self.bg = torch.zeros(3, dtype=torch.float32, device=dev)
+        self.last_num_views = 0
+
+    # -- activations exactly as the reference applies them each iteration (gaussian_model.cpp:46-68)
+    def activated(self):
+        p = self.params
+        return dict(means3D=p["xyz"], shs=torch.cat([p["features_dc"], p["features_rest"]], dim=1),
+                    lang_feats=p["lang_feat"], opacities=torch.sigmoid(p["opacity"]),
+                    scales=torch.exp(p["scaling"]), rotations=torch.nn.functional.normalize(p["rotation"]))
+
+    def _render(self, cam: Camera, a: dict):
+        rs = GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, self.bg, 1.0,
+                                           cam.viewmatrix, cam.projmatrix, self.sh_degree, cam.campos, False, True)
+        means2D = torch.zeros_like(a["means3D"], requires_grad=True)  # screenspace_points (gaussian_renderer.cpp:41-48)
+        return GaussianRasterizer(rs)(a["means3D"], means2D, a["opacities"], shs=a["shs"], lang_feats=a["lang_feats"],
+                                      scales=a["scales"], rotations=a["rotations"])
+
+    def train_step(self, window: Sequence[Keyframe], presharded: bool = False):
+        """Render + back-propagate this rank's share of `window`, sum gradients over ranks, Adam.
+        `window` is the iteration's global list of keyframes (every rank passes the same list and
+        takes its round-robin share) unless `presharded`, in which case it already holds only this
+        rank's keyframes.  Returns the (detached) sum of this rank's view losses."""
+        self.grads.zero_()
+        self.grads.attach(self.params)
+        mine = list(range(len(window))) if presharded else shard_views(len(window), self.rank, self.world_size)
+        self.last_num_views = len(mine)
+        total = None
+        for i in mine:
+            kf = window[i]
+            a = self.activated()
+            image, lf, depth, _radii = self.render_fn(kf.camera, a)
+            # gt feature map resized to the render size, nearest (src/gaussian_mapper.cpp:707-708)
+            gt_lf = kf.gt_lf
+            if gt_lf.shape[-2:] != lf.shape[-2:]:
+                gt_lf = torch.nn.functional.interpolate(gt_lf.unsqueeze(0), size=tuple(lf.shape[-2:])).squeeze(0)
+            if kf.mask is not None:  # :711-713
+                image, lf, depth = image * kf.mask, lf * kf.mask[0:1], depth * kf.mask[0:1]
+            loss = loss_mod.mapping_loss(image, lf, depth, kf.gt_image, gt_lf, kf.gt_depth,
+                                         faithful_sign=self.faithful_loss_sign)
+            loss.backward()  # accumulates into the flat buffer through the .grad views
+            total = loss.detach() if total is None else total + loss.detach()
+        if self.world_size > 1:
+            dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.pg)
+        self.optimizer.step()
+        return total if total is not None else torch.zeros((), device=self.grads.flat.device)
