@@ -193,6 +193,7 @@ class KernelPath:
         if self.R > self.binning_cap:  # grow-only, like a caching allocator would settle
             self.binning_cap = int(self.R * 1.25) + 1024
             self.binning = torch.empty(self.L.lgs_binning_bytes(self.binning_cap), dtype=torch.uint8, device=self.dev)
+            self.scratch_bwd = torch.empty(self.L.lgs_backward_scratch_bytes(self.binning_cap), dtype=torch.uint8, device=self.dev)
         self.check(L.lgs_forward_stage2(P, WIDTH, HEIGHT, self.R, self.bg.data_ptr(), a["lang_feats"].data_ptr(),
                                         self.geom.data_ptr(), self.binning.data_ptr(), self.img.data_ptr(),
                                         self.out_color.data_ptr(), self.out_lf.data_ptr(), self.out_depth.data_ptr(), 1,
@@ -208,7 +209,7 @@ class KernelPath:
                                   self.up["dd"].data_ptr(), sc["m2d"].data_ptr(), sc["conic"].data_ptr(), g["opacities"].data_ptr(),
                                   sc["color"].data_ptr(), g["lang_feats"].data_ptr(), None, g["means3D"].data_ptr(),
                                   sc["cov"].data_ptr(), g["shs"].data_ptr(), g["scales"].data_ptr(), g["rotations"].data_ptr(),
-                                  1, 1, self.stream), "backward")
+                                  1, 1, self.scratch_bwd.data_ptr(), self.stream), "backward")
 
     def adam(self):
         self.iteration += 1
@@ -223,16 +224,16 @@ class KernelPath:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
         self.adam()
 
-    # hand-written kernels per step: preprocess, emit_keys, tile_ranges, render_fwd, zero_grads, render_bwd,
-    # preprocess_bwd, adam (the CUB scan and radix-sort launches are library kernels and not counted)
-    KERNELS_PER_STEP = 8
+    # hand-written kernels per step: preprocess, emit_keys, tile_ranges, render_fwd, zero_grads, render_bwd_pix,
+    # render_bwd_chan, preprocess_bwd, adam (the CUB scan and radix-sort launches are library kernels, not counted)
+    KERNELS_PER_STEP = 9
 
     def stage_times(self, reps=20):
         """Per-kernel device time (ms, mean over reps) from CUDA events on the launch stream."""
         L = self.L
         L.lgs_profile_enable(1)
-        acc = [0.0] * 10
-        buf = (ctypes.c_float * 9)()
+        acc = [0.0] * 11
+        buf = (ctypes.c_float * 10)()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(reps):
             self.forward()
@@ -241,13 +242,13 @@ class KernelPath:
             self.adam()
             e1.record()
             torch.cuda.synchronize(self.dev)
-            L.lgs_profile_read(buf, 9)
-            for i in range(9):
+            L.lgs_profile_read(buf, 10)
+            for i in range(10):
                 acc[i] += max(buf[i], 0.0)
-            acc[9] += e0.elapsed_time(e1)
+            acc[10] += e0.elapsed_time(e1)
         L.lgs_profile_enable(0)
-        names = ["preprocess", "scan", "emit_keys", "sort", "tile_ranges", "render_fwd", "zero_grads", "render_bwd",
-                 "preprocess_bwd", "adam"]
+        names = ["preprocess", "scan", "emit_keys", "sort", "tile_ranges", "render_fwd", "zero_grads", "render_bwd_pix",
+                 "render_bwd_chan", "preprocess_bwd", "adam"]
         return {n: acc[i] / reps for i, n in enumerate(names)}
 
     def workload_counts(self):
@@ -453,7 +454,11 @@ def main():
         top = max(stage, key=stage.get)
         roof = {}
         if n_blend is not None:
-            fl = {"render_bwd": 604.0 * n_blend + 14.0 * counts["N_tested"], "render_fwd": 136.0 * n_blend + 14.0 * counts["N_tested"]}
+            # render bwd = 604*N_blend + 14*N_tested flop, split here as the pixel kernel's
+            # replay + 68-term dot + recurrence (136+60 per blend, 14 per test) and the channel kernel's 74-column
+            # reduction (2*74 per blend); the remainder of the reference's 604 is work the restructuring removed
+            fl = {"render_bwd_pix": 196.0 * n_blend + 14.0 * counts["N_tested"], "render_bwd_chan": 148.0 * n_blend,
+                  "render_fwd": 136.0 * n_blend + 14.0 * counts["N_tested"]}
         else:
             fl = {}
         by = {"adam": 3444.0 * P_GAUSS,
@@ -492,11 +497,11 @@ def main():
                                                     "reference loss + FusedAdam), inputs from pinned host memory"},
             "gpu_launches": KernelPath.KERNELS_PER_STEP * args.steps,
             "gpu_launches_note": "hand-written kernels per step: preprocess, emit_keys, tile_ranges, render_fwd, zero_grads, "
-                                 "render_bwd, preprocess_bwd, adam; CUB scan (2) + radix sort (8) library launches not counted",
+                                 "render_bwd_pix, render_bwd_chan, preprocess_bwd, adam; CUB scan (2) + radix sort (8) library launches not counted",
             "clocks": clocks,
             "roofline": roof,
             "kernels": kernels,
-            "blended_mfrag_per_s": (round(2.0 * n_blend / ((stage["render_fwd"] + stage["render_bwd"]) * 1e-3) / 1e6, 1)
+            "blended_mfrag_per_s": (round(2.0 * n_blend / ((stage["render_fwd"] + stage["render_bwd_pix"] + stage["render_bwd_chan"]) * 1e-3) / 1e6, 1)
                                     if n_blend else None),
             "fp32_fma_peak_tflops_measured": round(fma_peak, 2),
         }

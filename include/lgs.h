@@ -101,6 +101,9 @@ int lgs_forward_stage2(
  * Gaussians are written, exactly like the reference.
  * dL_ddepth may be NULL (the reference computes and discards it,
  * rasterize_points.cu:161,207).
+ * bwd_scratch: lgs_backward_scratch_bytes(R) bytes of device memory for the render backward's
+ * pixel->channel hand-off, or NULL to take it from the CUDA stream-ordered pool
+ * (cudaMallocAsync/cudaFreeAsync on `stream`; no synchronisation).
  */
 int lgs_backward(
     int P, int D, int M, int R, int W, int H,
@@ -115,7 +118,9 @@ int lgs_backward(
     float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
     float* dL_dlang_feat, float* dL_ddepth, float* dL_dmean3D, float* dL_dcov3D,
     float* dL_dsh, float* dL_dscale, float* dL_drot,
-    int include_lang_feat, int zero_outputs, void* stream);
+    int include_lang_feat, int zero_outputs, char* bwd_scratch, void* stream);
+/* bytes of bwd_scratch for a backward over R instances (520 B/instance + slack) */
+size_t lgs_backward_scratch_bytes(int R);
 
 /* ---- markVisible  (rasterizer_impl.cu:54-66,141-153): present[i] = view-z > 0.2 --- */
 int lgs_mark_visible(int P, const float* means3D, const float* viewmatrix,
@@ -149,9 +154,9 @@ int lgs_view_geom(const char* geom_buffer, int P, lgs_geom_view* out);
 
 /* ---- optional per-stage timing (bench.py's roofline): when enabled, CUDA events are recorded
  *      on the launch stream between the kernels of stage1 / stage2 / backward.  After the caller
- *      has synchronised, lgs_profile_read fills ms[0..8] = preprocess, scan, emit_keys, sort,
- *      tile_ranges, render_fwd, zero_grads, render_bwd, preprocess_bwd (milliseconds, -1 if the
- *      stage did not run).  Not thread-safe; off by default. */
+ *      has synchronised, lgs_profile_read fills ms[0..9] = preprocess, scan, emit_keys, sort,
+ *      tile_ranges, render_fwd, zero_grads, render_bwd_pix, render_bwd_chan, preprocess_bwd
+ *      (milliseconds, -1 if the stage did not run).  Not thread-safe; off by default. */
 int lgs_profile_enable(int on);
 int lgs_profile_read(float* ms, int n);
 

@@ -64,6 +64,7 @@ size_t lgs_image_bytes(int W, int H) {
     const size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
     return (size_t)(reinterpret_cast<uintptr_t>(im.tile_last + (tiles > 0 ? tiles : 1))) + 256;
 }
+size_t lgs_backward_scratch_bytes(int R) { return R < 0 ? 0 : render_bwd_scratch_bytes(R); }
 size_t lgs_binning_bytes(int R) {
     if (R < 0) return 0;
     BinningState b = binning_from_chunk(nullptr, R);
@@ -153,7 +154,7 @@ int lgs_backward(int P, int D, int M, int R, int W, int H, const float* backgrou
                  const float* dL_dpix_depth, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
                  float* dL_dcolor, float* dL_dlang_feat, float* dL_ddepth, float* dL_dmean3D,
                  float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, int include_lang_feat,
-                 int zero_outputs, void* stream) {
+                 int zero_outputs, char* bwd_scratch, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (P < 0 || W <= 0 || H <= 0 || R < 0 || D < 0 || D > 3) return LGS_ERR_INVALID_ARG;
     if (P == 0) return LGS_OK;
@@ -185,9 +186,17 @@ int lgs_backward(int P, int D, int M, int R, int W, int H, const float* backgrou
     }
     prof_mark(PM_ZERO, s);
     if (R > 0) {
+        // the pixel -> channel hand-off records; callers that keep the reference's signature pass no
+        // scratch, then it comes from the stream-ordered pool (no synchronisation)
+        char* scratch = bwd_scratch;
+        if (!scratch) LGS_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), render_bwd_scratch_bytes(R), s));
         st = launch_render_bwd(P, W, H, R, g, b, im, background, lang_feat, dL_dpix, dL_dpix_lf, dL_dpix_depth,
                                dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dlang_feat, dL_ddepth,
-                               include_lang_feat != 0, s);
+                               include_lang_feat != 0, scratch, s);
+        if (!bwd_scratch) {
+            cudaError_t e = cudaFreeAsync(scratch, s);
+            if (st == LGS_OK && e != cudaSuccess) { set_last_cuda_error(e); st = LGS_ERR_CUDA; }
+        }
         if (st != LGS_OK) return st;
     }
     prof_mark(PM_RENDER_BWD, s);
@@ -206,15 +215,15 @@ int lgs_profile_enable(int on) {
     return LGS_OK;
 }
 int lgs_profile_read(float* ms, int n) {
-    // ms[0..8] = preprocess, scan, emit_keys(+memset), sort, tile_ranges, render_fwd, zero_grads,
-    //            render_bwd, preprocess_bwd of the most recent forward+backward; the caller must have
-    //            synchronised the stream.  Entries whose stage did not run are -1.
-    static const int a[9] = {PM_S1_BEGIN, PM_PREPROCESS, PM_S2_BEGIN, PM_EMIT, PM_SORT, PM_RANGES, PM_BWD_BEGIN,
-                             PM_ZERO, PM_RENDER_BWD};
-    static const int b[9] = {PM_PREPROCESS, PM_SCAN, PM_EMIT, PM_SORT, PM_RANGES, PM_RENDER_FWD, PM_ZERO,
-                             PM_RENDER_BWD, PM_PREPROCESS_BWD};
-    if (!ms || n < 9) return LGS_ERR_INVALID_ARG;
-    for (int i = 0; i < 9; ++i) {
+    // ms[0..9] = preprocess, scan, emit_keys(+memset), sort, tile_ranges, render_fwd, zero_grads,
+    //            render_bwd_pix, render_bwd_chan, preprocess_bwd of the most recent forward+backward; the
+    //            caller must have synchronised the stream.  Entries whose stage did not run are -1.
+    static const int a[10] = {PM_S1_BEGIN, PM_PREPROCESS, PM_S2_BEGIN, PM_EMIT, PM_SORT, PM_RANGES, PM_BWD_BEGIN,
+                              PM_ZERO, PM_RENDER_BWD_PIX, PM_RENDER_BWD};
+    static const int b[10] = {PM_PREPROCESS, PM_SCAN, PM_EMIT, PM_SORT, PM_RANGES, PM_RENDER_FWD, PM_ZERO,
+                              PM_RENDER_BWD_PIX, PM_RENDER_BWD, PM_PREPROCESS_BWD};
+    if (!ms || n < 10) return LGS_ERR_INVALID_ARG;
+    for (int i = 0; i < 10; ++i) {
         ms[i] = -1.f;
         if (g_ev_made && g_ev_set[a[i]] && g_ev_set[b[i]]) {
             float t = 0.f;

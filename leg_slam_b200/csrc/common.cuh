@@ -76,7 +76,7 @@ void set_last_cuda_error(cudaError_t e);
 
 // ---- optional per-stage timing (lgs_profile_enable): CUDA events recorded on the launch stream
 enum ProfMark { PM_S1_BEGIN = 0, PM_PREPROCESS, PM_SCAN, PM_S2_BEGIN, PM_EMIT, PM_SORT, PM_RANGES, PM_RENDER_FWD,
-                PM_BWD_BEGIN, PM_ZERO, PM_RENDER_BWD, PM_PREPROCESS_BWD, PM_COUNT };
+                PM_BWD_BEGIN, PM_ZERO, PM_RENDER_BWD_PIX, PM_RENDER_BWD, PM_PREPROCESS_BWD, PM_COUNT };
 void prof_mark(int id, cudaStream_t s);
 
 // ---- kernel launchers (one per .cu) ------------------------------------------------
@@ -107,7 +107,8 @@ int launch_render_bwd(int P, int W, int H, int R, const GeomState& g, const Binn
                       const ImageState& im, const float* background, const float* lang_feat,
                       const float* dL_dpix, const float* dL_dpix_lf, const float* dL_dpix_depth,
                       float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
-                      float* dL_dlang_feat, float* dL_ddepth, bool include_lf, cudaStream_t s);
+                      float* dL_dlang_feat, float* dL_ddepth, bool include_lf, char* scratch, cudaStream_t s);
+size_t render_bwd_scratch_bytes(int R);
 int launch_preprocess_bwd(int P, int D, int M, const float* means3D, const int* radii,
                           const float* shs, const float* scales, const float* rotations,
                           float scale_modifier, const float* cov3D, const float* viewmatrix,

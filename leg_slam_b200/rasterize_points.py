@@ -112,6 +112,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, lang_feat, 
             campos, dL_dout_color, dL_dout_lang_feat, dL_dout_depth = map(
                 _f32c, (background, means3D, colors, lang_feat, scales, rotations, cov3D_precomp, viewmatrix,
                         projmatrix, sh, campos, dL_dout_color, dL_dout_lang_feat, dL_dout_depth))
+        scratch = torch.empty(L.lgs_backward_scratch_bytes(int(R)), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             check(L.lgs_backward(
                 P, int(degree), M, int(R), W, H, ptr(background), ptr(means3D), ptr(sh), ptr(colors),
@@ -121,7 +122,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, lang_feat, 
                 ptr(dL_dout_lang_feat) if include_lf else None, ptr(dL_dout_depth), dL_dmeans2D.data_ptr(),
                 dL_dconic.data_ptr(), dL_dopacity.data_ptr(), dL_dcolors.data_ptr(), dL_dlang.data_ptr(), None,
                 dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr(), ptr(dL_dsh), ptr(dL_dscales), ptr(dL_drot),
-                int(include_lf), 1, _stream(means3D)), "lgs_backward")
+                int(include_lf), 1, scratch.data_ptr(), _stream(means3D)), "lgs_backward")
     return dL_dmeans2D, dL_dcolors, dL_dlang, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drot
 
 
