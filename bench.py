@@ -193,7 +193,7 @@ class KernelPath:
         if self.R > self.binning_cap:  # grow-only, like a caching allocator would settle
             self.binning_cap = int(self.R * 1.25) + 1024
             self.binning = torch.empty(self.L.lgs_binning_bytes(self.binning_cap), dtype=torch.uint8, device=self.dev)
-            self.scratch_bwd = torch.empty(self.L.lgs_backward_scratch_bytes(self.binning_cap), dtype=torch.uint8, device=self.dev)
+            self.scratch_bwd = torch.empty(self.L.lgs_backward_scratch_bytes(self.binning_cap, WIDTH, HEIGHT), dtype=torch.uint8, device=self.dev)
         self.check(L.lgs_forward_stage2(P, WIDTH, HEIGHT, self.R, self.bg.data_ptr(), a["lang_feats"].data_ptr(),
                                         self.geom.data_ptr(), self.binning.data_ptr(), self.img.data_ptr(),
                                         self.out_color.data_ptr(), self.out_lf.data_ptr(), self.out_depth.data_ptr(), 1,

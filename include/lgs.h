@@ -101,7 +101,7 @@ int lgs_forward_stage2(
  * Gaussians are written, exactly like the reference.
  * dL_ddepth may be NULL (the reference computes and discards it,
  * rasterize_points.cu:161,207).
- * bwd_scratch: lgs_backward_scratch_bytes(R) bytes of device memory for the render backward's
+ * bwd_scratch: lgs_backward_scratch_bytes(R, W, H) bytes of device memory for the render backward's
  * pixel->channel hand-off, or NULL to take it from the CUDA stream-ordered pool
  * (cudaMallocAsync/cudaFreeAsync on `stream`; no synchronisation).
  */
@@ -119,8 +119,8 @@ int lgs_backward(
     float* dL_dlang_feat, float* dL_ddepth, float* dL_dmean3D, float* dL_dcov3D,
     float* dL_dsh, float* dL_dscale, float* dL_drot,
     int include_lang_feat, int zero_outputs, char* bwd_scratch, void* stream);
-/* bytes of bwd_scratch for a backward over R instances (520 B/instance + slack) */
-size_t lgs_backward_scratch_bytes(int R);
+/* bytes of bwd_scratch for a backward over R instances of a WxH image (544 B/instance + 8 B/tile) */
+size_t lgs_backward_scratch_bytes(int R, int W, int H);
 
 /* ---- markVisible  (rasterizer_impl.cu:54-66,141-153): present[i] = view-z > 0.2 --- */
 int lgs_mark_visible(int P, const float* means3D, const float* viewmatrix,
@@ -141,7 +141,7 @@ typedef struct lgs_image_view {
     const uint32_t* n_contrib;       /* [H*W]                                           */
 } lgs_image_view;
 typedef struct lgs_geom_view {
-    const float*    records;         /* [P][12]: x,y,depth,0 | conic a,b,c, opacity | r,g,b,0 */
+    const float*    records;         /* [P][12]: x,y,depth,idx bits | conic a,b,c, opacity | r,g,b,0 */
     const float*    cov3D;           /* [P][6]                                          */
     const uint32_t* tiles_touched;   /* [P]                                             */
     const uint32_t* point_offsets;   /* [P] inclusive scan                              */

@@ -64,7 +64,9 @@ size_t lgs_image_bytes(int W, int H) {
     const size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
     return (size_t)(reinterpret_cast<uintptr_t>(im.tile_last + (tiles > 0 ? tiles : 1))) + 256;
 }
-size_t lgs_backward_scratch_bytes(int R) { return R < 0 ? 0 : render_bwd_scratch_bytes(R); }
+size_t lgs_backward_scratch_bytes(int R, int W, int H) {
+    return (R < 0 || W <= 0 || H <= 0) ? 0 : render_bwd_scratch_bytes(R, W, H);
+}
 size_t lgs_binning_bytes(int R) {
     if (R < 0) return 0;
     BinningState b = binning_from_chunk(nullptr, R);
@@ -189,7 +191,7 @@ int lgs_backward(int P, int D, int M, int R, int W, int H, const float* backgrou
         // the pixel -> channel hand-off records; callers that keep the reference's signature pass no
         // scratch, then it comes from the stream-ordered pool (no synchronisation)
         char* scratch = bwd_scratch;
-        if (!scratch) LGS_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), render_bwd_scratch_bytes(R), s));
+        if (!scratch) LGS_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), render_bwd_scratch_bytes(R, W, H), s));
         st = launch_render_bwd(P, W, H, R, g, b, im, background, lang_feat, dL_dpix, dL_dpix_lf, dL_dpix_depth,
                                dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dlang_feat, dL_ddepth,
                                include_lang_feat != 0, scratch, s);

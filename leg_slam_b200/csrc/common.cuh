@@ -17,7 +17,7 @@ constexpr int REC_FLOATS = 12;          // per-Gaussian render record, 48 B (3 x
 // One 48-byte record replaces the reference's separate means2D / depths /
 // conic_opacity / rgb arrays (rasterizer_impl.h:33-48): the render kernels move
 // one contiguous 48 B chunk per (tile, Gaussian) instance instead of four gathers.
-//   q0 = (x, y, depth, 0)   q1 = (conic.a, conic.b, conic.c, opacity)   q2 = (r, g, b, 0)
+//   q0 = (x, y, depth, Gaussian index bits)   q1 = (conic.a, conic.b, conic.c, opacity)   q2 = (r, g, b, 0)
 struct __align__(16) GaussRec {
     float4 q0, q1, q2;
 };
@@ -108,13 +108,13 @@ int launch_render_bwd(int P, int W, int H, int R, const GeomState& g, const Binn
                       const float* dL_dpix, const float* dL_dpix_lf, const float* dL_dpix_depth,
                       float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
                       float* dL_dlang_feat, float* dL_ddepth, bool include_lf, char* scratch, cudaStream_t s);
-size_t render_bwd_scratch_bytes(int R);
+size_t render_bwd_scratch_bytes(int R, int W, int H);
 int launch_preprocess_bwd(int P, int D, int M, const float* means3D, const int* radii,
                           const float* shs, const float* scales, const float* rotations,
                           float scale_modifier, const float* cov3D, const float* viewmatrix,
                           const float* projmatrix, const float* cam_pos, int W, int H,
                           float tan_fovx, float tan_fovy, const GeomState& g,
-                          const float* dL_dmean2D, const float* dL_dconic, float* dL_dmean3D,
+                          float* dL_dmean2D, float* dL_dconic, float* dL_dmean3D,
                           const float* dL_dcolor, float* dL_dcov3D, float* dL_dsh,
                           float* dL_dscale, float* dL_drot, bool write_zeros, cudaStream_t s);
 int launch_zero_grads(int P, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,

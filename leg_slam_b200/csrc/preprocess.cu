@@ -275,7 +275,7 @@ preprocess_kernel(int P, int D, int M,
     }
 
     GaussRec r;
-    r.q0 = make_float4(pix_x, pix_y, depth, 0.f);
+    r.q0 = make_float4(pix_x, pix_y, depth, __int_as_float(idx));
     r.q1 = make_float4(cx, cy, cz, opac[idx]);
     r.q2 = make_float4(cr, cg, cb, 0.f);
     rec[idx] = r;

@@ -103,8 +103,9 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means, cons
                       const float* __restrict__ scales, const float* __restrict__ rots, float mod,
                       const float* __restrict__ cov3Ds, const float* __restrict__ view,
                       const float* __restrict__ proj, const float* __restrict__ campos, float h_x, float h_y,
-                      float tan_fovx, float tan_fovy, const float* __restrict__ dL_dmean2D,
-                      const float* __restrict__ dL_dconics, const float* __restrict__ dL_dcolor,
+                      float tan_fovx, float tan_fovy, const GaussRec* __restrict__ rec, float ddelx_dx, float ddely_dy,
+                      float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconics,
+                      const float* __restrict__ dL_dcolor,
                       float* __restrict__ dL_dmeans, float* __restrict__ dL_dcov, float* __restrict__ dL_dsh,
                       float* __restrict__ dL_dscale, float* __restrict__ dL_drot, bool write_zeros) {
     __shared__ float sV[16], sP[16];
@@ -133,8 +134,22 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means, cons
     const float c0 = cov3D[0], c1 = cov3D[1], c2 = cov3D[2], c3 = cov3D[3], c4 = cov3D[4], c5 = cov3D[5];
 
     // ------------------------------------------------------------------ cov2D backward (:144-274)
-    const float4 dcon = reinterpret_cast<const float4*>(dL_dconics)[idx];
-    const float dLx = dcon.x, dLy = dcon.y, dLz = dcon.w;
+    // The render backward left raw pixel sums here (render_bwd.cu, channel kernel): sum t*dx^2,
+    // sum t*dx*dy, -, sum t*dy^2 in the conic slots and sum t*dx, sum t*dy in mean2D.xy.  Apply the
+    // per-Gaussian factors of backward.cu:592-606 once, and publish the finished gradients.
+    float dLx, dLy, dLz, gm2x, gm2y;
+    {
+        const float4 q1 = rec[idx].q1;  // conic a, b, c, opacity
+        const float4 sc = reinterpret_cast<const float4*>(dL_dconics)[idx];
+        const float sdx = dL_dmean2D[3 * (size_t)idx + 0], sdy = dL_dmean2D[3 * (size_t)idx + 1];
+        const float h = -0.5f * q1.w;
+        dLx = h * sc.x; dLy = h * sc.y; dLz = h * sc.w;
+        gm2x = -q1.w * ddelx_dx * (q1.x * sdx + q1.y * sdy);
+        gm2y = -q1.w * ddely_dy * (q1.z * sdy + q1.y * sdx);
+        reinterpret_cast<float4*>(dL_dconics)[idx] = make_float4(dLx, dLy, 0.f, dLz);
+        dL_dmean2D[3 * (size_t)idx + 0] = gm2x;
+        dL_dmean2D[3 * (size_t)idx + 1] = gm2y;
+    }
     float tx = sV[0] * mean.x + sV[4] * mean.y + sV[8] * mean.z + sV[12];
     float ty = sV[1] * mean.x + sV[5] * mean.y + sV[9] * mean.z + sV[13];
     const float tz = sV[2] * mean.x + sV[6] * mean.y + sV[10] * mean.z + sV[14];
@@ -202,7 +217,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means, cons
         const float hw = sP[3] * mean.x + sP[7] * mean.y + sP[11] * mean.z + sP[15];
         const float m_w = 1.0f / (hw + 0.0000001f);
         const float mul1 = hx * m_w * m_w, mul2 = hy * m_w * m_w;
-        const float gx = dL_dmean2D[3 * (size_t)idx + 0], gy = dL_dmean2D[3 * (size_t)idx + 1];
+        const float gx = gm2x, gy = gm2y;
         dmean.x += (sP[0] * m_w - sP[3] * mul1) * gx + (sP[1] * m_w - sP[3] * mul2) * gy;
         dmean.y += (sP[4] * m_w - sP[7] * mul1) * gx + (sP[5] * m_w - sP[7] * mul2) * gy;
         dmean.z += (sP[8] * m_w - sP[11] * mul1) * gx + (sP[9] * m_w - sP[11] * mul2) * gy;
@@ -267,14 +282,15 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means, cons
 int launch_preprocess_bwd(int P, int D, int M, const float* means3D, const int* radii, const float* shs,
                           const float* scales, const float* rotations, float scale_modifier, const float* cov3D,
                           const float* viewmatrix, const float* projmatrix, const float* cam_pos, int W, int H,
-                          float tan_fovx, float tan_fovy, const GeomState& g, const float* dL_dmean2D,
-                          const float* dL_dconic, float* dL_dmean3D, const float* dL_dcolor, float* dL_dcov3D,
+                          float tan_fovx, float tan_fovy, const GeomState& g, float* dL_dmean2D,
+                          float* dL_dconic, float* dL_dmean3D, const float* dL_dcolor, float* dL_dcov3D,
                           float* dL_dsh, float* dL_dscale, float* dL_drot, bool write_zeros, cudaStream_t s) {
     const float focal_y = H / (2.0f * tan_fovy);  // rasterizer_impl.cu:392-393
     const float focal_x = W / (2.0f * tan_fovx);
     preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(
         P, D, M, means3D, radii, shs, g.clamped, scales, rotations, scale_modifier, cov3D, viewmatrix, projmatrix,
-        cam_pos, focal_x, focal_y, tan_fovx, tan_fovy, dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dcov3D,
+        cam_pos, focal_x, focal_y, tan_fovx, tan_fovy, g.rec, 0.5f * (float)W, 0.5f * (float)H, dL_dmean2D, dL_dconic,
+        dL_dcolor, dL_dmean3D, dL_dcov3D,
         dL_dsh, dL_dscale, dL_drot, write_zeros);
     LGS_LAUNCH_CHECK();
     return LGS_OK;

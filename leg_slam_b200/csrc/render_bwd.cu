@@ -23,9 +23,10 @@
 //    column) -- 74 per (tile, Gaussian) instead of 74 per (pixel, Gaussian).
 //  * the two roles want different register files (68-float g ROW per pixel thread vs 64-float g
 //    COLUMN per channel thread), different thread counts (64 vs 74) and run at different,
-//    bursty rates, so they are two kernels: the pixel kernel streams compact w/t records
-//    (256 B per instance-half with an active pixel, plus a ballot) to a scratch buffer, the
-//    channel kernel streams them back through a TMA ring.  An earlier single-kernel,
+//    bursty rates, so they are two kernels: the pixel kernel appends compact 272-byte
+//    half-records (id, centre, w[32], t[32]; only for instance-halves with an active pixel) to
+//    per-(tile, warp) streams in a scratch buffer, the channel kernel streams them back through
+//    a ring of 4 KB TMA bulk copies.  An earlier single-kernel,
 //    warp-specialised version (named-barrier hand-off through shared memory) spent 46 % of its
 //    warp samples in barrier stalls (profiles/r01_render_bwd_v1.md); the scratch round trip is
 //    ~0.6 GB of mostly L2-resident traffic per iteration at cfgB.
@@ -43,10 +44,9 @@ namespace lgs {
 
 constexpr int BB = 32;       // Gaussians per TMA batch of the pixel kernel
 constexpr int BSTAGES = 3;   // its staging ring depth
-constexpr int CB = 16;       // instances per TMA batch of the channel kernel
+constexpr int CB = 16;       // half-records per TMA batch of the channel kernel
 constexpr int CSTAGES = 4;   // its staging ring depth
-constexpr int NCOL = 74;     // 64 feature + 3 colour + 1 depth + 6 moment columns
-constexpr int PAIR_FLOATS = 128;  // per instance: [half0: W[32] | t[32]] [half1: W[32] | t[32]]
+constexpr int HREC_FLOATS = 68;  // half-record: {gx - cx, gy - cy, 0, id} | w[32] | t[32]  (272 B)
 
 template <bool WITH_LF>
 struct BwdStage {
@@ -54,18 +54,13 @@ struct BwdStage {
     float lf[WITH_LF ? BB * LF : 4];
 };
 
-struct ChanStage {
-    float pairs[CB][PAIR_FLOATS];  // TMA destination: only the active halves are copied
-    GaussRec rec[CB];              // TMA destination
-    uint2 mask[CB];                // ballots of the two pixel warps
-    uint32_t id[CB];               // Gaussian index
-};
-
 // ================================ pixel kernel =====================================================
 // One CTA (2 warps) per tile, one pixel per thread.  Walks the tile's list back to front, replays
-// alpha, evaluates d_j = <feature_j, g_pix>, runs the scalar recurrences and writes, per
-// (instance, pixel warp) with at least one active pixel, w = alpha*T and t = G*dL/dalpha for its
-// 32 pixels (one coalesced 256-byte record) plus the warp's ballot, to the pair buffer.
+// alpha, evaluates d_j = <feature_j, g_pix>, runs the scalar recurrences and, for every
+// (instance, pixel warp) with at least one active pixel, APPENDS one 272-byte half-record
+// {Gaussian id, centre relative to the tile, w = alpha*T and t = G*dL/dalpha of the warp's 32
+// pixels} to that (tile, warp)'s contiguous stream in the scratch buffer.  Streams need no atomics:
+// each warp owns its stream and counts in a register; the count is stored once at the end.
 template <bool WITH_LF>
 __global__ void __launch_bounds__(TILE_PIX)
 render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
@@ -73,8 +68,8 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                       const float* __restrict__ lang_feat, const float* __restrict__ final_T,
                       const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ tile_last,
                       const float* __restrict__ dL_dpix, const float* __restrict__ dL_dpix_lf,
-                      const float* __restrict__ dL_dpix_depth, float* __restrict__ pair_buf,
-                      uint32_t* __restrict__ pair_mask) {
+                      const float* __restrict__ dL_dpix_depth, float* __restrict__ hrec_buf,
+                      uint32_t* __restrict__ hrec_count) {
     using Stage = BwdStage<WITH_LF>;
     __shared__ __align__(128) Stage stages[BSTAGES];
     __shared__ __align__(8) uint64_t full_bar[BSTAGES];
@@ -83,8 +78,12 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const int lane = tid & 31, wrp = tid >> 5;
     const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
     const uint2 range = ranges[tile_id];
-    const int n = min((int)(range.y - range.x), (int)tile_last[tile_id]);  // entries behind tile_last touch no pixel
-    if (n <= 0) return;
+    const int n_all = (int)(range.y - range.x);
+    const int n = min(n_all, (int)tile_last[tile_id]);  // entries behind tile_last touch no pixel
+    if (n <= 0) {
+        if (tid < 2) hrec_count[2 * tile_id + tid] = 0;
+        return;
+    }
     const int nb = (n + BB - 1) / BB;
     const size_t HW = (size_t)H * W;
 
@@ -100,6 +99,7 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const bool inside = pxi < (uint32_t)W && pyi < (uint32_t)H;
     const uint32_t pix_id = (uint32_t)W * pyi + pxi;
     const float pxf = (float)pxi, pyf = (float)pyi;
+    const float cxf = (float)(blockIdx.x * TILE) + 3.5f, cyf = (float)(blockIdx.y * TILE) + 3.5f;
 
     const float T_final = inside ? final_T[pix_id] : 0.f;
     const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
@@ -122,11 +122,15 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const float bgdot = bg[0] * g_r + bg[1] * g_g + bg[2] * g_b;  // backward.cu:585-588
     float Acc = 0.f, last_alpha = 0.f, last_d = 0.f;
 
+    // this warp's half-record stream: capacity n_all records, after the other warp's
+    float* out = hrec_buf + ((size_t)2 * range.x + (size_t)wrp * n_all) * HREC_FLOATS;
+    uint32_t nrec = 0;
+
     // producer state (warp 0): Gaussian ids of the next batch to issue (back to front)
     uint32_t pf_id = 0;
     if (tid < BB && tid < n) pf_id = point_list[range.x + (n - 1 - tid)];
     auto issue = [&](int b) {
-        if (tid < BB) {
+        if (tid < 32) {  // the whole of warp 0 (BB <= 32 lanes carry an instance each)
             const int cnt = min(BB, n - b * BB);
             Stage& S = stages[b % BSTAGES];
             uint64_t* bar = &full_bar[b % BSTAGES];
@@ -138,7 +142,7 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                 if (WITH_LF) tma_bulk_g2s(&S.lf[tid * LF], lang_feat + (size_t)pf_id * LF, LF * 4, bar);
             }
             const int nxt = (b + 1) * BB + tid;
-            if (nxt < n) pf_id = point_list[range.x + (n - 1 - nxt)];
+            if (tid < BB && nxt < n) pf_id = point_list[range.x + (n - 1 - nxt)];
         }
     };
     for (int b = 0; b < BSTAGES - 1 && b < nb; ++b) issue(b);
@@ -154,7 +158,7 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 #pragma unroll 1
         for (int j = 0; j < cnt; ++j) {
             const int p = hi - j;
-            const float4 q0 = S.rec[j].q0;
+            const float4 q0 = S.rec[j].q0;  // x, y, depth, id bits
             const float4 q1 = S.rec[j].q1;
             float dx, dy;
             const float power = eval_power(q0.x, q0.y, pxf, pyf, q1.x, q1.y, q1.z, dx, dy);
@@ -163,10 +167,7 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
             // backward.cu:513-530: behind the pixel's last contributor, outside the falloff, or below
             // the alpha threshold -> no contribution
             const bool act = (p < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-            const uint32_t m = __ballot_sync(0xffffffffu, act);
-            const size_t inst = (size_t)range.x + (size_t)p;
-            if (lane == 0) pair_mask[2 * inst + wrp] = m;
-            if (m == 0) continue;
+            if (!__any_sync(0xffffffffu, act)) continue;
 
             const float4 q2 = S.rec[j].q2;
             float d0 = q2.x * g_r, d1 = q2.y * g_g, d2 = q2.z * g_b, d3 = q0.z * g_d;
@@ -193,36 +194,42 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                 Wv = alpha * T;
                 Tv = G * dL_dalpha;
             }
-            float* dst = pair_buf + inst * PAIR_FLOATS + wrp * 64 + lane;
-            __stcg(dst, Wv);
-            __stcg(dst + 32, Tv);
+            float* dst = out + (size_t)nrec * HREC_FLOATS;
+            if (lane == 0) __stcg(reinterpret_cast<float4*>(dst), make_float4(q0.x - cxf, q0.y - cyf, 0.f, q0.w));
+            __stcg(dst + 4 + lane, Wv);
+            __stcg(dst + 36 + lane, Tv);
+            ++nrec;
         }
     }
+    if (lane == 0) hrec_count[2 * tile_id + wrp] = nrec;
 }
 
 // ================================ channel kernel ===================================================
 // One CTA per tile; every thread owns one of the 74 columns (64 feature channels, 3 colour, depth,
 // 6 moment bases) of the tile's [64 pixel x 74] matrix in registers and reduces the pixel kernel's
-// w / t records against it: ONE red.global.add per (tile, Gaussian, column).
+// half-records against it: ONE red.global.add per (half-record, column).  Records arrive through a
+// ring of TMA bulk copies (one 4 KB copy per batch of 16 records).
+//
+// Moment lanes accumulate sums of t, t*dx, t*dy, t*dx^2, t*dx*dy, t*dy^2 (dx, dy = Gaussian centre
+// minus pixel) into dL_dopacity / dL_dmean2D.xy / dL_dconic.{x,y,w}; the per-Gaussian factors
+// (opacity, conic, viewport scale) are applied once per Gaussian by the preprocess backward.
 template <bool WITH_LF>
-__global__ void __launch_bounds__(WITH_LF ? 96 : 32)
-render_bwd_chan_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
-                       const GaussRec* __restrict__ rec, const uint32_t* __restrict__ tile_last,
-                       const float* __restrict__ dL_dpix, const float* __restrict__ dL_dpix_lf,
-                       const float* __restrict__ dL_dpix_depth, const float* __restrict__ pair_buf,
-                       const uint32_t* __restrict__ pair_mask, float* __restrict__ dL_dmean2D,
-                       float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity,
-                       float* __restrict__ dL_dcolor, float* __restrict__ dL_dlang_feat,
-                       float* __restrict__ dL_ddepth) {
-    __shared__ __align__(128) ChanStage stages[CSTAGES];
+__global__ void __launch_bounds__(WITH_LF ? 96 : 32, WITH_LF ? 6 : 16)
+render_bwd_chan_kernel(const uint2* __restrict__ ranges, int W, int H, const float* __restrict__ dL_dpix,
+                       const float* __restrict__ dL_dpix_lf, const float* __restrict__ dL_dpix_depth,
+                       const float* __restrict__ hrec_buf, const uint32_t* __restrict__ hrec_count,
+                       float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic,
+                       float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor,
+                       float* __restrict__ dL_dlang_feat, float* __restrict__ dL_ddepth) {
+    __shared__ __align__(128) float stages[CSTAGES][CB * HREC_FLOATS];
     __shared__ __align__(8) uint64_t full_bar[CSTAGES];
 
     const int tid = threadIdx.x;
     const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+    const uint32_t cnt0 = hrec_count[2 * tile_id], cnt1 = hrec_count[2 * tile_id + 1];
+    if (cnt0 + cnt1 == 0) return;
     const uint2 range = ranges[tile_id];
-    const int n = min((int)(range.y - range.x), (int)tile_last[tile_id]);
-    if (n <= 0) return;
-    const int nb = (n + CB - 1) / CB;
+    const int n_all = (int)(range.y - range.x);
     const size_t HW = (size_t)H * W;
 
     if (tid == 0) {
@@ -253,123 +260,91 @@ render_bwd_chan_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
         }
         colv[i] = x;
     }
-    const int toff = (col >= LF + 4) ? 32 : 0;  // moment columns reduce t, the others reduce w
-    const bool live = col < NCOL;
-    const float ddelx_dx = 0.5f * (float)W, ddely_dy = 0.5f * (float)H;  // backward.cu:478-479
-    const float cxf = (float)(blockIdx.x * TILE) + 3.5f, cyf = (float)(blockIdx.y * TILE) + 3.5f;
+    const int toff = (col >= LF + 4) ? 36 : 4;  // moment columns reduce t, the others reduce w
+    // per-thread output slot: out_base[id * out_stride]
+    float* out_base = nullptr;
+    uint32_t out_stride = 0;
+    if (col < LF) { out_base = dL_dlang_feat + col; out_stride = LF; }
+    else if (col < LF + 3) { out_base = dL_dcolor + (col - LF); out_stride = 3; }
+    else if (col == LF + 3) { out_base = dL_ddepth; out_stride = 1; }          // may be NULL
+    else if (col == LF + 4) { out_base = dL_dopacity; out_stride = 1; }         // sum t
+    else if (col == LF + 5) { out_base = dL_dmean2D; out_stride = 3; }          // sum t*dx
+    else if (col == LF + 6) { out_base = dL_dmean2D + 1; out_stride = 3; }      // sum t*dy
+    else if (col == LF + 7) { out_base = dL_dconic; out_stride = 4; }           // sum t*dx*dx
+    else if (col == LF + 8) { out_base = dL_dconic + 1; out_stride = 4; }       // sum t*dx*dy
+    else if (col == LF + 9) { out_base = dL_dconic + 3; out_stride = 4; }       // sum t*dy*dy
+    const int mk = col - (LF + 4);  // moment index 0..5 on the moment lanes
     __syncthreads();
 
-    // producer (warp 0, lanes 0..CB-1): one instance per lane.  Fills stage b % CSTAGES: mask/id by
-    // plain stores, record + active halves by TMA bulk copies.
-    auto issue = [&](int b) {
-        if (tid < 32) {
-            const int cnt = min(CB, n - b * CB);
-            ChanStage& S = stages[b % CSTAGES];
-            uint64_t* bar = &full_bar[b % CSTAGES];
-            uint2 m = make_uint2(0u, 0u);
-            uint32_t id = 0;
-            const size_t inst = (size_t)range.x + (size_t)(b * CB + tid);
-            if (tid < cnt) {
-                m = *reinterpret_cast<const uint2*>(pair_mask + 2 * inst);
-                id = point_list[inst];
-                S.mask[tid] = m;
-                S.id[tid] = id;
-            }
-            const bool any = (m.x | m.y) != 0;
-            uint32_t bytes = any ? (uint32_t)sizeof(GaussRec) + (m.x ? 256u : 0u) + (m.y ? 256u : 0u) : 0u;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
-            if (tid == 0) mbar_arrive_expect_tx(bar, bytes);
-            __syncwarp();
-            if (any) {
-                tma_bulk_g2s(&S.rec[tid], rec + id, sizeof(GaussRec), bar);
-                if (m.x) tma_bulk_g2s(&S.pairs[tid][0], pair_buf + inst * PAIR_FLOATS, 256, bar);
-                if (m.y) tma_bulk_g2s(&S.pairs[tid][64], pair_buf + inst * PAIR_FLOATS + 64, 256, bar);
-            }
-        }
-    };
-    for (int b = 0; b < CSTAGES - 1 && b < nb; ++b) issue(b);
-
-    for (int b = 0; b < nb; ++b) {
-        const int cnt = min(CB, n - b * CB);
-        __syncthreads();  // every warp is done with stage (b-1) % CSTAGES; its mask/id stores are ordered too
-        if (b + CSTAGES - 1 < nb) issue(b + CSTAGES - 1);
-        mbar_wait(&full_bar[b % CSTAGES], (uint32_t)((b / CSTAGES) & 1));
-        const ChanStage& S = stages[b % CSTAGES];
 #pragma unroll 1
-        for (int j = 0; j < cnt; ++j) {
-            const uint2 m = S.mask[j];
-            if ((m.x | m.y) == 0) continue;
-            const float* src = &S.pairs[j][toff];
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            if (m.x != 0) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float4 x = reinterpret_cast<const float4*>(src)[k];
-                    a0 = fmaf(x.x, colv[4 * k + 0], a0);
-                    a1 = fmaf(x.y, colv[4 * k + 1], a1);
-                    a2 = fmaf(x.z, colv[4 * k + 2], a2);
-                    a3 = fmaf(x.w, colv[4 * k + 3], a3);
-                }
+    for (int half = 0; half < 2; ++half) {
+        const int n = (int)(half == 0 ? cnt0 : cnt1);
+        if (n == 0) continue;
+        const int nb = (n + CB - 1) / CB;
+        const float* src_base = hrec_buf + ((size_t)2 * range.x + (size_t)half * n_all) * HREC_FLOATS;
+        // the ring's barriers keep flipping across the two halves: batch index continues
+        const int b0 = half == 0 ? 0 : (int)((cnt0 + CB - 1) / CB);
+        auto issue = [&](int b) {  // b = batch within this half
+            if (tid == 0) {
+                const int cnt = min(CB, n - b * CB);
+                const int s = (b0 + b) % CSTAGES;
+                const uint32_t bytes = (uint32_t)cnt * HREC_FLOATS * 4u;
+                mbar_arrive_expect_tx(&full_bar[s], bytes);
+                tma_bulk_g2s(&stages[s][0], src_base + (size_t)b * CB * HREC_FLOATS, bytes, &full_bar[s]);
             }
-            if (m.y != 0) {
+        };
+        for (int b = 0; b < CSTAGES - 1 && b < nb; ++b) issue(b);
+        for (int b = 0; b < nb; ++b) {
+            const int cnt = min(CB, n - b * CB);
+            __syncthreads();  // every warp is done with the stage about to be refilled
+            if (b + CSTAGES - 1 < nb) issue(b + CSTAGES - 1);
+            const int s = (b0 + b) % CSTAGES;
+            mbar_wait(&full_bar[s], (uint32_t)(((b0 + b) / CSTAGES) & 1));
+            const float* S = &stages[s][0];
+#pragma unroll 1
+            for (int j = 0; j < cnt; ++j) {
+                const float* r = S + j * HREC_FLOATS;
+                const float4 hd = *reinterpret_cast<const float4*>(r);  // gx, gy, -, id
+                const float4* src = reinterpret_cast<const float4*>(r + toff);
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                if (half == 0) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float4 x = reinterpret_cast<const float4*>(src + 64)[k];
-                    a0 = fmaf(x.x, colv[32 + 4 * k + 0], a0);
-                    a1 = fmaf(x.y, colv[32 + 4 * k + 1], a1);
-                    a2 = fmaf(x.z, colv[32 + 4 * k + 2], a2);
-                    a3 = fmaf(x.w, colv[32 + 4 * k + 3], a3);
-                }
-            }
-            const float acc = (a0 + a1) + (a2 + a3);
-            const uint32_t id = S.id[j];
-            if (col < LF) {
-                red_add_f32(dL_dlang_feat + (size_t)id * LF + col, acc);
-            } else {
-                // extras warp: lanes 0-2 colour, 3 depth, 4-9 moments
-                const float S0 = __shfl_sync(0xffffffffu, acc, 4);
-                const float Su = __shfl_sync(0xffffffffu, acc, 5);
-                const float Sv = __shfl_sync(0xffffffffu, acc, 6);
-                const float Suu = __shfl_sync(0xffffffffu, acc, 7);
-                const float Suv = __shfl_sync(0xffffffffu, acc, 8);
-                const float Svv = __shfl_sync(0xffffffffu, acc, 9);
-                if (live) {
-                    const float4 q0 = S.rec[j].q0, q1 = S.rec[j].q1;
-                    const float gx = q0.x - cxf, gy = q0.y - cyf, ca = q1.x, cb = q1.y, cc = q1.z, op = q1.w;
-                    // sums over the tile's pixels of t*dx, t*dy (dx = gx - u, dy = gy - v)
-                    const float sdx = gx * S0 - Su, sdy = gy * S0 - Sv;
-                    switch (col - LF) {
-                        case 0: case 1: case 2:
-                            red_add_f32(dL_dcolor + (size_t)id * 3 + (col - LF), acc);
-                            break;
-                        case 3:
-                            if (dL_ddepth != nullptr) red_add_f32(dL_ddepth + id, acc);
-                            break;
-                        case 4:  // dL_dmean2D.x  (backward.cu:592-601)
-                            red_add_f32(dL_dmean2D + (size_t)id * 3 + 0, -op * ddelx_dx * (ca * sdx + cb * sdy));
-                            break;
-                        case 5:  // dL_dmean2D.y
-                            red_add_f32(dL_dmean2D + (size_t)id * 3 + 1, -op * ddely_dy * (cc * sdy + cb * sdx));
-                            break;
-                        case 6:  // dL_dconic.x   (:604)
-                            red_add_f32(dL_dconic + (size_t)id * 4 + 0, -0.5f * op * (gx * gx * S0 - 2.f * gx * Su + Suu));
-                            break;
-                        case 7:  // dL_dconic.y   (:605)
-                            red_add_f32(dL_dconic + (size_t)id * 4 + 1,
-                                        -0.5f * op * (gx * gy * S0 - gx * Sv - gy * Su + Suv));
-                            break;
-                        case 8:  // dL_dconic.w   (:606)
-                            red_add_f32(dL_dconic + (size_t)id * 4 + 3, -0.5f * op * (gy * gy * S0 - 2.f * gy * Sv + Svv));
-                            break;
-                        case 9:  // dL_dopacity   (:609)
-                            red_add_f32(dL_dopacity + id, S0);
-                            break;
-                        default: break;
+                    for (int k = 0; k < 8; ++k) {
+                        const float4 x = src[k];
+                        a0 = fmaf(x.x, colv[4 * k + 0], a0);
+                        a1 = fmaf(x.y, colv[4 * k + 1], a1);
+                        a2 = fmaf(x.z, colv[4 * k + 2], a2);
+                        a3 = fmaf(x.w, colv[4 * k + 3], a3);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float4 x = src[k];
+                        a0 = fmaf(x.x, colv[32 + 4 * k + 0], a0);
+                        a1 = fmaf(x.y, colv[32 + 4 * k + 1], a1);
+                        a2 = fmaf(x.z, colv[32 + 4 * k + 2], a2);
+                        a3 = fmaf(x.w, colv[32 + 4 * k + 3], a3);
                     }
                 }
+                float acc = (a0 + a1) + (a2 + a3);
+                const uint32_t id = __float_as_uint(hd.w);
+                if (col >= LF) {
+                    // extras warp: lanes 4..9 hold S0, Su, Sv, Suu, Suv, Svv (u, v = pixel - tile centre).
+                    // With dx = gx - u, dy = gy - v:  sum t*dx = gx*S0 - Su,  sum t*dx^2 = gx^2*S0 - 2gx*Su + Suu, ...
+                    const float S0 = __shfl_sync(0xffffffffu, acc, 4);
+                    const float Su = __shfl_sync(0xffffffffu, acc, 5);
+                    const float Sv = __shfl_sync(0xffffffffu, acc, 6);
+                    const float gx = hd.x, gy = hd.y;
+                    if (mk == 1) acc = gx * S0 - Su;
+                    else if (mk == 2) acc = gy * S0 - Sv;
+                    else if (mk == 3) acc = gx * gx * S0 - 2.f * gx * Su + acc;
+                    else if (mk == 4) acc = gx * gy * S0 - gx * Sv - gy * Su + acc;
+                    else if (mk == 5) acc = gy * gy * S0 - 2.f * gy * Sv + acc;
+                }
+                if (out_base != nullptr) red_add_f32(out_base + (size_t)id * out_stride, acc);
             }
         }
+        __syncthreads();  // all stages drained before the next half re-arms them
     }
 }
 
@@ -403,9 +378,10 @@ int launch_zero_grads(int P, float* dL_dmean2D, float* dL_dconic, float* dL_dopa
     return LGS_OK;
 }
 
-size_t render_bwd_scratch_bytes(int R) {
+size_t render_bwd_scratch_bytes(int R, int W, int H) {
     const size_t n = (size_t)(R > 0 ? R : 1);
-    return n * PAIR_FLOATS * sizeof(float) + n * 2 * sizeof(uint32_t) + 512;
+    const size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    return 2 * n * HREC_FLOATS * sizeof(float) + tiles * 2 * sizeof(uint32_t) + 1024;
 }
 
 int launch_render_bwd(int P, int W, int H, int R, const GeomState& g, const BinningState& b,
@@ -415,28 +391,28 @@ int launch_render_bwd(int P, int W, int H, int R, const GeomState& g, const Binn
                       float* dL_dlang_feat, float* dL_ddepth, bool include_lf, char* scratch, cudaStream_t s) {
     (void)P;
     const dim3 grid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE, 1);
-    // scratch: [R][128] floats of w/t records (256-byte aligned) followed by [R][2] ballots
+    // scratch: [2R] half-records of 272 B (256-byte aligned base) followed by [tiles][2] record counts
     uintptr_t base = (reinterpret_cast<uintptr_t>(scratch) + 255) & ~(uintptr_t)255;
-    float* pair_buf = reinterpret_cast<float*>(base);
-    uint32_t* pair_mask = reinterpret_cast<uint32_t*>(pair_buf + (size_t)(R > 0 ? R : 1) * PAIR_FLOATS);
+    float* hrec = reinterpret_cast<float*>(base);
+    uint32_t* hcount = reinterpret_cast<uint32_t*>(hrec + (size_t)2 * (R > 0 ? R : 1) * HREC_FLOATS);
     if (include_lf) {
         render_bwd_pix_kernel<true><<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, W, H, background, g.rec, lang_feat,
                                                               im.final_T, im.n_contrib, im.tile_last, dL_dpix, dL_dpix_lf,
-                                                              dL_dpix_depth, pair_buf, pair_mask);
+                                                              dL_dpix_depth, hrec, hcount);
         LGS_LAUNCH_CHECK();
         prof_mark(PM_RENDER_BWD_PIX, s);
-        render_bwd_chan_kernel<true><<<grid, 96, 0, s>>>(im.ranges, b.point_list, W, H, g.rec, im.tile_last, dL_dpix,
-                                                         dL_dpix_lf, dL_dpix_depth, pair_buf, pair_mask, dL_dmean2D,
-                                                         dL_dconic, dL_dopacity, dL_dcolor, dL_dlang_feat, dL_ddepth);
+        render_bwd_chan_kernel<true><<<grid, 96, 0, s>>>(im.ranges, W, H, dL_dpix, dL_dpix_lf, dL_dpix_depth, hrec, hcount,
+                                                         dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dlang_feat,
+                                                         dL_ddepth);
     } else {
         render_bwd_pix_kernel<false><<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, W, H, background, g.rec, lang_feat,
                                                                im.final_T, im.n_contrib, im.tile_last, dL_dpix, dL_dpix_lf,
-                                                               dL_dpix_depth, pair_buf, pair_mask);
+                                                               dL_dpix_depth, hrec, hcount);
         LGS_LAUNCH_CHECK();
         prof_mark(PM_RENDER_BWD_PIX, s);
-        render_bwd_chan_kernel<false><<<grid, 32, 0, s>>>(im.ranges, b.point_list, W, H, g.rec, im.tile_last, dL_dpix,
-                                                          dL_dpix_lf, dL_dpix_depth, pair_buf, pair_mask, dL_dmean2D,
-                                                          dL_dconic, dL_dopacity, dL_dcolor, dL_dlang_feat, dL_ddepth);
+        render_bwd_chan_kernel<false><<<grid, 32, 0, s>>>(im.ranges, W, H, dL_dpix, dL_dpix_lf, dL_dpix_depth, hrec, hcount,
+                                                          dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dlang_feat,
+                                                          dL_ddepth);
     }
     LGS_LAUNCH_CHECK();
     return LGS_OK;

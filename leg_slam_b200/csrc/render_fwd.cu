@@ -84,7 +84,7 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     if (USE_TMA && tid < FB && tid < n) pf_id = point_list[range.x + tid];
 
     auto issue = [&](int b) {  // called by every thread, acts on warp 0
-        if (tid < FB) {
+        if (tid < 32) {  // the whole of warp 0 (FB <= 32 lanes carry an instance each)
             const int cnt = min(FB, n - b * FB);
             Stage& S = stages[b % FSTAGES];
             uint64_t* bar = &full_bar[b % FSTAGES];
@@ -95,7 +95,7 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
                 if (WITH_LF) tma_bulk_g2s(&S.lf[tid * LF], lang_feat + (size_t)pf_id * LF, LF * 4, bar);
             }
             const int nxt = (b + 1) * FB + tid;
-            if (nxt < n) pf_id = point_list[range.x + nxt];
+            if (tid < FB && nxt < n) pf_id = point_list[range.x + nxt];
         }
         ++issued;
     };

@@ -24,6 +24,27 @@ def _stream(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+_scratch = {}
+
+
+def _workspace(dev, stream, nbytes):
+    """Grow-only scratch per (device, stream) for buffers that only live inside one call (the render
+    backward's hand-off records): avoids a fresh ~0.5 KB/instance allocation of varying size every
+    iteration, which fragments the caching allocator."""
+    key = (dev.index, stream)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _scratch.pop(key, None)
+        buf = torch.empty(int(nbytes * 1.25) + (1 << 20), dtype=torch.uint8, device=dev)
+        _scratch[key] = buf
+    return buf
+
+
+def _round_up(n, q):
+    return ((int(n) + q - 1) // q) * q
+
+
 def _f32c(t):
     """`.contiguous()` as the reference does on every input (float32 is assumed there too)."""
     if t is None:
@@ -75,7 +96,8 @@ def rasterize_gaussians(background, means3D, colors, lang_feat, opacity, scales,
                                    ptr(viewmatrix), ptr(projmatrix), ptr(campos), float(tan_fovx), float(tan_fovy),
                                    int(bool(prefiltered)), geom.data_ptr(), radii.data_ptr(), ctypes.byref(R), s),
               "lgs_forward_stage1")
-        binning = torch.empty(L.lgs_binning_bytes(R.value), **byte)
+        # capacity rounded up so that consecutive iterations (R drifts slowly) reuse the same cached block
+        binning = torch.empty(L.lgs_binning_bytes(_round_up(R.value, 1 << 18)), **byte)
         check(L.lgs_forward_stage2(P, W, H, R.value, ptr(background), ptr(lang_feat) if include_lf else None,
                                    geom.data_ptr(), binning.data_ptr(), img.data_ptr(), out_color.data_ptr(),
                                    out_lf.data_ptr(), out_depth.data_ptr(), int(include_lf), s),
@@ -112,7 +134,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, lang_feat, 
             campos, dL_dout_color, dL_dout_lang_feat, dL_dout_depth = map(
                 _f32c, (background, means3D, colors, lang_feat, scales, rotations, cov3D_precomp, viewmatrix,
                         projmatrix, sh, campos, dL_dout_color, dL_dout_lang_feat, dL_dout_depth))
-        scratch = torch.empty(L.lgs_backward_scratch_bytes(int(R)), dtype=torch.uint8, device=dev)
+        scratch = _workspace(dev, _stream(means3D), L.lgs_backward_scratch_bytes(int(R), W, H))
         with torch.cuda.device(dev):
             check(L.lgs_backward(
                 P, int(degree), M, int(R), W, H, ptr(background), ptr(means3D), ptr(sh), ptr(colors),
