@@ -44,7 +44,7 @@ namespace lgs {
 
 constexpr int BB = 32;       // Gaussians per TMA batch of the pixel kernel
 constexpr int BSTAGES = 3;   // its staging ring depth
-constexpr int CB = 16;       // half-records per TMA batch of the channel kernel
+constexpr int CB = 8;        // half-records per TMA batch of the channel kernel
 constexpr int CSTAGES = 4;   // its staging ring depth
 constexpr int HREC_FLOATS = 68;  // half-record: {gx - cx, gy - cy, 0, id} | w[32] | t[32]  (272 B)
 
@@ -205,45 +205,51 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 }
 
 // ================================ channel kernel ===================================================
-// One CTA per tile; every thread owns one of the 74 columns (64 feature channels, 3 colour, depth,
-// 6 moment bases) of the tile's [64 pixel x 74] matrix in registers and reduces the pixel kernel's
-// half-records against it: ONE red.global.add per (half-record, column).  Records arrive through a
-// ring of TMA bulk copies (one 4 KB copy per batch of 16 records).
+// One single-warp CTA per (tile, column group): group 0/1 = feature channels 0-31 / 32-63, group 2 =
+// 3 colour + depth + 6 moment columns.  Every lane owns one column of the tile's [64 pixel x 74]
+// matrix in 64 registers and reduces the pixel kernel's half-records against it: ONE
+// red.global.add per (half-record, column).  Records arrive through the warp's own ring of TMA
+// bulk copies (one 2 KB copy per batch of 8 records); there is no CTA-wide barrier anywhere, so a
+// slow group never stalls the others (the first version with one 3-warp CTA per tile and a
+// __syncthreads per batch spent 47 % of its warp samples in barrier stalls).
 //
 // Moment lanes accumulate sums of t, t*dx, t*dy, t*dx^2, t*dx*dy, t*dy^2 (dx, dy = Gaussian centre
 // minus pixel) into dL_dopacity / dL_dmean2D.xy / dL_dconic.{x,y,w}; the per-Gaussian factors
 // (opacity, conic, viewport scale) are applied once per Gaussian by the preprocess backward.
 template <bool WITH_LF>
-__global__ void __launch_bounds__(WITH_LF ? 96 : 32, WITH_LF ? 6 : 16)
-render_bwd_chan_kernel(const uint2* __restrict__ ranges, int W, int H, const float* __restrict__ dL_dpix,
-                       const float* __restrict__ dL_dpix_lf, const float* __restrict__ dL_dpix_depth,
-                       const float* __restrict__ hrec_buf, const uint32_t* __restrict__ hrec_count,
-                       float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic,
-                       float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor,
-                       float* __restrict__ dL_dlang_feat, float* __restrict__ dL_ddepth) {
+__global__ void __launch_bounds__(32)
+render_bwd_chan_kernel(const uint2* __restrict__ ranges, int W, int H, int tiles_x,
+                       const float* __restrict__ dL_dpix, const float* __restrict__ dL_dpix_lf,
+                       const float* __restrict__ dL_dpix_depth, const float* __restrict__ hrec_buf,
+                       const uint32_t* __restrict__ hrec_count, float* __restrict__ dL_dmean2D,
+                       float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity,
+                       float* __restrict__ dL_dcolor, float* __restrict__ dL_dlang_feat,
+                       float* __restrict__ dL_ddepth) {
     __shared__ __align__(128) float stages[CSTAGES][CB * HREC_FLOATS];
     __shared__ __align__(8) uint64_t full_bar[CSTAGES];
 
-    const int tid = threadIdx.x;
-    const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+    const int lane = threadIdx.x;
+    const int tile_id = WITH_LF ? (int)(blockIdx.x / 3) : (int)blockIdx.x;
+    const int grp = WITH_LF ? (int)(blockIdx.x % 3) : 2;
     const uint32_t cnt0 = hrec_count[2 * tile_id], cnt1 = hrec_count[2 * tile_id + 1];
     if (cnt0 + cnt1 == 0) return;
     const uint2 range = ranges[tile_id];
     const int n_all = (int)(range.y - range.x);
     const size_t HW = (size_t)H * W;
+    const uint32_t tx0 = (uint32_t)(tile_id % tiles_x) * TILE, ty0 = (uint32_t)(tile_id / tiles_x) * TILE;
 
-    if (tid == 0) {
+    if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < CSTAGES; ++s) mbar_init(&full_bar[s], 1);
         mbar_fence_init();
     }
 
-    const int col = tid + (WITH_LF ? 0 : LF);  // 0..63 lf, 64..66 rgb, 67 depth, 68..73 moments
+    const int col = grp * 32 + lane;  // 0..63 lf, 64..66 rgb, 67 depth, 68..73 moments, 74.. idle
     float colv[TILE_PIX];
 #pragma unroll
     for (int i = 0; i < TILE_PIX; ++i) {
-        const uint32_t pxi = blockIdx.x * TILE + (i & 7);
-        const uint32_t pyi = blockIdx.y * TILE + (i >> 3);
+        const uint32_t pxi = tx0 + (i & 7);
+        const uint32_t pyi = ty0 + (i >> 3);
         const bool inside = pxi < (uint32_t)W && pyi < (uint32_t)H;
         const size_t pix_id = (size_t)W * pyi + pxi;
         const float u = (float)(i & 7) - 3.5f, v = (float)(i >> 3) - 3.5f;
@@ -256,12 +262,12 @@ render_bwd_chan_kernel(const uint2* __restrict__ ranges, int W, int H, const flo
             if (inside) x = dL_dpix_depth[pix_id];
         } else {
             const int k = col - (LF + 4);
-            x = k == 0 ? 1.f : k == 1 ? u : k == 2 ? v : k == 3 ? u * u : k == 4 ? u * v : v * v;
+            x = k == 0 ? 1.f : k == 1 ? u : k == 2 ? v : k == 3 ? u * u : k == 4 ? u * v : k == 5 ? v * v : 0.f;
         }
         colv[i] = x;
     }
     const int toff = (col >= LF + 4) ? 36 : 4;  // moment columns reduce t, the others reduce w
-    // per-thread output slot: out_base[id * out_stride]
+    // per-lane output slot: out_base[id * out_stride]
     float* out_base = nullptr;
     uint32_t out_stride = 0;
     if (col < LF) { out_base = dL_dlang_feat + col; out_stride = LF; }
@@ -273,21 +279,28 @@ render_bwd_chan_kernel(const uint2* __restrict__ ranges, int W, int H, const flo
     else if (col == LF + 7) { out_base = dL_dconic; out_stride = 4; }           // sum t*dx*dx
     else if (col == LF + 8) { out_base = dL_dconic + 1; out_stride = 4; }       // sum t*dx*dy
     else if (col == LF + 9) { out_base = dL_dconic + 3; out_stride = 4; }       // sum t*dy*dy
-    const int mk = col - (LF + 4);  // moment index 0..5 on the moment lanes
-    __syncthreads();
+    // Moment lanes hold S0, Su, Sv, Suu, Suv, Svv with u, v = pixel - tile centre.  With dx = gx - u,
+    // dy = gy - v:  sum t*dx = gx*S0 - Su,  sum t*dx^2 = gx^2*S0 - 2*gx*Su + Suu,  ... written branch-free as
+    //   out = k_own*own + S0*(kxx*gx*gx + kxy*gx*gy + kyy*gy*gy + kx*gx + ky*gy) + Su*(cux*gx + cuy*gy) + Sv*(cvx*gx + cvy*gy)
+    const int mk = col - (LF + 4);
+    const float k_own = (mk == 1 || mk == 2) ? -1.f : 1.f;
+    const float kx = mk == 1 ? 1.f : 0.f, ky = mk == 2 ? 1.f : 0.f;
+    const float kxx = mk == 3 ? 1.f : 0.f, kxy = mk == 4 ? 1.f : 0.f, kyy = mk == 5 ? 1.f : 0.f;
+    const float cux = mk == 3 ? -2.f : 0.f, cuy = mk == 4 ? -1.f : 0.f;
+    const float cvx = mk == 4 ? -1.f : 0.f, cvy = mk == 5 ? -2.f : 0.f;
+    __syncwarp();
 
+    int gb = 0;  // global batch counter: the ring's stage / parity sequence runs across both halves
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
         const int n = (int)(half == 0 ? cnt0 : cnt1);
         if (n == 0) continue;
         const int nb = (n + CB - 1) / CB;
         const float* src_base = hrec_buf + ((size_t)2 * range.x + (size_t)half * n_all) * HREC_FLOATS;
-        // the ring's barriers keep flipping across the two halves: batch index continues
-        const int b0 = half == 0 ? 0 : (int)((cnt0 + CB - 1) / CB);
         auto issue = [&](int b) {  // b = batch within this half
-            if (tid == 0) {
+            if (lane == 0) {
                 const int cnt = min(CB, n - b * CB);
-                const int s = (b0 + b) % CSTAGES;
+                const int s = (gb + b) % CSTAGES;
                 const uint32_t bytes = (uint32_t)cnt * HREC_FLOATS * 4u;
                 mbar_arrive_expect_tx(&full_bar[s], bytes);
                 tma_bulk_g2s(&stages[s][0], src_base + (size_t)b * CB * HREC_FLOATS, bytes, &full_bar[s]);
@@ -296,10 +309,10 @@ render_bwd_chan_kernel(const uint2* __restrict__ ranges, int W, int H, const flo
         for (int b = 0; b < CSTAGES - 1 && b < nb; ++b) issue(b);
         for (int b = 0; b < nb; ++b) {
             const int cnt = min(CB, n - b * CB);
-            __syncthreads();  // every warp is done with the stage about to be refilled
+            __syncwarp();  // all lanes are done with the stage about to be refilled (batch b-1's)
             if (b + CSTAGES - 1 < nb) issue(b + CSTAGES - 1);
-            const int s = (b0 + b) % CSTAGES;
-            mbar_wait(&full_bar[s], (uint32_t)(((b0 + b) / CSTAGES) & 1));
+            const int s = (gb + b) % CSTAGES;
+            mbar_wait(&full_bar[s], (uint32_t)(((gb + b) / CSTAGES) & 1));
             const float* S = &stages[s][0];
 #pragma unroll 1
             for (int j = 0; j < cnt; ++j) {
@@ -328,23 +341,19 @@ render_bwd_chan_kernel(const uint2* __restrict__ ranges, int W, int H, const flo
                 }
                 float acc = (a0 + a1) + (a2 + a3);
                 const uint32_t id = __float_as_uint(hd.w);
-                if (col >= LF) {
-                    // extras warp: lanes 4..9 hold S0, Su, Sv, Suu, Suv, Svv (u, v = pixel - tile centre).
-                    // With dx = gx - u, dy = gy - v:  sum t*dx = gx*S0 - Su,  sum t*dx^2 = gx^2*S0 - 2gx*Su + Suu, ...
+                if (grp == 2) {
                     const float S0 = __shfl_sync(0xffffffffu, acc, 4);
                     const float Su = __shfl_sync(0xffffffffu, acc, 5);
                     const float Sv = __shfl_sync(0xffffffffu, acc, 6);
                     const float gx = hd.x, gy = hd.y;
-                    if (mk == 1) acc = gx * S0 - Su;
-                    else if (mk == 2) acc = gy * S0 - Sv;
-                    else if (mk == 3) acc = gx * gx * S0 - 2.f * gx * Su + acc;
-                    else if (mk == 4) acc = gx * gy * S0 - gx * Sv - gy * Su + acc;
-                    else if (mk == 5) acc = gy * gy * S0 - 2.f * gy * Sv + acc;
+                    const float c0 = gx * (kxx * gx + kxy * gy + kx) + gy * (kyy * gy + ky);
+                    acc = k_own * acc + S0 * c0 + Su * (cux * gx + cuy * gy) + Sv * (cvx * gx + cvy * gy);
                 }
                 if (out_base != nullptr) red_add_f32(out_base + (size_t)id * out_stride, acc);
             }
         }
-        __syncthreads();  // all stages drained before the next half re-arms them
+        gb += nb;
+        __syncwarp();
     }
 }
 
@@ -391,6 +400,7 @@ int launch_render_bwd(int P, int W, int H, int R, const GeomState& g, const Binn
                       float* dL_dlang_feat, float* dL_ddepth, bool include_lf, char* scratch, cudaStream_t s) {
     (void)P;
     const dim3 grid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE, 1);
+    const unsigned tiles = grid.x * grid.y;
     // scratch: [2R] half-records of 272 B (256-byte aligned base) followed by [tiles][2] record counts
     uintptr_t base = (reinterpret_cast<uintptr_t>(scratch) + 255) & ~(uintptr_t)255;
     float* hrec = reinterpret_cast<float*>(base);
@@ -401,18 +411,18 @@ int launch_render_bwd(int P, int W, int H, int R, const GeomState& g, const Binn
                                                               dL_dpix_depth, hrec, hcount);
         LGS_LAUNCH_CHECK();
         prof_mark(PM_RENDER_BWD_PIX, s);
-        render_bwd_chan_kernel<true><<<grid, 96, 0, s>>>(im.ranges, W, H, dL_dpix, dL_dpix_lf, dL_dpix_depth, hrec, hcount,
-                                                         dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dlang_feat,
-                                                         dL_ddepth);
+        render_bwd_chan_kernel<true><<<3 * tiles, 32, 0, s>>>(im.ranges, W, H, (int)grid.x, dL_dpix, dL_dpix_lf, dL_dpix_depth,
+                                                              hrec, hcount, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
+                                                              dL_dlang_feat, dL_ddepth);
     } else {
         render_bwd_pix_kernel<false><<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, W, H, background, g.rec, lang_feat,
                                                                im.final_T, im.n_contrib, im.tile_last, dL_dpix, dL_dpix_lf,
                                                                dL_dpix_depth, hrec, hcount);
         LGS_LAUNCH_CHECK();
         prof_mark(PM_RENDER_BWD_PIX, s);
-        render_bwd_chan_kernel<false><<<grid, 32, 0, s>>>(im.ranges, W, H, dL_dpix, dL_dpix_lf, dL_dpix_depth, hrec, hcount,
-                                                          dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dlang_feat,
-                                                          dL_ddepth);
+        render_bwd_chan_kernel<false><<<tiles, 32, 0, s>>>(im.ranges, W, H, (int)grid.x, dL_dpix, dL_dpix_lf, dL_dpix_depth,
+                                                           hrec, hcount, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
+                                                           dL_dlang_feat, dL_ddepth);
     }
     LGS_LAUNCH_CHECK();
     return LGS_OK;
