@@ -292,7 +292,9 @@ class E2EPath:
         lrs = {k: v * LR_SCALE for k, v in M.DEFAULT_LRS.items()}
         kw = {}
         if impl == "reference":
-            kw = dict(optimizer_factory=lambda g: torch.optim.Adam(g, lr=0.0, eps=1e-15), render_fn=self._ref_render_fn())
+            # the reference's stock path: eager torch ops for the loss, unfused torch Adam
+            kw = dict(optimizer_factory=lambda g: torch.optim.Adam(g, lr=0.0, eps=1e-15), render_fn=self._ref_render_fn(),
+                      use_cuda_graph=False)
         self.mapper = M.Mapper(params, lrs=lrs, sh_degree=SH_DEGREE, **kw)
         if impl == "reference":
             self.mapper.world_size, self.mapper.rank = 1, 0  # the reference is single-GPU: rank 0 does every view

@@ -70,7 +70,8 @@ class Mapper:
 
     def __init__(self, params: dict, lrs: Optional[dict] = None, sh_degree: int = 3,
                  process_group=None, optimizer_factory: Optional[Callable] = None,
-                 render_fn: Optional[Callable] = None, faithful_loss_sign: bool = True):
+                 render_fn: Optional[Callable] = None, faithful_loss_sign: bool = True,
+                 use_cuda_graph: bool = True):
         self.params = {k: torch.nn.Parameter(params[k].detach().clone().contiguous()) for k in PARAM_ORDER}
         lrs = dict(DEFAULT_LRS, **(lrs or {}))
         groups = [dict(params=[self.params[k]], lr=lrs[k], name=k) for k in PARAM_ORDER]
@@ -85,6 +86,8 @@ class Mapper:
         dev = self.params["xyz"].device
         self.bg = torch.zeros(3, dtype=torch.float32, device=dev)
         self.last_num_views = 0
+        self.use_cuda_graph = use_cuda_graph
+        self._loss_graphs = {}
 
     # -- activations exactly as the reference applies them each iteration (gaussian_model.cpp:46-68)
     def activated(self):
@@ -100,6 +103,62 @@ class Mapper:
         return GaussianRasterizer(rs)(a["means3D"], means2D, a["opacities"], shs=a["shs"], lang_feats=a["lang_feats"],
                                       scales=a["scales"], rotations=a["rotations"])
 
+    # -- the loss and its gradient w.r.t. the rendered images as ONE CUDA-graph replay -----------------
+    def _graphed_loss(self, image, lf, depth, gt_image, gt_lf, gt_depth, mask):
+        """loss and dL/d(image, lf, depth) of `loss_mod.mapping_loss`, captured once per image shape
+        into a CUDA graph (static shapes, ~60 small torch kernels forward+backward) and replayed:
+        the same stock ops, without their per-launch host overhead."""
+        key = (tuple(image.shape), tuple(gt_lf.shape), mask is not None)
+        g = self._loss_graphs.get(key)
+        if g is None:
+            st = dict(image=torch.empty_like(image), lf=torch.empty_like(lf), depth=torch.empty_like(depth),
+                      gt_image=torch.empty_like(gt_image), gt_lf=torch.empty_like(gt_lf),
+                      gt_depth=torch.empty_like(gt_depth), mask=None if mask is None else torch.empty_like(mask))
+
+            def run():
+                im = st["image"].detach().requires_grad_(True)  # fresh leaves aliasing the static buffers
+                l_ = st["lf"].detach().requires_grad_(True)
+                d_ = st["depth"].detach().requires_grad_(True)
+                loss = self._loss_from_images(im, l_, d_, st["gt_image"], st["gt_lf"], st["gt_depth"], st["mask"])
+                gi, gl, gd = torch.autograd.grad(loss, [im, l_, d_])
+                return loss.detach(), gi, gl, gd
+
+            for k, v in (("image", image), ("lf", lf), ("depth", depth), ("gt_image", gt_image), ("gt_lf", gt_lf),
+                         ("gt_depth", gt_depth)):
+                st[k].copy_(v.detach())
+            if mask is not None:
+                st["mask"].copy_(mask)
+            side = torch.cuda.Stream(device=image.device)
+            side.wait_stream(torch.cuda.current_stream(image.device))
+            with torch.cuda.stream(side):  # warm-up off the capture stream (cuDNN/allocator init)
+                for _ in range(3):
+                    run()
+            torch.cuda.current_stream(image.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = run()
+            g = (graph, st, out)
+            self._loss_graphs[key] = g
+        graph, st, out = g
+        st["image"].copy_(image.detach())
+        st["lf"].copy_(lf.detach())
+        st["depth"].copy_(depth.detach())
+        st["gt_image"].copy_(gt_image)
+        st["gt_lf"].copy_(gt_lf)
+        st["gt_depth"].copy_(gt_depth)
+        if mask is not None:
+            st["mask"].copy_(mask)
+        graph.replay()
+        return out
+
+    def _loss_from_images(self, image, lf, depth, gt_image, gt_lf, gt_depth, mask):
+        # gt feature map resized to the render size, nearest (src/gaussian_mapper.cpp:707-708)
+        if gt_lf.shape[-2:] != lf.shape[-2:]:
+            gt_lf = torch.nn.functional.interpolate(gt_lf.unsqueeze(0), size=tuple(lf.shape[-2:])).squeeze(0)
+        if mask is not None:  # :711-713
+            image, lf, depth = image * mask, lf * mask[0:1], depth * mask[0:1]
+        return loss_mod.mapping_loss(image, lf, depth, gt_image, gt_lf, gt_depth, faithful_sign=self.faithful_loss_sign)
+
     def train_step(self, window: Sequence[Keyframe], presharded: bool = False):
         """Render + back-propagate this rank's share of `window`, sum gradients over ranks, Adam.
         `window` is the iteration's global list of keyframes (every rank passes the same list and
@@ -114,16 +173,15 @@ class Mapper:
             kf = window[i]
             a = self.activated()
             image, lf, depth, _radii = self.render_fn(kf.camera, a)
-            # gt feature map resized to the render size, nearest (src/gaussian_mapper.cpp:707-708)
-            gt_lf = kf.gt_lf
-            if gt_lf.shape[-2:] != lf.shape[-2:]:
-                gt_lf = torch.nn.functional.interpolate(gt_lf.unsqueeze(0), size=tuple(lf.shape[-2:])).squeeze(0)
-            if kf.mask is not None:  # :711-713
-                image, lf, depth = image * kf.mask, lf * kf.mask[0:1], depth * kf.mask[0:1]
-            loss = loss_mod.mapping_loss(image, lf, depth, kf.gt_image, gt_lf, kf.gt_depth,
-                                         faithful_sign=self.faithful_loss_sign)
-            loss.backward()  # accumulates into the flat buffer through the .grad views
-            total = loss.detach() if total is None else total + loss.detach()
+            if self.use_cuda_graph and image.is_cuda:
+                loss, gi, gl, gd = self._graphed_loss(image, lf, depth, kf.gt_image, kf.gt_lf, kf.gt_depth, kf.mask)
+                torch.autograd.backward([image, lf, depth], [gi, gl, gd])
+                loss = loss.clone()
+            else:
+                loss = self._loss_from_images(image, lf, depth, kf.gt_image, kf.gt_lf, kf.gt_depth, kf.mask)
+                loss.backward()  # accumulates into the flat buffer through the .grad views
+                loss = loss.detach()
+            total = loss if total is None else total + loss
         if self.world_size > 1:
             dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.pg)
         self.optimizer.step()
