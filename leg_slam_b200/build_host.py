@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Build the C++ host layers above the C ABI, in-tree (g++ only, no nvcc):
+
+  leg_slam_b200/liblgs_host.so : CudaRasterizer::Rasterizer (include/cuda_rasterizer/rasterizer.h), no torch
+  leg_slam_b200/_C.so          : libtorch RasterizeGaussiansCUDA / ...BackwardCUDA / markVisible
+                                 (include/rasterize_points.h) + the pybind module `_C`
+
+    python -m leg_slam_b200.build_host [--force]
+"""
+import os
+import subprocess
+import sys
+import sysconfig
+
+from . import build as lgs_build
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+HOST = os.path.join(PKG, "csrc", "host")
+LIB_HOST = os.path.join(PKG, "liblgs_host.so")
+LIB_C = os.path.join(PKG, "_C.so")
+
+
+def _stale(target, deps):
+    return (not os.path.exists(target)) or any(os.path.getmtime(d) > os.path.getmtime(target) for d in deps)
+
+
+def build(force=False, verbose=False):
+    lgs_build.build()
+    inc = os.path.join(ROOT, "include")
+    hdrs = [os.path.join(inc, "lgs.h"), os.path.join(inc, "cuda_rasterizer", "rasterizer.h"),
+            os.path.join(inc, "rasterize_points.h")]
+
+    def run(cmd):
+        if verbose:
+            print("[lgs host]", " ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+
+    src0 = os.path.join(HOST, "rasterizer.cpp")
+    if force or _stale(LIB_HOST, [src0] + hdrs):
+        run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I" + inc, src0, "-o", LIB_HOST, "-L" + PKG, "-llgs",
+             "-Wl,-rpath,$ORIGIN"])
+    srcs = [os.path.join(HOST, "rasterize_points.cpp"), os.path.join(HOST, "ext.cpp")]
+    if force or _stale(LIB_C, srcs + hdrs):
+        import torch  # noqa: F401
+        from torch.utils import cpp_extension as ce
+        cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=_C",
+               "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=1", "-I" + inc,
+               "-I" + os.path.join(cuda, "include"), "-I" + sysconfig.get_paths()["include"]]
+        cmd += ["-I" + p for p in ce.include_paths()] + srcs + ["-o", LIB_C, "-L" + PKG, "-llgs", "-Wl,-rpath,$ORIGIN"]
+        cmd += ["-L" + p for p in ce.library_paths()] + ["-L" + os.path.join(cuda, "lib64"), "-lc10", "-ltorch_cpu",
+                                                          "-ltorch", "-ltorch_python", "-lc10_cuda", "-ltorch_cuda",
+                                                          "-lcudart"]
+        cmd += ["-Wl,-rpath," + p for p in ce.library_paths()]
+        run(cmd)
+    return LIB_HOST, LIB_C
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

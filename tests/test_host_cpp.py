@@ -1,0 +1,101 @@
+"""The C++ host layers above the C ABI: the L0 class with the reference's signatures
+(include/cuda_rasterizer/rasterizer.h, liblgs_host.so) and the L1 libtorch functions + pybind
+module `_C` (include/rasterize_points.h, _C.so)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def host_libs():
+    from leg_slam_b200 import build_host
+    return build_host.build()
+
+
+def test_l0_library_exports_reference_class(host_libs):
+    out = subprocess.run(["nm", "-D", "--defined-only", "-C", host_libs[0]], capture_output=True, text=True).stdout
+    for sym in ("CudaRasterizer::Rasterizer::forward(", "CudaRasterizer::Rasterizer::backward(",
+                "CudaRasterizer::Rasterizer::markVisible(", "lgs_host_set_stream"):
+        assert sym in out, sym
+
+
+def test_l1_module_exports_reference_names(host_libs):
+    from leg_slam_b200 import _C
+    for name in ("rasterize_gaussians", "rasterize_gaussians_backward", "mark_visible"):
+        assert callable(getattr(_C, name))
+    cs = cases.make_case("sh3_lf")
+    with pytest.raises(RuntimeError, match="num_points, 3"):
+        bad = dict(cs, means3D=cs["means3D"][:, :2])
+        _C.rasterize_gaussians(*cases.fwd_args(bad))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        _C.rasterize_gaussians(*cases.fwd_args(cs))
+
+
+@pytest.mark.gpu
+def test_l1_cpp_equals_python_binding(host_libs):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from leg_slam_b200 import _C, rasterize_points as rp
+    dev = torch.device("cuda:0")
+    for name in ("sh3_lf", "precomp_nolf"):
+        cs = cases.make_case(name, dev)
+        a = _C.rasterize_gaussians(*cases.fwd_args(cs))
+        b = rp.rasterize_gaussians(*cases.fwd_args(cs))
+        assert a[0] == b[0]
+        for x, y in zip(a[1:5], b[1:5]):
+            assert torch.equal(x, y)
+        ga = _C.rasterize_gaussians_backward(*cases.bwd_args(cs, a[4], a[5], a[0], a[6], a[7]))
+        gb = rp.rasterize_gaussians_backward(*cases.bwd_args(cs, b[4], b[5], b[0], b[6], b[7]))
+        for n, x, y in zip(cases.GRAD_NAMES, ga, gb):
+            assert x.shape == y.shape, n
+            assert cases.rel_err(x.cpu().numpy(), y.cpu().numpy()) <= 1e-3, n
+        assert torch.equal(_C.mark_visible(cs["means3D"], cs["viewmatrix"], cs["projmatrix"]),
+                           rp.mark_visible(cs["means3D"], cs["viewmatrix"], cs["projmatrix"]))
+
+
+@pytest.mark.gpu
+def test_l0_cpp_class_vs_oracle(host_libs, oracle_mod, tmp_path):
+    """A C++ program that uses the class the way the reference's rasterize_points.cu does."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    exe = str(tmp_path / "l0_driver")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    pkg = os.path.join(ROOT, "leg_slam_b200")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", os.path.join(ROOT, "tests", "cpp", "l0_driver.cpp"),
+                           "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(cuda, "include"), "-o", exe,
+                           "-L" + pkg, "-llgs_host", "-llgs", "-L" + os.path.join(cuda, "lib64"), "-lcudart",
+                           "-Wl,-rpath," + pkg])
+    cs = cases.make_case("sh3_lf")
+    P, W, H = cs["P"], cs["W"], cs["H"]
+    with open(tmp_path / "in.bin", "wb") as f:
+        np.array([P, W, H, cs["degree"], 16, 1], np.int32).tofile(f)
+        np.array([cs["tanfovx"], cs["tanfovy"], 1.0], np.float32).tofile(f)
+        for k in ("bg", "means3D", "shs", "lang_feats", "opacities", "scales", "rotations", "viewmatrix", "projmatrix",
+                  "campos", "dL_dcolor", "dL_dlf", "dL_ddepth"):
+            cs[k].contiguous().numpy().astype(np.float32).tofile(f)
+    r = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    f = cases.oracle_forward(cs, oracle_mod)
+    g = cases.oracle_backward(cs, f, oracle_mod)
+    with open(tmp_path / "out.bin", "rb") as fh:
+        R = int(np.fromfile(fh, np.int32, 1)[0])
+        radii = np.fromfile(fh, np.int32, P)
+        present = np.fromfile(fh, np.uint8, P).astype(bool)
+        rdf = lambda *s: np.fromfile(fh, np.float32, int(np.prod(s))).reshape(s)  # noqa: E731
+        color, lf, depth = rdf(3, H, W), rdf(64, H, W), rdf(1, H, W)
+        grads = dict(dL_dmeans2D=rdf(P, 3), dL_dcolors=rdf(P, 3), dL_dlang_feats=rdf(P, 64), dL_dopacity=rdf(P, 1),
+                     dL_dmeans3D=rdf(P, 3), dL_dcov3D=rdf(P, 6), dL_dsh=rdf(P, 16, 3), dL_dscales=rdf(P, 3),
+                     dL_drotations=rdf(P, 4))
+    assert R == f["num_rendered"] and np.array_equal(radii, f["radii"])
+    assert np.array_equal(present, oracle_mod.mark_visible(cs["means3D"].numpy(), cs["viewmatrix"].numpy()))
+    assert cases.rel_err(color, f["out_color"]) <= 1e-4 and cases.rel_err(lf, f["out_lf"]) <= 1e-4
+    assert cases.rel_err(depth, f["out_depth"]) <= 1e-4
+    for n in cases.GRAD_NAMES:
+        assert cases.rel_err(grads[n], g[n]) <= 1e-3, n
