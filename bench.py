@@ -495,8 +495,8 @@ def main():
                        "adam_lr_scale_kernel_path": 1e-3, "e2e_lr_scale": LR_SCALE},
             "e2e": {"value": round(world * 1000.0 / ms_e2e, 3), "unit": "iters/s", "ms_per_step": round(ms_e2e, 4),
                     "h2d_bytes_per_step": int((35 + 3 * HEIGHT * WIDTH + HEIGHT * WIDTH + 64 * LF_LOWRES * LF_LOWRES) * 4),
-                    "d2h_bytes_per_step": 8, "api": "leg_slam_b200.mapper.Mapper.train_step (GaussianRasterizer autograd + "
-                                                    "reference loss + FusedAdam), inputs from pinned host memory"},
+                    "d2h_bytes_per_step": 8, "api": "leg_slam_b200.mapper.Mapper.train_step (fused activations + rasterizer + "
+                                                    "fused loss + FusedAdam, all liblgs launches), inputs from pinned host memory"},
             "gpu_launches": KernelPath.KERNELS_PER_STEP * args.steps,
             "gpu_launches_note": "hand-written kernels per step: preprocess, emit_keys, tile_ranges, render_fwd, zero_grads, "
                                  "render_bwd_pix, render_bwd_chan, preprocess_bwd, adam; CUB scan (2) + radix sort (8) library launches not counted",

@@ -177,6 +177,34 @@ int lgs_adam_multi(int n_tensors, float* const* params, const float* const* grad
                    const int64_t* numel, const double* lr,
                    double beta1, double beta2, double eps, int step, void* stream);
 
+/* ---- activations  (reference src/gaussian_model.cpp:46-68) ---------------
+ * forward : scales = exp(scaling) [P,3], rotations = normalize(rotation) [P,4], opacities =
+ *           sigmoid(opacity) [P,1], shs = cat(features_dc [P,1,3], features_rest [P,n_rest,3]) [P,1+n_rest,3]
+ * backward: raw-parameter gradients from the gradients w.r.t. those four tensors (what autograd
+ *           computes through exp / F.normalize / sigmoid / cat); accumulate != 0 adds to the outputs. */
+int lgs_activations_fwd(int P, int n_rest, const float* scaling, const float* rotation, const float* opacity,
+                        const float* features_dc, const float* features_rest, float* scales, float* rotations,
+                        float* opacities, float* shs, void* stream);
+int lgs_activations_bwd(int P, int n_rest, int accumulate, const float* rotation, const float* scales,
+                        const float* opacities, const float* dL_dscales, const float* dL_drotations,
+                        const float* dL_dopacities, const float* dL_dshs, float* dL_dscaling, float* dL_drotation,
+                        float* dL_dopacity, float* dL_dfeatures_dc, float* dL_dfeatures_rest, void* stream);
+
+/* ---- mapping loss + its gradient w.r.t. the rendered images, fused (reference
+ *      src/gaussian_mapper.cpp:707-724, include/loss_utils.h:27-131) --------
+ * loss = (1-l)*L1(image*mask, gt_image) + l*(1 - SSIM(image*mask, gt_image))
+ *        + (cos_sign >= 0 ? +mean_px cos(lf*mask0, up(gt_lf)) : 1 - mean_px cos(...))
+ *        + L1(depth*mask0, gt_depth)
+ * image [3,H,W], lf [64,H,W], depth [1,H,W]; gt_lf [64,lf_h,lf_w] is up-sampled nearest on the fly;
+ * mask [3,H,W] or NULL.  Writes dL/dimage, dL/dlf, dL/ddepth (fully overwritten) and loss_out[0..4] =
+ * total, L1, SSIM, mean cosine, depth L1 (device memory).  The reference ADDS the mean cosine
+ * (cos_sign = +1). */
+size_t lgs_mapping_loss_scratch_bytes(int W, int H);
+int lgs_mapping_loss(int W, int H, int lf_w, int lf_h, const float* image, const float* lf, const float* depth,
+                     const float* gt_image, const float* gt_lf, const float* gt_depth, const float* mask,
+                     float lambda_dssim, int cos_sign, float* dL_dimage, float* dL_dlf, float* dL_ddepth,
+                     float* loss_out, char* scratch, void* stream);
+
 /* ---- semantic query (reference eval/find_objects_gaussians.py:160-175) ------------
  * sim[p,q] = <f_p/|f_p|, t_q/|t_q|> for feats [P,64] and text [Q,64] (both row-major,
  * un-normalised; eps 1e-12 like F.normalize).  out is [P,Q] row-major.

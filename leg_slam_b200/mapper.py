@@ -18,7 +18,9 @@ from typing import Callable, NamedTuple, Optional, Sequence
 import torch
 import torch.distributed as dist
 
+from . import fused as fused_mod
 from . import loss as loss_mod
+from . import rasterize_points as rp
 from .optim import FusedAdam
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
 from .synthetic import Camera
@@ -71,7 +73,7 @@ class Mapper:
     def __init__(self, params: dict, lrs: Optional[dict] = None, sh_degree: int = 3,
                  process_group=None, optimizer_factory: Optional[Callable] = None,
                  render_fn: Optional[Callable] = None, faithful_loss_sign: bool = True,
-                 use_cuda_graph: bool = True):
+                 use_cuda_graph: bool = True, fused: bool = True):
         self.params = {k: torch.nn.Parameter(params[k].detach().clone().contiguous()) for k in PARAM_ORDER}
         lrs = dict(DEFAULT_LRS, **(lrs or {}))
         groups = [dict(params=[self.params[k]], lr=lrs[k], name=k) for k in PARAM_ORDER]
@@ -88,6 +90,11 @@ class Mapper:
         self.last_num_views = 0
         self.use_cuda_graph = use_cuda_graph
         self._loss_graphs = {}
+        # fused fast path: activations, loss and their backward as liblgs kernels, gradients written
+        # straight into the flat buffer (no autograd graph).  Needs our rasterizer and CUDA tensors.
+        self.fused = bool(fused and render_fn is None and dev.type == "cuda")
+        self._fused_loss = fused_mod.FusedMappingLoss(faithful_sign=faithful_loss_sign) if self.fused else None
+        self._fbuf = None
 
     # -- activations exactly as the reference applies them each iteration (gaussian_model.cpp:46-68)
     def activated(self):
@@ -159,15 +166,66 @@ class Mapper:
             image, lf, depth = image * mask, lf * mask[0:1], depth * mask[0:1]
         return loss_mod.mapping_loss(image, lf, depth, gt_image, gt_lf, gt_depth, faithful_sign=self.faithful_loss_sign)
 
+    def _train_views_fused(self, window, mine):
+        """The views of this rank without autograd: every op between the raw parameters and the flat
+        gradient buffer is a liblgs launch."""
+        p = {k: v.data for k, v in self.params.items()}
+        P = p["xyz"].shape[0]
+        dev = p["xyz"].device
+        n_rest = p["features_rest"].shape[1]
+        if self._fbuf is None:
+            f = dict(dtype=torch.float32, device=dev)
+            self._fbuf = dict(act=dict(scales=torch.empty(P, 3, **f), rotations=torch.empty(P, 4, **f),
+                                       opacities=torch.empty(P, 1, **f), shs=torch.empty(P, n_rest + 1, 3, **f)),
+                              tmp=rp.backward_outputs(P, n_rest + 1, dev, True, True, True),
+                              empty=torch.empty(0, **f))
+        fb = self._fbuf
+        e = fb["empty"]
+        a = fused_mod.activations_fwd(p, out=fb["act"])  # parameters do not change between the views of a step
+        gv = self.grads.views
+        total = None
+        for n_done, i in enumerate(mine):
+            kf = window[i]
+            cam = kf.camera
+            R, color, lf, depth, radii, geom, binning, img = rp.rasterize_gaussians(
+                self.bg, a["means3D"], e, a["lang_feats"], a["opacities"], a["scales"], a["rotations"], 1.0, e,
+                cam.viewmatrix, cam.projmatrix, cam.tanfovx, cam.tanfovy, cam.height, cam.width, a["shs"], self.sh_degree,
+                cam.campos, False, True)
+            loss, gi, gl, gd = self._fused_loss(color, lf, depth, kf.gt_image, kf.gt_lf, kf.gt_depth, kf.mask)
+            first = n_done == 0
+            out = dict(fb["tmp"])
+            if first:  # xyz and language-feature gradients need no activation backward: write them in place
+                out["dL_dmeans3D"], out["dL_dlang_feats"] = gv["xyz"], gv["lang_feat"]
+            rp.rasterize_gaussians_backward_into(
+                out, self.bg, a["means3D"], radii, e, a["lang_feats"], a["scales"], a["rotations"], 1.0, e, cam.viewmatrix,
+                cam.projmatrix, cam.tanfovx, cam.tanfovy, gi, gl, gd, a["shs"], self.sh_degree, cam.campos, geom, R, binning,
+                img, True)
+            if not first:
+                gv["xyz"].add_(out["dL_dmeans3D"])
+                gv["lang_feat"].add_(out["dL_dlang_feats"])
+            fused_mod.activations_bwd(p, a, out["dL_dscales"], out["dL_drotations"], out["dL_dopacity"], out["dL_dsh"],
+                                      gv, accumulate=not first)
+            l0 = loss[0:1].clone().reshape(())
+            total = l0 if total is None else total + l0
+            self.last_num_rendered = R
+        return total
+
     def train_step(self, window: Sequence[Keyframe], presharded: bool = False):
         """Render + back-propagate this rank's share of `window`, sum gradients over ranks, Adam.
         `window` is the iteration's global list of keyframes (every rank passes the same list and
         takes its round-robin share) unless `presharded`, in which case it already holds only this
         rank's keyframes.  Returns the (detached) sum of this rank's view losses."""
-        self.grads.zero_()
-        self.grads.attach(self.params)
         mine = list(range(len(window))) if presharded else shard_views(len(window), self.rank, self.world_size)
         self.last_num_views = len(mine)
+        self.grads.attach(self.params)
+        if self.fused and len(mine) > 0:
+            with torch.no_grad():
+                total = self._train_views_fused(window, mine)  # overwrites the flat buffer: no memset needed
+                if self.world_size > 1:
+                    dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.pg)
+            self.optimizer.step()
+            return total
+        self.grads.zero_()
         total = None
         for i in mine:
             kf = window[i]

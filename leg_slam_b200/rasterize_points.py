@@ -105,47 +105,71 @@ def rasterize_gaussians(background, means3D, colors, lang_feat, opacity, scales,
     return R.value, out_color, out_lf, out_depth, radii, geom, binning, img
 
 
+def backward_outputs(P, M, dev, include_lf, has_sh, has_scales):
+    """Freshly allocated gradient tensors of one backward call (torch.empty where the kernels write
+    every row, zeros where a path is absent)."""
+    mk = (lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)) if P else \
+         (lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev))
+    z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)  # noqa: E731
+    return dict(dL_dmeans2D=mk(P, 3), dL_dcolors=mk(P, NUM_CHANNELS),
+                # without language features nothing accumulates into dL_dlang_feats: it must still be zeros
+                dL_dlang_feats=mk(P, LF_NUM_CHANNELS) if include_lf else z(P, LF_NUM_CHANNELS),
+                dL_dopacity=mk(P, 1), dL_dmeans3D=mk(P, 3), dL_dcov3D=mk(P, 6), dL_dconic=mk(P, 2, 2),
+                # the kernel fills (or zero-fills) these only on the path that produces them
+                dL_dsh=mk(P, M, 3) if has_sh else z(P, M, 3), dL_dscales=mk(P, 3) if has_scales else z(P, 3),
+                dL_drotations=mk(P, 4) if has_scales else z(P, 4))
+
+
+def rasterize_gaussians_backward_into(out, background, means3D, radii, colors, lang_feat, scales, rotations,
+                                      scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
+                                      dL_dout_color, dL_dout_lang_feat, dL_dout_depth, sh, degree, campos, geomBuffer, R,
+                                      binningBuffer, imageBuffer, include_lang_feat):
+    """RasterizeGaussiansBackwardCUDA writing into caller-provided tensors `out` (keys of
+    backward_outputs; any contiguous float32 storage, e.g. slices of a flat gradient buffer)."""
+    L = _lib.lib()
+    P = int(means3D.size(0))
+    if P == 0:
+        return out
+    H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
+    dev = means3D.device
+    M = int(sh.size(1)) if sh is not None and sh.size(0) != 0 else 0
+    include_lf = bool(include_lang_feat)
+    background, means3D, colors, lang_feat, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, sh, \
+        campos, dL_dout_color, dL_dout_lang_feat, dL_dout_depth = map(
+            _f32c, (background, means3D, colors, lang_feat, scales, rotations, cov3D_precomp, viewmatrix,
+                    projmatrix, sh, campos, dL_dout_color, dL_dout_lang_feat, dL_dout_depth))
+    scratch = _workspace(dev, _stream(means3D), L.lgs_backward_scratch_bytes(int(R), W, H))
+    with torch.cuda.device(dev):
+        check(L.lgs_backward(
+            P, int(degree), M, int(R), W, H, ptr(background), ptr(means3D), ptr(sh), ptr(colors),
+            ptr(lang_feat) if include_lf else None, ptr(scales), float(scale_modifier), ptr(rotations),
+            ptr(cov3D_precomp), ptr(viewmatrix), ptr(projmatrix), ptr(campos), float(tan_fovx), float(tan_fovy),
+            ptr(radii.contiguous()), ptr(geomBuffer), ptr(binningBuffer), ptr(imageBuffer), ptr(dL_dout_color),
+            ptr(dL_dout_lang_feat) if include_lf else None, ptr(dL_dout_depth), out["dL_dmeans2D"].data_ptr(),
+            out["dL_dconic"].data_ptr(), out["dL_dopacity"].data_ptr(), out["dL_dcolors"].data_ptr(),
+            out["dL_dlang_feats"].data_ptr(), None, out["dL_dmeans3D"].data_ptr(), out["dL_dcov3D"].data_ptr(),
+            ptr(out["dL_dsh"]), ptr(out["dL_dscales"]), ptr(out["dL_drotations"]), int(include_lf), 1,
+            scratch.data_ptr(), _stream(means3D)), "lgs_backward")
+    return out
+
+
 def rasterize_gaussians_backward(background, means3D, radii, colors, lang_feat, scales, rotations, scale_modifier,
                                  cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
                                  dL_dout_lang_feat, dL_dout_depth, sh, degree, campos, geomBuffer, R, binningBuffer,
                                  imageBuffer, include_lang_feat):
     """-> (dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dlang_feats[P,64], dL_dopacity[P,1], dL_dmeans3D[P,3],
            dL_dcov3D[P,6], dL_dsh[P,M,3], dL_dscales[P,3], dL_drotations[P,4])"""
-    L = _lib.lib()
     P = int(means3D.size(0))
-    H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
-    dev = means3D.device
     M = int(sh.size(1)) if sh is not None and sh.size(0) != 0 else 0
-    include_lf = bool(include_lang_feat)
-    mk = (lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)) if P else \
-         (lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev))
-    dL_dmeans3D, dL_dmeans2D, dL_dcolors = mk(P, 3), mk(P, 3), mk(P, NUM_CHANNELS)
-    # without language features nothing accumulates into dL_dlang_feats: it must still be zeros
-    dL_dlang = mk(P, LF_NUM_CHANNELS) if include_lf else torch.zeros((P, LF_NUM_CHANNELS), dtype=torch.float32, device=dev)
-    dL_dconic, dL_dopacity, dL_dcov3D = mk(P, 2, 2), mk(P, 1), mk(P, 6)
-    # the kernel fills (or zero-fills) these only on the path that produces them
     has_sh = M != 0 and sh is not None and sh.numel() != 0
     has_scales = scales is not None and scales.numel() != 0
-    dL_dsh = mk(P, M, 3) if has_sh else torch.zeros((P, M, 3), dtype=torch.float32, device=dev)
-    dL_dscales = mk(P, 3) if has_scales else torch.zeros((P, 3), dtype=torch.float32, device=dev)
-    dL_drot = mk(P, 4) if has_scales else torch.zeros((P, 4), dtype=torch.float32, device=dev)
-    if P != 0:
-        background, means3D, colors, lang_feat, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, sh, \
-            campos, dL_dout_color, dL_dout_lang_feat, dL_dout_depth = map(
-                _f32c, (background, means3D, colors, lang_feat, scales, rotations, cov3D_precomp, viewmatrix,
-                        projmatrix, sh, campos, dL_dout_color, dL_dout_lang_feat, dL_dout_depth))
-        scratch = _workspace(dev, _stream(means3D), L.lgs_backward_scratch_bytes(int(R), W, H))
-        with torch.cuda.device(dev):
-            check(L.lgs_backward(
-                P, int(degree), M, int(R), W, H, ptr(background), ptr(means3D), ptr(sh), ptr(colors),
-                ptr(lang_feat) if include_lf else None, ptr(scales), float(scale_modifier), ptr(rotations),
-                ptr(cov3D_precomp), ptr(viewmatrix), ptr(projmatrix), ptr(campos), float(tan_fovx), float(tan_fovy),
-                ptr(radii.contiguous()), ptr(geomBuffer), ptr(binningBuffer), ptr(imageBuffer), ptr(dL_dout_color),
-                ptr(dL_dout_lang_feat) if include_lf else None, ptr(dL_dout_depth), dL_dmeans2D.data_ptr(),
-                dL_dconic.data_ptr(), dL_dopacity.data_ptr(), dL_dcolors.data_ptr(), dL_dlang.data_ptr(), None,
-                dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr(), ptr(dL_dsh), ptr(dL_dscales), ptr(dL_drot),
-                int(include_lf), 1, scratch.data_ptr(), _stream(means3D)), "lgs_backward")
-    return dL_dmeans2D, dL_dcolors, dL_dlang, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drot
+    o = backward_outputs(P, M, means3D.device, bool(include_lang_feat), has_sh, has_scales)
+    rasterize_gaussians_backward_into(o, background, means3D, radii, colors, lang_feat, scales, rotations, scale_modifier,
+                                      cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
+                                      dL_dout_lang_feat, dL_dout_depth, sh, degree, campos, geomBuffer, R, binningBuffer,
+                                      imageBuffer, include_lang_feat)
+    return (o["dL_dmeans2D"], o["dL_dcolors"], o["dL_dlang_feats"], o["dL_dopacity"], o["dL_dmeans3D"], o["dL_dcov3D"],
+            o["dL_dsh"], o["dL_dscales"], o["dL_drotations"])
 
 
 def mark_visible(means3D, viewmatrix, projmatrix):

@@ -287,8 +287,10 @@ def test_mapper_step_matches_reference_rasterizer_and_torch_adam(dev, ref_mod):
     import bench
     from leg_slam_b200 import mapper as M
     sc, win = _mapper_window(dev)
-    ours = M.Mapper(sc, sh_degree=3)
-    eager = M.Mapper(sc, sh_degree=3, use_cuda_graph=False)
+    ours = M.Mapper(sc, sh_degree=3)                                       # fused, autograd-free path
+    eager = M.Mapper(sc, sh_degree=3, use_cuda_graph=False, fused=False)   # autograd + eager torch loss
+    graphed = M.Mapper(sc, sh_degree=3, fused=False)                       # autograd + CUDA-graphed loss
+    assert ours.fused and not eager.fused
 
     class _Shim(bench.E2EPath):  # borrow the reference autograd glue of the bench
         def __init__(self):
@@ -300,15 +302,70 @@ def test_mapper_step_matches_reference_rasterizer_and_torch_adam(dev, ref_mod):
     shim.mapper = refm
     refm.render_fn = shim._ref_render_fn()
     for _ in range(3):
-        lo, le, lr = ours.train_step(win), eager.train_step(win), refm.train_step(win)
-        assert abs(float(lo) - float(lr)) <= 1e-4 * abs(float(lr)) and abs(float(le) - float(lr)) <= 1e-4 * abs(float(lr))
+        lo, le, lg, lr = ours.train_step(win), eager.train_step(win), graphed.train_step(win), refm.train_step(win)
+        for l_ in (lo, le, lg):
+            assert abs(float(l_) - float(lr)) <= 1e-4 * abs(float(lr))
     for k in M.PARAM_ORDER:
         r = refm.params[k].detach().cpu().numpy()
         # Adam's sign-like first steps amplify gradient noise near zero gradients; compare updates to the lr scale
         step = 3 * M.DEFAULT_LRS[k]
-        for m in (ours, eager):
+        for m in (ours, eager, graphed):
             d = np.abs(m.params[k].detach().cpu().numpy() - r)
             assert (d > 0.05 * step).mean() <= 2e-3, (k, float(d.max()), step)
+
+
+def test_fused_loss_matches_torch_loss(dev):
+    """lgs_mapping_loss vs the stock-torch statement of include/loss_utils.h + gaussian_mapper.cpp:707-721."""
+    from leg_slam_b200 import loss as loss_mod
+    from leg_slam_b200.fused import FusedMappingLoss
+    g = torch.Generator().manual_seed(61)
+    for (H, W, with_mask, faithful) in ((64, 96, False, True), (61, 93, True, False), (480, 640, False, True)):
+        image = torch.rand(3, H, W, generator=g).to(dev)
+        lf = torch.randn(64, H, W, generator=g).to(dev)
+        depth = (torch.rand(1, H, W, generator=g) * 3).to(dev)
+        gt_image = torch.rand(3, H, W, generator=g).to(dev)
+        gt_lf = torch.randn(64, 37, 37, generator=g).to(dev)
+        gt_depth = (torch.rand(1, H, W, generator=g) * 3).to(dev)
+        mask = None
+        if with_mask:
+            mask = (torch.rand(1, H, W, generator=g) > 0.2).float().expand(3, H, W).contiguous().to(dev)
+        lf[:, 3, 5] = 0.0  # a zero feature vector exercises the eps clamp of cosine_similarity
+        im, l_, d_ = image.clone().requires_grad_(True), lf.clone().requires_grad_(True), depth.clone().requires_grad_(True)
+        up = torch.nn.functional.interpolate(gt_lf.unsqueeze(0), size=(H, W)).squeeze(0)
+        a, b, c = (im * mask, l_ * mask[0:1], d_ * mask[0:1]) if with_mask else (im, l_, d_)
+        ref = loss_mod.mapping_loss(a, b, c, gt_image, up, gt_depth, faithful_sign=faithful)
+        gi, gl, gd = torch.autograd.grad(ref, [im, l_, d_])
+        out, fi, fl, fd = FusedMappingLoss(faithful_sign=faithful)(image, lf, depth, gt_image, gt_lf, gt_depth, mask)
+        assert abs(float(out[0]) - float(ref)) <= 2e-5 * max(1.0, abs(float(ref)))
+        assert abs(float(out[2]) - float(loss_mod.ssim(a.detach(), gt_image))) <= 2e-5
+        assert cases.rel_err(fi.cpu().numpy(), gi.cpu().numpy()) <= 1e-4
+        assert cases.rel_err(fd.cpu().numpy(), gd.cpu().numpy()) <= 1e-5
+        # the eps-clamped pixel has an enormous (1/eps) gradient in both; compare the rest at 1e-4
+        fl2, gl2 = fl.clone(), gl.clone()
+        fl2[:, 3, 5] = 0
+        gl2[:, 3, 5] = 0
+        assert cases.rel_err(fl2.cpu().numpy(), gl2.cpu().numpy()) <= 1e-4
+
+
+def test_fused_activations_match_torch(dev):
+    from leg_slam_b200 import fused, synthetic
+    sc = synthetic.make_scene(5000, seed=71, device=dev)
+    sc["rotation"] = sc["rotation"] * 1.7  # un-normalised storage, as during training
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
+    ref = synthetic.activate(leaves)
+    act = fused.activations_fwd(sc)
+    for k in ("shs", "opacities", "scales", "rotations"):
+        assert cases.rel_err(act[k].cpu().numpy(), ref[k].detach().cpu().numpy()) <= 2e-6, k
+    g = torch.Generator().manual_seed(72)
+    up = {k: torch.randn(ref[k].shape, generator=g).to(dev) for k in ("shs", "opacities", "scales", "rotations")}
+    torch.autograd.backward([ref[k] for k in up], [up[k] for k in up])
+    out = {k: torch.full_like(sc[k], 7.0) for k in ("scaling", "rotation", "opacity", "features_dc", "features_rest")}
+    fused.activations_bwd(sc, act, up["scales"], up["rotations"], up["opacities"], up["shs"], out, accumulate=False)
+    for k in out:
+        assert cases.rel_err(out[k].cpu().numpy(), leaves[k].grad.cpu().numpy()) <= 5e-6, k
+    fused.activations_bwd(sc, act, up["scales"], up["rotations"], up["opacities"], up["shs"], out, accumulate=True)
+    for k in out:
+        assert cases.rel_err(out[k].cpu().numpy(), 2 * leaves[k].grad.cpu().numpy()) <= 5e-6, k
 
 
 # ---------------------------------------------------------------------------- Adam / cosine
