@@ -134,6 +134,23 @@ __device__ __forceinline__ float eval_power(float gx, float gy, float px, float 
     const float s = __fmaf_rn(dx, __fmul_rn(dx, a), __fmul_rn(dy, __fmul_rn(dy, c)));
     return __fmaf_rn(s, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, b)));
 }
+
+// Conservative footprint test of one Gaussian against a pixel rectangle [x0,x1] x [y0,y1] (pixel
+// centres): can ANY pixel in it pass the blend kernels' tests power <= 0 and alpha = o*exp(power) >=
+// 1/255?  alpha >= 1/255 needs 0.5 * d^T Q d <= tau = ln(255 o), whose bounding box has half-extents
+// sqrt(2 tau c / det Q), sqrt(2 tau a / det Q).  Inflated by 1 % + 0.01 px so that rounding can never
+// reject a pair the exact per-pixel test accepts; degenerate conics are reported as touching.
+__device__ __forceinline__ bool footprint_touches(float gx, float gy, float a, float b, float c, float o, float x0,
+                                                  float x1, float y0, float y1) {
+    const float tau = __logf(255.0f * o) * 1.01f + 0.01f;
+    if (!(tau > 0.f)) return !(tau <= 0.f);  // o < 1/255: nothing can pass; NaN: stay conservative
+    const float det = a * c - b * b;
+    if (!(det > 0.f)) return true;
+    const float k = 2.0f * tau / det;
+    const float ex = sqrtf(k * c) * 1.01f + 0.01f, ey = sqrtf(k * a) * 1.01f + 0.01f;
+    if (!(ex == ex) || !(ey == ey)) return true;
+    return (gx + ex >= x0) && (gx - ex <= x1) && (gy + ey >= y0) && (gy - ey <= y1);
+}
 #endif
 
 }  // namespace lgs

@@ -100,6 +100,7 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const uint32_t pix_id = (uint32_t)W * pyi + pxi;
     const float pxf = (float)pxi, pyf = (float)pyi;
     const float cxf = (float)(blockIdx.x * TILE) + 3.5f, cyf = (float)(blockIdx.y * TILE) + 3.5f;
+    const float wx0 = (float)(blockIdx.x * TILE), wy0 = (float)(blockIdx.y * TILE + 4 * wrp);  // this warp's 8x4 pixels
 
     const float T_final = inside ? final_T[pix_id] : 0.f;
     const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
@@ -155,8 +156,17 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         mbar_wait(&full_bar[b % BSTAGES], (uint32_t)((b / BSTAGES) & 1));
         const Stage& S = stages[b % BSTAGES];
 
+        // lane j tests Gaussian j's opacity-aware bounding box against this warp's 8x4 pixels (common.cuh)
+        bool touch = false;
+        if (lane < cnt) {
+            const float4 t0 = S.rec[lane].q0, t1 = S.rec[lane].q1;
+            touch = footprint_touches(t0.x, t0.y, t1.x, t1.y, t1.z, t1.w, wx0, wx0 + 7.0f, wy0, wy0 + 3.0f);
+        }
+        const uint32_t vis = __ballot_sync(0xffffffffu, touch);
+
 #pragma unroll 1
         for (int j = 0; j < cnt; ++j) {
+            if (!((vis >> j) & 1u)) continue;
             const int p = hi - j;
             const float4 q0 = S.rec[j].q0;  // x, y, depth, id bits
             const float4 q1 = S.rec[j].q1;

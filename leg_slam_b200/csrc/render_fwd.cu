@@ -72,7 +72,8 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 
     bool done = !inside;
     float T = 1.0f;
-    uint32_t contributor = 0, last_contributor = 0;
+    uint32_t last_contributor = 0;
+    const float wx0 = (float)(blockIdx.x * TILE), wy0 = (float)(blockIdx.y * TILE + 4 * (tid >> 5));  // this warp's 8x4 pixels
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, Dacc = 0.f;
     float LFacc[WITH_LF ? LF : 1];
 #pragma unroll
@@ -131,9 +132,20 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
         }
         const Stage& S = *Sp;
 
+        // which of this batch's Gaussians can touch this warp's 8x4 pixels at all?  lane j tests Gaussian j
+        // (opacity-aware bounding box, common.cuh); the ballot lets the warp skip the others in 3 instructions
+        // instead of evaluating 32 alphas
+        bool touch = false;
+        if (lane < cnt) {
+            const float4 t0 = S.rec[lane].q0, t1 = S.rec[lane].q1;
+            touch = footprint_touches(t0.x, t0.y, t1.x, t1.y, t1.z, t1.w, wx0, wx0 + 7.0f, wy0, wy0 + 3.0f);
+        }
+        const uint32_t vis = __ballot_sync(0xffffffffu, touch);
+
 #pragma unroll 1
         for (int j = 0; j < cnt; ++j) {
-            if (!done) ++contributor;
+            if (!((vis >> j) & 1u)) continue;
+            const uint32_t contributor = (uint32_t)(b * FB + j + 1);  // 1-based position in the tile's list
             const float4 q0 = S.rec[j].q0;  // x, y, depth
             const float4 q1 = S.rec[j].q1;  // conic a,b,c, opacity
             float dx, dy;
