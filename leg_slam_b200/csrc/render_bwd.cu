@@ -164,51 +164,67 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         }
         const uint32_t vis = __ballot_sync(0xffffffffu, touch);
 
+        // Visible Gaussians four at a time: the alpha replays (load, falloff, expf) are stateless, independent
+        // chains that overlap; the scalar recurrences then run in list order.
+        uint32_t v = vis;
 #pragma unroll 1
-        for (int j = 0; j < cnt; ++j) {
-            if (!((vis >> j) & 1u)) continue;
-            const int p = hi - j;
-            const float4 q0 = S.rec[j].q0;  // x, y, depth, id bits
-            const float4 q1 = S.rec[j].q1;
-            float dx, dy;
-            const float power = eval_power(q0.x, q0.y, pxf, pyf, q1.x, q1.y, q1.z, dx, dy);
-            const float G = expf(power);
-            const float alpha = fminf(0.99f, __fmul_rn(q1.w, G));
-            // backward.cu:513-530: behind the pixel's last contributor, outside the falloff, or below
-            // the alpha threshold -> no contribution
-            const bool act = (p < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-            if (!__any_sync(0xffffffffu, act)) continue;
-
-            const float4 q2 = S.rec[j].q2;
-            float d0 = q2.x * g_r, d1 = q2.y * g_g, d2 = q2.z * g_b, d3 = q0.z * g_d;
-            if (WITH_LF) {
-                const float4* f4 = reinterpret_cast<const float4*>(&S.lf[j * LF]);
+        while (v != 0) {
+            int jj[4];
+            float al[4], Gs[4];
+            bool ok[4];
 #pragma unroll
-                for (int k = 0; k < LF / 4; ++k) {
-                    const float4 f = f4[k];
-                    d0 = fmaf(f.x, g_lf[4 * k + 0], d0);
-                    d1 = fmaf(f.y, g_lf[4 * k + 1], d1);
-                    d2 = fmaf(f.z, g_lf[4 * k + 2], d2);
-                    d3 = fmaf(f.w, g_lf[4 * k + 3], d3);
+            for (int u = 0; u < 4; ++u) {
+                const bool valid = v != 0;
+                jj[u] = valid ? (__ffs(v) - 1) : 0;
+                v &= v - 1;  // 0 stays 0
+                const float4 q0 = S.rec[jj[u]].q0;  // x, y, depth, id bits
+                const float4 q1 = S.rec[jj[u]].q1;
+                float dx, dy;
+                const float power = eval_power(q0.x, q0.y, pxf, pyf, q1.x, q1.y, q1.z, dx, dy);
+                Gs[u] = expf(power);
+                al[u] = fminf(0.99f, __fmul_rn(q1.w, Gs[u]));
+                // backward.cu:513-530: behind the pixel's last contributor, outside the falloff, or below
+                // the alpha threshold -> no contribution
+                ok[u] = valid && ((hi - jj[u]) < last_contributor) && !(power > 0.0f) && !(al[u] < 1.0f / 255.0f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool act = ok[u];
+                if (!__any_sync(0xffffffffu, act)) continue;
+                const int j = jj[u];
+                const float alpha = al[u], G = Gs[u];
+                const float4 q0 = S.rec[j].q0;
+                const float4 q2 = S.rec[j].q2;
+                float d0 = q2.x * g_r, d1 = q2.y * g_g, d2 = q2.z * g_b, d3 = q0.z * g_d;
+                if (WITH_LF) {
+                    const float4* f4 = reinterpret_cast<const float4*>(&S.lf[j * LF]);
+#pragma unroll
+                    for (int k = 0; k < LF / 4; ++k) {
+                        const float4 f = f4[k];
+                        d0 = fmaf(f.x, g_lf[4 * k + 0], d0);
+                        d1 = fmaf(f.y, g_lf[4 * k + 1], d1);
+                        d2 = fmaf(f.z, g_lf[4 * k + 2], d2);
+                        d3 = fmaf(f.w, g_lf[4 * k + 3], d3);
+                    }
                 }
+                const float d = (d0 + d1) + (d2 + d3);
+                float Wv = 0.f, Tv = 0.f;
+                if (act) {
+                    const float inv = __frcp_rn(1.0f - alpha);
+                    T = T * inv;                                                // :536
+                    Acc = fmaf(last_alpha, last_d, (1.0f - last_alpha) * Acc);  // :549,563,573 (dotted with g)
+                    last_d = d;
+                    last_alpha = alpha;
+                    const float dL_dalpha = fmaf(d - Acc, T, -T_final * inv * bgdot);  // :553-589
+                    Wv = alpha * T;
+                    Tv = G * dL_dalpha;
+                }
+                float* dst = out + (size_t)nrec * HREC_FLOATS;
+                if (lane == 0) __stcg(reinterpret_cast<float4*>(dst), make_float4(q0.x - cxf, q0.y - cyf, 0.f, q0.w));
+                __stcg(dst + 4 + lane, Wv);
+                __stcg(dst + 36 + lane, Tv);
+                ++nrec;
             }
-            const float d = (d0 + d1) + (d2 + d3);
-            float Wv = 0.f, Tv = 0.f;
-            if (act) {
-                const float inv = __frcp_rn(1.0f - alpha);
-                T = T * inv;                                                // :536
-                Acc = fmaf(last_alpha, last_d, (1.0f - last_alpha) * Acc);  // :549,563,573 (dotted with g)
-                last_d = d;
-                last_alpha = alpha;
-                const float dL_dalpha = fmaf(d - Acc, T, -T_final * inv * bgdot);  // :553-589
-                Wv = alpha * T;
-                Tv = G * dL_dalpha;
-            }
-            float* dst = out + (size_t)nrec * HREC_FLOATS;
-            if (lane == 0) __stcg(reinterpret_cast<float4*>(dst), make_float4(q0.x - cxf, q0.y - cyf, 0.f, q0.w));
-            __stcg(dst + 4 + lane, Wv);
-            __stcg(dst + 36 + lane, Tv);
-            ++nrec;
         }
     }
     if (lane == 0) hrec_count[2 * tile_id + wrp] = nrec;
@@ -324,42 +340,56 @@ render_bwd_chan_kernel(const uint2* __restrict__ ranges, int W, int H, int tiles
             const int s = (gb + b) % CSTAGES;
             mbar_wait(&full_bar[s], (uint32_t)(((gb + b) / CSTAGES) & 1));
             const float* S = &stages[s][0];
+            // two records per iteration: their load -> FMA chains are independent and overlap
 #pragma unroll 1
-            for (int j = 0; j < cnt; ++j) {
-                const float* r = S + j * HREC_FLOATS;
-                const float4 hd = *reinterpret_cast<const float4*>(r);  // gx, gy, -, id
-                const float4* src = reinterpret_cast<const float4*>(r + toff);
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            for (int j = 0; j < cnt; j += 2) {
+                const bool two = j + 1 < cnt;
+                const float* r0 = S + j * HREC_FLOATS;
+                const float* r1 = S + (two ? j + 1 : j) * HREC_FLOATS;
+                const float4 hd0 = *reinterpret_cast<const float4*>(r0);  // gx, gy, -, id
+                const float4 hd1 = *reinterpret_cast<const float4*>(r1);
+                const float4* s0 = reinterpret_cast<const float4*>(r0 + toff);
+                const float4* s1 = reinterpret_cast<const float4*>(r1 + toff);
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
                 if (half == 0) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const float4 x = src[k];
-                        a0 = fmaf(x.x, colv[4 * k + 0], a0);
-                        a1 = fmaf(x.y, colv[4 * k + 1], a1);
-                        a2 = fmaf(x.z, colv[4 * k + 2], a2);
-                        a3 = fmaf(x.w, colv[4 * k + 3], a3);
+                        const float4 x = s0[k], y = s1[k];
+                        a0 = fmaf(x.x, colv[4 * k + 0], a0); b0 = fmaf(y.x, colv[4 * k + 0], b0);
+                        a1 = fmaf(x.y, colv[4 * k + 1], a1); b1 = fmaf(y.y, colv[4 * k + 1], b1);
+                        a2 = fmaf(x.z, colv[4 * k + 2], a2); b2 = fmaf(y.z, colv[4 * k + 2], b2);
+                        a3 = fmaf(x.w, colv[4 * k + 3], a3); b3 = fmaf(y.w, colv[4 * k + 3], b3);
                     }
                 } else {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const float4 x = src[k];
-                        a0 = fmaf(x.x, colv[32 + 4 * k + 0], a0);
-                        a1 = fmaf(x.y, colv[32 + 4 * k + 1], a1);
-                        a2 = fmaf(x.z, colv[32 + 4 * k + 2], a2);
-                        a3 = fmaf(x.w, colv[32 + 4 * k + 3], a3);
+                        const float4 x = s0[k], y = s1[k];
+                        a0 = fmaf(x.x, colv[32 + 4 * k + 0], a0); b0 = fmaf(y.x, colv[32 + 4 * k + 0], b0);
+                        a1 = fmaf(x.y, colv[32 + 4 * k + 1], a1); b1 = fmaf(y.y, colv[32 + 4 * k + 1], b1);
+                        a2 = fmaf(x.z, colv[32 + 4 * k + 2], a2); b2 = fmaf(y.z, colv[32 + 4 * k + 2], b2);
+                        a3 = fmaf(x.w, colv[32 + 4 * k + 3], a3); b3 = fmaf(y.w, colv[32 + 4 * k + 3], b3);
                     }
                 }
-                float acc = (a0 + a1) + (a2 + a3);
-                const uint32_t id = __float_as_uint(hd.w);
+                float acc0 = (a0 + a1) + (a2 + a3), acc1 = (b0 + b1) + (b2 + b3);
                 if (grp == 2) {
-                    const float S0 = __shfl_sync(0xffffffffu, acc, 4);
-                    const float Su = __shfl_sync(0xffffffffu, acc, 5);
-                    const float Sv = __shfl_sync(0xffffffffu, acc, 6);
-                    const float gx = hd.x, gy = hd.y;
-                    const float c0 = gx * (kxx * gx + kxy * gy + kx) + gy * (kyy * gy + ky);
-                    acc = k_own * acc + S0 * c0 + Su * (cux * gx + cuy * gy) + Sv * (cvx * gx + cvy * gy);
+                    const float S0a = __shfl_sync(0xffffffffu, acc0, 4), S0b = __shfl_sync(0xffffffffu, acc1, 4);
+                    const float Sua = __shfl_sync(0xffffffffu, acc0, 5), Sub = __shfl_sync(0xffffffffu, acc1, 5);
+                    const float Sva = __shfl_sync(0xffffffffu, acc0, 6), Svb = __shfl_sync(0xffffffffu, acc1, 6);
+                    {
+                        const float gx = hd0.x, gy = hd0.y;
+                        const float c0 = gx * (kxx * gx + kxy * gy + kx) + gy * (kyy * gy + ky);
+                        acc0 = k_own * acc0 + S0a * c0 + Sua * (cux * gx + cuy * gy) + Sva * (cvx * gx + cvy * gy);
+                    }
+                    {
+                        const float gx = hd1.x, gy = hd1.y;
+                        const float c0 = gx * (kxx * gx + kxy * gy + kx) + gy * (kyy * gy + ky);
+                        acc1 = k_own * acc1 + S0b * c0 + Sub * (cux * gx + cuy * gy) + Svb * (cvx * gx + cvy * gy);
+                    }
                 }
-                if (out_base != nullptr) red_add_f32(out_base + (size_t)id * out_stride, acc);
+                if (out_base != nullptr) {
+                    red_add_f32(out_base + (size_t)__float_as_uint(hd0.w) * out_stride, acc0);
+                    if (two) red_add_f32(out_base + (size_t)__float_as_uint(hd1.w) * out_stride, acc1);
+                }
             }
         }
         gb += nb;

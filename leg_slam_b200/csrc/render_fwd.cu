@@ -142,43 +142,60 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
         }
         const uint32_t vis = __ballot_sync(0xffffffffu, touch);
 
+        // Visible Gaussians are taken four at a time: the four alpha evaluations (load, falloff, expf) are
+        // independent chains that overlap (ILP), the state-dependent part (T, early termination, blend) then
+        // runs in list order.
+        uint32_t v = vis;
 #pragma unroll 1
-        for (int j = 0; j < cnt; ++j) {
-            if (!((vis >> j) & 1u)) continue;
-            const uint32_t contributor = (uint32_t)(b * FB + j + 1);  // 1-based position in the tile's list
-            const float4 q0 = S.rec[j].q0;  // x, y, depth
-            const float4 q1 = S.rec[j].q1;  // conic a,b,c, opacity
-            float dx, dy;
-            const float power = eval_power(q0.x, q0.y, pxf, pyf, q1.x, q1.y, q1.z, dx, dy);
-            // forward.cu:342-357 (same comparisons, same float ops)
-            const float alpha = fminf(0.99f, __fmul_rn(q1.w, expf(power)));
-            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-            bool act = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-            if (act && test_T < 0.0001f) {
-                done = true;
-                act = false;
-            }
-            if (__any_sync(0xffffffffu, act)) {
-                const float w = act ? __fmul_rn(alpha, T) : 0.0f;
-                const float4 q2 = S.rec[j].q2;
-                C0 = fmaf(w, q2.x, C0);
-                C1 = fmaf(w, q2.y, C1);
-                C2 = fmaf(w, q2.z, C2);
-                Dacc = fmaf(w, q0.z, Dacc);
-                if (WITH_LF) {
-                    const float4* f4 = reinterpret_cast<const float4*>(&S.lf[j * LF]);
+        while (v != 0) {
+            int jj[4];
+            float al[4];
+            bool ok[4];
 #pragma unroll
-                    for (int k = 0; k < LF / 4; ++k) {
-                        const float4 f = f4[k];
-                        LFacc[4 * k + 0] = fmaf(w, f.x, LFacc[4 * k + 0]);
-                        LFacc[4 * k + 1] = fmaf(w, f.y, LFacc[4 * k + 1]);
-                        LFacc[4 * k + 2] = fmaf(w, f.z, LFacc[4 * k + 2]);
-                        LFacc[4 * k + 3] = fmaf(w, f.w, LFacc[4 * k + 3]);
-                    }
+            for (int u = 0; u < 4; ++u) {
+                const bool valid = v != 0;
+                jj[u] = valid ? (__ffs(v) - 1) : 0;
+                v &= v - 1;  // 0 stays 0
+                const float4 q0 = S.rec[jj[u]].q0;  // x, y, depth
+                const float4 q1 = S.rec[jj[u]].q1;  // conic a,b,c, opacity
+                float dx, dy;
+                const float power = eval_power(q0.x, q0.y, pxf, pyf, q1.x, q1.y, q1.z, dx, dy);
+                // forward.cu:342-357 (same comparisons, same float ops)
+                al[u] = fminf(0.99f, __fmul_rn(q1.w, expf(power)));
+                ok[u] = valid && !(power > 0.0f) && !(al[u] < 1.0f / 255.0f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = jj[u];
+                const float alpha = al[u];
+                const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                bool act = ok[u] && !done;
+                if (act && test_T < 0.0001f) {
+                    done = true;
+                    act = false;
                 }
-                if (act) {
-                    T = test_T;
-                    last_contributor = contributor;
+                if (__any_sync(0xffffffffu, act)) {
+                    const float w = act ? __fmul_rn(alpha, T) : 0.0f;
+                    const float4 q2 = S.rec[j].q2;
+                    C0 = fmaf(w, q2.x, C0);
+                    C1 = fmaf(w, q2.y, C1);
+                    C2 = fmaf(w, q2.z, C2);
+                    Dacc = fmaf(w, S.rec[j].q0.z, Dacc);
+                    if (WITH_LF) {
+                        const float4* f4 = reinterpret_cast<const float4*>(&S.lf[j * LF]);
+#pragma unroll
+                        for (int k = 0; k < LF / 4; ++k) {
+                            const float4 f = f4[k];
+                            LFacc[4 * k + 0] = fmaf(w, f.x, LFacc[4 * k + 0]);
+                            LFacc[4 * k + 1] = fmaf(w, f.y, LFacc[4 * k + 1]);
+                            LFacc[4 * k + 2] = fmaf(w, f.z, LFacc[4 * k + 2]);
+                            LFacc[4 * k + 3] = fmaf(w, f.w, LFacc[4 * k + 3]);
+                        }
+                    }
+                    if (act) {
+                        T = test_T;
+                        last_contributor = (uint32_t)(b * FB + j + 1);  // 1-based position in the tile's list
+                    }
                 }
             }
         }
