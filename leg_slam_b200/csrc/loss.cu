@@ -237,10 +237,9 @@ __global__ void loss_finalize_kernel(const float* __restrict__ acc, float n_img,
 // forward: scales = exp(scaling), rotations = normalize(rotation) (F.normalize, eps 1e-12), opacities =
 // sigmoid(opacity), shs = cat(features_dc [P,1,3], features_rest [P,15,3]).  One thread per Gaussian.
 __global__ void __launch_bounds__(256)
-activations_fwd_kernel(int P, int n_rest, const float* __restrict__ scaling, const float* __restrict__ rotation,
-                       const float* __restrict__ opacity, const float* __restrict__ f_dc, const float* __restrict__ f_rest,
-                       float* __restrict__ scales, float* __restrict__ rots, float* __restrict__ opac,
-                       float* __restrict__ shs) {
+activations_fwd_kernel(int P, const float* __restrict__ scaling, const float* __restrict__ rotation,
+                       const float* __restrict__ opacity, float* __restrict__ scales, float* __restrict__ rots,
+                       float* __restrict__ opac) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
 #pragma unroll
@@ -249,22 +248,36 @@ activations_fwd_kernel(int P, int n_rest, const float* __restrict__ scaling, con
     const float inv = 1.f / fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
     reinterpret_cast<float4*>(rots)[i] = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
     opac[i] = 1.f / (1.f + expf(-opacity[i]));
-    const int M = n_rest + 1;
-    float* o = shs + (size_t)i * M * 3;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) o[k] = f_dc[3 * (size_t)i + k];
-    for (int k = 0; k < 3 * n_rest; ++k) o[3 + k] = f_rest[(size_t)i * 3 * n_rest + k];
+}
+
+// shs [P, 1+n_rest, 3] = cat(f_dc [P,1,3], f_rest [P,n_rest,3]) and its inverse, one ELEMENT per thread so
+// that both sides are coalesced (a thread-per-Gaussian copy strides 192 B between lanes).
+template <bool SCATTER>
+__global__ void __launch_bounds__(256)
+sh_cat_kernel(long long n, int row, const float* __restrict__ a_dc, const float* __restrict__ a_rest,
+              float* __restrict__ shs, const float* __restrict__ g_shs, float* __restrict__ g_dc,
+              float* __restrict__ g_rest, int accumulate) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long g = i / row;
+        const int c = (int)(i - g * row);
+        if (!SCATTER) {
+            shs[i] = c < 3 ? a_dc[g * 3 + c] : a_rest[g * (row - 3) + (c - 3)];
+        } else {
+            float* dst = c < 3 ? g_dc + g * 3 + c : g_rest + g * (row - 3) + (c - 3);
+            const float v = __ldcs(g_shs + i);
+            *dst = accumulate ? *dst + v : v;
+        }
+    }
 }
 
 // backward: raw-parameter gradients from the gradients w.r.t. the activated tensors; `accumulate` adds
 // to the outputs (several views per iteration) instead of overwriting them.
 __global__ void __launch_bounds__(256)
-activations_bwd_kernel(int P, int n_rest, int accumulate, const float* __restrict__ rotation,
+activations_bwd_kernel(int P, int accumulate, const float* __restrict__ rotation,
                        const float* __restrict__ scales, const float* __restrict__ opac,
                        const float* __restrict__ g_scales, const float* __restrict__ g_rots,
-                       const float* __restrict__ g_opac, const float* __restrict__ g_shs, float* __restrict__ g_scaling,
-                       float* __restrict__ g_rotation, float* __restrict__ g_opacity, float* __restrict__ g_dc,
-                       float* __restrict__ g_rest) {
+                       const float* __restrict__ g_opac, float* __restrict__ g_scaling,
+                       float* __restrict__ g_rotation, float* __restrict__ g_opacity) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     const float keep = accumulate ? 1.f : 0.f;
@@ -291,17 +304,6 @@ activations_bwd_kernel(int P, int n_rest, int accumulate, const float* __restric
         const float s = opac[i];
         const float v = g_opac[i] * s * (1.f - s);
         g_opacity[i] = accumulate ? g_opacity[i] + v : v;
-    }
-    const int M = n_rest + 1;
-    const float* gs = g_shs + (size_t)i * M * 3;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const size_t j = 3 * (size_t)i + k;
-        g_dc[j] = accumulate ? g_dc[j] + gs[k] : gs[k];
-    }
-    for (int k = 0; k < 3 * n_rest; ++k) {
-        const size_t j = (size_t)i * 3 * n_rest + k;
-        g_rest[j] = accumulate ? g_rest[j] + gs[3 + k] : gs[3 + k];
     }
 }
 
@@ -365,8 +367,14 @@ extern "C" int lgs_activations_fwd(int P, int n_rest, const float* scaling, cons
         !opacities || !shs)
         return LGS_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(rotation) | reinterpret_cast<uintptr_t>(rotations)) & 15u) return LGS_ERR_ALIGNMENT;
-    activations_fwd_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, n_rest, scaling, rotation, opacity, features_dc,
-                                                                              features_rest, scales, rotations, opacities, shs);
+    activations_fwd_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, scaling, rotation, opacity, scales, rotations,
+                                                                              opacities);
+    LGS_LAUNCH_CHECK();
+    const int row = 3 * (n_rest + 1);
+    const long long n = (long long)P * row;
+    const int grid = (int)((n + 255) / 256 < 148LL * 32 ? (n + 255) / 256 : 148LL * 32);
+    sh_cat_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(n, row, features_dc, features_rest, shs, nullptr, nullptr,
+                                                                 nullptr, 0);
     LGS_LAUNCH_CHECK();
     return LGS_OK;
 }
@@ -384,8 +392,14 @@ extern "C" int lgs_activations_bwd(int P, int n_rest, int accumulate, const floa
          reinterpret_cast<uintptr_t>(dL_drotation)) & 15u)
         return LGS_ERR_ALIGNMENT;
     activations_bwd_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        P, n_rest, accumulate, rotation, scales, opacities, dL_dscales, dL_drotations, dL_dopacities, dL_dshs, dL_dscaling,
-        dL_drotation, dL_dopacity, dL_dfeatures_dc, dL_dfeatures_rest);
+        P, accumulate, rotation, scales, opacities, dL_dscales, dL_drotations, dL_dopacities, dL_dscaling, dL_drotation,
+        dL_dopacity);
+    LGS_LAUNCH_CHECK();
+    const int row = 3 * (n_rest + 1);
+    const long long n = (long long)P * row;
+    const int grid = (int)((n + 255) / 256 < 148LL * 32 ? (n + 255) / 256 : 148LL * 32);
+    sh_cat_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(n, row, nullptr, nullptr, nullptr, dL_dshs, dL_dfeatures_dc,
+                                                                dL_dfeatures_rest, accumulate);
     LGS_LAUNCH_CHECK();
     return LGS_OK;
 }

@@ -97,7 +97,10 @@ __device__ __forceinline__ V3 sh_backward(int deg, int M, const float* __restric
     return r;
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int PB_THREADS = 128;
+constexpr int PB_ROW = 48;  // 16 SH coefficients x 3 channels
+
+__global__ void __launch_bounds__(PB_THREADS)
 preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means, const int* __restrict__ radii,
                       const float* __restrict__ shs, const uint8_t* __restrict__ clamped,
                       const float* __restrict__ scales, const float* __restrict__ rots, float mod,
@@ -109,25 +112,35 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means, cons
                       float* __restrict__ dL_dmeans, float* __restrict__ dL_dcov, float* __restrict__ dL_dsh,
                       float* __restrict__ dL_dscale, float* __restrict__ dL_drot, bool write_zeros) {
     __shared__ float sV[16], sP[16];
+    // dL_dsh rows (up to 48 floats per Gaussian) are staged here and flushed by the whole warp, so the
+    // 192-byte rows leave as full 128-byte transactions instead of 32 scattered 4-byte stores per instruction
+    __shared__ float s_sh[PB_THREADS][PB_ROW + 1];
     if (threadIdx.x < 16) sV[threadIdx.x] = view[threadIdx.x];
     else if (threadIdx.x < 32) sP[threadIdx.x - 16] = proj[threadIdx.x - 16];
     __syncthreads();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    if (!(radii[idx] > 0)) {
-        if (write_zeros) {
-            dL_dmeans[3 * idx + 0] = 0.f; dL_dmeans[3 * idx + 1] = 0.f; dL_dmeans[3 * idx + 2] = 0.f;
+    const int row = 3 * M;
+    const bool stage_sh = shs != nullptr && row <= PB_ROW;
+    const bool visible = idx < P && radii[idx] > 0;
+    bool sh_written = false;  // does this thread's staged row hold data to flush?
+    if (idx < P && !visible && write_zeros) {
+        dL_dmeans[3 * idx + 0] = 0.f; dL_dmeans[3 * idx + 1] = 0.f; dL_dmeans[3 * idx + 2] = 0.f;
 #pragma unroll
-            for (int i = 0; i < 6; ++i) dL_dcov[6 * (size_t)idx + i] = 0.f;
-            if (shs != nullptr)
-                for (int i = 0; i < 3 * M; ++i) dL_dsh[(size_t)idx * 3 * M + i] = 0.f;
-            if (scales != nullptr) {
-                dL_dscale[3 * idx + 0] = 0.f; dL_dscale[3 * idx + 1] = 0.f; dL_dscale[3 * idx + 2] = 0.f;
-                reinterpret_cast<float4*>(dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 6; ++i) dL_dcov[6 * (size_t)idx + i] = 0.f;
+        if (shs != nullptr) {
+            if (stage_sh) {
+                for (int i = 0; i < row; ++i) s_sh[threadIdx.x][i] = 0.f;
+                sh_written = true;
+            } else {
+                for (int i = 0; i < row; ++i) dL_dsh[(size_t)idx * row + i] = 0.f;
             }
         }
-        return;
+        if (scales != nullptr) {
+            dL_dscale[3 * idx + 0] = 0.f; dL_dscale[3 * idx + 1] = 0.f; dL_dscale[3 * idx + 2] = 0.f;
+            reinterpret_cast<float4*>(dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
+    if (visible) {
 
     const V3 mean = ld3(means + 3 * (size_t)idx);
     const float* cov3D = cov3Ds + 6 * (size_t)idx;
@@ -231,7 +244,9 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means, cons
         if (cl & 2) dRGB.y = 0.f;
         if (cl & 4) dRGB.z = 0.f;
         const V3 dir{mean.x - campos[0], mean.y - campos[1], mean.z - campos[2]};
-        const V3 dm = sh_backward(D, M, shs + (size_t)idx * 3 * M, dir, dRGB, dL_dsh + (size_t)idx * 3 * M);
+        const V3 dm = sh_backward(D, M, shs + (size_t)idx * 3 * M, dir, dRGB,
+                                  stage_sh ? &s_sh[threadIdx.x][0] : dL_dsh + (size_t)idx * 3 * M);
+        sh_written = stage_sh;
         dmean.x += dm.x; dmean.y += dm.y; dmean.z += dm.z;
     }
     dL_dmeans[3 * (size_t)idx + 0] = dmean.x;
@@ -277,6 +292,19 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means, cons
         dq.w = 2.f * r * (t01 - t10) + 2.f * x * (t20 + t02) + 2.f * y * (t12 + t21) - 4.f * z * (t11 + t00);
         reinterpret_cast<float4*>(dL_drot)[idx] = dq;
     }
+    }  // visible
+
+    if (stage_sh) {
+        // warp-cooperative flush of the staged rows: lane-consecutive addresses in global memory
+        __syncwarp();
+        const int lane = threadIdx.x & 31, w0 = threadIdx.x & ~31;
+        const uint32_t wmask = __ballot_sync(0xffffffffu, sh_written);
+        const long long gbase = ((long long)blockIdx.x * blockDim.x + w0) * row;
+        for (int i = lane; i < 32 * row; i += 32) {
+            const int r = i / row, c = i - r * row;
+            if ((wmask >> r) & 1u) dL_dsh[gbase + i] = s_sh[w0 + r][c];
+        }
+    }
 }
 
 int launch_preprocess_bwd(int P, int D, int M, const float* means3D, const int* radii, const float* shs,
@@ -287,7 +315,7 @@ int launch_preprocess_bwd(int P, int D, int M, const float* means3D, const int* 
                           float* dL_dsh, float* dL_dscale, float* dL_drot, bool write_zeros, cudaStream_t s) {
     const float focal_y = H / (2.0f * tan_fovy);  // rasterizer_impl.cu:392-393
     const float focal_x = W / (2.0f * tan_fovx);
-    preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(
+    preprocess_bwd_kernel<<<(P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, 0, s>>>(
         P, D, M, means3D, radii, shs, g.clamped, scales, rotations, scale_modifier, cov3D, viewmatrix, projmatrix,
         cam_pos, focal_x, focal_y, tan_fovx, tan_fovy, g.rec, 0.5f * (float)W, 0.5f * (float)H, dL_dmean2D, dL_dconic,
         dL_dcolor, dL_dmean3D, dL_dcov3D,
