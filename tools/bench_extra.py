@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Secondary configurations of BASELINE.json (not bench.py lines): cfgD render sizes and cfgE semantic query.
+Prints one JSON object; used for profiles/ and DESIGN.md."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+from leg_slam_b200 import cosine_query, rasterize_points as rp, synthetic  # noqa: E402
+
+
+def t(fn, n=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def main():
+    dev = torch.device("cuda:0")
+    out = {}
+    # cfgE: 2M x 64 against 256 text embeddings
+    g = torch.Generator().manual_seed(1)
+    feats = torch.randn(2_000_000, 64, generator=g).to(dev)
+    text = torch.randn(256, 64, generator=g).to(dev)
+    ms = t(lambda: cosine_query(feats, text))
+    ref_ms = t(lambda: torch.nn.functional.normalize(feats, dim=1) @ torch.nn.functional.normalize(text, dim=1).t())
+    a = cosine_query(feats, text)
+    b = torch.nn.functional.normalize(feats.double(), dim=1) @ torch.nn.functional.normalize(text.double(), dim=1).t()
+    out["cfgE_cosine_2M_x_256"] = dict(ms=ms, torch_normalize_matmul_ms=ref_ms, out_GBps=2e6 * 256 * 4 / ms / 1e6,
+                                       algorithmic_GBps=(2e6 * 256 + 4 * 256 * 2e6) / ms / 1e6,
+                                       max_abs_err_vs_fp64=float((a.double() - b).abs().max()))
+    del a, b, feats, text
+    # cfgD: ScanNet-shaped 2M Gaussians, 1296x968
+    W, H, P = 1296, 968, 2_000_000
+    sc = synthetic.make_scene(P, seed=4, room=(8.0, 6.0, 3.0), device=dev)
+    cam = synthetic.make_cameras(1, W, H, fx=1169.7, fy=1169.7, room=(8.0, 6.0, 3.0), seed=4)[0].to(dev)
+    act = synthetic.activate(sc)
+    e = torch.empty(0, device=dev)
+    bg = torch.zeros(3, device=dev)
+    args = (bg, act["means3D"], e, act["lang_feats"], act["opacities"], act["scales"], act["rotations"], 1.0, e, cam.viewmatrix,
+            cam.projmatrix, cam.tanfovx, cam.tanfovy, H, W, act["shs"], 3, cam.campos, False, True)
+    R, color, lf, depth, radii, geom, binning, img = rp.rasterize_gaussians(*args)
+    gg = torch.Generator().manual_seed(2)
+    dc = (torch.randn(3, H, W, generator=gg) / (H * W)).to(dev)
+    dl = (torch.randn(64, H, W, generator=gg) / (H * W)).to(dev)
+    dd = (torch.randn(1, H, W, generator=gg) / (H * W)).to(dev)
+    bargs = (bg, act["means3D"], radii, e, act["lang_feats"], act["scales"], act["rotations"], 1.0, e, cam.viewmatrix,
+             cam.projmatrix, cam.tanfovx, cam.tanfovy, dc, dl, dd, act["shs"], 3, cam.campos, geom, R, binning, img, True)
+    out["cfgD_2M_1296x968"] = dict(R=R, visible=int((radii > 0).sum()), fwd_ms=t(lambda: rp.rasterize_gaussians(*args), 5, 2),
+                                   bwd_ms=t(lambda: rp.rasterize_gaussians_backward(*bargs), 5, 2))
+    try:
+        import build_ref
+        ref = build_ref.load()
+        Rr, *_r, gr, br, ir = ref.rasterize_gaussians(*args)
+        rb = (bg, act["means3D"], _r[3], e, act["lang_feats"], act["scales"], act["rotations"], 1.0, e, cam.viewmatrix,
+              cam.projmatrix, cam.tanfovx, cam.tanfovy, dc, dl, dd, act["shs"], 3, cam.campos, gr, Rr, br, ir, True)
+        out["cfgD_2M_1296x968"].update(ref_fwd_ms=t(lambda: ref.rasterize_gaussians(*args), 3, 1),
+                                       ref_bwd_ms=t(lambda: ref.rasterize_gaussians_backward(*rb), 3, 1), ref_R=Rr)
+    except Exception as ex:  # reference .so not shipped
+        out["cfgD_2M_1296x968"]["ref"] = str(ex)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
