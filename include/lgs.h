@@ -212,7 +212,9 @@ int lgs_mapping_loss(int W, int H, int lf_w, int lf_h, const float* image, const
  *   1 - (s-min)/(max-min)   (find_objects_gaussians.py:173-175), in place.
  */
 int lgs_cosine_query(int P, int Q, const float* feats, const float* text, float* out,
-                     void* stream);
+                     void* stream);       /* tcgen05 tensor cores, 3xTF32 (fp32-level accuracy), TMEM accumulators */
+int lgs_cosine_query_simt(int P, int Q, const float* feats, const float* text, float* out,
+                          void* stream);  /* fp32 SIMT cross-check of the same contraction */
 int lgs_minmax_invert(int64_t n, float* scores, float* scratch2, void* stream);
 
 #ifdef __cplusplus

@@ -55,6 +55,7 @@ SIGNATURES = {
     "lgs_mapping_loss_scratch_bytes": (c_size_t, [c_int, c_int]),
     "lgs_mapping_loss": (c_int, [c_int] * 4 + [c_void_p] * 7 + [c_float, c_int] + [c_void_p] * 6),
     "lgs_cosine_query": (c_int, [c_int, c_int] + [c_void_p] * 4),
+    "lgs_cosine_query_simt": (c_int, [c_int, c_int] + [c_void_p] * 4),
     "lgs_minmax_invert": (c_int, [c_int64] + [c_void_p] * 3),
 }
 

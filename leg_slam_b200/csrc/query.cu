@@ -132,11 +132,30 @@ minmax_apply_kernel(long long n, float* __restrict__ s, const unsigned* __restri
 
 using namespace lgs;
 
-extern "C" int lgs_cosine_query(int P, int Q, const float* feats, const float* text, float* out, void* stream) {
+static int query_args_ok(int P, int Q, const float* feats, const float* text, float* out) {
     if (P < 0 || Q < 0) return LGS_ERR_INVALID_ARG;
-    if (P == 0 || Q == 0) return LGS_OK;
+    if (P == 0 || Q == 0) return -1;  // nothing to do
     if (!feats || !text || !out) return LGS_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(feats) & 15u) || (reinterpret_cast<uintptr_t>(text) & 15u)) return LGS_ERR_ALIGNMENT;
+    return LGS_OK;
+}
+
+namespace lgs {
+int launch_cosine_tc(int P, int Q, const float* feats, const float* text, float* out, cudaStream_t s);
+}
+
+// tensor-core path (query_tc.cu: tcgen05 3xTF32, TMEM accumulators)
+extern "C" int lgs_cosine_query(int P, int Q, const float* feats, const float* text, float* out, void* stream) {
+    const int st = query_args_ok(P, Q, feats, text, out);
+    if (st != LGS_OK) return st < 0 ? LGS_OK : st;
+    if (reinterpret_cast<uintptr_t>(out) & 15u) return LGS_ERR_ALIGNMENT;
+    return launch_cosine_tc(P, Q, feats, text, out, (cudaStream_t)stream);
+}
+
+// SIMT fp32 path (round-1 kernel; kept as the cross-check of the tensor-core one)
+extern "C" int lgs_cosine_query_simt(int P, int Q, const float* feats, const float* text, float* out, void* stream) {
+    const int st = query_args_ok(P, Q, feats, text, out);
+    if (st != LGS_OK) return st < 0 ? LGS_OK : st;
     const long long tiles = ((long long)P + QROWS - 1) / QROWS;
     const int grid = (int)(tiles < 148LL * 8 ? tiles : 148LL * 8);
     cosine_query_kernel<<<grid, QTHREADS, 0, (cudaStream_t)stream>>>(P, Q, feats, text, out);

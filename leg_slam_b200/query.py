@@ -6,9 +6,10 @@ from . import _lib
 from ._lib import check, ptr
 
 
-def cosine_query(feats, text):
+def cosine_query(feats, text, simt=False):
     """feats [P,64], text [Q,64] or [64] -> similarities [P,Q] (or [P]); rows are normalised like
-    F.normalize(eps=1e-12) inside the kernel."""
+    F.normalize(eps=1e-12) inside the kernel.  Default: tcgen05 tensor-core kernel (3xTF32);
+    simt=True runs the fp32 SIMT cross-check kernel."""
     L = _lib.lib()
     if not feats.is_cuda:
         raise _lib.LgsError("cosine_query has no CPU path")
@@ -20,8 +21,9 @@ def cosine_query(feats, text):
     P, Q = feats.size(0), text2.size(0)
     out = torch.empty((P, Q), dtype=torch.float32, device=feats.device)
     with torch.cuda.device(feats.device):
-        check(L.lgs_cosine_query(P, Q, ptr(feats), ptr(text2), ptr(out),
-                                 torch.cuda.current_stream(feats.device).cuda_stream), "lgs_cosine_query")
+        fn = L.lgs_cosine_query_simt if simt else L.lgs_cosine_query
+        check(fn(P, Q, ptr(feats), ptr(text2), ptr(out), torch.cuda.current_stream(feats.device).cuda_stream),
+              "lgs_cosine_query")
     return out[:, 0] if squeeze else out
 
 

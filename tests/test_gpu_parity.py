@@ -417,11 +417,22 @@ def test_adam_odd_sizes_and_unaligned(dev, oracle_mod):
 
 
 def test_cosine_query(dev, oracle_mod):
+    """Tensor-core kernel (tcgen05, 3xTF32) and the SIMT cross-check kernel against the fp64-accumulating oracle."""
     from leg_slam_b200 import cosine_query, relevance_scores
     feats, text = cases.cosine_case()
     sim = cosine_query(feats.to(dev), text.to(dev)).cpu().numpy()
     ref = oracle_mod.cosine(feats.numpy(), text.numpy())
     assert sim.shape == ref.shape and np.abs(sim - ref).max() <= 2e-6
+    simt = cosine_query(feats.to(dev), text.to(dev), simt=True).cpu().numpy()
+    assert np.abs(simt - ref).max() <= 1e-6
+    # shapes that exercise the tile / column-chunk edges of the tensor-core kernel: rows not a multiple of 128,
+    # > 148 tiles (persistent loop, TMEM double buffering wraps), Q not a multiple of 4 / 16 / 256
+    g = torch.Generator().manual_seed(33)
+    for P, Q in ((1, 1), (127, 3), (129, 16), (40001, 17), (5000, 256), (1000, 300)):
+        f = (torch.randn(P, 64, generator=g) * (0.1 + torch.rand(P, 1, generator=g)))
+        t = torch.randn(Q, 64, generator=g)
+        got = cosine_query(f.to(dev), t.to(dev)).cpu().numpy()
+        assert np.abs(got - oracle_mod.cosine(f.numpy(), t.numpy())).max() <= 2e-6, (P, Q)
     one = cosine_query(feats.to(dev), text[0].to(dev)).cpu().numpy()
     np.testing.assert_array_equal(one, sim[:, 0])
     rel = relevance_scores(feats.to(dev), text[0].to(dev)).cpu().numpy()
