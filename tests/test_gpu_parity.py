@@ -314,6 +314,62 @@ def test_mapper_step_matches_reference_rasterizer_and_torch_adam(dev, ref_mod):
             assert (d > 0.05 * step).mean() <= 2e-3, (k, float(d.max()), step)
 
 
+def test_psnr_after_n_iterations_matches_reference(dev, ref_mod):
+    """north_star gate: PSNR after N mapping iterations within 0.05 dB of the reference trajectory.  Same seeded
+    scene, same ground truth (rendered by the reference from a perturbed copy of the scene), same loss; ours =
+    fused path + FusedAdam, reference = compiled reference rasterizer + eager torch loss + torch.optim.Adam."""
+    import bench
+    from leg_slam_b200 import loss as loss_mod, mapper as M, synthetic
+    W, H, P, N_IT = 160, 120, 20000, 60
+    truth = synthetic.make_scene(P, seed=81, mean_scale=0.05, device=dev)
+    cams = [c.to(dev) for c in synthetic.make_cameras(3, W, H, seed=81)]
+    g = torch.Generator().manual_seed(82)
+    start = {k: v.clone() for k, v in truth.items()}
+    start["xyz"] = start["xyz"] + 0.01 * torch.randn(P, 3, generator=g).to(dev)
+    start["features_dc"] = start["features_dc"] + 0.3 * torch.randn(P, 1, 3, generator=g).to(dev)
+    start["lang_feat"] = start["lang_feat"] + 0.1 * torch.randn(P, 64, generator=g).to(dev)
+    start["opacity"] = start["opacity"] - 0.5
+    bench.SH_DEGREE = 3
+
+    class _Shim(bench.E2EPath):
+        def __init__(self):
+            self.mapper = None
+    shim = _Shim()
+    refm = M.Mapper(start, sh_degree=3, use_cuda_graph=False, optimizer_factory=lambda gr: torch.optim.Adam(gr, lr=0.0, eps=1e-15))
+    shim.mapper = refm
+    refm.render_fn = shim._ref_render_fn()
+    ours = M.Mapper(start, sh_degree=3)
+    assert ours.fused
+    # ground truth from the TRUE scene through the reference rasterizer
+    gt_m = M.Mapper(truth, sh_degree=3, use_cuda_graph=False, optimizer_factory=lambda gr: torch.optim.Adam(gr, lr=0.0))
+    shim2 = _Shim()
+    shim2.mapper = gt_m
+    render_ref = shim2._ref_render_fn()
+    window = []
+    with torch.no_grad():
+        for c in cams:
+            img, lf, dep, _ = render_ref(c, gt_m.activated())
+            lf_low = torch.nn.functional.interpolate(lf.unsqueeze(0), size=(37, 37)).squeeze(0)
+            window.append(M.Keyframe(c, img.clone(), lf_low.contiguous(), dep.clone()))
+
+    def psnr_of(m):
+        vals = []
+        with torch.no_grad():
+            for kf in window:
+                img, _, _, _ = render_ref(kf.camera, m.activated())
+                vals.append(float(loss_mod.psnr(img, kf.gt_image)))
+        return sum(vals) / len(vals)
+
+    p0 = psnr_of(ours)
+    for it in range(N_IT):  # one keyframe per iteration, like the reference mapper
+        kf = [window[it % len(window)]]
+        ours.train_step(kf)
+        refm.train_step(kf)
+    po, pr = psnr_of(ours), psnr_of(refm)
+    assert pr > p0 + 0.5, (p0, pr)          # the optimisation actually moved the image
+    assert abs(po - pr) <= 0.05, (p0, po, pr)
+
+
 def test_fused_loss_matches_torch_loss(dev):
     """lgs_mapping_loss vs the stock-torch statement of include/loss_utils.h + gaussian_mapper.cpp:707-721."""
     from leg_slam_b200 import loss as loss_mod
