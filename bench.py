@@ -147,6 +147,7 @@ class KernelPath:
         self.dev, self.world = device, world
         a = synthetic.activate({k: v.to(device) for k, v in sc.items()})
         self.a = {k: v.contiguous() for k, v in a.items()}
+        self.dp = None
         self.cam = cam.to(device)
         self.up = {k: v.to(device) for k, v in up.items()}
         P, W, H = P_GAUSS, WIDTH, HEIGHT
@@ -161,7 +162,30 @@ class KernelPath:
         self.radii = torch.empty(P, dtype=torch.int32, device=device)
         # flat gradient buffer in Adam order: means3D 3 | sh 48 | lf 64 | opacity 1 | scales 3 | rot 4
         self.order = [("means3D", 3), ("shs", 48), ("lang_feats", 64), ("opacities", 1), ("scales", 3), ("rotations", 4)]
-        self.flat = torch.zeros(P * FLOATS_PER_GAUSSIAN, **f32)
+        lrs = dict(means3D=3.2e-4, shs=2.5e-3, lang_feats=1.5e-3, opacities=0.05, scales=5e-3, rotations=1e-3)
+        self.dp_mode = "single GPU"
+        if world > 1:
+            self.dp_mode = "NCCL all-reduce + fused Adam on every replica"
+            try:  # parameters and gradients in symmetric memory: one peer-memory kernel does reduce-scatter + Adam + all-gather
+                from leg_slam_b200 import dp as dp_mod
+                pflat = dp_mod.symmetric_empty(P * FLOATS_PER_GAUSSIAN, device)
+                gflat = dp_mod.symmetric_empty(P * FLOATS_PER_GAUSSIAN, device)
+                gflat.zero_()
+                off = 0
+                for k, n in self.order:
+                    view = pflat[off:off + P * n].view_as(self.a[k])
+                    view.copy_(self.a[k])
+                    self.a[k] = view
+                    off += P * n
+                self.flat = gflat
+                self.dp = dp_mod.FusedDPAdam(pflat, gflat, [P * n for _, n in self.order], [lrs[k] * 1e-3 for k, _ in self.order])
+                self.dp_mode = "fused peer-memory reduce-scatter + Adam + all-gather (lgs_dp_adam_shard, " + \
+                               ("NVSwitch multimem" if self.dp.uses_multicast else "P2P loads/stores") + ")"
+            except Exception as ex:  # symmetric memory unavailable on this box: NCCL path
+                self.dp = None
+                self.dp_mode += f" (symmetric memory unavailable: {type(ex).__name__})"
+        if self.dp is None:
+            self.flat = torch.zeros(P * FLOATS_PER_GAUSSIAN, **f32)
         self.g, off = {}, 0
         for k, n in self.order:
             self.g[k] = self.flat[off:off + P * n]
@@ -170,7 +194,6 @@ class KernelPath:
                             cov=torch.empty(P, 6, **f32))
         self.m = {k: torch.zeros_like(self.a[k]) for k, _ in self.order}
         self.v = {k: torch.zeros_like(self.a[k]) for k, _ in self.order}
-        lrs = dict(means3D=3.2e-4, shs=2.5e-3, lang_feats=1.5e-3, opacities=0.05, scales=5e-3, rotations=1e-3)
         n = len(self.order)
         VP = ctypes.c_void_p * n
         self.ad = dict(p=VP(*[self.a[k].data_ptr() for k, _ in self.order]), g=VP(*[self.g[k].data_ptr() for k, _ in self.order]),
@@ -220,6 +243,9 @@ class KernelPath:
     def step(self, _i=0):
         self.forward()
         self.backward()
+        if self.dp is not None:
+            self.dp.step()
+            return
         if self.world > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
         self.adam()
@@ -295,7 +321,13 @@ class E2EPath:
             # the reference's stock path: eager torch ops for the loss, unfused torch Adam
             kw = dict(optimizer_factory=lambda g: torch.optim.Adam(g, lr=0.0, eps=1e-15), render_fn=self._ref_render_fn(),
                       use_cuda_graph=False)
-        self.mapper = M.Mapper(params, lrs=lrs, sh_degree=SH_DEGREE, **kw)
+        if impl == "ours" and world > 1:
+            kw["dp_mode"] = "fused"
+        try:
+            self.mapper = M.Mapper(params, lrs=lrs, sh_degree=SH_DEGREE, **kw)
+        except Exception:  # symmetric memory unavailable: NCCL all-reduce path
+            kw.pop("dp_mode", None)
+            self.mapper = M.Mapper(params, lrs=lrs, sh_degree=SH_DEGREE, **kw)
         if impl == "reference":
             self.mapper.world_size, self.mapper.rank = 1, 0  # the reference is single-GPU: rank 0 does every view
         self.M = M
@@ -501,7 +533,7 @@ def main():
             "config": {"workload": "cfgB: Replica-shaped 500k Gaussians, 640x480, SH deg 3, 64-D language feature, "
                                    "1 keyframe per GPU per iteration, fwd+bwd+Adam (BASELINE.json configs[1])",
                        "P": P_GAUSS, "width": WIDTH, "height": HEIGHT, "views_per_iteration": world,
-                       "parallelism": f"data-parallel over views x{world}, NCCL all-reduce of 492 B/Gaussian" if world > 1 else "single GPU",
+                       "parallelism": f"data-parallel over views x{world}, 492 B/Gaussian exchanged: {kp.dp_mode}" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2: params+grads+Adam state 984 MB per iteration (L2 126 MB), no flush",
                        "R": counts["R"], "P_visible": counts["P_visible"], "N_tested": counts["N_tested"], "N_blend": n_blend,
                        "adam_lr_scale_kernel_path": 1e-3, "e2e_lr_scale": LR_SCALE},

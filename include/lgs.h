@@ -177,6 +177,19 @@ int lgs_adam_multi(int n_tensors, float* const* params, const float* const* grad
                    const int64_t* numel, const double* lr,
                    double beta1, double beta2, double eps, int step, void* stream);
 
+/* ---- data-parallel exchange fused with Adam, over NVLink peer memory (new) -------
+ * One launch per rank: for flat indices [shard_begin, shard_end) (multiples of 4) it sums the G ranks'
+ * gradients (multimem.ld_reduce on grads_mc when non-NULL, else peer loads of grads_peers[0..G) in rank
+ * order), applies Adam (state arrays cover the shard only), and writes the updated parameters to every
+ * rank (multimem.st on params_mc when non-NULL, else peer stores to params_peers[0..G)).
+ * seg_start[0..n_seg] are the flat offsets of the parameter tensors (multiples of 4), lr[t] their rates.
+ * grads_peers / params_peers are HOST arrays of device pointers into symmetric (peer-mapped) buffers; the
+ * caller synchronises the ranks before (gradients complete) and after (parameters landed) the launch. */
+int lgs_dp_adam_shard(int n_seg, const int64_t* seg_start, const double* lr, int world, int rank,
+                      const float* const* grads_peers, float* const* params_peers, const float* grads_mc,
+                      float* params_mc, int64_t shard_begin, int64_t shard_end, float* exp_avg_shard,
+                      float* exp_avg_sq_shard, double beta1, double beta2, double eps, int step, void* stream);
+
 /* ---- activations  (reference src/gaussian_model.cpp:46-68) ---------------
  * forward : scales = exp(scaling) [P,3], rotations = normalize(rotation) [P,4], opacities =
  *           sigmoid(opacity) [P,1], shs = cat(features_dc [P,1,3], features_rest [P,n_rest,3]) [P,1+n_rest,3]

@@ -18,6 +18,7 @@
 // Memory-bound (HBM roofline): grid-stride over 16-byte vectors, streaming loads/stores.
 #include <cmath>
 #include "common.cuh"
+#include "adam_math.cuh"
 
 namespace lgs {
 
@@ -34,14 +35,6 @@ struct AdamTable {
     int chunk_start[ADAM_MAX_TENSORS + 1];
     int n_tensors;
 };
-
-__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float b1, float omb1, float b2,
-                                          float omb2, float inv_bc2_sqrt, float eps, float neg_step) {
-    m = __fmaf_rn(omb1, g, __fmul_rn(m, b1));
-    v = __fmaf_rn(__fmul_rn(omb2, g), g, __fmul_rn(v, b2));
-    const float dn = __fadd_rn(__fmul_rn(__fsqrt_rn(v), inv_bc2_sqrt), eps);
-    p = __fmaf_rn(neg_step, __fdiv_rn(m, dn), p);
-}
 
 __device__ __forceinline__ float4 ldcs4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 

@@ -1,0 +1,115 @@
+// dp_adam.cu -- data-parallel gradient exchange fused with the optimizer, over NVLink peer memory.
+//
+// New relative to the reference (single GPU).  After every rank has back-propagated its views into its
+// flat gradient buffer [123*P], the baseline is  ncclAllReduce(grads) ; Adam on every replica  (SURVEY.md
+// 8e).  Here ONE kernel per rank does reduce-scatter + Adam + all-gather on its shard of the flat index
+// space, with no NCCL call and no intermediate buffer:
+//     g  = sum over ranks of grads_r[i]          multimem.ld_reduce on the NVSwitch multicast address (the
+//                                                switch adds), or G peer loads in fixed rank order
+//     p, m, v <- Adam(p, g, m, v)                m, v exist only for the owned shard (optimizer state / G)
+//     params_r[i] = p  for every rank r          multimem.st (switch broadcast), or G peer stores
+// Every element is reduced and updated by exactly one rank and broadcast, so replicas stay bit-identical
+// by construction.  Per rank it moves (G-1)/G of the gradient bytes in and of the parameter bytes out --
+// the same wire traffic as reduce-scatter + all-gather -- while Adam's HBM traffic drops by G.
+// The buffers must be symmetric allocations (torch.distributed._symmetric_memory); the caller brackets the
+// launch with cross-rank barriers (gradients complete before, parameters landed after).
+#include <cmath>
+#include "common.cuh"
+#include "adam_math.cuh"
+
+namespace lgs {
+
+constexpr int DP_MAX_SEG = 16;
+constexpr int DP_MAX_WORLD = 16;
+
+struct DpTable {
+    long long seg_start[DP_MAX_SEG + 1];  // flat offsets of the parameter tensors (multiples of 4)
+    float neg_step[DP_MAX_SEG];           // -(lr / bias_correction1) per tensor
+    const float* grads[DP_MAX_WORLD];     // every rank's flat gradient buffer (peer pointers)
+    float* params[DP_MAX_WORLD];          // every rank's flat parameter buffer (peer pointers)
+    int n_seg, world;
+};
+
+__device__ __forceinline__ float4 mc_ld_reduce_add(const float* mc) {
+    float4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc) : "memory");
+    return r;
+}
+__device__ __forceinline__ void mc_st(float* mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+dp_adam_kernel(const __grid_constant__ DpTable tab, const float* __restrict__ grads_mc, float* __restrict__ params_mc,
+               long long begin, long long end, float* __restrict__ p_local, float* __restrict__ m, float* __restrict__ v,
+               float b1, float omb1, float b2, float omb2, float inv_bc2_sqrt, float eps) {
+    const long long n4 = (end - begin) >> 2;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += (long long)gridDim.x * blockDim.x) {
+        const long long i = begin + 4 * k;
+        float4 g;
+        if (grads_mc != nullptr) {
+            g = mc_ld_reduce_add(grads_mc + i);  // in-switch reduction over all ranks
+        } else {
+            g = *reinterpret_cast<const float4*>(tab.grads[0] + i);
+            for (int r = 1; r < tab.world; ++r) {
+                const float4 x = *reinterpret_cast<const float4*>(tab.grads[r] + i);
+                g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+            }
+        }
+        int t = 0;
+        while (t + 1 < tab.n_seg && i >= tab.seg_start[t + 1]) ++t;
+        const float ns = tab.neg_step[t];
+        float4 p = *reinterpret_cast<const float4*>(p_local + i);
+        float4 mm = *reinterpret_cast<const float4*>(m + 4 * k), vv = *reinterpret_cast<const float4*>(v + 4 * k);
+        adam_elem(p.x, g.x, mm.x, vv.x, b1, omb1, b2, omb2, inv_bc2_sqrt, eps, ns);
+        adam_elem(p.y, g.y, mm.y, vv.y, b1, omb1, b2, omb2, inv_bc2_sqrt, eps, ns);
+        adam_elem(p.z, g.z, mm.z, vv.z, b1, omb1, b2, omb2, inv_bc2_sqrt, eps, ns);
+        adam_elem(p.w, g.w, mm.w, vv.w, b1, omb1, b2, omb2, inv_bc2_sqrt, eps, ns);
+        *reinterpret_cast<float4*>(m + 4 * k) = mm;
+        *reinterpret_cast<float4*>(v + 4 * k) = vv;
+        if (params_mc != nullptr) {
+            mc_st(params_mc + i, p);  // switch broadcast to every rank, this one included
+        } else {
+            for (int r = 0; r < tab.world; ++r) *reinterpret_cast<float4*>(tab.params[r] + i) = p;
+        }
+    }
+}
+
+}  // namespace lgs
+
+using namespace lgs;
+
+extern "C" int lgs_dp_adam_shard(int n_seg, const int64_t* seg_start, const double* lr, int world, int rank,
+                                 const float* const* grads_peers, float* const* params_peers, const float* grads_mc,
+                                 float* params_mc, int64_t shard_begin, int64_t shard_end, float* exp_avg_shard,
+                                 float* exp_avg_sq_shard, double beta1, double beta2, double eps, int step, void* stream) {
+    if (n_seg < 1 || n_seg > DP_MAX_SEG || world < 1 || world > DP_MAX_WORLD || rank < 0 || rank >= world || step < 1)
+        return LGS_ERR_INVALID_ARG;
+    if (!seg_start || !lr || !grads_peers || !params_peers || !exp_avg_shard || !exp_avg_sq_shard) return LGS_ERR_INVALID_ARG;
+    if (shard_begin < 0 || shard_end < shard_begin || ((shard_begin | shard_end) & 3)) return LGS_ERR_INVALID_ARG;
+    if (shard_end == shard_begin) return LGS_OK;
+    DpTable tab;
+    const double bc1 = 1.0 - std::pow(beta1, (double)step), bc2 = 1.0 - std::pow(beta2, (double)step);
+    for (int t = 0; t <= n_seg; ++t) {
+        if (seg_start[t] & 3) return LGS_ERR_ALIGNMENT;
+        tab.seg_start[t] = seg_start[t];
+    }
+    for (int t = 0; t < n_seg; ++t) tab.neg_step[t] = (float)(-(lr[t] / bc1));
+    for (int r = 0; r < world; ++r) {
+        if (!grads_peers[r] || !params_peers[r]) return LGS_ERR_INVALID_ARG;
+        tab.grads[r] = grads_peers[r];
+        tab.params[r] = params_peers[r];
+    }
+    tab.n_seg = n_seg;
+    tab.world = world;
+    const long long n4 = (shard_end - shard_begin) >> 2;
+    const int grid = (int)((n4 + 255) / 256 < 148LL * 16 ? (n4 + 255) / 256 : 148LL * 16);
+    dp_adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tab, grads_mc, params_mc, shard_begin, shard_end, params_peers[rank],
+                                                           exp_avg_shard, exp_avg_sq_shard, (float)beta1, (float)(1.0 - beta1),
+                                                           (float)beta2, (float)(1.0 - beta2), 1.0f / (float)std::sqrt(bc2),
+                                                           (float)eps);
+    LGS_LAUNCH_CHECK();
+    return LGS_OK;
+}

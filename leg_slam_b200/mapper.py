@@ -48,10 +48,10 @@ class FlatGrads:
     """The 7 parameters' .grad tensors as views into one contiguous buffer (one collective,
     one memset)."""
 
-    def __init__(self, params: dict):
+    def __init__(self, params: dict, flat: Optional[torch.Tensor] = None):
         n = sum(params[k].numel() for k in PARAM_ORDER)
         any_p = params[PARAM_ORDER[0]]
-        self.flat = torch.zeros(n, dtype=torch.float32, device=any_p.device)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=any_p.device) if flat is None else flat
         off = 0
         self.views = {}
         for k in PARAM_ORDER:
@@ -73,12 +73,36 @@ class Mapper:
     def __init__(self, params: dict, lrs: Optional[dict] = None, sh_degree: int = 3,
                  process_group=None, optimizer_factory: Optional[Callable] = None,
                  render_fn: Optional[Callable] = None, faithful_loss_sign: bool = True,
-                 use_cuda_graph: bool = True, fused: bool = True):
-        self.params = {k: torch.nn.Parameter(params[k].detach().clone().contiguous()) for k in PARAM_ORDER}
+                 use_cuda_graph: bool = True, fused: bool = True, dp_mode: str = "allreduce"):
+        """dp_mode: "allreduce" = NCCL all-reduce of the flat gradient, then Adam on every replica;
+        "fused" = one peer-memory kernel per rank doing reduce-scatter + Adam-on-shard + all-gather
+        (leg_slam_b200.dp.FusedDPAdam; needs world_size > 1, CUDA, P % 4 == 0)."""
         lrs = dict(DEFAULT_LRS, **(lrs or {}))
-        groups = [dict(params=[self.params[k]], lr=lrs[k], name=k) for k in PARAM_ORDER]
-        self.optimizer = (optimizer_factory or (lambda g: FusedAdam(g, lr=0.0, eps=1e-15)))(groups)
-        self.grads = FlatGrads(self.params)
+        world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.dp = None
+        if dp_mode == "fused" and world > 1 and params["xyz"].is_cuda and render_fn is None and fused:
+            from . import dp as dp_mod
+            dev0 = params["xyz"].device
+            n = sum(params[k].numel() for k in PARAM_ORDER)
+            pflat = dp_mod.symmetric_empty(n, dev0)
+            gflat = dp_mod.symmetric_empty(n, dev0)
+            gflat.zero_()
+            off, self.params = 0, {}
+            for k in PARAM_ORDER:
+                t = params[k].detach().contiguous()
+                view = pflat[off:off + t.numel()].view_as(t)
+                view.copy_(t)
+                self.params[k] = torch.nn.Parameter(view, requires_grad=False)
+                off += t.numel()
+            self.grads = FlatGrads(self.params, flat=gflat)
+            self.dp = dp_mod.FusedDPAdam(pflat, gflat, [params[k].numel() for k in PARAM_ORDER], [lrs[k] for k in PARAM_ORDER],
+                                         group=process_group)
+            self.optimizer = None
+        else:
+            self.params = {k: torch.nn.Parameter(params[k].detach().clone().contiguous()) for k in PARAM_ORDER}
+            groups = [dict(params=[self.params[k]], lr=lrs[k], name=k) for k in PARAM_ORDER]
+            self.optimizer = (optimizer_factory or (lambda g: FusedAdam(g, lr=0.0, eps=1e-15)))(groups)
+            self.grads = FlatGrads(self.params)
         self.sh_degree = sh_degree
         self.pg = process_group
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -217,10 +241,14 @@ class Mapper:
         rank's keyframes.  Returns the (detached) sum of this rank's view losses."""
         mine = list(range(len(window))) if presharded else shard_views(len(window), self.rank, self.world_size)
         self.last_num_views = len(mine)
-        self.grads.attach(self.params)
+        if self.dp is None:
+            self.grads.attach(self.params)
         if self.fused and len(mine) > 0:
             with torch.no_grad():
                 total = self._train_views_fused(window, mine)  # overwrites the flat buffer: no memset needed
+                if self.dp is not None:
+                    self.dp.step()  # reduce-scatter + Adam + all-gather in one peer-memory kernel
+                    return total
                 if self.world_size > 1:
                     dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.pg)
             self.optimizer.step()
