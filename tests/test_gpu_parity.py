@@ -472,6 +472,42 @@ def test_adam_odd_sizes_and_unaligned(dev, oracle_mod):
         np.testing.assert_array_equal(p.detach().cpu().numpy().view(np.uint32), ref.view(np.uint32))
 
 
+def test_dp_adam_shard_kernel_single_rank(dev, oracle_mod):
+    """lgs_dp_adam_shard with world = 1 (no peers, no multicast) is exactly the oracle's Adam over the flat
+    buffer, per-tensor learning rates resolved from the segment table, two shards covering the index space.
+    The multi-rank exchange itself is exercised by tools/check_dp_fused.py under torchrun (needs >= 2 GPUs)."""
+    import ctypes
+    from leg_slam_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(91)
+    sizes = [1200, 400, 6000, 8192, 400, 1200, 1600]
+    lrs = [3.2e-4, 2.5e-3, 1.25e-4, 1.5e-3, 0.05, 5e-3, 1e-3]
+    n = sum(sizes)
+    p0 = torch.randn(n, generator=g)
+    grads = [torch.randn(n, generator=g) * 1e-3 for _ in range(2)]
+    p = p0.clone().to(dev)
+    m = torch.zeros(n, device=dev)
+    v = torch.zeros(n, device=dev)
+    ref_p, ref_m, ref_v = p0.clone().numpy(), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    starts = np.cumsum([0] + sizes)
+    seg = (ctypes.c_int64 * (len(sizes) + 1))(*[int(x) for x in starts])
+    lr = (ctypes.c_double * len(sizes))(*lrs)
+    half = (n // 8) * 4
+    for step, gr in enumerate(grads, start=1):
+        gd = gr.to(dev)
+        gp = (ctypes.c_void_p * 1)(gd.data_ptr())
+        pp = (ctypes.c_void_p * 1)(p.data_ptr())
+        for b, e in ((0, half), (half, n)):
+            _lib.check(L.lgs_dp_adam_shard(len(sizes), seg, lr, 1, 0, gp, pp, None, None, b, e, m[b:].data_ptr(), v[b:].data_ptr(),
+                                           0.9, 0.999, 1e-15, step, torch.cuda.current_stream(dev).cuda_stream), "dp_adam")
+        for t in range(len(sizes)):
+            a, z = int(starts[t]), int(starts[t + 1])
+            oracle_mod.adam(ref_p[a:z], gr.numpy()[a:z], ref_m[a:z], ref_v[a:z], lrs[t], step=step)
+        np.testing.assert_array_equal(p.cpu().numpy().view(np.uint32), ref_p.view(np.uint32))
+    np.testing.assert_array_equal(m.cpu().numpy().view(np.uint32), ref_m.view(np.uint32))
+    np.testing.assert_array_equal(v.cpu().numpy().view(np.uint32), ref_v.view(np.uint32))
+
+
 def test_cosine_query(dev, oracle_mod):
     """Tensor-core kernel (tcgen05, 3xTF32) and the SIMT cross-check kernel against the fp64-accumulating oracle."""
     from leg_slam_b200 import cosine_query, relevance_scores
