@@ -170,6 +170,59 @@ def test_radii_pointer_optional_and_mark_visible(dev, oracle_mod):
     assert rp.mark_visible(cs["means3D"][:0], cs["viewmatrix"], cs["projmatrix"]).numel() == 0
 
 
+def test_no_writes_outside_caller_buffers(dev):
+    """compute-sanitizer is closed on this pool, so: every buffer handed to the C ABI sits between two 64 KB
+    guard regions filled with a pattern; after forward + backward the guards must be untouched, and buffers
+    sized exactly by lgs_*_bytes must suffice."""
+    import ctypes
+    from leg_slam_b200 import _lib
+    L = _lib.lib()
+    G = 1 << 16
+    held = []
+
+    def guarded(nbytes, dtype=torch.uint8):
+        esz = torch.empty((), dtype=dtype).element_size()
+        raw = torch.full((G + ((nbytes + 255) // 256) * 256 + G,), 0xA5, dtype=torch.uint8, device=dev)
+        held.append((raw, nbytes))
+        return raw[G:G + nbytes].view(dtype) if nbytes % esz == 0 else raw[G:G + nbytes]
+
+    for name in ("ragged_sh1", "dense_opaque"):
+        held.clear()
+        cs = cases.make_case(name, dev)
+        P, W, H, M_ = cs["P"], cs["W"], cs["H"], 16
+        s = torch.cuda.current_stream(dev).cuda_stream
+        geom, img = guarded(L.lgs_geom_bytes(P)), guarded(L.lgs_image_bytes(W, H))
+        radii = guarded(4 * P, torch.int32)
+        color, lf, depth = guarded(12 * H * W, torch.float32), guarded(256 * H * W, torch.float32), guarded(4 * H * W, torch.float32)
+        R = ctypes.c_int(0)
+        t = {k: cs[k].contiguous() for k in ("means3D", "shs", "opacities", "scales", "rotations", "viewmatrix", "projmatrix",
+                                              "campos", "bg", "lang_feats", "dL_dcolor", "dL_dlf", "dL_ddepth")}
+        _lib.check(L.lgs_forward_stage1(P, cs["degree"], M_, W, H, t["means3D"].data_ptr(), t["shs"].data_ptr(), None,
+                                        t["opacities"].data_ptr(), t["scales"].data_ptr(), 1.0, t["rotations"].data_ptr(), None,
+                                        t["viewmatrix"].data_ptr(), t["projmatrix"].data_ptr(), t["campos"].data_ptr(),
+                                        cs["tanfovx"], cs["tanfovy"], 0, geom.data_ptr(), radii.data_ptr(), ctypes.byref(R), s), "s1")
+        binning = guarded(L.lgs_binning_bytes(R.value))
+        _lib.check(L.lgs_forward_stage2(P, W, H, R.value, t["bg"].data_ptr(), t["lang_feats"].data_ptr(), geom.data_ptr(),
+                                        binning.data_ptr(), img.data_ptr(), color.data_ptr(), lf.data_ptr(), depth.data_ptr(), 1, s), "s2")
+        scratch = guarded(L.lgs_backward_scratch_bytes(R.value, W, H))
+        g = {k: guarded(4 * n, torch.float32) for k, n in (("m2d", 3 * P), ("conic", 4 * P), ("op", P), ("col", 3 * P), ("lf", 64 * P),
+                                                            ("dep", P), ("m3d", 3 * P), ("cov", 6 * P), ("sh", 48 * P), ("sc", 3 * P),
+                                                            ("rot", 4 * P))}
+        _lib.check(L.lgs_backward(P, cs["degree"], M_, R.value, W, H, t["bg"].data_ptr(), t["means3D"].data_ptr(), t["shs"].data_ptr(),
+                                  None, t["lang_feats"].data_ptr(), t["scales"].data_ptr(), 1.0, t["rotations"].data_ptr(), None,
+                                  t["viewmatrix"].data_ptr(), t["projmatrix"].data_ptr(), t["campos"].data_ptr(), cs["tanfovx"],
+                                  cs["tanfovy"], radii.data_ptr(), geom.data_ptr(), binning.data_ptr(), img.data_ptr(),
+                                  t["dL_dcolor"].data_ptr(), t["dL_dlf"].data_ptr(), t["dL_ddepth"].data_ptr(), g["m2d"].data_ptr(),
+                                  g["conic"].data_ptr(), g["op"].data_ptr(), g["col"].data_ptr(), g["lf"].data_ptr(), g["dep"].data_ptr(),
+                                  g["m3d"].data_ptr(), g["cov"].data_ptr(), g["sh"].data_ptr(), g["sc"].data_ptr(), g["rot"].data_ptr(),
+                                  1, 1, scratch.data_ptr(), s), "bwd")
+        torch.cuda.synchronize()
+        for raw, nbytes in held:
+            assert bool((raw[:G] == 0xA5).all()), "write before a buffer"
+            assert bool((raw[G + ((nbytes + 255) // 256) * 256:] == 0xA5).all()), "write past a buffer"
+        assert bool(torch.isfinite(g["lf"]).all() and torch.isfinite(color).all())
+
+
 # ---------------------------------------------------------------------------- full-size properties
 @pytest.fixture(scope="module")
 def cfgB(dev):
