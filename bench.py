@@ -343,6 +343,8 @@ class E2EPath:
         self.h2d_bytes = sum(t.numel() * 4 for k, t in self.host[0].items() if k != "cam") * len(self.host)
         self.loss_host = torch.zeros(1).pin_memory()
         self.last_R = 0
+        self.copy_stream = None
+        self._next = None
 
     def _ref_render_fn(self):
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -382,16 +384,38 @@ class E2EPath:
                                        a["rotations"], cam, outer.mapper.bg)
         return render
 
-    def step(self, _i=0):
+    def _upload(self):
+        """Host -> device copies of one step's inputs (camera + ground truth of every local keyframe) from pinned
+        memory, issued on the copy stream; returns the device-side window and the event that marks their arrival."""
         from leg_slam_b200.synthetic import Camera
         dev = self.dev
         window = []
-        for h in self.host:  # host -> device copies of this step's inputs (pinned, async on the compute stream)
-            c = h["cam"]
-            cam = Camera(c.width, c.height, c.tanfovx, c.tanfovy, h["view"].to(dev, non_blocking=True),
-                         h["proj"].to(dev, non_blocking=True), h["campos"].to(dev, non_blocking=True))
-            window.append(self.M.Keyframe(cam, h["gt_image"].to(dev, non_blocking=True), h["gt_lf"].to(dev, non_blocking=True),
-                                          h["gt_depth"].to(dev, non_blocking=True)))
+        with torch.cuda.stream(self.copy_stream):
+            for h in self.host:
+                c = h["cam"]
+                cam = Camera(c.width, c.height, c.tanfovx, c.tanfovy, h["view"].to(dev, non_blocking=True),
+                             h["proj"].to(dev, non_blocking=True), h["campos"].to(dev, non_blocking=True))
+                window.append(self.M.Keyframe(cam, h["gt_image"].to(dev, non_blocking=True), h["gt_lf"].to(dev, non_blocking=True),
+                                              h["gt_depth"].to(dev, non_blocking=True)))
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        return window, ev
+
+    def step(self, _i=0):
+        """One mapping iteration.  The step's inputs were uploaded on the copy stream while the previous
+        step computed (the next keyframe of a mapper is known one iteration ahead); this step waits for them,
+        starts the upload for the next step, computes, and reads the loss back."""
+        cur = torch.cuda.current_stream(self.dev)
+        if self.copy_stream is None:
+            self.copy_stream = torch.cuda.Stream(device=self.dev)
+            self._next = self._upload()
+        window, ev = self._next
+        cur.wait_event(ev)
+        self.copy_stream.wait_stream(cur)  # do not overwrite device inputs a still-running step may read
+        self._next = self._upload()
+        for kf in window:  # tensors produced on the copy stream, consumed on the compute stream
+            for t in (kf.camera.viewmatrix, kf.camera.projmatrix, kf.camera.campos, kf.gt_image, kf.gt_lf, kf.gt_depth):
+                t.record_stream(cur)
         loss = self.mapper.train_step(window, presharded=True)
         self.loss_host.copy_(loss.reshape(1), non_blocking=False)  # device -> host read of the step's result
         return float(self.loss_host[0])
