@@ -12,6 +12,7 @@ constexpr int TILE_PIX = TILE * TILE;   // 64
 constexpr int LF = LGS_LF_DIM;          // 64 language-feature channels
 constexpr int NCH = LGS_NUM_CHANNELS;   // 3 colour channels
 constexpr int REC_FLOATS = 12;          // per-Gaussian render record, 48 B (3 x float4)
+constexpr int HREC_FLOATS = 68;         // render-backward half-record: {gx - cx, gy - cy, 0, id} | w[32] | t[32]  (272 B)
 
 // ---- per-Gaussian render record (geometry buffer) --------------------------------
 // One 48-byte record replaces the reference's separate means2D / depths /
@@ -109,6 +110,10 @@ int launch_render_bwd(int P, int W, int H, int R, const GeomState& g, const Binn
                       float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
                       float* dL_dlang_feat, float* dL_ddepth, bool include_lf, char* scratch, cudaStream_t s);
 size_t render_bwd_scratch_bytes(int R, int W, int H);
+int launch_render_bwd_chan_tc(int W, int H, const ImageState& im, const float* dL_dpix, const float* dL_dpix_lf,
+                              const float* dL_dpix_depth, const float* hrec, const uint32_t* hcount, uint32_t* work_counter,
+                              float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                              float* dL_dlang_feat, float* dL_ddepth, cudaStream_t s);
 int launch_preprocess_bwd(int P, int D, int M, const float* means3D, const int* radii,
                           const float* shs, const float* scales, const float* rotations,
                           float scale_modifier, const float* cov3D, const float* viewmatrix,

@@ -37,6 +37,7 @@
 //
 // Summation order differs from the reference's atomics (and from run to run), which is why
 // the gradient parity gate is 1e-3 relative.
+#include <cstdlib>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -46,7 +47,6 @@ constexpr int BB = 32;       // Gaussians per TMA batch of the pixel kernel
 constexpr int BSTAGES = 3;   // its staging ring depth
 constexpr int CB = 8;        // half-records per TMA batch of the channel kernel
 constexpr int CSTAGES = 4;   // its staging ring depth
-constexpr int HREC_FLOATS = 68;  // half-record: {gx - cx, gy - cy, 0, id} | w[32] | t[32]  (272 B)
 
 template <bool WITH_LF>
 struct BwdStage {
@@ -69,7 +69,7 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                       const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ tile_last,
                       const float* __restrict__ dL_dpix, const float* __restrict__ dL_dpix_lf,
                       const float* __restrict__ dL_dpix_depth, float* __restrict__ hrec_buf,
-                      uint32_t* __restrict__ hrec_count) {
+                      uint32_t* __restrict__ hrec_count, uint32_t* __restrict__ work_counter) {
     using Stage = BwdStage<WITH_LF>;
     __shared__ __align__(128) Stage stages[BSTAGES];
     __shared__ __align__(8) uint64_t full_bar[BSTAGES];
@@ -77,6 +77,7 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const int tid = threadIdx.x;
     const int lane = tid & 31, wrp = tid >> 5;
     const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+    if (tile_id == 0 && tid == 0) *work_counter = 0;  // the tensor-core channel kernel's tile queue (next launch in stream order)
     const uint2 range = ranges[tile_id];
     const int n_all = (int)(range.y - range.x);
     const int n = min(n_all, (int)tile_last[tile_id]);  // entries behind tile_last touch no pixel
@@ -427,6 +428,17 @@ int launch_zero_grads(int P, float* dL_dmean2D, float* dL_dconic, float* dL_dopa
     return LGS_OK;
 }
 
+// LGS_BWD_CHAN=simt (environment, read at the first launch) keeps the SIMT channel kernel for the 64-D feature path: a
+// differential-debugging aid for the tensor-core kernel (render_bwd_tc.cu), not a fallback for other hardware.
+static bool env_simt_chan() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("LGS_BWD_CHAN");
+        v = (e && e[0] == 's') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 size_t render_bwd_scratch_bytes(int R, int W, int H) {
     const size_t n = (size_t)(R > 0 ? R : 1);
     const size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
@@ -445,19 +457,23 @@ int launch_render_bwd(int P, int W, int H, int R, const GeomState& g, const Binn
     uintptr_t base = (reinterpret_cast<uintptr_t>(scratch) + 255) & ~(uintptr_t)255;
     float* hrec = reinterpret_cast<float*>(base);
     uint32_t* hcount = reinterpret_cast<uint32_t*>(hrec + (size_t)2 * (R > 0 ? R : 1) * HREC_FLOATS);
+    uint32_t* work_counter = hcount + 2 * (size_t)tiles;
     if (include_lf) {
         render_bwd_pix_kernel<true><<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, W, H, background, g.rec, lang_feat,
                                                               im.final_T, im.n_contrib, im.tile_last, dL_dpix, dL_dpix_lf,
-                                                              dL_dpix_depth, hrec, hcount);
+                                                              dL_dpix_depth, hrec, hcount, work_counter);
         LGS_LAUNCH_CHECK();
         prof_mark(PM_RENDER_BWD_PIX, s);
+        if (!env_simt_chan())
+            return launch_render_bwd_chan_tc(W, H, im, dL_dpix, dL_dpix_lf, dL_dpix_depth, hrec, hcount, work_counter, dL_dmean2D,
+                                             dL_dconic, dL_dopacity, dL_dcolor, dL_dlang_feat, dL_ddepth, s);
         render_bwd_chan_kernel<true><<<3 * tiles, 32, 0, s>>>(im.ranges, W, H, (int)grid.x, dL_dpix, dL_dpix_lf, dL_dpix_depth,
                                                               hrec, hcount, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
                                                               dL_dlang_feat, dL_ddepth);
     } else {
         render_bwd_pix_kernel<false><<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, W, H, background, g.rec, lang_feat,
                                                                im.final_T, im.n_contrib, im.tile_last, dL_dpix, dL_dpix_lf,
-                                                               dL_dpix_depth, hrec, hcount);
+                                                               dL_dpix_depth, hrec, hcount, work_counter);
         LGS_LAUNCH_CHECK();
         prof_mark(PM_RENDER_BWD_PIX, s);
         render_bwd_chan_kernel<false><<<tiles, 32, 0, s>>>(im.ranges, W, H, (int)grid.x, dL_dpix, dL_dpix_lf, dL_dpix_depth,
