@@ -104,6 +104,9 @@ int launch_render_fwd(int W, int H, int R, const GeomState& g, const BinningStat
                       ImageState& im, const float* background, const float* lang_feat,
                       float* out_color, float* out_lang_feat, float* out_depth,
                       bool include_lf, cudaStream_t s);
+int launch_render_fwd_tc(int W, int H, const GeomState& g, const BinningState& b, ImageState& im,
+                         const float* background, const float* lang_feat, float* out_color,
+                         float* out_lang_feat, float* out_depth, cudaStream_t s);
 int launch_render_bwd(int P, int W, int H, int R, const GeomState& g, const BinningState& b,
                       const ImageState& im, const float* background, const float* lang_feat,
                       const float* dL_dpix, const float* dL_dpix_lf, const float* dL_dpix_depth,

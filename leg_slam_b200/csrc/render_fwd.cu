@@ -238,10 +238,23 @@ static bool env_no_tma() {
     return v == 1;
 }
 
+// LGS_FWD=simt (environment, read at the first launch) keeps this file's SIMT kernel for the 64-D feature path: a
+// differential-debugging aid for the tensor-core kernel (render_fwd_tc.cu), not a fallback for other hardware.
+static bool env_simt_fwd() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("LGS_FWD");
+        v = (e && e[0] == 's') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 int launch_render_fwd(int W, int H, int R, const GeomState& g, const BinningState& b, ImageState& im,
                       const float* background, const float* lang_feat, float* out_color,
                       float* out_lang_feat, float* out_depth, bool include_lf, cudaStream_t s) {
     (void)R;
+    if (include_lf && !env_simt_fwd())
+        return launch_render_fwd_tc(W, H, g, b, im, background, lang_feat, out_color, out_lang_feat, out_depth, s);
     const dim3 grid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE, 1);
     const bool tma = !env_no_tma();
 #define LGS_FWD_LAUNCH(LFV, TMAV)                                                                        \

@@ -10,6 +10,16 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
+// 3xTF32 operand split without conversions.  kind::tf32 reads the upper 19 bits of each 32-bit operand (the low 13
+// mantissa bits are ignored), so hi = x with those bits cleared is exactly what the tensor core sees, lo = x - hi is
+// exact in fp32, and hi*hi' + hi*lo' + lo*hi' + lo*lo' reproduces x*x' to ~2^-20 relative (lo is itself truncated by
+// the hardware).  Two instructions per element instead of the ~12 of cvt.rna.tf32 (emulated on sm_100a).
+__device__ __forceinline__ void split_trunc4(const float4 x, float4& h, float4& l) {
+    h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
+}
 // byte offset of 16-byte K-chunk c (4 floats) of row r in an R-row operand, canonical K-major / no swizzle:
 // 8-row x 16-byte core matrices, consecutive 8-row groups 128 B apart (SBO), consecutive K-chunks R*16 B apart (LBO)
 __device__ __forceinline__ uint32_t canon_off(int r, int c, int R) { return (uint32_t)(c * (R * 16) + (r >> 3) * 128 + (r & 7) * 16); }
@@ -56,6 +66,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
                  : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t cols) {  // one full warp
