@@ -182,54 +182,34 @@ render_fwd_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
 #pragma unroll 1
             for (int c = 0; c < TF_B / 4; ++c) {
                 const uint32_t m = (vis >> (4 * c)) & 15u;
-                float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (m != 0) {
-                    float al[4], dep[4];
-                    bool ok[4];
+                float wv[4] = {0.f, 0.f, 0.f, 0.f};
+                // one warp-uniform block per Gaussian that touches this warp's pixels: alpha test, T update, colour and
+                // depth on the CUDA cores (forward.cu:337-369; same comparisons, same float ops)
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        al[u] = 0.f;
-                        dep[u] = 0.f;
-                        ok[u] = false;
-                        if (m & (1u << u)) {
-                            const float4 q0 = lds128(recs + (4 * c + u) * 48);       // x, y, depth, id
-                            const float4 q1 = lds128(recs + (4 * c + u) * 48 + 16);  // conic a,b,c, opacity
-                            dep[u] = q0.z;
-                            float dx, dy;
-                            const float power = eval_power(q0.x, q0.y, pxf, pyf, q1.x, q1.y, q1.z, dx, dy);
-                            // forward.cu:342-357 (same comparisons, same float ops)
-                            al[u] = fminf(0.99f, __fmul_rn(q1.w, expf(power)));
-                            ok[u] = !(power > 0.0f) && !(al[u] < 1.0f / 255.0f);
-                        }
+                for (int u = 0; u < 4; ++u) {
+                    if (m & (1u << u)) {
+                        const float4 q0 = lds128(recs + (4 * c + u) * 48);       // x, y, depth, id
+                        const float4 q1 = lds128(recs + (4 * c + u) * 48 + 16);  // conic a,b,c, opacity
+                        const float4 q2 = lds128(recs + (4 * c + u) * 48 + 32);  // r, g, b
+                        float dx, dy;
+                        const float power = eval_power(q0.x, q0.y, pxf, pyf, q1.x, q1.y, q1.z, dx, dy);
+                        const float alpha = fminf(0.99f, __fmul_rn(q1.w, expf(power)));
+                        const bool ok = !(power > 0.0f) && !(alpha < 1.0f / 255.0f) && !done;
+                        const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                        const bool term = ok && test_T < 0.0001f;
+                        done = done || term;
+                        const bool act = ok && !term;
+                        const float w = act ? __fmul_rn(alpha, T) : 0.0f;
+                        wv[u] = w;
+                        C0 = fmaf(w, q2.x, C0);
+                        C1 = fmaf(w, q2.y, C1);
+                        C2 = fmaf(w, q2.z, C2);
+                        Dacc = fmaf(w, q0.z, Dacc);
+                        T = act ? test_T : T;
+                        last_contributor = act ? (uint32_t)(b * TF_B + 4 * c + u + 1) : last_contributor;  // 1-based list position
                     }
-                    float wv[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float test_T = __fmul_rn(T, __fsub_rn(1.0f, al[u]));
-                        bool act = ok[u] && !done;
-                        if (act && test_T < 0.0001f) {
-                            done = true;
-                            act = false;
-                        }
-                        wv[u] = act ? __fmul_rn(al[u], T) : 0.0f;
-                        if (act) {
-                            T = test_T;
-                            last_contributor = (uint32_t)(b * TF_B + 4 * c + u + 1);  // 1-based position in the tile's list
-                        }
-                    }
-                    // colour and depth on the CUDA cores (forward.cu:360-368); untouched Gaussians have w = 0
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (m & (1u << u)) {
-                            const float4 q2 = lds128(recs + (4 * c + u) * 48 + 32);
-                            C0 = fmaf(wv[u], q2.x, C0);
-                            C1 = fmaf(wv[u], q2.y, C1);
-                            C2 = fmaf(wv[u], q2.z, C2);
-                            Dacc = fmaf(wv[u], dep[u], Dacc);
-                        }
-                    }
-                    w4 = make_float4(wv[0], wv[1], wv[2], wv[3]);
                 }
+                const float4 w4 = make_float4(wv[0], wv[1], wv[2], wv[3]);
                 float4 h, l;
                 split_trunc4(w4, h, l);
                 sts128(arow + c * TF_LBO_A, h);
