@@ -84,6 +84,18 @@ int lgs_forward_stage1(
     float tan_fovx, float tan_fovy, int prefiltered,
     char* geom_buffer, int* radii, int* num_rendered_host, void* stream);
 
+/* stage1 with the SH coefficients given as the reference's two parameter tensors features_dc [P,1,3] and
+ * features_rest [P,M-1,3] (gaussian_model.h; M <= 16) instead of their concatenation: the caller skips the
+ * torch::cat the reference runs every iteration (src/gaussian_model.cpp:58-62).  Otherwise identical. */
+int lgs_forward_stage1_split_sh(
+    int P, int D, int M, int W, int H,
+    const float* means3D, const float* features_dc, const float* features_rest,
+    const float* opacities, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+    float tan_fovx, float tan_fovy, int prefiltered,
+    char* geom_buffer, int* radii, int* num_rendered_host, void* stream);
+
 int lgs_forward_stage2(
     int P, int W, int H, int R,
     const float* background, const float* lang_feat,
@@ -118,6 +130,23 @@ int lgs_backward(
     float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
     float* dL_dlang_feat, float* dL_ddepth, float* dL_dmean3D, float* dL_dcov3D,
     float* dL_dsh, float* dL_dscale, float* dL_drot,
+    int include_lang_feat, int zero_outputs, char* bwd_scratch, void* stream);
+/* backward for the split SH layout of lgs_forward_stage1_split_sh: dL/dSH goes to dL_dfeatures_dc [P,1,3] and
+ * dL_dfeatures_rest [P,M-1,3] (what autograd's cat-backward would produce).  accumulate_sh != 0 ADDS the visible
+ * Gaussians' rows to those two arrays (several views per iteration) and leaves culled rows untouched. */
+int lgs_backward_split_sh(
+    int P, int D, int M, int R, int W, int H,
+    const float* background,
+    const float* means3D, const float* features_dc, const float* features_rest,
+    const float* lang_feat, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+    float tan_fovx, float tan_fovy, const int* radii,
+    const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
+    const float* dL_dpix, const float* dL_dpix_lf, const float* dL_dpix_depth,
+    float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+    float* dL_dlang_feat, float* dL_ddepth, float* dL_dmean3D, float* dL_dcov3D,
+    float* dL_dfeatures_dc, float* dL_dfeatures_rest, int accumulate_sh, float* dL_dscale, float* dL_drot,
     int include_lang_feat, int zero_outputs, char* bwd_scratch, void* stream);
 /* bytes of bwd_scratch for a backward over R instances of a WxH image (544 B/instance + 8 B/tile) */
 size_t lgs_backward_scratch_bytes(int R, int W, int H);
@@ -193,8 +222,10 @@ int lgs_dp_adam_shard(int n_seg, const int64_t* seg_start, const double* lr, int
 /* ---- activations  (reference src/gaussian_model.cpp:46-68) ---------------
  * forward : scales = exp(scaling) [P,3], rotations = normalize(rotation) [P,4], opacities =
  *           sigmoid(opacity) [P,1], shs = cat(features_dc [P,1,3], features_rest [P,n_rest,3]) [P,1+n_rest,3]
+ *           (shs == NULL skips the cat: callers of the *_split_sh entry points do not need it)
  * backward: raw-parameter gradients from the gradients w.r.t. those four tensors (what autograd
- *           computes through exp / F.normalize / sigmoid / cat); accumulate != 0 adds to the outputs. */
+ *           computes through exp / F.normalize / sigmoid / cat); accumulate != 0 adds to the outputs;
+ *           dL_dshs == NULL skips the cat backward. */
 int lgs_activations_fwd(int P, int n_rest, const float* scaling, const float* rotation, const float* opacity,
                         const float* features_dc, const float* features_rest, float* scales, float* rotations,
                         float* opacities, float* shs, void* stream);

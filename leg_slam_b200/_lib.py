@@ -38,9 +38,13 @@ SIGNATURES = {
     "lgs_binning_bytes": (c_size_t, [c_int]),
     "lgs_forward_stage1": (c_int, [c_int, c_int, c_int, c_int, c_int] + [c_void_p] * 5 + [c_float] +
                            [c_void_p] * 5 + [c_float, c_float, c_int] + [c_void_p] * 4),
+    "lgs_forward_stage1_split_sh": (c_int, [c_int, c_int, c_int, c_int, c_int] + [c_void_p] * 5 + [c_float] +
+                                    [c_void_p] * 5 + [c_float, c_float, c_int] + [c_void_p] * 4),
     "lgs_forward_stage2": (c_int, [c_int, c_int, c_int, c_int] + [c_void_p] * 8 + [c_int, c_void_p]),
     "lgs_backward": (c_int, [c_int] * 6 + [c_void_p] * 6 + [c_float] + [c_void_p] * 5 + [c_float, c_float] +
                      [c_void_p] * 18 + [c_int, c_int, c_void_p, c_void_p]),
+    "lgs_backward_split_sh": (c_int, [c_int] * 6 + [c_void_p] * 6 + [c_float] + [c_void_p] * 5 + [c_float, c_float] +
+                              [c_void_p] * 17 + [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "lgs_backward_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
     "lgs_mark_visible": (c_int, [c_int] + [c_void_p] * 5),
     "lgs_view_binning": (c_int, [c_void_p, c_int, ctypes.POINTER(BinningView)]),

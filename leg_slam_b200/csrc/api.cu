@@ -74,12 +74,12 @@ size_t lgs_binning_bytes(int R) {
 }
 
 // ---- forward ---------------------------------------------------------------------------
-int lgs_forward_stage1(int P, int D, int M, int W, int H, const float* means3D, const float* shs,
-                       const float* colors_precomp, const float* opacities, const float* scales,
-                       float scale_modifier, const float* rotations, const float* cov3D_precomp,
-                       const float* viewmatrix, const float* projmatrix, const float* cam_pos,
-                       float tan_fovx, float tan_fovy, int prefiltered, char* geom_buffer, int* radii,
-                       int* num_rendered_host, void* stream) {
+static int forward_stage1_impl(int P, int D, int M, int W, int H, const float* means3D, const float* shs,
+                               const float* shs_rest, const float* colors_precomp, const float* opacities,
+                               const float* scales, float scale_modifier, const float* rotations,
+                               const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                               const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered, char* geom_buffer,
+                               int* radii, int* num_rendered_host, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (!num_rendered_host) return LGS_ERR_INVALID_ARG;
     *num_rendered_host = 0;
@@ -90,12 +90,12 @@ int lgs_forward_stage1(int P, int D, int M, int W, int H, const float* means3D, 
     if (!colors_precomp && (!cam_pos || M < (D + 1) * (D + 1))) return LGS_ERR_INVALID_ARG;
     if (!cov3D_precomp && (!scales || !rotations)) return LGS_ERR_NO_COV;
     if (rotations && !aligned16(rotations)) return LGS_ERR_ALIGNMENT;
-    if (shs && !aligned16(shs)) return LGS_ERR_ALIGNMENT;
+    if (shs && !shs_rest && !aligned16(shs)) return LGS_ERR_ALIGNMENT;
 
     GeomState g = geom_from_chunk(geom_buffer, P);
     if (!radii) radii = g.internal_radii;
     prof_mark(PM_S1_BEGIN, s);
-    int st = launch_preprocess(P, D, M, means3D, shs, colors_precomp, opacities, scales, scale_modifier,
+    int st = launch_preprocess(P, D, M, means3D, shs, shs_rest, colors_precomp, opacities, scales, scale_modifier,
                                rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, W, H, tan_fovx,
                                tan_fovy, prefiltered, g, radii, s);
     if (st != LGS_OK) return st;
@@ -109,6 +109,30 @@ int lgs_forward_stage1(int P, int D, int M, int W, int H, const float* means3D, 
     LGS_CUDA_TRY(cudaStreamSynchronize(s));
     *num_rendered_host = (int)R;
     return LGS_OK;
+}
+
+int lgs_forward_stage1(int P, int D, int M, int W, int H, const float* means3D, const float* shs,
+                       const float* colors_precomp, const float* opacities, const float* scales,
+                       float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                       const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                       float tan_fovx, float tan_fovy, int prefiltered, char* geom_buffer, int* radii,
+                       int* num_rendered_host, void* stream) {
+    return forward_stage1_impl(P, D, M, W, H, means3D, shs, nullptr, colors_precomp, opacities, scales, scale_modifier,
+                               rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy, prefiltered,
+                               geom_buffer, radii, num_rendered_host, stream);
+}
+
+int lgs_forward_stage1_split_sh(int P, int D, int M, int W, int H, const float* means3D, const float* features_dc,
+                                const float* features_rest, const float* opacities, const float* scales,
+                                float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                                const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                                float tan_fovy, int prefiltered, char* geom_buffer, int* radii, int* num_rendered_host,
+                                void* stream) {
+    if (!features_dc || M < 1 || M > 16 || (M > 1 && !features_rest)) return LGS_ERR_INVALID_ARG;
+    static const float no_rest[4] = {0.f, 0.f, 0.f, 0.f};  // M == 1: the rest pointer only selects the split layout
+    return forward_stage1_impl(P, D, M, W, H, means3D, features_dc, M > 1 ? features_rest : no_rest, nullptr, opacities,
+                               scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx,
+                               tan_fovy, prefiltered, geom_buffer, radii, num_rendered_host, stream);
 }
 
 int lgs_forward_stage2(int P, int W, int H, int R, const float* background, const float* lang_feat,
@@ -147,16 +171,16 @@ int lgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const
 }
 
 // ---- backward --------------------------------------------------------------------------
-int lgs_backward(int P, int D, int M, int R, int W, int H, const float* background, const float* means3D,
-                 const float* shs, const float* colors_precomp, const float* lang_feat, const float* scales,
+static int backward_impl(int P, int D, int M, int R, int W, int H, const float* background, const float* means3D,
+                 const float* shs, const float* shs_rest, const float* colors_precomp, const float* lang_feat, const float* scales,
                  float scale_modifier, const float* rotations, const float* cov3D_precomp,
                  const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
                  float tan_fovy, const int* radii, const char* geom_buffer, const char* binning_buffer,
                  const char* image_buffer, const float* dL_dpix, const float* dL_dpix_lf,
                  const float* dL_dpix_depth, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
                  float* dL_dcolor, float* dL_dlang_feat, float* dL_ddepth, float* dL_dmean3D,
-                 float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, int include_lang_feat,
-                 int zero_outputs, char* bwd_scratch, void* stream) {
+                 float* dL_dcov3D, float* dL_dsh, float* dL_dsh_rest, int accumulate_sh, float* dL_dscale, float* dL_drot,
+                 int include_lang_feat, int zero_outputs, char* bwd_scratch, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (P < 0 || W <= 0 || H <= 0 || R < 0 || D < 0 || D > 3) return LGS_ERR_INVALID_ARG;
     if (P == 0) return LGS_OK;
@@ -203,12 +227,51 @@ int lgs_backward(int P, int D, int M, int R, int W, int H, const float* backgrou
     }
     prof_mark(PM_RENDER_BWD, s);
     const float* cov3D = cov3D_precomp ? cov3D_precomp : g.cov3D;
-    st = launch_preprocess_bwd(P, D, M, means3D, radii, shs, scales, rotations, scale_modifier, cov3D,
-                                 viewmatrix, projmatrix, cam_pos, W, H, tan_fovx, tan_fovy, g, dL_dmean2D,
-                               dL_dconic, dL_dmean3D, dL_dcolor, dL_dcov3D, dL_dsh, dL_dscale, dL_drot,
-                               zero_outputs != 0, s);
+    st = launch_preprocess_bwd(P, D, M, means3D, radii, shs, shs_rest, scales, rotations, scale_modifier, cov3D,
+                               viewmatrix, projmatrix, cam_pos, W, H, tan_fovx, tan_fovy, g, dL_dmean2D,
+                               dL_dconic, dL_dmean3D, dL_dcolor, dL_dcov3D, dL_dsh, dL_dsh_rest, accumulate_sh != 0,
+                               dL_dscale, dL_drot, zero_outputs != 0, s);
     prof_mark(PM_PREPROCESS_BWD, s);
     return st;
+}
+
+int lgs_backward(int P, int D, int M, int R, int W, int H, const float* background, const float* means3D,
+                 const float* shs, const float* colors_precomp, const float* lang_feat, const float* scales,
+                 float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                 const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                 float tan_fovy, const int* radii, const char* geom_buffer, const char* binning_buffer,
+                 const char* image_buffer, const float* dL_dpix, const float* dL_dpix_lf,
+                 const float* dL_dpix_depth, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                 float* dL_dcolor, float* dL_dlang_feat, float* dL_ddepth, float* dL_dmean3D,
+                 float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, int include_lang_feat,
+                 int zero_outputs, char* bwd_scratch, void* stream) {
+    return backward_impl(P, D, M, R, W, H, background, means3D, shs, nullptr, colors_precomp, lang_feat, scales,
+                         scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy, radii,
+                         geom_buffer, binning_buffer, image_buffer, dL_dpix, dL_dpix_lf, dL_dpix_depth, dL_dmean2D, dL_dconic,
+                         dL_dopacity, dL_dcolor, dL_dlang_feat, dL_ddepth, dL_dmean3D, dL_dcov3D, dL_dsh, nullptr, 0,
+                         dL_dscale, dL_drot, include_lang_feat, zero_outputs, bwd_scratch, stream);
+}
+
+int lgs_backward_split_sh(int P, int D, int M, int R, int W, int H, const float* background, const float* means3D,
+                          const float* features_dc, const float* features_rest, const float* lang_feat,
+                          const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                          const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                          float tan_fovy, const int* radii, const char* geom_buffer, const char* binning_buffer,
+                          const char* image_buffer, const float* dL_dpix, const float* dL_dpix_lf,
+                          const float* dL_dpix_depth, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                          float* dL_dcolor, float* dL_dlang_feat, float* dL_ddepth, float* dL_dmean3D, float* dL_dcov3D,
+                          float* dL_dfeatures_dc, float* dL_dfeatures_rest, int accumulate_sh, float* dL_dscale,
+                          float* dL_drot, int include_lang_feat, int zero_outputs, char* bwd_scratch, void* stream) {
+    if (!features_dc || !dL_dfeatures_dc || M < 1 || M > 16 || (M > 1 && (!features_rest || !dL_dfeatures_rest)))
+        return LGS_ERR_INVALID_ARG;
+    static const float no_rest[4] = {0.f, 0.f, 0.f, 0.f};
+    // M == 1: any non-NULL rest pointers select the split layout; they are never dereferenced (row = 3)
+    return backward_impl(P, D, M, R, W, H, background, means3D, features_dc, M > 1 ? features_rest : no_rest, nullptr,
+                         lang_feat, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos,
+                         tan_fovx, tan_fovy, radii, geom_buffer, binning_buffer, image_buffer, dL_dpix, dL_dpix_lf,
+                         dL_dpix_depth, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dlang_feat, dL_ddepth, dL_dmean3D,
+                         dL_dcov3D, dL_dfeatures_dc, M > 1 ? dL_dfeatures_rest : dL_dfeatures_dc, accumulate_sh, dL_dscale,
+                         dL_drot, include_lang_feat, zero_outputs, bwd_scratch, stream);
 }
 
 // ---- per-stage timing ------------------------------------------------------------------

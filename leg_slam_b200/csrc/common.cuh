@@ -89,7 +89,7 @@ struct ViewParams {
     int W, H, tiles_x, tiles_y;
 };
 
-int launch_preprocess(int P, int D, int M, const float* means3D, const float* shs,
+int launch_preprocess(int P, int D, int M, const float* means3D, const float* shs, const float* shs_rest,
                       const float* colors_precomp, const float* opacities, const float* scales,
                       float scale_modifier, const float* rotations, const float* cov3D_precomp,
                       const float* viewmatrix, const float* projmatrix, const float* cam_pos,
@@ -118,13 +118,13 @@ int launch_render_bwd_chan_tc(int W, int H, const ImageState& im, const float* d
                               float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
                               float* dL_dlang_feat, float* dL_ddepth, cudaStream_t s);
 int launch_preprocess_bwd(int P, int D, int M, const float* means3D, const int* radii,
-                          const float* shs, const float* scales, const float* rotations,
+                          const float* shs, const float* shs_rest, const float* scales, const float* rotations,
                           float scale_modifier, const float* cov3D, const float* viewmatrix,
                           const float* projmatrix, const float* cam_pos, int W, int H,
                           float tan_fovx, float tan_fovy, const GeomState& g,
                           float* dL_dmean2D, float* dL_dconic, float* dL_dmean3D,
-                          const float* dL_dcolor, float* dL_dcov3D, float* dL_dsh,
-                          float* dL_dscale, float* dL_drot, bool write_zeros, cudaStream_t s);
+                          const float* dL_dcolor, float* dL_dcov3D, float* dL_dsh, float* dL_dsh_rest,
+                          bool accumulate_sh, float* dL_dscale, float* dL_drot, bool write_zeros, cudaStream_t s);
 int launch_zero_grads(int P, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
                       float* dL_dcolor, float* dL_dlang_feat, float* dL_ddepth, bool include_lf,
                       cudaStream_t s);

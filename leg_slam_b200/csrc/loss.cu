@@ -363,13 +363,13 @@ extern "C" int lgs_activations_fwd(int P, int n_rest, const float* scaling, cons
                                    float* opacities, float* shs, void* stream) {
     if (P < 0 || n_rest < 0) return LGS_ERR_INVALID_ARG;
     if (P == 0) return LGS_OK;
-    if (!scaling || !rotation || !opacity || !features_dc || (n_rest > 0 && !features_rest) || !scales || !rotations ||
-        !opacities || !shs)
-        return LGS_ERR_INVALID_ARG;
+    if (!scaling || !rotation || !opacity || !scales || !rotations || !opacities) return LGS_ERR_INVALID_ARG;
+    if (shs && (!features_dc || (n_rest > 0 && !features_rest))) return LGS_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(rotation) | reinterpret_cast<uintptr_t>(rotations)) & 15u) return LGS_ERR_ALIGNMENT;
     activations_fwd_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, scaling, rotation, opacity, scales, rotations,
                                                                               opacities);
     LGS_LAUNCH_CHECK();
+    if (!shs) return LGS_OK;
     const int row = 3 * (n_rest + 1);
     const long long n = (long long)P * row;
     const int grid = (int)((n + 255) / 256 < 148LL * 32 ? (n + 255) / 256 : 148LL * 32);
@@ -385,9 +385,10 @@ extern "C" int lgs_activations_bwd(int P, int n_rest, int accumulate, const floa
                                    float* dL_dopacity, float* dL_dfeatures_dc, float* dL_dfeatures_rest, void* stream) {
     if (P < 0 || n_rest < 0) return LGS_ERR_INVALID_ARG;
     if (P == 0) return LGS_OK;
-    if (!rotation || !scales || !opacities || !dL_dscales || !dL_drotations || !dL_dopacities || !dL_dshs || !dL_dscaling ||
-        !dL_drotation || !dL_dopacity || !dL_dfeatures_dc || (n_rest > 0 && !dL_dfeatures_rest))
+    if (!rotation || !scales || !opacities || !dL_dscales || !dL_drotations || !dL_dopacities || !dL_dscaling ||
+        !dL_drotation || !dL_dopacity)
         return LGS_ERR_INVALID_ARG;
+    if (dL_dshs && (!dL_dfeatures_dc || (n_rest > 0 && !dL_dfeatures_rest))) return LGS_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(rotation) | reinterpret_cast<uintptr_t>(dL_drotations) |
          reinterpret_cast<uintptr_t>(dL_drotation)) & 15u)
         return LGS_ERR_ALIGNMENT;
@@ -395,6 +396,7 @@ extern "C" int lgs_activations_bwd(int P, int n_rest, int accumulate, const floa
         P, accumulate, rotation, scales, opacities, dL_dscales, dL_drotations, dL_dopacities, dL_dscaling, dL_drotation,
         dL_dopacity);
     LGS_LAUNCH_CHECK();
+    if (!dL_dshs) return LGS_OK;
     const int row = 3 * (n_rest + 1);
     const long long n = (long long)P * row;
     const int grid = (int)((n + 255) / 256 < 148LL * 32 ? (n + 255) / 256 : 148LL * 32);

@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(256)
 preprocess_kernel(int P, int D, int M,
                   const float* __restrict__ means, const float* __restrict__ scales, float mod,
                   const float* __restrict__ rots, const float* __restrict__ opac,
-                  const float* __restrict__ shs, const float* __restrict__ cov3D_pre,
+                  const float* __restrict__ shs, const float* __restrict__ shs_rest,
+                  const float* __restrict__ cov3D_pre,
                   const float* __restrict__ colors_pre, const float* __restrict__ view,
                   const float* __restrict__ proj, const float* __restrict__ campos,
                   int W, int H, float tan_fovx, float tan_fovy, float focal_x, float focal_y,
@@ -242,9 +243,23 @@ preprocess_kernel(int P, int D, int M,
         float basis[16];
         sh_basis(D, dx, dy, dz, basis);
         const int ncoef = (D + 1) * (D + 1);
-        const float* sh = shs + (size_t)idx * M * 3;
         float acc[3] = {0.f, 0.f, 0.f};
-        if (M == 16 && ncoef == 16) {
+        if (shs_rest != nullptr) {
+            // split layout: coefficient 0 in features_dc [P,1,3], coefficients 1.. in features_rest [P,M-1,3]
+            // (the reference's two parameter tensors, gaussian_model.cpp:58-62, without the per-iteration cat)
+            const float* d0 = shs + (size_t)idx * 3;
+            const float* rs = shs_rest + (size_t)idx * (M - 1) * 3;
+            acc[0] = basis[0] * __ldg(d0 + 0);
+            acc[1] = basis[0] * __ldg(d0 + 1);
+            acc[2] = basis[0] * __ldg(d0 + 2);
+#pragma unroll 5
+            for (int k = 1; k < ncoef; ++k) {
+                acc[0] += basis[k] * __ldg(rs + 3 * (k - 1) + 0);
+                acc[1] += basis[k] * __ldg(rs + 3 * (k - 1) + 1);
+                acc[2] += basis[k] * __ldg(rs + 3 * (k - 1) + 2);
+            }
+        } else if (M == 16 && ncoef == 16) {
+            const float* sh = shs + (size_t)idx * M * 3;
             const float4* sh4 = reinterpret_cast<const float4*>(sh);  // 192-byte row
             float v[48];
 #pragma unroll
@@ -259,6 +274,7 @@ preprocess_kernel(int P, int D, int M,
                 acc[2] += basis[k] * v[3 * k + 2];
             }
         } else {
+            const float* sh = shs + (size_t)idx * M * 3;
             for (int k = 0; k < ncoef; ++k) {
                 acc[0] += basis[k] * sh[3 * k + 0];
                 acc[1] += basis[k] * sh[3 * k + 1];
@@ -291,7 +307,7 @@ mark_visible_kernel(int P, const float* __restrict__ means, const float* __restr
     present[idx] = !(depth <= 0.2f) ? 1 : 0;
 }
 
-int launch_preprocess(int P, int D, int M, const float* means3D, const float* shs,
+int launch_preprocess(int P, int D, int M, const float* means3D, const float* shs, const float* shs_rest,
                       const float* colors_precomp, const float* opacities, const float* scales,
                       float scale_modifier, const float* rotations, const float* cov3D_precomp,
                       const float* viewmatrix, const float* projmatrix, const float* cam_pos,
@@ -302,7 +318,7 @@ int launch_preprocess(int P, int D, int M, const float* means3D, const float* sh
     const float focal_x = W / (2.0f * tan_fovx);
     const int tiles_x = (W + TILE - 1) / TILE, tiles_y = (H + TILE - 1) / TILE;
     preprocess_kernel<<<(P + 255) / 256, 256, 0, s>>>(
-        P, D, M, means3D, scales, scale_modifier, rotations, opacities, shs, cov3D_precomp,
+        P, D, M, means3D, scales, scale_modifier, rotations, opacities, shs, shs_rest, cov3D_precomp,
         colors_precomp, viewmatrix, projmatrix, cam_pos, W, H, tan_fovx, tan_fovy, focal_x, focal_y,
         tiles_x, tiles_y, radii == g.internal_radii ? nullptr : radii, g.internal_radii, g.rec, g.cov3D,
         g.clamped, g.tiles_touched);

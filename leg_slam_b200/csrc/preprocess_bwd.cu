@@ -30,7 +30,8 @@ __device__ __forceinline__ V3 ld3(const float* p) { return V3{p[0], p[1], p[2]};
 __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 
 // dL/dsh rows and d(colour)/d(direction), reference backward.cu:20-139
-__device__ __forceinline__ V3 sh_backward(int deg, int M, const float* __restrict__ sh, V3 dir_orig, V3 dL_dRGB,
+// sh1 points at coefficient 1 of the Gaussian's row (coefficient 0 has no direction derivative)
+__device__ __forceinline__ V3 sh_backward(int deg, int M, const float* __restrict__ sh1, V3 dir_orig, V3 dL_dRGB,
                                           float* __restrict__ dL_dsh) {
     const float inv_len = 1.0f / sqrtf(dot(dir_orig, dir_orig));
     const float x = dir_orig.x * inv_len, y = dir_orig.y * inv_len, z = dir_orig.z * inv_len;
@@ -41,9 +42,9 @@ __device__ __forceinline__ V3 sh_backward(int deg, int M, const float* __restric
         dL_dsh[3 * k + 2] = w * dL_dRGB.z;
     };
     auto axpy = [&](V3& acc, float w, int k) {
-        acc.x = fmaf(w, sh[3 * k + 0], acc.x);
-        acc.y = fmaf(w, sh[3 * k + 1], acc.y);
-        acc.z = fmaf(w, sh[3 * k + 2], acc.z);
+        acc.x = fmaf(w, sh1[3 * (k - 1) + 0], acc.x);
+        acc.y = fmaf(w, sh1[3 * (k - 1) + 1], acc.y);
+        acc.z = fmaf(w, sh1[3 * (k - 1) + 2], acc.z);
     };
     st(0, 0.28209479177387814f);
     if (deg > 0) {
@@ -102,7 +103,8 @@ constexpr int PB_ROW = 48;  // 16 SH coefficients x 3 channels
 
 __global__ void __launch_bounds__(PB_THREADS)
 preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means, const int* __restrict__ radii,
-                      const float* __restrict__ shs, const uint8_t* __restrict__ clamped,
+                      const float* __restrict__ shs, const float* __restrict__ shs_rest,
+                      const uint8_t* __restrict__ clamped,
                       const float* __restrict__ scales, const float* __restrict__ rots, float mod,
                       const float* __restrict__ cov3Ds, const float* __restrict__ view,
                       const float* __restrict__ proj, const float* __restrict__ campos, float h_x, float h_y,
@@ -110,6 +112,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means, cons
                       float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconics,
                       const float* __restrict__ dL_dcolor,
                       float* __restrict__ dL_dmeans, float* __restrict__ dL_dcov, float* __restrict__ dL_dsh,
+                      float* __restrict__ dL_dsh_rest, bool accumulate_sh,
                       float* __restrict__ dL_dscale, float* __restrict__ dL_drot, bool write_zeros) {
     __shared__ float sV[16], sP[16];
     // dL_dsh rows (up to 48 floats per Gaussian) are staged here and flushed by the whole warp, so the
@@ -127,7 +130,7 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means, cons
         dL_dmeans[3 * idx + 0] = 0.f; dL_dmeans[3 * idx + 1] = 0.f; dL_dmeans[3 * idx + 2] = 0.f;
 #pragma unroll
         for (int i = 0; i < 6; ++i) dL_dcov[6 * (size_t)idx + i] = 0.f;
-        if (shs != nullptr) {
+        if (shs != nullptr && !accumulate_sh) {
             if (stage_sh) {
                 for (int i = 0; i < row; ++i) s_sh[threadIdx.x][i] = 0.f;
                 sh_written = true;
@@ -244,7 +247,8 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means, cons
         if (cl & 2) dRGB.y = 0.f;
         if (cl & 4) dRGB.z = 0.f;
         const V3 dir{mean.x - campos[0], mean.y - campos[1], mean.z - campos[2]};
-        const V3 dm = sh_backward(D, M, shs + (size_t)idx * 3 * M, dir, dRGB,
+        const float* sh1 = shs_rest != nullptr ? shs_rest + (size_t)idx * 3 * (M - 1) : shs + (size_t)idx * 3 * M + 3;
+        const V3 dm = sh_backward(D, M, sh1, dir, dRGB,
                                   stage_sh ? &s_sh[threadIdx.x][0] : dL_dsh + (size_t)idx * 3 * M);
         sh_written = stage_sh;
         dmean.x += dm.x; dmean.y += dm.y; dmean.z += dm.z;
@@ -302,24 +306,34 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means, cons
         const long long gbase = ((long long)blockIdx.x * blockDim.x + w0) * row;
         for (int i = lane; i < 32 * row; i += 32) {
             const int r = i / row, c = i - r * row;
-            if ((wmask >> r) & 1u) dL_dsh[gbase + i] = s_sh[w0 + r][c];
+            if ((wmask >> r) & 1u) {
+                // split layout (dL_dsh_rest != NULL): coefficient 0 -> dL_dsh [P,1,3], the rest -> dL_dsh_rest [P,M-1,3]
+                float* dst = dL_dsh + gbase + i;
+                if (dL_dsh_rest != nullptr) {
+                    const long long gi = (long long)blockIdx.x * blockDim.x + w0 + r;
+                    dst = c < 3 ? dL_dsh + gi * 3 + c : dL_dsh_rest + gi * (row - 3) + (c - 3);
+                }
+                const float v = s_sh[w0 + r][c];
+                *dst = accumulate_sh ? *dst + v : v;
+            }
         }
     }
 }
 
 int launch_preprocess_bwd(int P, int D, int M, const float* means3D, const int* radii, const float* shs,
-                          const float* scales, const float* rotations, float scale_modifier, const float* cov3D,
+                          const float* shs_rest, const float* scales, const float* rotations, float scale_modifier, const float* cov3D,
                           const float* viewmatrix, const float* projmatrix, const float* cam_pos, int W, int H,
                           float tan_fovx, float tan_fovy, const GeomState& g, float* dL_dmean2D,
                           float* dL_dconic, float* dL_dmean3D, const float* dL_dcolor, float* dL_dcov3D,
-                          float* dL_dsh, float* dL_dscale, float* dL_drot, bool write_zeros, cudaStream_t s) {
+                          float* dL_dsh, float* dL_dsh_rest, bool accumulate_sh, float* dL_dscale, float* dL_drot,
+                          bool write_zeros, cudaStream_t s) {
     const float focal_y = H / (2.0f * tan_fovy);  // rasterizer_impl.cu:392-393
     const float focal_x = W / (2.0f * tan_fovx);
     preprocess_bwd_kernel<<<(P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, 0, s>>>(
-        P, D, M, means3D, radii, shs, g.clamped, scales, rotations, scale_modifier, cov3D, viewmatrix, projmatrix,
+        P, D, M, means3D, radii, shs, shs_rest, g.clamped, scales, rotations, scale_modifier, cov3D, viewmatrix, projmatrix,
         cam_pos, focal_x, focal_y, tan_fovx, tan_fovy, g.rec, 0.5f * (float)W, 0.5f * (float)H, dL_dmean2D, dL_dconic,
         dL_dcolor, dL_dmean3D, dL_dcov3D,
-        dL_dsh, dL_dscale, dL_drot, write_zeros);
+        dL_dsh, dL_dsh_rest, accumulate_sh, dL_dscale, dL_drot, write_zeros);
     LGS_LAUNCH_CHECK();
     return LGS_OK;
 }

@@ -13,9 +13,11 @@ def _s(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
-def activations_fwd(params, out=None):
+def activations_fwd(params, out=None, cat_sh=True):
     """raw parameter dict (xyz, features_dc, features_rest, lang_feat, opacity, scaling, rotation) ->
-    dict(means3D, shs, lang_feats, opacities, scales, rotations); `out` reuses the four computed tensors."""
+    dict(means3D, shs, lang_feats, opacities, scales, rotations); `out` reuses the four computed tensors.
+    cat_sh=False skips the SH concatenation (shs is None): the split-SH rasterizer entry points read
+    features_dc / features_rest in place."""
     L = _lib.lib()
     P = params["xyz"].shape[0]
     n_rest = params["features_rest"].shape[1]
@@ -23,24 +25,27 @@ def activations_fwd(params, out=None):
     if out is None:
         f = dict(dtype=torch.float32, device=dev)
         out = dict(scales=torch.empty(P, 3, **f), rotations=torch.empty(P, 4, **f), opacities=torch.empty(P, 1, **f),
-                   shs=torch.empty(P, n_rest + 1, 3, **f))
+                   shs=torch.empty(P, n_rest + 1, 3, **f) if cat_sh else None)
     with torch.cuda.device(dev):
         check(L.lgs_activations_fwd(P, n_rest, ptr(params["scaling"]), ptr(params["rotation"]), ptr(params["opacity"]),
                                     ptr(params["features_dc"]), ptr(params["features_rest"]), ptr(out["scales"]),
-                                    ptr(out["rotations"]), ptr(out["opacities"]), ptr(out["shs"]), _s(params["xyz"])),
+                                    ptr(out["rotations"]), ptr(out["opacities"]), ptr(out["shs"]) if cat_sh else None,
+                                    _s(params["xyz"])),
               "lgs_activations_fwd")
-    return dict(means3D=params["xyz"], shs=out["shs"], lang_feats=params["lang_feat"], opacities=out["opacities"],
+    return dict(means3D=params["xyz"], shs=out["shs"] if cat_sh else None, lang_feats=params["lang_feat"], opacities=out["opacities"],
                 scales=out["scales"], rotations=out["rotations"])
 
 
 def activations_bwd(params, act, g_scales, g_rotations, g_opacities, g_shs, out, accumulate=False):
-    """Gradients of the raw parameters into out[scaling|rotation|opacity|features_dc|features_rest]."""
+    """Gradients of the raw parameters into out[scaling|rotation|opacity|features_dc|features_rest];
+    g_shs=None skips the SH part (already written by the split-SH backward)."""
     L = _lib.lib()
     P = params["xyz"].shape[0]
     n_rest = params["features_rest"].shape[1]
     with torch.cuda.device(params["xyz"].device):
         check(L.lgs_activations_bwd(P, n_rest, int(accumulate), ptr(params["rotation"]), ptr(act["scales"]),
-                                    ptr(act["opacities"]), ptr(g_scales), ptr(g_rotations), ptr(g_opacities), ptr(g_shs),
+                                    ptr(act["opacities"]), ptr(g_scales), ptr(g_rotations), ptr(g_opacities),
+                                    None if g_shs is None else ptr(g_shs),
                                     ptr(out["scaling"]), ptr(out["rotation"]), ptr(out["opacity"]), ptr(out["features_dc"]),
                                     ptr(out["features_rest"]), _s(params["xyz"])), "lgs_activations_bwd")
 

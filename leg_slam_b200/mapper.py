@@ -200,12 +200,14 @@ class Mapper:
         if self._fbuf is None:
             f = dict(dtype=torch.float32, device=dev)
             self._fbuf = dict(act=dict(scales=torch.empty(P, 3, **f), rotations=torch.empty(P, 4, **f),
-                                       opacities=torch.empty(P, 1, **f), shs=torch.empty(P, n_rest + 1, 3, **f)),
-                              tmp=rp.backward_outputs(P, n_rest + 1, dev, True, True, True),
+                                       opacities=torch.empty(P, 1, **f), shs=None),
+                              tmp=rp.backward_outputs(P, 0, dev, True, False, True),
                               empty=torch.empty(0, **f))
         fb = self._fbuf
         e = fb["empty"]
-        a = fused_mod.activations_fwd(p, out=fb["act"])  # parameters do not change between the views of a step
+        # parameters do not change between the views of a step.  No SH cat: the rasterizer reads features_dc /
+        # features_rest in place and writes their gradients straight into the flat buffer (split-SH entry points)
+        a = fused_mod.activations_fwd(p, out=fb["act"], cat_sh=False)
         gv = self.grads.views
         total = None
         for n_done, i in enumerate(mine):
@@ -213,22 +215,23 @@ class Mapper:
             cam = kf.camera
             R, color, lf, depth, radii, geom, binning, img = rp.rasterize_gaussians(
                 self.bg, a["means3D"], e, a["lang_feats"], a["opacities"], a["scales"], a["rotations"], 1.0, e,
-                cam.viewmatrix, cam.projmatrix, cam.tanfovx, cam.tanfovy, cam.height, cam.width, a["shs"], self.sh_degree,
-                cam.campos, False, True)
+                cam.viewmatrix, cam.projmatrix, cam.tanfovx, cam.tanfovy, cam.height, cam.width, p["features_dc"],
+                self.sh_degree, cam.campos, False, True, sh_rest=p["features_rest"])
             loss, gi, gl, gd = self._fused_loss(color, lf, depth, kf.gt_image, kf.gt_lf, kf.gt_depth, kf.mask)
             first = n_done == 0
             out = dict(fb["tmp"])
+            out["dL_dfeatures_dc"], out["dL_dfeatures_rest"] = gv["features_dc"], gv["features_rest"]
             if first:  # xyz and language-feature gradients need no activation backward: write them in place
                 out["dL_dmeans3D"], out["dL_dlang_feats"] = gv["xyz"], gv["lang_feat"]
             rp.rasterize_gaussians_backward_into(
                 out, self.bg, a["means3D"], radii, e, a["lang_feats"], a["scales"], a["rotations"], 1.0, e, cam.viewmatrix,
-                cam.projmatrix, cam.tanfovx, cam.tanfovy, gi, gl, gd, a["shs"], self.sh_degree, cam.campos, geom, R, binning,
-                img, True)
+                cam.projmatrix, cam.tanfovx, cam.tanfovy, gi, gl, gd, p["features_dc"], self.sh_degree, cam.campos, geom, R,
+                binning, img, True, sh_rest=p["features_rest"], accumulate_sh=not first)
             if not first:
                 gv["xyz"].add_(out["dL_dmeans3D"])
                 gv["lang_feat"].add_(out["dL_dlang_feats"])
-            fused_mod.activations_bwd(p, a, out["dL_dscales"], out["dL_drotations"], out["dL_dopacity"], out["dL_dsh"],
-                                      gv, accumulate=not first)
+            fused_mod.activations_bwd(p, a, out["dL_dscales"], out["dL_drotations"], out["dL_dopacity"], None, gv,
+                                      accumulate=not first)
             l0 = loss[0:1].clone().reshape(())
             total = l0 if total is None else total + l0
             self.last_num_rendered = R

@@ -56,9 +56,13 @@ def _f32c(t):
 
 def rasterize_gaussians(background, means3D, colors, lang_feat, opacity, scales, rotations, scale_modifier,
                         cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width,
-                        sh, degree, campos, prefiltered, include_lang_feat):
+                        sh, degree, campos, prefiltered, include_lang_feat, sh_rest=None):
     """-> (num_rendered, out_color[3,H,W], out_lang_feat[64,H,W], out_depth[1,H,W], radii[P] int32,
-           geomBuffer, binningBuffer, imgBuffer)"""
+           geomBuffer, binningBuffer, imgBuffer)
+
+    `sh_rest` (not in the reference signature): when given, `sh` is features_dc [P,1,3] and `sh_rest` is
+    features_rest [P,M-1,3] -- the reference's two parameter tensors, read in place instead of their
+    per-iteration torch::cat (lgs_forward_stage1_split_sh)."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise ValueError("means3D must have dimensions (num_points, 3)")  # AT_ERROR, rasterize_points.cu:59-61
     L = _lib.lib()
@@ -91,11 +95,20 @@ def rasterize_gaussians(background, means3D, colors, lang_feat, opacity, scales,
     img = torch.empty(L.lgs_image_bytes(W, H), **byte)
     R = ctypes.c_int(0)
     with torch.cuda.device(dev):
-        check(L.lgs_forward_stage1(P, int(degree), M, W, H, ptr(means3D), ptr(sh), ptr(colors), ptr(opacity),
-                                   ptr(scales), float(scale_modifier), ptr(rotations), ptr(cov3D_precomp),
-                                   ptr(viewmatrix), ptr(projmatrix), ptr(campos), float(tan_fovx), float(tan_fovy),
-                                   int(bool(prefiltered)), geom.data_ptr(), radii.data_ptr(), ctypes.byref(R), s),
-              "lgs_forward_stage1")
+        if sh_rest is not None:
+            sh_rest = _f32c(sh_rest)
+            M = 1 + int(sh_rest.size(1))
+            check(L.lgs_forward_stage1_split_sh(P, int(degree), M, W, H, ptr(means3D), ptr(sh), ptr(sh_rest), ptr(opacity),
+                                                ptr(scales), float(scale_modifier), ptr(rotations), ptr(cov3D_precomp),
+                                                ptr(viewmatrix), ptr(projmatrix), ptr(campos), float(tan_fovx),
+                                                float(tan_fovy), int(bool(prefiltered)), geom.data_ptr(), radii.data_ptr(),
+                                                ctypes.byref(R), s), "lgs_forward_stage1_split_sh")
+        else:
+            check(L.lgs_forward_stage1(P, int(degree), M, W, H, ptr(means3D), ptr(sh), ptr(colors), ptr(opacity),
+                                       ptr(scales), float(scale_modifier), ptr(rotations), ptr(cov3D_precomp),
+                                       ptr(viewmatrix), ptr(projmatrix), ptr(campos), float(tan_fovx), float(tan_fovy),
+                                       int(bool(prefiltered)), geom.data_ptr(), radii.data_ptr(), ctypes.byref(R), s),
+                  "lgs_forward_stage1")
         # capacity rounded up so that consecutive iterations (R drifts slowly) reuse the same cached block
         binning = torch.empty(L.lgs_binning_bytes(_round_up(R.value, 1 << 18)), **byte)
         check(L.lgs_forward_stage2(P, W, H, R.value, ptr(background), ptr(lang_feat) if include_lf else None,
@@ -123,9 +136,12 @@ def backward_outputs(P, M, dev, include_lf, has_sh, has_scales):
 def rasterize_gaussians_backward_into(out, background, means3D, radii, colors, lang_feat, scales, rotations,
                                       scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
                                       dL_dout_color, dL_dout_lang_feat, dL_dout_depth, sh, degree, campos, geomBuffer, R,
-                                      binningBuffer, imageBuffer, include_lang_feat):
+                                      binningBuffer, imageBuffer, include_lang_feat, sh_rest=None, accumulate_sh=False):
     """RasterizeGaussiansBackwardCUDA writing into caller-provided tensors `out` (keys of
-    backward_outputs; any contiguous float32 storage, e.g. slices of a flat gradient buffer)."""
+    backward_outputs; any contiguous float32 storage, e.g. slices of a flat gradient buffer).
+
+    Split SH layout (`sh_rest` given, see rasterize_gaussians): dL/dSH is written to out["dL_dfeatures_dc"] [P,1,3]
+    and out["dL_dfeatures_rest"] [P,M-1,3]; `accumulate_sh` adds to them instead of overwriting."""
     L = _lib.lib()
     P = int(means3D.size(0))
     if P == 0:
@@ -139,6 +155,22 @@ def rasterize_gaussians_backward_into(out, background, means3D, radii, colors, l
             _f32c, (background, means3D, colors, lang_feat, scales, rotations, cov3D_precomp, viewmatrix,
                     projmatrix, sh, campos, dL_dout_color, dL_dout_lang_feat, dL_dout_depth))
     scratch = _workspace(dev, _stream(means3D), L.lgs_backward_scratch_bytes(int(R), W, H))
+    if sh_rest is not None:
+        sh_rest = _f32c(sh_rest)
+        M = 1 + int(sh_rest.size(1))
+        with torch.cuda.device(dev):
+            check(L.lgs_backward_split_sh(
+                P, int(degree), M, int(R), W, H, ptr(background), ptr(means3D), ptr(sh), ptr(sh_rest),
+                ptr(lang_feat) if include_lf else None, ptr(scales), float(scale_modifier), ptr(rotations),
+                ptr(cov3D_precomp), ptr(viewmatrix), ptr(projmatrix), ptr(campos), float(tan_fovx), float(tan_fovy),
+                ptr(radii.contiguous()), ptr(geomBuffer), ptr(binningBuffer), ptr(imageBuffer), ptr(dL_dout_color),
+                ptr(dL_dout_lang_feat) if include_lf else None, ptr(dL_dout_depth), out["dL_dmeans2D"].data_ptr(),
+                out["dL_dconic"].data_ptr(), out["dL_dopacity"].data_ptr(), out["dL_dcolors"].data_ptr(),
+                out["dL_dlang_feats"].data_ptr(), None, out["dL_dmeans3D"].data_ptr(), out["dL_dcov3D"].data_ptr(),
+                out["dL_dfeatures_dc"].data_ptr(), out["dL_dfeatures_rest"].data_ptr(), int(bool(accumulate_sh)),
+                ptr(out["dL_dscales"]), ptr(out["dL_drotations"]), int(include_lf), 1, scratch.data_ptr(),
+                _stream(means3D)), "lgs_backward_split_sh")
+        return out
     with torch.cuda.device(dev):
         check(L.lgs_backward(
             P, int(degree), M, int(R), W, H, ptr(background), ptr(means3D), ptr(sh), ptr(colors),

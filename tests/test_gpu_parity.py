@@ -321,6 +321,35 @@ def test_autograd_wrapper_matches_direct_call(dev):
         assert cases.rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-4  # atomics reorder between runs
 
 
+def test_split_sh_entry_points_match_concatenated(dev):
+    """lgs_forward_stage1_split_sh / lgs_backward_split_sh (features_dc + features_rest read and written in
+    place) vs the reference-layout calls on cat(features_dc, features_rest): same images, same gradients;
+    accumulate_sh adds a second backward on top."""
+    from leg_slam_b200 import rasterize_points as rp
+    cs = cases.make_case("sh3_lf", dev)
+    R, c1, l1, d1, rad1, geom, binning, img = rp.rasterize_gaussians(*cases.fwd_args(cs))
+    g1 = dict(zip(cases.GRAD_NAMES, rp.rasterize_gaussians_backward(*cases.bwd_args(cs, rad1, geom, R, binning, img))))
+    dc, rest = cs["shs"][:, :1, :].contiguous(), cs["shs"][:, 1:, :].contiguous()
+    fa = list(cases.fwd_args(cs))
+    fa[15] = dc
+    R2, c2, l2, d2, rad2, geom2, binning2, img2 = rp.rasterize_gaussians(*fa, sh_rest=rest)
+    assert R2 == R and torch.equal(rad1, rad2)
+    for a, b in ((c1, c2), (l1, l2), (d1, d2)):
+        assert cases.rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-6
+    P = cs["means3D"].shape[0]
+    out = rp.backward_outputs(P, 0, dev, True, False, True)
+    out["dL_dfeatures_dc"], out["dL_dfeatures_rest"] = torch.full_like(dc, 7.0), torch.full_like(rest, 7.0)
+    ba = list(cases.bwd_args(cs, rad2, geom2, R2, binning2, img2))
+    ba[16] = dc
+    rp.rasterize_gaussians_backward_into(out, *ba, sh_rest=rest)
+    got = torch.cat([out["dL_dfeatures_dc"], out["dL_dfeatures_rest"]], dim=1)
+    assert cases.rel_err(got.cpu().numpy(), g1["dL_dsh"].cpu().numpy()) <= 1e-4
+    assert cases.rel_err(out["dL_dmeans3D"].cpu().numpy(), g1["dL_dmeans3D"].cpu().numpy()) <= 1e-4
+    rp.rasterize_gaussians_backward_into(out, *ba, sh_rest=rest, accumulate_sh=True)
+    got2 = torch.cat([out["dL_dfeatures_dc"], out["dL_dfeatures_rest"]], dim=1)
+    assert cases.rel_err(got2.cpu().numpy(), 2 * g1["dL_dsh"].cpu().numpy()) <= 1e-4
+
+
 # ---------------------------------------------------------------------------- mapper
 def _mapper_window(dev, n_views=2):
     from leg_slam_b200 import mapper as M, synthetic
