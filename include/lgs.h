@@ -173,11 +173,23 @@ typedef struct lgs_geom_view {
     const float*    records;         /* [P][12]: x,y,depth,idx bits | conic a,b,c, opacity | r,g,b,0 */
     const float*    cov3D;           /* [P][6]                                          */
     const uint32_t* tiles_touched;   /* [P]                                             */
-    const uint32_t* point_offsets;   /* [P] inclusive scan                              */
+    const uint32_t* point_offsets;   /* [P] inclusive scan of tiles_touched (binning mode 1 only)  */
     const int32_t*  internal_radii;  /* [P]                                             */
     const uint8_t*  clamped;         /* [P] bit c set if colour channel c was clamped   */
 } lgs_geom_view;
 int lgs_view_binning(const char* binning_buffer, int R, lgs_binning_view* out);
+/* Binning algorithm (process-wide; set it before lgs_forward_stage1, not between stage1 and stage2):
+ *   1 (default) the reference's single stable radix sort of all instances by (tile, depth bits)
+ *               (rasterizer_impl.cu:304-309), over fewer key bits: depth bits are rebased to bits(0.2f) (the near
+ *               cull) and bounded by the frame's largest depth, which preprocess accumulates;
+ *   0           tile-local: instances are counted and scattered per tile, every tile's list is sorted by
+ *               (depth bits, Gaussian index) in shared memory -- no device-wide sort (experimental: slower than
+ *               mode 1 at 640x480 / 1.4 M instances).
+ * point_list and ranges are bit-identical in both modes and to the reference.  The 64-bit key arrays of
+ * lgs_binning_view hold the reference's exact keys only while lgs_debug_keys(1) is in effect (mode 1 then sorts the
+ * uncompacted keys; mode 0 materialises them, keys_unsorted / values_unsorted in scatter order). */
+int lgs_binning_mode(int mode);
+int lgs_debug_keys(int on);
 int lgs_view_image(const char* image_buffer, int W, int H, lgs_image_view* out);
 int lgs_view_geom(const char* geom_buffer, int P, lgs_geom_view* out);
 

@@ -26,6 +26,14 @@ void prof_mark(int id, cudaStream_t s) {
     g_ev_set[id] = true;
 }
 
+// stage1 -> stage2 hand-off on the calling host thread: the depth bound that lets the sort skip key bits.  stage2
+// uses it only when it is called with the same geometry buffer; otherwise it sorts all 32 depth bits.
+struct Stage1Note {
+    const char* geom = nullptr;
+    uint32_t max_depth_bits = 0xffffffffu;
+};
+static thread_local Stage1Note g_stage1_note;
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace lgs
@@ -62,7 +70,7 @@ size_t lgs_image_bytes(int W, int H) {
     if (W < 0 || H < 0) return 0;
     ImageState im = image_from_chunk(nullptr, W, H);
     const size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
-    return (size_t)(reinterpret_cast<uintptr_t>(im.tile_last + (tiles > 0 ? tiles : 1))) + 256;
+    return (size_t)(reinterpret_cast<uintptr_t>(im.tile_cursor + (tiles > 0 ? tiles : 1))) + 256;
 }
 size_t lgs_backward_scratch_bytes(int R, int W, int H) {
     return (R < 0 || W <= 0 || H <= 0) ? 0 : render_bwd_scratch_bytes(R, W, H);
@@ -105,8 +113,12 @@ static int forward_stage1_impl(int P, int D, int M, int W, int H, const float* m
     prof_mark(PM_SCAN, s);
     // the one readback of the forward (reference rasterizer_impl.cu:281-282)
     uint32_t R = 0;
-    LGS_CUDA_TRY(cudaMemcpyAsync(&R, g.point_offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    uint32_t rd[2] = {0, 0};  // R, largest depth bit pattern of a rendered Gaussian (both accumulated by preprocess)
+    LGS_CUDA_TRY(cudaMemcpyAsync(rd, g.total_touched, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     LGS_CUDA_TRY(cudaStreamSynchronize(s));
+    R = rd[0];
+    g_stage1_note.geom = geom_buffer;
+    g_stage1_note.max_depth_bits = rd[1];
     *num_rendered_host = (int)R;
     return LGS_OK;
 }
@@ -152,7 +164,8 @@ int lgs_forward_stage2(int P, int W, int H, int R, const float* background, cons
     // radii for key emission: the internal copy is always written by stage1 when the
     // caller passed NULL; otherwise stage1 wrote the caller's array and mirrors it here.
     prof_mark(PM_S2_BEGIN, s);
-    int st = launch_binning(P, R, W, H, g, g.internal_radii, b, im, s);
+    const uint32_t max_depth_bits = g_stage1_note.geom == geom_buffer ? g_stage1_note.max_depth_bits : 0xffffffffu;
+    int st = launch_binning(P, R, W, H, g, g.internal_radii, b, im, max_depth_bits, s);
     if (st != LGS_OK) return st;
     st = launch_render_fwd(W, H, R, g, b, im, background, lang_feat, out_color, out_lang_feat, out_depth,
                            include_lang_feat != 0, s);
@@ -296,6 +309,17 @@ int lgs_profile_read(float* ms, int n) {
             else (void)cudaGetLastError();
         }
     }
+    return LGS_OK;
+}
+
+// ---- binning mode / debug keys ---------------------------------------------------------
+int lgs_binning_mode(int mode) {
+    if (mode != 0 && mode != 1) return LGS_ERR_INVALID_ARG;
+    set_binning_mode(mode);
+    return LGS_OK;
+}
+int lgs_debug_keys(int on) {
+    set_debug_keys(on != 0);
     return LGS_OK;
 }
 

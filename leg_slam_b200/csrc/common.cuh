@@ -32,6 +32,8 @@ struct GeomState {
     uint32_t* point_offsets;  // [P]
     int32_t* internal_radii;  // [P]
     uint8_t* clamped;         // [P] bit c = colour channel c clamped at 0
+    uint32_t* total_touched;  // [2] sum of tiles_touched (= R) and the largest depth bit pattern of a rendered Gaussian,
+                              //     accumulated by preprocess
     char* scan_temp;          // CUB scan scratch
     size_t scan_temp_bytes;
 };
@@ -40,6 +42,8 @@ struct ImageState {
     float* final_T;       // [H*W]
     uint32_t* n_contrib;  // [H*W]
     uint32_t* tile_last;  // [tiles] max n_contrib over the tile's pixels (bwd skips the rest)
+    uint32_t* tile_count;   // [tiles] instances per tile (tile-local binning)
+    uint32_t* tile_cursor;  // [tiles] scatter cursor
 };
 struct BinningState {
     uint64_t* keys_unsorted;  // [R]
@@ -59,6 +63,9 @@ static inline void carve(char*& p, T*& out, size_t count, size_t align = 256) {
 
 size_t scan_temp_bytes(int P);
 size_t sort_temp_bytes(int R);
+void set_binning_mode(int m);
+int binning_mode();
+void set_debug_keys(int on);
 GeomState geom_from_chunk(char* chunk, int P);
 ImageState image_from_chunk(char* chunk, int W, int H);
 BinningState binning_from_chunk(char* chunk, int R);
@@ -98,8 +105,9 @@ int launch_preprocess(int P, int D, int M, const float* means3D, const float* sh
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix,
                         unsigned char* present, cudaStream_t s);
 int launch_scan(int P, GeomState& g, cudaStream_t s);
+// max_depth_bits: largest depth bit pattern among the rendered Gaussians, or 0xffffffff when unknown
 int launch_binning(int P, int R, int W, int H, const GeomState& g, const int* radii,
-                   BinningState& b, ImageState& im, cudaStream_t s);
+                   BinningState& b, ImageState& im, uint32_t max_depth_bits, cudaStream_t s);
 int launch_render_fwd(int W, int H, int R, const GeomState& g, const BinningState& b,
                       ImageState& im, const float* background, const float* lang_feat,
                       float* out_color, float* out_lang_feat, float* out_depth,

@@ -17,6 +17,8 @@
 // Layout: one thread per Gaussian, 256 threads per CTA.  Outputs go to the packed
 // 48-byte render record (common.cuh) written as three float4 stores; SH coefficients
 // are read as 12 float4 (a Gaussian's 16x3 coefficients are one 192-byte row).
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
 #include "common.cuh"
 
 namespace lgs {
@@ -78,7 +80,8 @@ preprocess_kernel(int P, int D, int M,
                   int tiles_x, int tiles_y,
                   int* __restrict__ radii_user, int* __restrict__ radii, GaussRec* __restrict__ rec,
                   float* __restrict__ cov3Ds,
-                  uint8_t* __restrict__ clamped, uint32_t* __restrict__ tiles_touched) {
+                  uint8_t* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
+                  uint32_t* __restrict__ total_touched) {
     __shared__ float sV[16], sP[16];
     if (threadIdx.x < 16) sV[threadIdx.x] = view[threadIdx.x];
     else if (threadIdx.x < 32) sP[threadIdx.x - 16] = proj[threadIdx.x - 16];
@@ -228,6 +231,15 @@ preprocess_kernel(int P, int D, int M,
     radii[idx] = out_radius;  // internal copy: key emission and the backward read this one
     if (radii_user != nullptr) radii_user[idx] = out_radius;
     tiles_touched[idx] = out_tiles;
+    {   // R = sum of tiles_touched without a scan pass: one atomic per converged group of threads
+        namespace cg = cooperative_groups;
+        auto grp = cg::coalesced_threads();
+        const uint32_t sum = cg::reduce(grp, out_tiles, cg::plus<uint32_t>());
+        if (grp.thread_rank() == 0 && sum != 0) atomicAdd(total_touched, sum);
+        // largest depth bit pattern among the rendered Gaussians: bounds the key bits the sort has to cover
+        const uint32_t dmax = cg::reduce(grp, out_tiles ? __float_as_uint(depth) : 0u, cg::greater<uint32_t>());
+        if (grp.thread_rank() == 0 && sum != 0) atomicMax(total_touched + 1, dmax);
+    }
     if (!live) return;
 
     // colour: precomputed, or SH -> RGB (+0.5, clamp at 0, remember which channel clamped)
@@ -317,11 +329,12 @@ int launch_preprocess(int P, int D, int M, const float* means3D, const float* sh
     const float focal_y = H / (2.0f * tan_fovy);  // rasterizer_impl.cu:224-225
     const float focal_x = W / (2.0f * tan_fovx);
     const int tiles_x = (W + TILE - 1) / TILE, tiles_y = (H + TILE - 1) / TILE;
+    LGS_CUDA_TRY(cudaMemsetAsync(g.total_touched, 0, 2 * sizeof(uint32_t), s));
     preprocess_kernel<<<(P + 255) / 256, 256, 0, s>>>(
         P, D, M, means3D, scales, scale_modifier, rotations, opacities, shs, shs_rest, cov3D_precomp,
         colors_precomp, viewmatrix, projmatrix, cam_pos, W, H, tan_fovx, tan_fovy, focal_x, focal_y,
         tiles_x, tiles_y, radii == g.internal_radii ? nullptr : radii, g.internal_radii, g.rec, g.cov3D,
-        g.clamped, g.tiles_touched);
+        g.clamped, g.tiles_touched, g.total_touched);
     LGS_LAUNCH_CHECK();
     return LGS_OK;
 }

@@ -43,3 +43,13 @@ def geom_view(geom_buffer, P):
                 point_offsets=_view(geom_buffer, v.point_offsets, P, torch.int32),
                 internal_radii=_view(geom_buffer, v.internal_radii, P, torch.int32),
                 clamped=_view(geom_buffer, v.clamped, P, torch.uint8))
+
+
+def binning_mode(mode):
+    """1 = the reference's single radix sort (default), 0 = tile-local binning (include/lgs.h)."""
+    check(_lib.lib().lgs_binning_mode(int(mode)), "lgs_binning_mode")
+
+
+def debug_keys(on):
+    """Keep / materialise the reference's exact 64-bit key arrays for binning_view (include/lgs.h)."""
+    check(_lib.lib().lgs_debug_keys(int(bool(on))), "lgs_debug_keys")

@@ -23,8 +23,39 @@ def dev():
     return torch.device("cuda:0")
 
 
-def run_ours(cs):
+@pytest.fixture(autouse=True)
+def _materialise_keys(dev):
+    """The binning keeps the reference's exact 64-bit keys only when asked (include/lgs.h lgs_debug_keys)."""
+    from leg_slam_b200 import debug
+    debug.debug_keys(True)
+    debug.binning_mode(1)
+    yield
+    debug.binning_mode(1)
+
+
+def _sorted_pairs(keys, vals):
+    """(key, value) pairs in lexicographic order: the emitted instance list as an order-free multiset."""
+    k, v = np.asarray(keys).view(np.uint64), np.asarray(vals).view(np.uint32)
+    o = np.lexsort((v, k))
+    return k[o], v[o]
+
+
+def assert_emitted_equal(ours, ref_keys, ref_vals, mode):
+    """Binning mode 1 emits in the reference's order (Gaussian-major): compare element-wise.  Mode 0 scatters them
+    per tile in any order: the same instances as a multiset."""
+    if mode == 1:
+        np.testing.assert_array_equal(ours["keys_unsorted"].view(np.uint64), np.asarray(ref_keys).view(np.uint64))
+        np.testing.assert_array_equal(ours["values_unsorted"].view(np.uint32), np.asarray(ref_vals).view(np.uint32))
+    else:
+        ak, av = _sorted_pairs(ours["keys_unsorted"], ours["values_unsorted"])
+        bk, bv = _sorted_pairs(ref_keys, ref_vals)
+        np.testing.assert_array_equal(ak, bk)
+        np.testing.assert_array_equal(av, bv)
+
+
+def run_ours(cs, mode=1):
     from leg_slam_b200 import rasterize_points as rp, debug
+    debug.binning_mode(mode)
     R, color, lf, depth, radii, geom, binning, img = rp.rasterize_gaussians(*cases.fwd_args(cs))
     grads = rp.rasterize_gaussians_backward(*cases.bwd_args(cs, radii, geom, R, binning, img))
     torch.cuda.synchronize()
@@ -41,10 +72,11 @@ def run_ours(cs):
     return out
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("name", list(cases.CASES))
-def test_forward_backward_vs_oracle(name, dev, oracle_mod):
+def test_forward_backward_vs_oracle(name, mode, dev, oracle_mod):
     cs = cases.make_case(name, dev)
-    ours = run_ours(cs)
+    ours = run_ours(cs, mode)
     f = cases.oracle_forward(cases.make_case(name), oracle_mod)
     g = cases.oracle_backward(cases.make_case(name), f, oracle_mod)
     vis = f["radii"] > 0
@@ -54,8 +86,7 @@ def test_forward_backward_vs_oracle(name, dev, oracle_mod):
     np.testing.assert_array_equal(ours["tiles_touched"].view(np.uint32), f["tiles_touched"])
     np.testing.assert_array_equal(ours["records"][vis, 2].view(np.uint32), f["depths"][vis].view(np.uint32))
     np.testing.assert_array_equal(ours["records"][vis, 0:2].copy().view(np.uint32), f["means2D"][vis].view(np.uint32))
-    np.testing.assert_array_equal(ours["keys_unsorted"].view(np.uint64), f["keys_unsorted"])
-    np.testing.assert_array_equal(ours["values_unsorted"].view(np.uint32), f["values_unsorted"])
+    assert_emitted_equal(ours, f["keys_unsorted"], f["values_unsorted"], mode)
     np.testing.assert_array_equal(ours["keys_sorted"].view(np.uint64), f["keys_sorted"])
     np.testing.assert_array_equal(ours["point_list"].view(np.uint32), f["point_list"])
     np.testing.assert_array_equal(ours["ranges"].view(np.uint32), f["ranges"])
@@ -76,16 +107,17 @@ def test_forward_backward_vs_oracle(name, dev, oracle_mod):
         assert cases.rel_err(ours[gname], g[gname]) <= GRAD_TOL, gname
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("name", list(cases.CASES))
-def test_vs_reference_golden(name, dev):
+def test_vs_reference_golden(name, mode, dev):
     gd = golden(name)
     cs = cases.make_case(name, dev)
-    ours = run_ours(cs)
+    ours = run_ours(cs, mode)
     vis = gd["visible"]
     assert ours["num_rendered"] == int(gd["num_rendered"])
-    for k in ("radii", "tiles_touched", "keys_unsorted", "values_unsorted", "keys_sorted", "point_list", "ranges",
-              "n_contrib"):
+    for k in ("radii", "tiles_touched", "keys_sorted", "point_list", "ranges", "n_contrib"):
         np.testing.assert_array_equal(ours[k].view(gd[k].dtype), gd[k], err_msg=k)
+    assert_emitted_equal(ours, gd["keys_unsorted"], gd["values_unsorted"], mode)
     np.testing.assert_array_equal(ours["records"][vis, 2].view(np.uint32), gd["depths"][vis].view(np.uint32))
     np.testing.assert_array_equal(ours["records"][vis, 0:2].copy().view(np.uint32), gd["means2D"][vis].view(np.uint32))
     np.testing.assert_array_equal(ours["final_T"].view(np.uint32), gd["final_T"].view(np.uint32))
@@ -227,7 +259,9 @@ def test_no_writes_outside_caller_buffers(dev):
 @pytest.fixture(scope="module")
 def cfgB(dev):
     """BASELINE.json configs[1]: 500k Gaussians, 640x480."""
-    from leg_slam_b200 import synthetic, rasterize_points as rp
+    from leg_slam_b200 import synthetic, rasterize_points as rp, debug
+    debug.debug_keys(True)  # module-scoped: runs before the function-scoped autouse fixture
+    debug.binning_mode(1)
     sc = synthetic.make_scene(500_000, seed=2, device=dev)
     cam = synthetic.make_cameras(1, 640, 480, seed=2)[0].to(dev)
     a = synthetic.activate(sc)
@@ -267,6 +301,27 @@ def test_fullsize_binning_properties(cfgB, dev):
     # depth bits in keys equal the stored depths of the listed Gaussians
     assert torch.equal((ks & 0xffffffff).int(), gv["records"][pl, 2].contiguous().view(torch.int32))
     assert bool((iv["n_contrib"].view(H, W).long() <= lens.view(H // 8, W // 8).repeat_interleave(8, 0).repeat_interleave(8, 1)).all())
+
+
+def test_compacted_sort_keys_give_the_same_lists(cfgB, dev):
+    """Without lgs_debug_keys the sort runs on rebased, bounded depth bits (fewer radix passes) and tile-local binning
+    sorts per tile: point_list and ranges must equal those of the reference's exact 64-bit keys."""
+    from leg_slam_b200 import rasterize_points as rp, debug
+    R, _c, _l, _d, radii, geom, binning, img = cfgB["out"]
+    pl = debug.binning_view(binning, R)["point_list"].clone()
+    rg = debug.image_view(img, 640, 480)["ranges"].clone()
+    nc = debug.image_view(img, 640, 480)["n_contrib"].clone()
+    for mode in (1, 0):
+        debug.debug_keys(False)
+        debug.binning_mode(mode)
+        R2, _c2, _l2, _d2, radii2, geom2, binning2, img2 = rp.rasterize_gaussians(*cfgB["args"])
+        torch.cuda.synchronize()
+        assert R2 == R and torch.equal(radii2, radii)
+        assert torch.equal(debug.binning_view(binning2, R2)["point_list"], pl), mode
+        iv = debug.image_view(img2, 640, 480)
+        assert torch.equal(iv["ranges"], rg) and torch.equal(iv["n_contrib"], nc), mode
+    debug.debug_keys(True)
+    debug.binning_mode(1)
 
 
 def test_fullsize_forward_idempotent_backward_linear(cfgB, dev):
