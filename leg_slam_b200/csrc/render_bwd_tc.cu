@@ -9,7 +9,8 @@
 //     raw moments          += sum_px t[rec][px] * {1, u, v, u^2, uv, v^2}[px]     (6 columns)
 // a [records x 32] by [32 x 74] product per stream.  The SIMT kernel spends 64 FFMA + 16 LDS per record and
 // column (301 M warp instructions at cfgB); here the products run as tcgen05.mma kind::tf32 with the fp32
-// operands split into TF32 hi + lo parts so the result keeps fp32-level accuracy:
+// operands split into hi + lo parts (hi = the 19 bits kind::tf32 reads, lo = the exact remainder) so the result
+// keeps fp32-level accuracy:
 //
 //   main  D[128 x 64]  = A_main[128 x 32] * W^T[32 x 64]      rows 0-63 = g_hi[ch], rows 64-127 = g_lo[ch];
 //                                                             two MMAs per k-step (W_hi, W_lo) give all four
@@ -44,14 +45,15 @@ constexpr int SM_BMOM = SM_BAUX + 2 * 1024;        // [2 halves][8 x 32]
 constexpr int SM_HDR = SM_BMOM + 2 * 1024;         // [64] float4 record headers of the current batch
 constexpr int SM_TOTAL = SM_HDR + TB * 16;
 constexpr int TMEM_COLS = 128;                     // main 0-63, aux 64-71, mom 72-79
+constexpr int RELAY_PITCH = 36;                    // floats per thread in the epilogue relay (16-byte aligned, spreads banks)
+static_assert(TC_THREADS * RELAY_PITCH * 4 <= 4 * WT_TILE, "relay must fit the operand tiles");
 
+// hi = x with the 13 low mantissa bits cleared (what kind::tf32 reads anyway), lo = x - hi (tc.cuh split_trunc4)
 __device__ __forceinline__ void split_store(const float4 x, uint8_t* hi, uint8_t* lo) {
-    uint4 h, l;
-    h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
-    l.x = to_tf32(x.x - __uint_as_float(h.x)); l.y = to_tf32(x.y - __uint_as_float(h.y));
-    l.z = to_tf32(x.z - __uint_as_float(h.z)); l.w = to_tf32(x.w - __uint_as_float(h.w));
-    *reinterpret_cast<uint4*>(hi) = h;
-    *reinterpret_cast<uint4*>(lo) = l;
+    float4 h, l;
+    split_trunc4(x, h, l);
+    *reinterpret_cast<float4*>(hi) = h;
+    *reinterpret_cast<float4*>(lo) = l;
 }
 
 // 8 consecutive pixels of one image row (zeros outside the image)
@@ -110,6 +112,11 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
     const uint32_t idesc_main = make_idesc_tf32(128, TB);
     const uint32_t idesc_aux = make_idesc_tf32(64, 8);
     const uint32_t smem_base = smem_u32(smem);
+    const uint64_t dA_base = make_desc(smem_base + SM_AMAIN, 128 * 16, 128);
+    const uint64_t dWh_base = make_desc(smem_base + SM_WT, TB * 16, 128), dWl_base = make_desc(smem_base + SM_WT + WT_TILE, TB * 16, 128);
+    const uint64_t dTh_base = make_desc(smem_base + SM_WT + 2 * WT_TILE, TB * 16, 128);
+    const uint64_t dTl_base = make_desc(smem_base + SM_WT + 3 * WT_TILE, TB * 16, 128);
+    const uint64_t dBa_base = make_desc(smem_base + SM_BAUX, 128, 128), dBm_base = make_desc(smem_base + SM_BMOM, 128, 128);
 
     uint32_t gq = 0;         // batches processed by this CTA: raw buffer = gq & 1, its parity = (gq >> 1) & 1
     uint32_t mma_phase = 0;
@@ -187,25 +194,20 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
 
             if (tid == 0) {
                 tc_fence_after();
-                const uint32_t a_main = smem_base + SM_AMAIN + half * AMAIN_HALF;
-                const uint32_t w_hi = smem_base + SM_WT, w_lo = w_hi + WT_TILE, t_hi = w_lo + WT_TILE, t_lo = t_hi + WT_TILE;
-                const uint32_t baux = smem_base + SM_BAUX + half * 1024, bmom = smem_base + SM_BMOM + half * 1024;
+                // descriptors differ between k-steps (and halves) only in the 14-bit start-address field (16-byte units)
+                const uint64_t dA0 = dA_base + (uint64_t)(half * (AMAIN_HALF >> 4));
+                const uint64_t dBa0 = dBa_base + (uint64_t)(half * (1024 >> 4)), dBm0 = dBm_base + (uint64_t)(half * (1024 >> 4));
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {  // K = 8 pixels per instruction = two 16-byte chunks
                     const uint32_t acc = ks > 0 ? 1u : 0u;
-                    const uint64_t dA = make_desc(a_main + ks * 2 * (128 * 16), 128 * 16, 128);
-                    const uint64_t dWh = make_desc(w_hi + ks * 2 * (TB * 16), TB * 16, 128);
-                    const uint64_t dWl = make_desc(w_lo + ks * 2 * (TB * 16), TB * 16, 128);
-                    const uint64_t dTh = make_desc(t_hi + ks * 2 * (TB * 16), TB * 16, 128);
-                    const uint64_t dTl = make_desc(t_lo + ks * 2 * (TB * 16), TB * 16, 128);
-                    const uint64_t dBa = make_desc(baux + ks * 2 * 128, 128, 128);
-                    const uint64_t dBm = make_desc(bmom + ks * 2 * 128, 128, 128);
-                    umma_tf32(tmem + 0, dA, dWh, idesc_main, acc);
-                    umma_tf32(tmem + 0, dA, dWl, idesc_main, 1u);
-                    umma_tf32(tmem + 64, dWh, dBa, idesc_aux, acc);
-                    umma_tf32(tmem + 64, dWl, dBa, idesc_aux, 1u);
-                    umma_tf32(tmem + 72, dTh, dBm, idesc_aux, acc);
-                    umma_tf32(tmem + 72, dTl, dBm, idesc_aux, 1u);
+                    const uint64_t kA = (uint64_t)(ks * ((2 * 128 * 16) >> 4)), kW = (uint64_t)(ks * ((2 * TB * 16) >> 4));
+                    const uint64_t kB = (uint64_t)(ks * ((2 * 128) >> 4));
+                    umma_tf32(tmem + 0, dA0 + kA, dWh_base + kW, idesc_main, acc);
+                    umma_tf32(tmem + 0, dA0 + kA, dWl_base + kW, idesc_main, 1u);
+                    umma_tf32(tmem + 64, dWh_base + kW, dBa0 + kB, idesc_aux, acc);
+                    umma_tf32(tmem + 64, dWl_base + kW, dBa0 + kB, idesc_aux, 1u);
+                    umma_tf32(tmem + 72, dTh_base + kW, dBm0 + kB, idesc_aux, acc);
+                    umma_tf32(tmem + 72, dTl_base + kW, dBm0 + kB, idesc_aux, 1u);
                 }
                 umma_commit(&mma_done);
             }
@@ -221,13 +223,19 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
             tmem_ld8(tb + 64, ax);
             tmem_ld8(tb + 72, mo);
             tmem_ld_wait();
-            float* relay = reinterpret_cast<float*>(raw);  // [64 ch][68]; the raw records are no longer needed
-            if (warp >= 2) {  // g_lo rows: hand over to the warp that holds the same channel's g_hi row
-                float* rl = relay + ((warp - 2) * 32 + lane) * HREC_FLOATS;
+            // Channel ch's sum is (g_hi row, warps 0-1) + (g_lo row, warps 2-3).  Each side hands the other half of its
+            // 64 record columns over through shared memory and finishes its own half: warps 0-1 records 0-31, warps
+            // 2-3 records 32-63 -- 32 red.global.add per thread, all four warps busy.  The W/T operand tiles are free
+            // (the MMAs have completed) and serve as the relay: [128 threads][36 floats].
+            float* relay = reinterpret_cast<float*>(smem + SM_WT);
+            {
+                float* rl = relay + tid * RELAY_PITCH;
+                if (warp < 2) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    *reinterpret_cast<uint4*>(rl + 4 * k) = make_uint4(va[4 * k], va[4 * k + 1], va[4 * k + 2], va[4 * k + 3]);
-                    *reinterpret_cast<uint4*>(rl + 32 + 4 * k) = make_uint4(vb[4 * k], vb[4 * k + 1], vb[4 * k + 2], vb[4 * k + 3]);
+                    for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(rl + 4 * k) = make_uint4(vb[4 * k], vb[4 * k + 1], vb[4 * k + 2], vb[4 * k + 3]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(rl + 4 * k) = make_uint4(va[4 * k], va[4 * k + 1], va[4 * k + 2], va[4 * k + 3]);
                 }
             }
             // colour / depth / moments: the M = 64 accumulators keep record 16*w + l on lane l < 16 of warp w
@@ -253,21 +261,22 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
                 }
             }
             __syncthreads();
-            if (warp < 2) {
-                const int ch = warp * 32 + lane;
-                const float* rl = relay + ch * HREC_FLOATS;
+            {
+                const int ch = (warp & 1) * 32 + lane;
+                const float* rl = relay + (tid ^ 64) * RELAY_PITCH;  // the partner thread holds the other half of channel ch
                 float* outp = dL_dlang_feat + ch;
+                const int c0 = warp < 2 ? 0 : 32;  // first record column this thread finishes
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const float4 lo = *reinterpret_cast<const float4*>(rl + 4 * k);
-                    const float l4[4] = {lo.x, lo.y, lo.z, lo.w};
+                for (int k = 0; k < 8; ++k) {
+                    const float4 o = *reinterpret_cast<const float4*>(rl + 4 * k);
+                    const float o4[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int c = 4 * k + e;
+                        const int c = c0 + 4 * k + e;
                         if (c < cnt) {
                             const uint32_t id = __float_as_uint(*reinterpret_cast<const float*>(smem + SM_HDR + c * 16 + 12));
-                            const float hi = __uint_as_float(c < 32 ? va[c & 31] : vb[c & 31]);
-                            red_add_f32(outp + (size_t)id * LF, hi + l4[e]);
+                            const float mine = __uint_as_float(warp < 2 ? va[4 * k + e] : vb[4 * k + e]);
+                            red_add_f32(outp + (size_t)id * LF, mine + o4[e]);
                         }
                     }
                 }
