@@ -19,11 +19,12 @@
 //   aux   D[64 x 8]    = W[64 x 32] * B_aux^T[32 x 8]         columns = {r,g,b,d}_hi, {r,g,b,d}_lo
 //   mom   D[64 x 8]    = T[64 x 32] * B_mom^T[32 x 8]         columns = 1,u,v,u^2,uv,v^2 (exact in TF32)
 //
-// One persistent CTA (128 threads, 2 per SM) takes tiles from a work counter.  Per batch of 64 records: one TMA
-// bulk copy brings the raw records (double-buffered, the next batch is in flight while this one is processed),
-// all threads split w/t into TF32 hi/lo tiles in the canonical K-major layout, one thread issues 24 MMAs,
-// and the four warps drain TMEM: the lo-row warps hand their half to the hi-row warps through shared
-// memory (so each sum is ONE red per record and channel), 16 lanes per warp finish colour / depth / moments.
+// Persistent CTAs (128 threads, 3 per SM) take (tile, pixel-warp half) work items from a counter.  Per batch of 64
+// records: one TMA bulk copy brings the raw records (re-issued for the next batch as soon as this one has been
+// split, so it flies during the MMAs and the epilogue), all threads split w/t into hi/lo tiles in the canonical
+// K-major layout, one thread issues 24 MMAs, and the four warps drain TMEM: hi-row and lo-row warps swap halves of
+// their record columns through shared memory (each sum is ONE red per record and channel, 32 reds per thread),
+// 16 lanes per warp finish colour / depth / moments.
 #include <cstdlib>
 #include "common.cuh"
 #include "ptx.cuh"
@@ -38,12 +39,13 @@ constexpr int RAW_BYTES = TB * HREC_BYTES;         // 17408; also the relay [64 
 constexpr int WT_TILE = TB * 32 * 4;               // 8192: one [64 rec x 32 px] TF32 tile
 constexpr int AMAIN_HALF = 128 * 32 * 4;           // 16384
 constexpr int SM_RAW = 0;
-constexpr int SM_WT = SM_RAW + 2 * RAW_BYTES;      // W_hi, W_lo, T_hi, T_lo
-constexpr int SM_AMAIN = SM_WT + 4 * WT_TILE;      // [2 halves][128 x 32]
-constexpr int SM_BAUX = SM_AMAIN + 2 * AMAIN_HALF; // [2 halves][8 x 32]
-constexpr int SM_BMOM = SM_BAUX + 2 * 1024;        // [2 halves][8 x 32]
+constexpr int SM_WT = SM_RAW + RAW_BYTES;          // W_hi, W_lo, T_hi, T_lo
+constexpr int SM_AMAIN = SM_WT + 4 * WT_TILE;      // [128 x 32]: the work item's half
+constexpr int SM_BAUX = SM_AMAIN + AMAIN_HALF;     // [8 x 32]
+constexpr int SM_BMOM = SM_BAUX + 1024;            // [2 halves][8 x 32]
 constexpr int SM_HDR = SM_BMOM + 2 * 1024;         // [64] float4 record headers of the current batch
-constexpr int SM_TOTAL = SM_HDR + TB * 16;
+constexpr int SM_TOTAL = SM_HDR + TB * 16;         // 70656: three CTAs per SM
+constexpr int TC_CTAS = 3;
 constexpr int TMEM_COLS = 128;                     // main 0-63, aux 64-71, mom 72-79
 constexpr int RELAY_PITCH = 36;                    // floats per thread in the epilogue relay (16-byte aligned, spreads banks)
 static_assert(TC_THREADS * RELAY_PITCH * 4 <= 4 * WT_TILE, "relay must fit the operand tiles");
@@ -74,7 +76,7 @@ __device__ __forceinline__ void load_row8(const float* __restrict__ plane, int W
     }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, TC_CTAS)
 render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int tiles_x, int n_tiles,
                           const float* __restrict__ dL_dpix, const float* __restrict__ dL_dpix_lf,
                           const float* __restrict__ dL_dpix_depth, const float* __restrict__ hrec_buf,
@@ -82,7 +84,7 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
                           float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity,
                           float* __restrict__ dL_dcolor, float* __restrict__ dL_dlang_feat, float* __restrict__ dL_ddepth) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t raw_full[2];
+    __shared__ __align__(8) uint64_t raw_full;
     __shared__ __align__(8) uint64_t mma_done;
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_tile;
@@ -91,8 +93,7 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
     const size_t HW = (size_t)H * W;
 
     if (tid == 0) {
-        mbar_init(&raw_full[0], 1);
-        mbar_init(&raw_full[1], 1);
+        mbar_init(&raw_full, 1);
         mbar_init(&mma_done, 1);
         mbar_fence_init();
     }
@@ -118,64 +119,60 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
     const uint64_t dTl_base = make_desc(smem_base + SM_WT + 3 * WT_TILE, TB * 16, 128);
     const uint64_t dBa_base = make_desc(smem_base + SM_BAUX, 128, 128), dBm_base = make_desc(smem_base + SM_BMOM, 128, 128);
 
-    uint32_t gq = 0;         // batches processed by this CTA: raw buffer = gq & 1, its parity = (gq >> 1) & 1
-    uint32_t mma_phase = 0;
+    uint32_t raw_phase = 0, mma_phase = 0;
 
     for (;;) {
         __syncthreads();
         if (tid == 0) s_tile = (int)atomicAdd(work_counter, 1u);
         __syncthreads();
-        const int tile = s_tile;
-        if (tile >= n_tiles) break;
-        const int cnt0 = (int)hrec_count[2 * tile], cnt1 = (int)hrec_count[2 * tile + 1];
-        if (cnt0 + cnt1 == 0) continue;
+        const int item = s_tile;  // work item = (tile, pixel-warp half)
+        if (item >= 2 * n_tiles) break;
+        const int tile = item >> 1, half = item & 1;
+        const int cnt_all = (int)hrec_count[item];
+        if (cnt_all == 0) continue;
         const uint2 range = ranges[tile];
         const int n_all = (int)(range.y - range.x);
-        const int nb0 = (cnt0 + TB - 1) / TB, nb1 = (cnt1 + TB - 1) / TB, nbt = nb0 + nb1;
-        const float* stream0 = hrec_buf + (size_t)2 * range.x * HREC_FLOATS;
+        const int nbt = (cnt_all + TB - 1) / TB;
+        const float* stream = hrec_buf + ((size_t)2 * range.x + (size_t)half * n_all) * HREC_FLOATS;
 
-        auto issue = [&](int q, uint32_t seq) {  // thread 0: bulk copy of the tile's q-th batch into raw buffer seq & 1
-            const int half = q < nb0 ? 0 : 1, b = half ? q - nb0 : q;
-            const int cnt = min(TB, (half ? cnt1 : cnt0) - b * TB);
-            const float* src = stream0 + ((size_t)half * n_all + (size_t)b * TB) * HREC_FLOATS;
-            uint64_t* bar = &raw_full[seq & 1];
+        auto issue = [&](int q) {  // thread 0: bulk copy of the item's q-th batch into the raw buffer
+            const int cnt = min(TB, cnt_all - q * TB);
             const uint32_t bytes = (uint32_t)cnt * HREC_BYTES;
-            mbar_arrive_expect_tx(bar, bytes);
-            tma_bulk_g2s(smem + SM_RAW + (seq & 1) * RAW_BYTES, src, bytes, bar);
+            mbar_arrive_expect_tx(&raw_full, bytes);
+            tma_bulk_g2s(smem + SM_RAW, stream + (size_t)q * TB * HREC_FLOATS, bytes, &raw_full);
         };
-        if (tid == 0) issue(0, gq);
+        if (tid == 0) issue(0);
 
-        // ---- the tile's upstream gradients as MMA operands (all earlier MMAs have completed: mma_done was waited on)
+        // ---- the half's upstream gradients as MMA operands (all earlier MMAs have completed: mma_done was waited on)
         {
-            const uint32_t tx0 = (uint32_t)(tile % tiles_x) * TILE, ty0 = (uint32_t)(tile / tiles_x) * TILE;
+            const uint32_t tx0 = (uint32_t)(tile % tiles_x) * TILE, ty0 = (uint32_t)(tile / tiles_x) * TILE + 4 * half;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {  // A_main: task = (row y, channel ch); consecutive lanes = consecutive channels
+            for (int i = 0; i < 2; ++i) {  // A_main: task = (row y, channel ch); consecutive lanes = consecutive channels
                 const int task = tid + TC_THREADS * i;
                 const int y = task >> 6, ch = task & 63;
                 float4 a, b;
                 load_row8(dL_dpix_lf + (size_t)ch * HW, W, H, tx0, ty0 + y, a, b);
-                uint8_t* base = smem + SM_AMAIN + (y >> 2) * AMAIN_HALF;
-                const int kc = (y & 3) * 2;
+                uint8_t* base = smem + SM_AMAIN;
+                const int kc = y * 2;
                 split_store(a, base + canon_off(ch, kc, 128), base + canon_off(64 + ch, kc, 128));
                 split_store(b, base + canon_off(ch, kc + 1, 128), base + canon_off(64 + ch, kc + 1, 128));
             }
-            if (tid < 32) {  // B_aux: rows {r,g,b,d}_hi, {r,g,b,d}_lo
+            if (tid < 16) {  // B_aux: rows {r,g,b,d}_hi, {r,g,b,d}_lo
                 const int c = tid & 3, y = tid >> 2;
                 float4 a, b;
                 load_row8(c < 3 ? dL_dpix + (size_t)c * HW : dL_dpix_depth, W, H, tx0, ty0 + y, a, b);
-                uint8_t* base = smem + SM_BAUX + (y >> 2) * 1024;
-                const int kc = (y & 3) * 2;
+                uint8_t* base = smem + SM_BAUX;
+                const int kc = y * 2;
                 split_store(a, base + canon_off(c, kc, 8), base + canon_off(4 + c, kc, 8));
                 split_store(b, base + canon_off(c, kc + 1, 8), base + canon_off(4 + c, kc + 1, 8));
             }
         }
 
-        for (int q = 0; q < nbt; ++q, ++gq) {
-            const int half = q < nb0 ? 0 : 1, b = half ? q - nb0 : q;
-            const int cnt = min(TB, (half ? cnt1 : cnt0) - b * TB);
-            uint8_t* raw = smem + SM_RAW + (gq & 1) * RAW_BYTES;
-            if (tid == 0 && q + 1 < nbt) issue(q + 1, gq + 1);  // the other buffer: batch gq-1 is completely finished
-            mbar_wait(&raw_full[gq & 1], (gq >> 1) & 1);
+        for (int q = 0; q < nbt; ++q) {
+            const int cnt = min(TB, cnt_all - q * TB);
+            uint8_t* raw = smem + SM_RAW;
+            mbar_wait(&raw_full, raw_phase);
+            raw_phase ^= 1u;
 
             // ---- split w / t into TF32 hi / lo tiles, canonical K-major [64 rec][32 px]
             {
@@ -193,10 +190,11 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
             __syncthreads();
 
             if (tid == 0) {
+                if (q + 1 < nbt) issue(q + 1);  // every thread has read the raw records: refill during the MMAs + epilogue
                 tc_fence_after();
                 // descriptors differ between k-steps (and halves) only in the 14-bit start-address field (16-byte units)
-                const uint64_t dA0 = dA_base + (uint64_t)(half * (AMAIN_HALF >> 4));
-                const uint64_t dBa0 = dBa_base + (uint64_t)(half * (1024 >> 4)), dBm0 = dBm_base + (uint64_t)(half * (1024 >> 4));
+                const uint64_t dA0 = dA_base, dBa0 = dBa_base;
+                const uint64_t dBm0 = dBm_base + (uint64_t)(half * (1024 >> 4));
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {  // K = 8 pixels per instruction = two 16-byte chunks
                     const uint32_t acc = ks > 0 ? 1u : 0u;
@@ -307,7 +305,7 @@ int launch_render_bwd_chan_tc(int W, int H, const ImageState& im, const float* d
     }
     const int tiles_x = (W + TILE - 1) / TILE, tiles_y = (H + TILE - 1) / TILE;
     const int n_tiles = tiles_x * tiles_y;
-    const int grid = n_tiles < 2 * n_sm ? n_tiles : 2 * n_sm;
+    const int grid = 2 * n_tiles < TC_CTAS * n_sm ? 2 * n_tiles : TC_CTAS * n_sm;
     render_bwd_chan_tc_kernel<<<grid, TC_THREADS, SM_TOTAL, s>>>(im.ranges, W, H, tiles_x, n_tiles, dL_dpix, dL_dpix_lf, dL_dpix_depth,
                                                                  hrec, hcount, work_counter, dL_dmean2D, dL_dconic, dL_dopacity,
                                                                  dL_dcolor, dL_dlang_feat, dL_ddepth);
