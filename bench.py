@@ -458,7 +458,30 @@ def cpu_baseline(sc, cam, up, target_seconds=12.0):
 
 
 # ------------------------------------------------------------------------------------------- main
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Route everything native code writes to fd 1 (NCCL prints its version banner there when NCCL_DEBUG is set in the
+    environment) to stderr, so that stdout carries exactly the one JSON line of the contract."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -471,7 +494,7 @@ def main():
 
     world, rank, local = dist_setup(args.gpus)
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: the hot path has no CPU fallback"}))
+        emit({"error": "no CUDA device: the hot path has no CPU fallback"})
         sys.exit(1)
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
@@ -581,7 +604,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
 
 
 def main_reference(args, world, rank, device):
@@ -595,7 +618,7 @@ def main_reference(args, world, rank, device):
         return
     so = os.path.join(ROOT, "oracle", "_ref", "ref_rasterizer.so")
     if not os.path.exists(so):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_rasterizer.so was not built (needs /root/reference)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/ref_rasterizer.so was not built (needs /root/reference)"})
         return
     from leg_slam_b200 import synthetic
     sc, cam, up = make_workload(0, world, device)
@@ -627,7 +650,7 @@ def main_reference(args, world, rank, device):
                                    "times its unmodified kernels on the same GPU instead of host cores"},
         "clocks": clocks,
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 if __name__ == "__main__":

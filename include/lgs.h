@@ -261,6 +261,34 @@ int lgs_mapping_loss(int W, int H, int lf_w, int lf_h, const float* image, const
                      float lambda_dssim, int cos_sign, float* dL_dimage, float* dL_dlf, float* dL_ddepth,
                      float* loss_out, char* scratch, void* stream);
 
+/* ---- adaptive density control with optimizer-state surgery, fused -------------------
+ * lgs_densify_stats: GaussianModel::addDensificationStats (src/gaussian_model.cpp:834-847) + the max_radii2D update
+ *   (src/gaussian_mapper.cpp:739-742) for the Gaussians with radii > 0: xyz_gradient_accum += |dL_dmeans2D.xy|,
+ *   denom += 1, max_radii2D = max(max_radii2D, radii).  All [P] float32 except radii (int32), dL_dmeans2D [P,3].
+ * lgs_densify_plan / lgs_densify_apply: GaussianModel::densifyAndPrune (src/gaussian_model.cpp:806-824 = clone :775-804,
+ *   split into N = 2 :729-773, prune :597-651, each with the Adam-state surgery of densificationPostfix :653-727) as ONE
+ *   classification pass, four scans and ONE gather of all tensors into their final rows.
+ *   plan   classifies every Gaussian (scaling [P,3] and opacity [P,1] are the RAW parameters), scans, and returns
+ *          totals_host[4] = { originals kept, clones kept, split parents whose 2 children are kept, split parents };
+ *          the new point count is totals[0] + totals[1] + 2*totals[2].  Synchronises `stream` once.
+ *          plan_scratch: lgs_densify_plan_bytes(P) bytes, handed unchanged to apply.
+ *   apply  gathers n_tensors <= 24 row-major float32 (or any 4-byte element) tensors src[t] [P,row_floats[t]] into
+ *          dst[t] [new P,row_floats[t]] in the reference's order (kept originals, clones, children copy 1, copy 2).
+ *          modes[t]: 0 copy the parent's row; 1 copy for originals, ZERO for appended points (Adam moments);
+ *          2 xyz: children get R(q/|q|) * (samples * exp(scaling)) + xyz; 3 scaling: children get log(exp(s)/1.6).
+ *          samples [2*totals[3],3]: standard-normal draws, row k*totals[3]+m for copy k of the m-th split parent
+ *          (the reference's at::normal(0, stds) consumes the generator identically).  map_scratch: 2*newP uint32.
+ *   src/dst/row_floats/modes are HOST arrays; the tensors they point to are device memory. */
+int lgs_densify_stats(int P, const int* radii, const float* dL_dmeans2D, float* xyz_gradient_accum, float* denom,
+                      float* max_radii2D, void* stream);
+size_t lgs_densify_plan_bytes(int P);
+int lgs_densify_plan(int P, const float* xyz_gradient_accum, const float* denom, const float* scaling, const float* opacity,
+                     float max_grad, float min_opacity, float extent, float percent_dense, int max_screen_size,
+                     char* plan_scratch, int* totals_host, void* stream);
+int lgs_densify_apply(int P, const char* plan_scratch, const int* totals, int n_tensors, const float* const* src,
+                      float* const* dst, const int* row_floats, const int* modes, const float* scaling,
+                      const float* rotation, const float* samples, uint32_t* map_scratch, void* stream);
+
 /* ---- semantic query (reference eval/find_objects_gaussians.py:160-175) ------------
  * sim[p,q] = <f_p/|f_p|, t_q/|t_q|> for feats [P,64] and text [Q,64] (both row-major,
  * un-normalised; eps 1e-12 like F.normalize).  out is [P,Q] row-major.

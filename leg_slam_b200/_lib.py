@@ -62,6 +62,10 @@ SIGNATURES = {
     "lgs_activations_bwd": (c_int, [c_int, c_int, c_int] + [c_void_p] * 13),
     "lgs_mapping_loss_scratch_bytes": (c_size_t, [c_int, c_int]),
     "lgs_mapping_loss": (c_int, [c_int] * 4 + [c_void_p] * 7 + [c_float, c_int] + [c_void_p] * 6),
+    "lgs_densify_stats": (c_int, [c_int] + [c_void_p] * 6),
+    "lgs_densify_plan_bytes": (c_size_t, [c_int]),
+    "lgs_densify_plan": (c_int, [c_int] + [c_void_p] * 4 + [c_float] * 4 + [c_int, c_void_p, c_void_p, c_void_p]),
+    "lgs_densify_apply": (c_int, [c_int, c_void_p, c_void_p, c_int] + [c_void_p] * 9),
     "lgs_cosine_query": (c_int, [c_int, c_int] + [c_void_p] * 4),
     "lgs_cosine_query_simt": (c_int, [c_int, c_int] + [c_void_p] * 4),
     "lgs_minmax_invert": (c_int, [c_int64] + [c_void_p] * 3),

@@ -49,7 +49,8 @@ class FlatGrads:
     one memset)."""
 
     def __init__(self, params: dict, flat: Optional[torch.Tensor] = None):
-        n = sum(params[k].numel() for k in PARAM_ORDER)
+        # every view starts on a 16-byte boundary (the kernels write float4 rows); no padding when P % 4 == 0
+        n = sum((params[k].numel() + 3) & ~3 for k in PARAM_ORDER)
         any_p = params[PARAM_ORDER[0]]
         self.flat = torch.zeros(n, dtype=torch.float32, device=any_p.device) if flat is None else flat
         off = 0
@@ -57,7 +58,7 @@ class FlatGrads:
         for k in PARAM_ORDER:
             p = params[k]
             self.views[k] = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            off += (p.numel() + 3) & ~3
 
     def attach(self, params: dict):
         for k in PARAM_ORDER:
@@ -73,11 +74,16 @@ class Mapper:
     def __init__(self, params: dict, lrs: Optional[dict] = None, sh_degree: int = 3,
                  process_group=None, optimizer_factory: Optional[Callable] = None,
                  render_fn: Optional[Callable] = None, faithful_loss_sign: bool = True,
-                 use_cuda_graph: bool = True, fused: bool = True, dp_mode: str = "allreduce"):
+                 use_cuda_graph: bool = True, fused: bool = True, dp_mode: str = "allreduce",
+                 track_densify_stats: bool = False):
         """dp_mode: "allreduce" = NCCL all-reduce of the flat gradient, then Adam on every replica;
         "fused" = one peer-memory kernel per rank doing reduce-scatter + Adam-on-shard + all-gather
-        (leg_slam_b200.dp.FusedDPAdam; needs world_size > 1, CUDA, P % 4 == 0)."""
+        (leg_slam_b200.dp.FusedDPAdam; needs world_size > 1, CUDA, P % 4 == 0).
+        track_densify_stats: accumulate the densification statistics of every rendered view inside train_step
+        (GaussianModel::addDensificationStats, reference src/gaussian_mapper.cpp:737-744) for densify_and_prune."""
         lrs = dict(DEFAULT_LRS, **(lrs or {}))
+        self._lrs = lrs
+        self._optimizer_factory = optimizer_factory
         world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.dp = None
         if dp_mode == "fused" and world > 1 and params["xyz"].is_cuda and render_fn is None and fused:
@@ -119,6 +125,12 @@ class Mapper:
         self.fused = bool(fused and render_fn is None and dev.type == "cuda")
         self._fused_loss = fused_mod.FusedMappingLoss(faithful_sign=faithful_loss_sign) if self.fused else None
         self._fbuf = None
+        self.stats = None
+        if track_densify_stats:
+            if not self.fused:
+                raise ValueError("track_densify_stats needs the fused path (CUDA tensors, our rasterizer)")
+            from .densify import DensifyStats
+            self.stats = DensifyStats(self.params["xyz"].shape[0], dev)
 
     # -- activations exactly as the reference applies them each iteration (gaussian_model.cpp:46-68)
     def activated(self):
@@ -227,6 +239,8 @@ class Mapper:
                 out, self.bg, a["means3D"], radii, e, a["lang_feats"], a["scales"], a["rotations"], 1.0, e, cam.viewmatrix,
                 cam.projmatrix, cam.tanfovx, cam.tanfovy, gi, gl, gd, p["features_dc"], self.sh_degree, cam.campos, geom, R,
                 binning, img, True, sh_rest=p["features_rest"], accumulate_sh=not first)
+            if self.stats is not None:  # max_radii2D + addDensificationStats of this view (gaussian_mapper.cpp:737-744)
+                self.stats.add(radii, out["dL_dmeans2D"])
             if not first:
                 gv["xyz"].add_(out["dL_dmeans3D"])
                 gv["lang_feat"].add_(out["dL_dlang_feats"])
@@ -236,6 +250,42 @@ class Mapper:
             total = l0 if total is None else total + l0
             self.last_num_rendered = R
         return total
+
+    def densify_and_prune(self, max_grad, min_opacity, extent, max_screen_size, percent_dense=0.01, generator=None):
+        """GaussianModel::densifyAndPrune (reference src/gaussian_model.cpp:806-824) on this mapper's Gaussian set: clone /
+        split / prune in one fused gather (leg_slam_b200.densify), carrying the Adam moments and step counts over and
+        rebuilding the flat gradient buffer.  With several ranks the statistics are summed (max for the radii) first and
+        every rank must pass a generator in the same state, so that the replicas stay identical."""
+        from . import densify as densify_mod
+        if self.stats is None:
+            raise ValueError("construct the Mapper with track_densify_stats=True")
+        if self.dp is not None:
+            raise NotImplementedError("dp_mode='fused' keeps parameters in symmetric memory: rebuild the Mapper from "
+                                      "densify.densify_and_prune's outputs instead")
+        if self.world_size > 1:
+            dist.all_reduce(self.stats.xyz_gradient_accum, op=dist.ReduceOp.SUM, group=self.pg)
+            dist.all_reduce(self.stats.denom, op=dist.ReduceOp.SUM, group=self.pg)
+            dist.all_reduce(self.stats.max_radii2D, op=dist.ReduceOp.MAX, group=self.pg)
+        p = {k: v.data for k, v in self.params.items()}
+        m, v, steps = {}, {}, {}
+        for k in PARAM_ORDER:
+            st = self.optimizer.state.get(self.params[k], {})
+            m[k] = st["exp_avg"] if "exp_avg" in st else torch.zeros_like(p[k])
+            v[k] = st["exp_avg_sq"] if "exp_avg_sq" in st else torch.zeros_like(p[k])
+            steps[k] = st.get("step", 0)
+        with torch.no_grad():
+            p2, m2, v2, stats2, info = densify_mod.densify_and_prune(p, m, v, self.stats, max_grad, min_opacity, extent,
+                                                                    max_screen_size, percent_dense, generator)
+        self.params = {k: torch.nn.Parameter(p2[k]) for k in PARAM_ORDER}
+        groups = [dict(params=[self.params[k]], lr=self._lrs[k], name=k) for k in PARAM_ORDER]
+        self.optimizer = (self._optimizer_factory or (lambda g: FusedAdam(g, lr=0.0, eps=1e-15)))(groups)
+        for k in PARAM_ORDER:  # the reference keeps step / exp_avg / exp_avg_sq per group (:683-699)
+            self.optimizer.state[self.params[k]] = dict(step=steps[k], exp_avg=m2[k], exp_avg_sq=v2[k])
+        self.grads = FlatGrads(self.params)
+        self.stats = stats2
+        self._fbuf = None  # per-P work buffers
+        torch.cuda.empty_cache()  # c10::cuda::CUDACachingAllocator::emptyCache(), :823
+        return info
 
     def train_step(self, window: Sequence[Keyframe], presharded: bool = False):
         """Render + back-propagate this rank's share of `window`, sum gradients over ranks, Adam.

@@ -1,0 +1,114 @@
+"""TEST INFRASTRUCTURE -- torch restatement of the reference's adaptive density control, statement by statement.
+
+Follows /root/reference/src/gaussian_model.cpp: addDensificationStats :834-847, densifyAndPrune :806-824,
+densifyAndClone :775-804, densifyAndSplit :729-773, densificationPostfix :653-727, prunePoints :597-651,
+resetOpacity :567-575 / replaceTensorToOptimizer :577-595, general_utils.h:25-53 (inverse_sigmoid, build_rotation),
+and the max_radii2D update of src/gaussian_mapper.cpp:739-742.  Runs on CPU or CUDA tensors.  Only tests/ may
+import it (the package never does).
+
+Parity unpinned: the reference's GaussianModel needs Eigen / OpenCV / Sophus / tinyply, none of which exist in this
+image, so it cannot be compiled here and it ships no fixtures for this path.  This restatement is checked by
+construction (same libtorch ops in the same order) and by its own invariants (tests/test_densify.py).
+"""
+import torch
+
+PARAMS = ("xyz", "features_dc", "features_rest", "lang_feat", "opacity", "scaling", "rotation")
+
+
+class Model:
+    """The seven parameter tensors + Adam moments + the four statistics vectors of GaussianModel."""
+
+    def __init__(self, params, percent_dense=0.01):
+        self.p = {k: params[k].detach().clone() for k in PARAMS}
+        self.m = {k: torch.zeros_like(v) for k, v in self.p.items()}   # exp_avg
+        self.v = {k: torch.zeros_like(v) for k, v in self.p.items()}   # exp_avg_sq
+        P, dev = self.p["xyz"].shape[0], self.p["xyz"].device
+        self.exist_since_iter = torch.zeros(P, dtype=torch.int32, device=dev)
+        self.xyz_gradient_accum = torch.zeros(P, 1, device=dev)
+        self.denom = torch.zeros(P, 1, device=dev)
+        self.max_radii2D = torch.zeros(P, device=dev)
+        self.percent_dense = percent_dense
+
+    # -- gaussian_mapper.cpp:739-742 + gaussian_model.cpp:834-847
+    def add_stats(self, radii, means2D_grad):
+        f = radii > 0
+        self.max_radii2D[f] = torch.max(self.max_radii2D[f], radii[f].to(self.max_radii2D.dtype))
+        self.xyz_gradient_accum[f] += torch.norm(means2D_grad[f][:, :2], dim=-1, keepdim=True)
+        self.denom[f] = self.denom[f] + 1
+
+    def _scale(self):
+        return torch.exp(self.p["scaling"])
+
+    # -- :597-651
+    def prune_points(self, mask):
+        keep = ~mask
+        for k in PARAMS:
+            self.p[k] = self.p[k][keep]
+            self.m[k] = self.m[k][keep].clone()
+            self.v[k] = self.v[k][keep].clone()
+        self.exist_since_iter = self.exist_since_iter[keep]
+        self.xyz_gradient_accum = self.xyz_gradient_accum[keep]
+        self.denom = self.denom[keep]
+        self.max_radii2D = self.max_radii2D[keep]
+
+    # -- :653-727
+    def postfix(self, new, new_exist):
+        for k in PARAMS:
+            self.m[k] = torch.cat([self.m[k].clone(), torch.zeros_like(new[k])], dim=0)
+            self.v[k] = torch.cat([self.v[k].clone(), torch.zeros_like(new[k])], dim=0)
+            self.p[k] = torch.cat([self.p[k], new[k]], dim=0)
+        self.exist_since_iter = torch.cat([self.exist_since_iter, new_exist], dim=0)
+        P, dev = self.p["xyz"].shape[0], self.p["xyz"].device
+        self.xyz_gradient_accum = torch.zeros(P, 1, device=dev)
+        self.denom = torch.zeros(P, 1, device=dev)
+        self.max_radii2D = torch.zeros(P, device=dev)
+
+    # -- :775-804
+    def densify_and_clone(self, grads, thr, extent):
+        sel = torch.norm(grads, dim=-1) >= thr
+        sel = torch.logical_and(sel, self._scale().max(dim=1).values <= self.percent_dense * extent)
+        self.postfix({k: self.p[k][sel] for k in PARAMS}, self.exist_since_iter[sel])
+
+    # -- :729-773; `normal01(n)` returns n x 3 standard-normal draws (at::normal(0, stds) = z * stds)
+    def densify_and_split(self, grads, thr, extent, normal01, N=2):
+        n_init = self.p["xyz"].shape[0]
+        padded = torch.zeros(n_init, device=grads.device)
+        padded[:grads.shape[0]] = grads.squeeze()
+        sel = padded >= thr
+        sel = torch.logical_and(sel, self._scale().max(dim=1).values > self.percent_dense * extent)
+        stds = self._scale()[sel].repeat(N, 1)
+        samples = normal01(stds.shape[0]) * stds
+        q = self.p["rotation"][sel]
+        q = q / torch.sqrt((q * q).sum(dim=1, keepdim=True))
+        r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                         2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                         2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], dim=1).view(-1, 3, 3).repeat(N, 1, 1)
+        new = {k: self.p[k][sel].repeat(*([N] + [1] * (self.p[k].dim() - 1))) for k in PARAMS}
+        new["xyz"] = torch.bmm(R, samples.unsqueeze(-1)).squeeze(-1) + self.p["xyz"][sel].repeat(N, 1)
+        new["scaling"] = torch.log(self._scale()[sel].repeat(N, 1) / (0.8 * N))
+        self.postfix(new, self.exist_since_iter[sel].repeat(N))
+        n_new = N * int(sel.sum())
+        self.prune_points(torch.cat([sel, torch.zeros(n_new, dtype=torch.bool, device=sel.device)]))
+        return int(sel.sum())
+
+    # -- :806-824
+    def densify_and_prune(self, max_grad, min_opacity, extent, max_screen_size, normal01):
+        grads = self.xyz_gradient_accum / self.denom
+        grads[grads.isnan()] = 0.0
+        self.densify_and_clone(grads, max_grad, extent)
+        self.densify_and_split(grads, max_grad, extent, normal01)
+        prune = (torch.sigmoid(self.p["opacity"]) < min_opacity).squeeze(-1)
+        if max_screen_size:
+            big_vs = self.max_radii2D > max_screen_size
+            big_ws = self._scale().max(dim=1).values > 0.1 * extent
+            prune = torch.logical_or(torch.logical_or(prune, big_vs), big_ws)
+        self.prune_points(prune)
+
+    # -- :567-595 (the clamp is against ones: a no-op; the moments ARE zeroed)
+    def reset_opacity(self):
+        op = torch.sigmoid(self.p["opacity"])
+        x = torch.min(op, torch.ones_like(op * 0.01))
+        self.p["opacity"] = torch.log(x / (1 - x))
+        self.m["opacity"] = torch.zeros_like(self.p["opacity"])
+        self.v["opacity"] = torch.zeros_like(self.p["opacity"])

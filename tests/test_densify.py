@@ -1,0 +1,170 @@
+"""Adaptive density control: the fused CUDA path (lgs_densify_*) against the torch
+restatement of the reference's densifyAndPrune sequence (oracle/densify_ref.py), plus the restatement's own
+invariants on CPU."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import densify_ref as DR  # noqa: E402
+
+
+def make_model(P, dev, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g)  # noqa: E731
+    params = dict(xyz=r(P, 3), features_dc=r(P, 1, 3), features_rest=r(P, 15, 3) * 0.1, lang_feat=r(P, 64),
+                  opacity=r(P, 1) * 3.0,                      # sigmoid spans (0, 1): some fall under min_opacity
+                  scaling=r(P, 3) * 0.8 - 3.5,                # exp -> around 0.03, both sides of percent_dense * extent
+                  rotation=r(P, 4))
+    params = {k: v.to(dev).contiguous() for k, v in params.items()}
+    m = DR.Model(params)
+    for k in DR.PARAMS:  # non-trivial Adam moments
+        m.m[k] = (r(*m.p[k].shape) * 0.01).to(dev)
+        m.v[k] = (r(*m.p[k].shape) ** 2 * 1e-4).to(dev)
+    m.exist_since_iter = torch.randint(0, 50, (P,), generator=g, dtype=torch.int32).to(dev)
+    # statistics: a few views' worth, some never seen (0/0 -> nan -> 0)
+    seen = torch.rand(P, generator=g) < 0.8
+    m.denom = (seen.float() * torch.randint(1, 6, (P,), generator=g).float()).unsqueeze(1).to(dev)
+    m.xyz_gradient_accum = (m.denom.cpu() * torch.rand(P, 1, generator=g) * 4e-4).to(dev)
+    m.max_radii2D = (torch.rand(P, generator=g) * 40).to(dev)
+    return m
+
+
+def clone_model(m):
+    c = DR.Model(m.p)
+    c.m = {k: v.clone() for k, v in m.m.items()}
+    c.v = {k: v.clone() for k, v in m.v.items()}
+    c.exist_since_iter = m.exist_since_iter.clone()
+    c.xyz_gradient_accum, c.denom, c.max_radii2D = m.xyz_gradient_accum.clone(), m.denom.clone(), m.max_radii2D.clone()
+    return c
+
+
+ARGS = dict(max_grad=2e-4, min_opacity=0.05, extent=4.0)
+
+
+def test_restatement_invariants_cpu():
+    m = make_model(3000, torch.device("cpu"), seed=3)
+    ref = clone_model(m)
+    g = torch.Generator().manual_seed(7)
+    z = {}
+    def normal01(n):
+        z["n"] = n
+        return torch.randn(n, 3, generator=g)
+    grads = torch.nan_to_num(m.xyz_gradient_accum / m.denom, nan=0.0).squeeze()
+    smax = torch.exp(m.p["scaling"]).max(dim=1).values
+    n_clone = int(((grads >= ARGS["max_grad"]) & (smax <= 0.01 * ARGS["extent"])).sum())
+    n_split = int(((grads >= ARGS["max_grad"]) & (smax > 0.01 * ARGS["extent"])).sum())
+    assert n_clone > 0 and n_split > 0  # the fixture exercises both branches
+    ref.densify_and_prune(ARGS["max_grad"], ARGS["min_opacity"], ARGS["extent"], 0, normal01)
+    assert z["n"] == 2 * n_split
+    P2 = ref.p["xyz"].shape[0]
+    for k in DR.PARAMS:
+        assert ref.p[k].shape[0] == P2 and ref.m[k].shape == ref.p[k].shape and ref.v[k].shape == ref.p[k].shape
+    assert ref.xyz_gradient_accum.shape == (P2, 1) and not ref.xyz_gradient_accum.any() and not ref.max_radii2D.any()
+    assert bool((torch.sigmoid(ref.p["opacity"]) >= ARGS["min_opacity"]).all())  # everything below was pruned
+    # the moments of appended points are zero, those of survivors are carried over
+    n_keep = int((~(((grads >= ARGS["max_grad"]) & (smax > 0.01 * ARGS["extent"]))) &
+                  (torch.sigmoid(m.p["opacity"]).squeeze(-1) >= ARGS["min_opacity"])).sum())
+    assert not ref.m["lang_feat"][n_keep:].any() and ref.m["lang_feat"][:n_keep].any()
+    ref.reset_opacity()
+    assert not ref.m["opacity"].any() and not ref.v["opacity"].any()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_screen_size", [0, 20])
+@pytest.mark.parametrize("P", [1, 4097, 60000])
+def test_fused_densify_matches_restatement(P, max_screen_size, dev):
+    from leg_slam_b200 import densify as D
+    m = make_model(P, dev, seed=P)
+    ref = clone_model(m)
+    zs = {}
+    def normal01(n):
+        if "z" not in zs:
+            zs["z"] = torch.randn(n, 3, generator=torch.Generator().manual_seed(11)).to(dev)
+        assert zs["z"].shape[0] == n
+        return zs["z"]
+    ref.densify_and_prune(ARGS["max_grad"], ARGS["min_opacity"], ARGS["extent"], max_screen_size, normal01)
+    st = D.DensifyStats(P, dev)
+    st.xyz_gradient_accum, st.denom, st.max_radii2D = m.xyz_gradient_accum.clone(), m.denom.clone(), m.max_radii2D.clone()
+    st.exist_since_iter = m.exist_since_iter.clone()
+    p2, m2, v2, st2, info = D.densify_and_prune(m.p, m.m, m.v, st, ARGS["max_grad"], ARGS["min_opacity"], ARGS["extent"],
+                                                max_screen_size, normal01=normal01)
+    torch.cuda.synchronize()
+    assert info["new_P"] == ref.p["xyz"].shape[0]
+    n_old = info["kept"] + info["cloned"]
+    for k in DR.PARAMS:
+        a, b = p2[k], ref.p[k]
+        assert a.shape == b.shape, k
+        if k in ("xyz", "scaling"):  # children are computed: same formula, different instruction order
+            assert torch.equal(a[:n_old], b[:n_old]), k
+            if a.shape[0] > n_old:
+                err = (a[n_old:] - b[n_old:]).abs().max() / b[n_old:].abs().max().clamp_min(1e-12)
+                assert float(err) <= 2e-6, (k, float(err))
+        else:
+            assert torch.equal(a, b), k
+        assert torch.equal(m2[k], ref.m[k]) and torch.equal(v2[k], ref.v[k]), k
+    assert torch.equal(st2.exist_since_iter, ref.exist_since_iter)
+    assert not st2.xyz_gradient_accum.any() and not st2.denom.any() and not st2.max_radii2D.any()
+    # inputs untouched
+    assert m.p["xyz"].shape[0] == P
+
+
+@pytest.mark.gpu
+def test_fused_stats_match_restatement(dev):
+    from leg_slam_b200 import densify as D
+    P = 50000
+    m = make_model(P, dev, seed=5)
+    g = torch.Generator().manual_seed(9)
+    radii = (torch.randint(-2, 30, (P,), generator=g, dtype=torch.int32)).clamp_min(0).to(dev)
+    grad = (torch.randn(P, 3, generator=g) * 1e-3).to(dev)
+    st = D.DensifyStats(P, dev)
+    st.xyz_gradient_accum, st.denom, st.max_radii2D = m.xyz_gradient_accum.clone(), m.denom.clone(), m.max_radii2D.clone()
+    st.add(radii, grad)
+    m.add_stats(radii, grad)
+    torch.cuda.synchronize()
+    assert torch.equal(st.denom, m.denom) and torch.equal(st.max_radii2D, m.max_radii2D)
+    np.testing.assert_allclose(st.xyz_gradient_accum.cpu().numpy(), m.xyz_gradient_accum.cpu().numpy(), rtol=1e-6, atol=0)  # norm: fused multiply-add vs torch.norm
+
+
+@pytest.mark.gpu
+def test_mapper_densify_keeps_training(dev):
+    """Statistics accumulate inside train_step, densify_and_prune rebuilds parameters + Adam state + the flat
+    gradient buffer, and the mapping iteration keeps running on the new point set."""
+    from leg_slam_b200 import mapper as M, synthetic
+    W, H = 96, 64
+    sc = synthetic.make_scene(6000, seed=61, mean_scale=0.06, device=dev)
+    cams = synthetic.make_cameras(2, W, H, seed=61)
+    g = torch.Generator().manual_seed(62)
+    win = [M.Keyframe(c.to(dev), torch.rand(3, H, W, generator=g).to(dev), torch.randn(64, 37, 37, generator=g).to(dev),
+                      (torch.rand(1, H, W, generator=g) * 3).to(dev)) for c in cams]
+    mp = M.Mapper(sc, sh_degree=3, track_densify_stats=True)
+    for _ in range(4):
+        l0 = mp.train_step(win)
+    assert float(mp.stats.denom.max()) == 8.0  # 4 iterations x 2 views for the always-visible Gaussians
+    P0 = mp.params["xyz"].shape[0]
+    m_before = mp.optimizer.state[mp.params["lang_feat"]]["exp_avg"].clone()
+    info = mp.densify_and_prune(max_grad=1e-7, min_opacity=0.005, extent=6.0, max_screen_size=0,
+                                generator=torch.Generator(device=dev).manual_seed(1))
+    P1 = mp.params["xyz"].shape[0]
+    assert P1 == info["new_P"] and P1 != P0 and info["cloned"] + info["split_selected"] > 0
+    st = mp.optimizer.state[mp.params["lang_feat"]]
+    assert st["step"] == 4 and st["exp_avg"].shape == (P1, 64)
+    assert not st["exp_avg"][info["kept"]:].any() and m_before.any() and st["exp_avg"][:info["kept"]].any()
+    assert 123 * P1 <= mp.grads.flat.numel() <= 123 * P1 + 7 * 3  # 16-byte aligned views
+    for _ in range(2):
+        l1 = mp.train_step(win)
+    assert torch.isfinite(l1) and mp.stats.denom.shape == (P1, 1)
