@@ -289,6 +289,19 @@ int lgs_densify_apply(int P, const char* plan_scratch, const int* totals, int n_
                       float* const* dst, const int* row_floats, const int* modes, const float* scaling,
                       const float* rotation, const float* samples, uint32_t* map_scratch, void* stream);
 
+/* ---- keyframe ingest geometry (the step before the path) --------------------------------
+ * lgs_reproject_depth_pinhole: reprojectDepthPinhole (src/stereo_vision.cu:40-61,135-162): points[i] =
+ *   ((u-cx)*d/fx, (v-cy)*d/fy, d) for pixel i = v*width+u where mask[i] (bool bytes), zeros elsewhere.  points [P,3].
+ * lgs_transform_points: transformPoints (src/operate_points.cu:39-94): out = transformPoint4x3(points, matrix), matrix
+ *   4x4 column-major as the reference indexes it.  out must not alias points.
+ * lgs_knn_mean_dist2: distCUDA2 (third_party/simple-knn/simple_knn.cu:185-220): mean squared distance of every point
+ *   to its 3 nearest neighbours (FLT_MAX terms when P < 4, like the reference).  scratch: lgs_knn_scratch_bytes(P). */
+int lgs_reproject_depth_pinhole(int P, int width, float fx, float fy, float cx, float cy, const float* depth,
+                                const unsigned char* mask, float* points, void* stream);
+int lgs_transform_points(int P, const float* points, const float* transformmatrix, float* out, void* stream);
+size_t lgs_knn_scratch_bytes(int P);
+int lgs_knn_mean_dist2(int P, const float* points, float* mean_dist2, char* scratch, void* stream);
+
 /* ---- semantic query (reference eval/find_objects_gaussians.py:160-175) ------------
  * sim[p,q] = <f_p/|f_p|, t_q/|t_q|> for feats [P,64] and text [Q,64] (both row-major,
  * un-normalised; eps 1e-12 like F.normalize).  out is [P,Q] row-major.

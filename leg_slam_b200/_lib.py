@@ -66,6 +66,10 @@ SIGNATURES = {
     "lgs_densify_plan_bytes": (c_size_t, [c_int]),
     "lgs_densify_plan": (c_int, [c_int] + [c_void_p] * 4 + [c_float] * 4 + [c_int, c_void_p, c_void_p, c_void_p]),
     "lgs_densify_apply": (c_int, [c_int, c_void_p, c_void_p, c_int] + [c_void_p] * 9),
+    "lgs_reproject_depth_pinhole": (c_int, [c_int, c_int] + [c_float] * 4 + [c_void_p] * 4),
+    "lgs_transform_points": (c_int, [c_int] + [c_void_p] * 4),
+    "lgs_knn_scratch_bytes": (c_size_t, [c_int]),
+    "lgs_knn_mean_dist2": (c_int, [c_int] + [c_void_p] * 4),
     "lgs_cosine_query": (c_int, [c_int, c_int] + [c_void_p] * 4),
     "lgs_cosine_query_simt": (c_int, [c_int, c_int] + [c_void_p] * 4),
     "lgs_minmax_invert": (c_int, [c_int64] + [c_void_p] * 3),

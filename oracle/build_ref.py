@@ -87,6 +87,38 @@ def build(force=False, verbose=True):
     return so
 
 
+KNN_REF = "/root/reference/third_party/simple-knn"
+KNN_SO = os.path.join(OUT, "ref_simple_knn.so")
+
+
+def build_knn(force=False, verbose=True):
+    """The UNMODIFIED reference simple-knn (third_party/simple-knn/simple_knn.cu, no torch in it) + our C entry point
+    oracle/ref_knn_wrap.cu -> oracle/_ref/ref_simple_knn.so (ctypes).  Oracle for SURVEY.md 8f row 4 (distCUDA2)."""
+    if os.path.exists(KNN_SO) and not force:
+        return KNN_SO
+    if not os.path.isdir(KNN_REF):
+        raise RuntimeError("reference tree not present (GPU box?) and no prebuilt " + KNN_SO)
+    os.makedirs(OUT, exist_ok=True)
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = [os.path.join(cuda, "bin", "nvcc"), "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+           "-gencode", "arch=compute_100,code=sm_100", "-include", "cfloat", "-I" + KNN_REF,
+           os.path.join(KNN_REF, "simple_knn.cu"), os.path.join(HERE, "ref_knn_wrap.cu"), "-o", KNN_SO, "-lcudart"]
+    if verbose:
+        print("[build_ref]", " ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return KNN_SO
+
+
+def load_knn():
+    import ctypes
+    if not os.path.exists(KNN_SO):
+        raise FileNotFoundError(KNN_SO + " missing: run `python oracle/build_ref.py` where /root/reference exists")
+    lib = ctypes.CDLL(KNN_SO)
+    lib.ref_simple_knn.restype = ctypes.c_int
+    lib.ref_simple_knn.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    return lib
+
+
 def load():
     """Import the prebuilt module (after `import torch`)."""
     import importlib.util
@@ -102,3 +134,4 @@ def load():
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
+    print(build_knn(force="--force" in sys.argv))
