@@ -69,7 +69,60 @@ def main():
                                        ref_bwd_ms=t(lambda: ref.rasterize_gaussians_backward(*rb), 3, 1), ref_R=Rr)
     except Exception as ex:  # reference .so not shipped
         out["cfgD_2M_1296x968"]["ref"] = str(ex)
+    del sc, act, color, lf, depth, geom, binning, img
+    torch.cuda.empty_cache()
+    out.update(extra_rows(dev))
     print(json.dumps(out))
+
+
+def extra_rows(dev):
+    """fused densify/prune vs the torch restatement of the reference sequence, k-NN vs the
+    compiled reference simple-knn."""
+    import densify_ref as DR
+    from leg_slam_b200 import densify as D, ingest
+    out = {}
+    for P in (500_000, 2_000_000):
+        sc = synthetic.make_scene(P, seed=7, device=dev)
+        g = torch.Generator().manual_seed(8)
+        m = DR.Model(sc)
+        for k in DR.PARAMS:
+            m.m[k] = torch.randn(m.p[k].shape, generator=g).to(dev) * 0.01
+            m.v[k] = torch.rand(m.p[k].shape, generator=g).to(dev) * 1e-4
+        m.denom = torch.randint(0, 6, (P, 1), generator=g).float().to(dev)
+        m.xyz_gradient_accum = m.denom * (torch.rand(P, 1, generator=g) * 4e-4).to(dev)
+        z = {}
+
+        def normal01(n):
+            if z.get("n") != n:
+                z["n"], z["z"] = n, torch.randn(n, 3, device=dev)
+            return z["z"]
+        st = D.DensifyStats(P, dev)
+        st.xyz_gradient_accum, st.denom = m.xyz_gradient_accum, m.denom
+        args = (2e-4, 0.005, 6.0, 20)
+        info = D.densify_and_prune(m.p, m.m, m.v, st, *args, normal01=normal01)[4]
+
+        def ref_once():
+            c = DR.Model(m.p)
+            c.m, c.v = dict(m.m), dict(m.v)
+            c.xyz_gradient_accum, c.denom = m.xyz_gradient_accum.clone(), m.denom.clone()
+            c.densify_and_prune(*args, normal01)
+        out[f"densify_prune_P{P}"] = dict(info=info, fused_ms=t(lambda: D.densify_and_prune(m.p, m.m, m.v, st, *args, normal01=normal01), 5, 2),
+                                          torch_restatement_ms=t(ref_once, 3, 1),
+                                          algorithmic_GB=round(info["new_P"] * 123 * 4 * 3 * 2 / 1e9, 3))
+        pts = sc["xyz"].contiguous()
+        row = dict(ours_ms=t(lambda: ingest.distCUDA2(pts), 5, 2))
+        try:
+            import build_ref
+            lib = build_ref.load_knn()
+            ref = torch.zeros(P, device=dev)
+            row["reference_simple_knn_ms"] = t(lambda: lib.ref_simple_knn(P, pts.data_ptr(), ref.data_ptr()), 3, 1)
+            row["bit_identical"] = bool(torch.equal(ingest.distCUDA2(pts), ref))
+        except Exception as ex:
+            row["ref"] = str(ex)
+        out[f"knn_dist2_P{P}"] = row
+        del m, sc, st
+        torch.cuda.empty_cache()
+    return out
 
 
 if __name__ == "__main__":
