@@ -6,8 +6,8 @@
 //     image, lf, depth *= mask                                      (undistortion mask, optional)
 //     loss   = (1-l)*L1(image, gt) + l*(1 - SSIM(image, gt)) +/- mean_px cos(lf, gt_lf) + L1(depth, gt_depth)
 // and autograd's walk back through them, by four launches that read each image once:
-//   loss_pix_kernel    per pixel: L1 terms, the 64-channel cosine (feature vector kept in registers, low-res
-//                      ground truth gathered), and dL/dlf, dL/ddepth, the L1 part of dL/dimage
+//   loss_pix_kernel    per pixel: L1 terms, the 64-channel cosine (feature vector kept in registers, 16 channels per
+//                      thread, low-res ground truth gathered), and dL/dlf, dL/ddepth, the L1 part of dL/dimage
 //   ssim_fwd_kernel    per 16x16 tile and channel: separable 11-tap Gaussian statistics in shared memory,
 //                      SSIM map sum, and the three partial-derivative maps the backward needs
 //   ssim_bwd_kernel    per tile: separable filter of those maps, adds the SSIM part of dL/dimage
@@ -44,18 +44,28 @@ __device__ __forceinline__ float block_sum(float v, float* red, int tid) {  // 2
     return r;  // valid in thread tid == 0
 }
 
-__global__ void __launch_bounds__(256)
+// 256 threads = 64 pixels x 4 channel groups of 16: thread (grp, px) keeps 16 feature values in registers, the three
+// dot products are completed across the groups through shared memory.  (One thread per pixel with all 64 channels
+// in registers ran at 2 CTAs/SM and a third of the HBM rate: too few loads in flight per SM.)
+constexpr int LP_PIX = 64;
+constexpr int LP_GRP = 4;
+constexpr int LP_CH = LF / LP_GRP;  // 16
+
+__global__ void __launch_bounds__(LP_PIX * LP_GRP)
 loss_pix_kernel(int W, int H, int lw, int lh, const float* __restrict__ image, const float* __restrict__ lf,
                 const float* __restrict__ depth, const float* __restrict__ gt_image, const float* __restrict__ gt_lf,
                 const float* __restrict__ gt_depth, const float* __restrict__ mask, float w_l1, float w_cos, float w_depth,
                 float* __restrict__ dL_dimage, float* __restrict__ dL_dlf, float* __restrict__ dL_ddepth,
                 float* __restrict__ acc) {
     __shared__ float red[8];
+    __shared__ float part[3][LP_GRP][LP_PIX];
     const size_t HW = (size_t)H * W;
-    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int px = threadIdx.x & (LP_PIX - 1), grp = threadIdx.x / LP_PIX;
+    const size_t p = (size_t)blockIdx.x * LP_PIX + px;
+    const bool live = p < HW;
     float s_l1 = 0.f, s_cos = 0.f, s_d = 0.f;
-    if (p < HW) {
-        const float m0 = mask ? mask[p] : 1.f;
+    const float m0 = (live && mask) ? mask[p] : 1.f;
+    if (live && grp == 0) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float mc = mask ? mask[c * HW + p] : 1.f;
@@ -63,40 +73,52 @@ loss_pix_kernel(int W, int H, int lw, int lh, const float* __restrict__ image, c
             s_l1 += fabsf(d);
             dL_dimage[c * HW + p] = w_l1 * sgn(d) * mc;
         }
-        {
-            const float d = depth[p] * m0 - gt_depth[p];
-            s_d = fabsf(d);
-            dL_ddepth[p] = w_depth * sgn(d) * m0;
-        }
+        const float d = depth[p] * m0 - gt_depth[p];
+        s_d = fabsf(d);
+        dL_ddepth[p] = w_depth * sgn(d) * m0;
+    }
+    float a[LP_CH], bv[LP_CH];
+    float w12 = 0.f, w1 = 0.f, w2 = 0.f;
+    if (live) {
         // nearest-neighbour source pixel of the low-resolution ground-truth feature map (torch `nearest`)
-        const int py = (int)(p / W), px = (int)(p - (size_t)py * W);
+        const int py = (int)(p / W), pxx = (int)(p - (size_t)py * W);
         const int sy = min((int)floorf(py * ((float)lh / (float)H)), lh - 1);
-        const int sx = min((int)floorf(px * ((float)lw / (float)W)), lw - 1);
-        const float* b = gt_lf + (size_t)sy * lw + sx;
+        const int sx = min((int)floorf(pxx * ((float)lw / (float)W)), lw - 1);
         const size_t bstride = (size_t)lh * lw;
-        float a[LF];
-        float w12 = 0.f, w1 = 0.f, w2 = 0.f;
+        const float* b = gt_lf + (size_t)(grp * LP_CH) * bstride + (size_t)sy * lw + sx;
+        const float* ap = lf + (size_t)(grp * LP_CH) * HW + p;
 #pragma unroll
-        for (int k = 0; k < LF; ++k) {
-            a[k] = __ldcs(lf + k * HW + p) * m0;
-            const float bk = __ldg(b + k * bstride);
-            w12 = fmaf(a[k], bk, w12);
-            w1 = fmaf(a[k], a[k], w1);
-            w2 = fmaf(bk, bk, w2);
+        for (int k = 0; k < LP_CH; ++k) {
+            a[k] = __ldcs(ap + k * HW) * m0;
+            bv[k] = __ldg(b + k * bstride);
         }
+#pragma unroll
+        for (int k = 0; k < LP_CH; ++k) {
+            w12 = fmaf(a[k], bv[k], w12);
+            w1 = fmaf(a[k], a[k], w1);
+            w2 = fmaf(bv[k], bv[k], w2);
+        }
+    }
+    part[0][grp][px] = w12;
+    part[1][grp][px] = w1;
+    part[2][grp][px] = w2;
+    __syncthreads();
+    if (live) {
+        // fixed summation order over the groups: every thread of a pixel gets the same totals
+        w12 = (part[0][0][px] + part[0][1][px]) + (part[0][2][px] + part[0][3][px]);
+        w1 = (part[1][0][px] + part[1][1][px]) + (part[1][2][px] + part[1][3][px]);
+        w2 = (part[2][0][px] + part[2][1][px]) + (part[2][2][px] + part[2][3][px]);
         const float na_true = sqrtf(w1);
         const float na = fmaxf(na_true, 1e-8f), nb = fmaxf(sqrtf(w2), 1e-8f);
         const float inv_na = 1.f / na, inv_nb = 1.f / nb;
         const float c = w12 * inv_na * inv_nb;
-        s_cos = c;
+        if (grp == 0) s_cos = c;
         // d cos / d a = (b/|b| - cos * a/|a|) / |a|   (the second term vanishes where the norm is clamped)
         const float k_b = w_cos * m0 * inv_na * inv_nb;
         const float k_a = (na_true > 1e-8f) ? -w_cos * m0 * c * inv_na * inv_na : 0.f;
+        float* gp = dL_dlf + (size_t)(grp * LP_CH) * HW + p;
 #pragma unroll
-        for (int k = 0; k < LF; ++k) {
-            const float bk = __ldg(b + k * bstride);
-            __stcs(dL_dlf + k * HW + p, fmaf(k_b, bk, k_a * a[k]));
-        }
+        for (int k = 0; k < LP_CH; ++k) __stcs(gp + k * HW, fmaf(k_b, bv[k], k_a * a[k]));
     }
     const float t_l1 = block_sum(s_l1, red, threadIdx.x);
     const float t_cos = block_sum(s_cos, red, threadIdx.x);
@@ -344,7 +366,7 @@ extern "C" int lgs_mapping_loss(int W, int H, int lf_w, int lf_h, const float* i
     const float n_img = 3.f * (float)HW, n_pix = (float)HW;
     LGS_CUDA_TRY(cudaMemsetAsync(acc, 0, 4 * sizeof(float), s));
     const float w_cos = (cos_sign >= 0 ? 1.f : -1.f) / n_pix;
-    loss_pix_kernel<<<(unsigned)((HW + 255) / 256), 256, 0, s>>>(W, H, lf_w, lf_h, image, lf, depth, gt_image, gt_lf, gt_depth,
+    loss_pix_kernel<<<(unsigned)((HW + LP_PIX - 1) / LP_PIX), LP_PIX * LP_GRP, 0, s>>>(W, H, lf_w, lf_h, image, lf, depth, gt_image, gt_lf, gt_depth,
                                                                  mask, (1.f - lambda_dssim) / n_img, w_cos, 1.f / n_pix,
                                                                  dL_dimage, dL_dlf, dL_ddepth, acc);
     LGS_LAUNCH_CHECK();
