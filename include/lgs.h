@@ -302,6 +302,16 @@ int lgs_transform_points(int P, const float* points, const float* transformmatri
 size_t lgs_knn_scratch_bytes(int P);
 int lgs_knn_mean_dist2(int P, const float* points, float* mean_dist2, char* scratch, void* stream);
 
+/* ---- .ply checkpoint records (reference GaussianModel::savePly / loadPly,
+ *      src/gaussian_model.cpp:854-1075) ------------------------------------------------------------------
+ * block is the [P][C] float32 vertex block exactly as it lies in a binary_little_endian .ply.  Column c holds element
+ * col_elem[c] of the row of tensor col_tensor[c] (device int arrays; -1 = zero column when packing, skipped when
+ * unpacking).  tensors / row_floats are HOST arrays of n_tensors <= 24 device tensors [P,row_floats[t]]. */
+int lgs_ply_pack(long long P, int C, const int* col_tensor, const int* col_elem, int n_tensors,
+                 const float* const* tensors, const int* row_floats, float* block, void* stream);
+int lgs_ply_unpack(long long P, int C, const int* col_tensor, const int* col_elem, int n_tensors, float* const* tensors,
+                   const int* row_floats, const float* block, void* stream);
+
 /* ---- semantic query (reference eval/find_objects_gaussians.py:160-175) ------------
  * sim[p,q] = <f_p/|f_p|, t_q/|t_q|> for feats [P,64] and text [Q,64] (both row-major,
  * un-normalised; eps 1e-12 like F.normalize).  out is [P,Q] row-major.

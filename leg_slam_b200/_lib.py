@@ -70,6 +70,8 @@ SIGNATURES = {
     "lgs_transform_points": (c_int, [c_int] + [c_void_p] * 4),
     "lgs_knn_scratch_bytes": (c_size_t, [c_int]),
     "lgs_knn_mean_dist2": (c_int, [c_int] + [c_void_p] * 4),
+    "lgs_ply_pack": (c_int, [ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lgs_ply_unpack": (c_int, [ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lgs_cosine_query": (c_int, [c_int, c_int] + [c_void_p] * 4),
     "lgs_cosine_query_simt": (c_int, [c_int, c_int] + [c_void_p] * 4),
     "lgs_minmax_invert": (c_int, [c_int64] + [c_void_p] * 3),

@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "liblgs.so")
 SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "render_fwd.cu", "render_fwd_tc.cu", "render_bwd.cu", "render_bwd_tc.cu",
-           "preprocess_bwd.cu", "adam.cu", "dp_adam.cu", "query.cu", "query_tc.cu", "loss.cu", "densify.cu", "ingest.cu", "bench_kernels.cu"]
+           "preprocess_bwd.cu", "adam.cu", "dp_adam.cu", "query.cu", "query_tc.cu", "loss.cu", "densify.cu", "ingest.cu", "ply.cu", "bench_kernels.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "ptx.cuh"), os.path.join(CSRC, "adam_math.cuh"), os.path.join(CSRC, "tc.cuh"),
            os.path.join(ROOT, "include", "lgs.h")]
 

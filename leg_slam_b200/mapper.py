@@ -251,6 +251,42 @@ class Mapper:
             self.last_num_rendered = R
         return total
 
+    # -- .ply checkpoints (reference GaussianModel::savePly / loadPly, src/gaussian_model.cpp:854-1075)
+    def save_checkpoint(self, path):
+        """The Gaussian set in the reference's .ply layout plus the Adam moments and step counts (leg_slam_b200.ply_io):
+        loads in the reference as a plain model, resumes here with `load_checkpoint`."""
+        from . import ply_io
+        if self.dp is not None:
+            raise NotImplementedError("dp_mode='fused' shards the Adam state over the ranks")
+        p = {k: v.data for k, v in self.params.items()}
+        m, v, steps = {}, {}, {}
+        for k in PARAM_ORDER:
+            st = self.optimizer.state.get(self.params[k], {})
+            m[k] = st["exp_avg"] if "exp_avg" in st else torch.zeros_like(p[k])
+            v[k] = st["exp_avg_sq"] if "exp_avg_sq" in st else torch.zeros_like(p[k])
+            steps[k] = int(st.get("step", 0))
+        ply_io.save_ply(path, p, m, v, steps)
+
+    def load_checkpoint(self, path):
+        """Replace this mapper's Gaussian set and optimizer state by a checkpoint written by `save_checkpoint` (or by a
+        plain reference .ply: fresh Adam state)."""
+        from . import ply_io
+        if self.dp is not None:
+            raise NotImplementedError("dp_mode='fused' keeps parameters in symmetric memory")
+        dev = self.params["xyz"].device
+        p2, m2, v2, steps = ply_io.load_ply(path, dev, self.sh_degree)
+        self.params = {k: torch.nn.Parameter(p2[k]) for k in PARAM_ORDER}
+        groups = [dict(params=[self.params[k]], lr=self._lrs[k], name=k) for k in PARAM_ORDER]
+        self.optimizer = (self._optimizer_factory or (lambda g: FusedAdam(g, lr=0.0, eps=1e-15)))(groups)
+        if m2 is not None:
+            for k in PARAM_ORDER:
+                self.optimizer.state[self.params[k]] = dict(step=steps[k], exp_avg=m2[k], exp_avg_sq=v2[k])
+        self.grads = FlatGrads(self.params)
+        self._fbuf = None
+        if self.stats is not None:
+            from .densify import DensifyStats
+            self.stats = DensifyStats(self.params["xyz"].shape[0], dev)
+
     def densify_and_prune(self, max_grad, min_opacity, extent, max_screen_size, percent_dense=0.01, generator=None):
         """GaussianModel::densifyAndPrune (reference src/gaussian_model.cpp:806-824) on this mapper's Gaussian set: clone /
         split / prune in one fused gather (leg_slam_b200.densify), carrying the Adam moments and step counts over and
