@@ -61,6 +61,18 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+// Ampere-style asynchronous 16-byte copies global -> shared (SASS: LDGSTS), one per thread and instruction, tracked in
+// per-thread commit groups.  Used where a batch is a GATHER of many small rows: a TMA bulk copy per row costs ~7 issue
+// slots on the uniform datapath of ONE warp, a warp-wide LDGSTS moves 32 rows' chunks per instruction.
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // fire-and-forget float reductions into global memory (SASS: RED.E.ADD.F32 / .v2 / .v4)
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");

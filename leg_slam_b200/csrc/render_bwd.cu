@@ -72,7 +72,7 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                       uint32_t* __restrict__ hrec_count, uint32_t* __restrict__ work_counter) {
     using Stage = BwdStage<WITH_LF>;
     __shared__ __align__(128) Stage stages[BSTAGES];
-    __shared__ __align__(8) uint64_t full_bar[BSTAGES];
+    __shared__ uint32_t s_ids[BSTAGES][BB];  // Gaussian ids of the batches in flight (batch b in slot b % BSTAGES)
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, wrp = tid >> 5;
@@ -88,13 +88,6 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const int nb = (n + BB - 1) / BB;
     const size_t HW = (size_t)H * W;
 
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < BSTAGES; ++s) mbar_init(&full_bar[s], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-
     const uint32_t pxi = blockIdx.x * TILE + (tid & 7);
     const uint32_t pyi = blockIdx.y * TILE + (tid >> 3);
     const bool inside = pxi < (uint32_t)W && pyi < (uint32_t)H;
@@ -107,10 +100,11 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
     float T = T_final;
 
-    float g_lf[WITH_LF ? LF : 1];
+    // the pixel's 64 feature gradients as register pairs: the dot product below runs on packed FFMA2 (sm_100)
+    float2 g_lf2[WITH_LF ? LF / 2 : 1];
     float g_r = 0.f, g_g = 0.f, g_b = 0.f, g_d = 0.f;
 #pragma unroll
-    for (int k = 0; k < (WITH_LF ? LF : 1); ++k) g_lf[k] = 0.f;
+    for (int k = 0; k < (WITH_LF ? LF / 2 : 1); ++k) g_lf2[k] = make_float2(0.f, 0.f);
     if (inside) {
         g_r = dL_dpix[0 * HW + pix_id];
         g_g = dL_dpix[1 * HW + pix_id];
@@ -118,7 +112,8 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         g_d = dL_dpix_depth[pix_id];
         if (WITH_LF) {
 #pragma unroll
-            for (int k = 0; k < LF; ++k) g_lf[k] = dL_dpix_lf[(size_t)k * HW + pix_id];
+            for (int k = 0; k < LF / 2; ++k)
+                g_lf2[k] = make_float2(dL_dpix_lf[(size_t)(2 * k) * HW + pix_id], dL_dpix_lf[(size_t)(2 * k + 1) * HW + pix_id]);
         }
     }
     const float bgdot = bg[0] * g_r + bg[1] * g_g + bg[2] * g_b;  // backward.cu:585-588
@@ -128,33 +123,43 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     float* out = hrec_buf + ((size_t)2 * range.x + (size_t)wrp * n_all) * HREC_FLOATS;
     uint32_t nrec = 0;
 
-    // producer state (warp 0): Gaussian ids of the next batch to issue (back to front)
-    uint32_t pf_id = 0;
-    if (tid < BB && tid < n) pf_id = point_list[range.x + (n - 1 - tid)];
-    auto issue = [&](int b) {
-        if (tid < 32) {  // the whole of warp 0 (BB <= 32 lanes carry an instance each)
+    // ---- staging: batch b = list positions n-1-b*BB ... (back to front); its records and feature rows are gathered into
+    // stages[b % BSTAGES] by 16-byte asynchronous copies spread over BOTH warps (19 chunks per Gaussian), two batches
+    // ahead.  (One TMA bulk copy per row, issued by warp 0, made that warp the critical path: 19 % of all warp samples
+    // were warp 1 waiting at the batch barrier, profiles/r01_bwd_pix_v6_ncu.txt.)
+    constexpr int CH = 3 + (WITH_LF ? LF / 4 : 0);  // 16-byte chunks per Gaussian: record, feature row
+    auto put_ids = [&](int b) {  // threads 0..BB-1: ids of batch b -> s_ids[b % BSTAGES]
+        const int pos = b * BB + tid;
+        if (tid < BB && pos < n) s_ids[b % BSTAGES][tid] = point_list[range.x + (n - 1 - pos)];
+    };
+    auto issue = [&](int b) {  // all threads; one commit group per call, empty past the end
+        if (b < nb) {
             const int cnt = min(BB, n - b * BB);
             Stage& S = stages[b % BSTAGES];
-            uint64_t* bar = &full_bar[b % BSTAGES];
-            if (tid == 0)
-                mbar_arrive_expect_tx(bar, (uint32_t)cnt * (uint32_t)(sizeof(GaussRec) + (WITH_LF ? LF * 4 : 0)));
-            __syncwarp();
-            if (tid < cnt) {
-                tma_bulk_g2s(&S.rec[tid], rec + pf_id, sizeof(GaussRec), bar);
-                if (WITH_LF) tma_bulk_g2s(&S.lf[tid * LF], lang_feat + (size_t)pf_id * LF, LF * 4, bar);
+            const uint32_t rec_s = smem_u32(&S.rec[0]), lf_s = smem_u32(&S.lf[0]);
+            const uint32_t* ids = s_ids[b % BSTAGES];
+            for (int k = tid; k < cnt * CH; k += TILE_PIX) {
+                const int j = k / CH, q = k - j * CH;
+                const uint32_t id = ids[j];
+                if (q < 3) cp_async16(rec_s + j * (uint32_t)sizeof(GaussRec) + q * 16, reinterpret_cast<const char*>(rec + id) + q * 16);
+                else cp_async16(lf_s + (j * LF) * 4 + (q - 3) * 16, reinterpret_cast<const char*>(lang_feat + (size_t)id * LF) + (q - 3) * 16);
             }
-            const int nxt = (b + 1) * BB + tid;
-            if (tid < BB && nxt < n) pf_id = point_list[range.x + (n - 1 - nxt)];
         }
+        cp_async_commit();
     };
-    for (int b = 0; b < BSTAGES - 1 && b < nb; ++b) issue(b);
+#pragma unroll
+    for (int b = 0; b < BSTAGES; ++b) put_ids(b);
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < BSTAGES - 1; ++b) issue(b);
 
     for (int b = 0; b < nb; ++b) {
         const int cnt = min(BB, n - b * BB);
         const int hi = n - 1 - b * BB;  // list position of slot 0
-        __syncthreads();                // both warps are done with stage (b-1) % BSTAGES -> refill it
-        if (b + BSTAGES - 1 < nb) issue(b + BSTAGES - 1);
-        mbar_wait(&full_bar[b % BSTAGES], (uint32_t)((b / BSTAGES) & 1));
+        cp_async_wait<BSTAGES - 2>();   // this thread's copies of batch b have landed
+        __syncthreads();                // ... everyone's; and both warps are done with stage (b-1) % BSTAGES -> refill it
+        issue(b + BSTAGES - 1);
+        put_ids(b + BSTAGES);           // slot b % BSTAGES: read by issue(b) two barriers ago
         const Stage& S = stages[b % BSTAGES];
 
         // lane j tests Gaussian j's opacity-aware bounding box against this warp's 8x4 pixels (common.cuh)
@@ -196,19 +201,18 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                 const float alpha = al[u], G = Gs[u];
                 const float4 q0 = S.rec[j].q0;
                 const float4 q2 = S.rec[j].q2;
-                float d0 = q2.x * g_r, d1 = q2.y * g_g, d2 = q2.z * g_b, d3 = q0.z * g_d;
+                // four interleaved partial sums d0..d3 (component-wise identical to scalar fmaf chains), two per FFMA2
+                float2 d01 = make_float2(q2.x * g_r, q2.y * g_g), d23 = make_float2(q2.z * g_b, q0.z * g_d);
                 if (WITH_LF) {
                     const float4* f4 = reinterpret_cast<const float4*>(&S.lf[j * LF]);
 #pragma unroll
                     for (int k = 0; k < LF / 4; ++k) {
                         const float4 f = f4[k];
-                        d0 = fmaf(f.x, g_lf[4 * k + 0], d0);
-                        d1 = fmaf(f.y, g_lf[4 * k + 1], d1);
-                        d2 = fmaf(f.z, g_lf[4 * k + 2], d2);
-                        d3 = fmaf(f.w, g_lf[4 * k + 3], d3);
+                        d01 = __ffma2_rn(make_float2(f.x, f.y), g_lf2[2 * k], d01);
+                        d23 = __ffma2_rn(make_float2(f.z, f.w), g_lf2[2 * k + 1], d23);
                     }
                 }
-                const float d = (d0 + d1) + (d2 + d3);
+                const float d = (d01.x + d01.y) + (d23.x + d23.y);
                 float Wv = 0.f, Tv = 0.f;
                 if (act) {
                     const float inv = __frcp_rn(1.0f - alpha);
