@@ -132,17 +132,25 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         const int pos = b * BB + tid;
         if (tid < BB && pos < n) s_ids[b % BSTAGES][tid] = point_list[range.x + (n - 1 - pos)];
     };
+    // chunk k = tid, tid + 64, ... of a batch is chunk q = k % CH of Gaussian j = k / CH; stepping k by 64 steps (j, q) by
+    // (64 / CH, 64 % CH) with one carry -- no division in the copy loop
+    const int j_first = tid / CH, q_first = tid - j_first * CH;
+    const char* const rec_g = reinterpret_cast<const char*>(rec);
+    const char* const lf_g = reinterpret_cast<const char*>(lang_feat);
     auto issue = [&](int b) {  // all threads; one commit group per call, empty past the end
         if (b < nb) {
             const int cnt = min(BB, n - b * BB);
             Stage& S = stages[b % BSTAGES];
             const uint32_t rec_s = smem_u32(&S.rec[0]), lf_s = smem_u32(&S.lf[0]);
             const uint32_t* ids = s_ids[b % BSTAGES];
-            for (int k = tid; k < cnt * CH; k += TILE_PIX) {
-                const int j = k / CH, q = k - j * CH;
+            int j = j_first, q = q_first;
+            while (j < cnt) {
                 const uint32_t id = ids[j];
-                if (q < 3) cp_async16(rec_s + j * (uint32_t)sizeof(GaussRec) + q * 16, reinterpret_cast<const char*>(rec + id) + q * 16);
-                else cp_async16(lf_s + (j * LF) * 4 + (q - 3) * 16, reinterpret_cast<const char*>(lang_feat + (size_t)id * LF) + (q - 3) * 16);
+                if (q < 3) cp_async16(rec_s + j * (uint32_t)sizeof(GaussRec) + q * 16, rec_g + (size_t)id * sizeof(GaussRec) + q * 16);
+                else cp_async16(lf_s + j * (LF * 4) + (q - 3) * 16, lf_g + (size_t)id * (LF * 4) + (q - 3) * 16);
+                j += TILE_PIX / CH;
+                q += TILE_PIX % CH;
+                if (q >= CH) { q -= CH; ++j; }
             }
         }
         cp_async_commit();
