@@ -30,8 +30,9 @@
 //    warp-specialised version (named-barrier hand-off through shared memory) spent 46 % of its
 //    warp samples in barrier stalls (profiles/r01_render_bwd_v1.md); the scratch round trip is
 //    ~0.6 GB of mostly L2-resident traffic per iteration at cfgB.
-//  * Gaussian records / feature rows are staged by TMA bulk copies (cp.async.bulk + mbarrier)
-//    two batches ahead, like the forward.
+//  * Gaussian records / feature rows are gathered into shared memory two batches ahead by 16-byte asynchronous
+//    copies (cp.async, LDGSTS) issued by both warps; the channel kernels stream the contiguous half-records back
+//    with TMA bulk copies (cp.async.bulk + mbarrier).
 //  * the tile's list is cut at tile_last = max over the tile's pixels of n_contrib (written
 //    by the forward): instances behind it contribute to no pixel.
 //
