@@ -121,19 +121,49 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
 
     uint32_t raw_phase = 0, mma_phase = 0;
 
+    // A work item's inputs -- its record count and range, and the half's upstream gradient rows -- are fetched ONE ITEM
+    // AHEAD into registers, so their global-memory round trips overlap the previous item's batches (they were 20 % of
+    // all warp samples when loaded at the start of the item, profiles/r01_chan_tc_v2_ncu.txt).
+    struct Item {
+        int id, cnt;
+        uint2 range;
+        float4 a[2][2];  // A_main rows of tasks tid, tid + 128
+        float4 b[2];     // B_aux row (threads 0..15)
+    };
+    auto fetch = [&](int id, Item& it) {
+        it.id = id;
+        it.cnt = 0;
+        if (id >= 2 * n_tiles) return;
+        const int tile = id >> 1, half = id & 1;
+        it.cnt = (int)hrec_count[id];
+        it.range = ranges[tile];
+        const uint32_t tx0 = (uint32_t)(tile % tiles_x) * TILE, ty0 = (uint32_t)(tile / tiles_x) * TILE + 4 * half;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {  // A_main: task = (row y, channel ch); consecutive lanes = consecutive channels
+            const int task = tid + TC_THREADS * i;
+            load_row8(dL_dpix_lf + (size_t)(task & 63) * HW, W, H, tx0, ty0 + (task >> 6), it.a[i][0], it.a[i][1]);
+        }
+        if (tid < 16) {  // B_aux: rows {r,g,b,d}
+            const int c = tid & 3;
+            load_row8(c < 3 ? dL_dpix + (size_t)c * HW : dL_dpix_depth, W, H, tx0, ty0 + (tid >> 2), it.b[0], it.b[1]);
+        }
+    };
+    if (tid == 0) s_tile = (int)atomicAdd(work_counter, 1u);
+    __syncthreads();
+    Item cur, nxt;
+    fetch(s_tile, cur);
+
     for (;;) {
-        __syncthreads();
+        if (cur.id >= 2 * n_tiles) break;
+        __syncthreads();  // everyone has read s_tile (and finished the previous item)
         if (tid == 0) s_tile = (int)atomicAdd(work_counter, 1u);
-        __syncthreads();
-        const int item = s_tile;  // work item = (tile, pixel-warp half)
-        if (item >= 2 * n_tiles) break;
-        const int tile = item >> 1, half = item & 1;
-        const int cnt_all = (int)hrec_count[item];
-        if (cnt_all == 0) continue;
-        const uint2 range = ranges[tile];
+        const int item = cur.id, tile = item >> 1, half = item & 1;
+        const int cnt_all = cur.cnt;
+        const uint2 range = cur.range;
         const int n_all = (int)(range.y - range.x);
         const int nbt = (cnt_all + TB - 1) / TB;
         const float* stream = hrec_buf + ((size_t)2 * range.x + (size_t)half * n_all) * HREC_FLOATS;
+        (void)tile;
 
         auto issue = [&](int q) {  // thread 0: bulk copy of the item's q-th batch into the raw buffer
             const int cnt = min(TB, cnt_all - q * TB);
@@ -141,32 +171,29 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
             mbar_arrive_expect_tx(&raw_full, bytes);
             tma_bulk_g2s(smem + SM_RAW, stream + (size_t)q * TB * HREC_FLOATS, bytes, &raw_full);
         };
-        if (tid == 0) issue(0);
+        if (tid == 0 && cnt_all > 0) issue(0);
 
         // ---- the half's upstream gradients as MMA operands (all earlier MMAs have completed: mma_done was waited on)
-        {
-            const uint32_t tx0 = (uint32_t)(tile % tiles_x) * TILE, ty0 = (uint32_t)(tile / tiles_x) * TILE + 4 * half;
+        if (cnt_all > 0) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {  // A_main: task = (row y, channel ch); consecutive lanes = consecutive channels
+            for (int i = 0; i < 2; ++i) {
                 const int task = tid + TC_THREADS * i;
                 const int y = task >> 6, ch = task & 63;
-                float4 a, b;
-                load_row8(dL_dpix_lf + (size_t)ch * HW, W, H, tx0, ty0 + y, a, b);
                 uint8_t* base = smem + SM_AMAIN;
                 const int kc = y * 2;
-                split_store(a, base + canon_off(ch, kc, 128), base + canon_off(64 + ch, kc, 128));
-                split_store(b, base + canon_off(ch, kc + 1, 128), base + canon_off(64 + ch, kc + 1, 128));
+                split_store(cur.a[i][0], base + canon_off(ch, kc, 128), base + canon_off(64 + ch, kc, 128));
+                split_store(cur.a[i][1], base + canon_off(ch, kc + 1, 128), base + canon_off(64 + ch, kc + 1, 128));
             }
             if (tid < 16) {  // B_aux: rows {r,g,b,d}_hi, {r,g,b,d}_lo
                 const int c = tid & 3, y = tid >> 2;
-                float4 a, b;
-                load_row8(c < 3 ? dL_dpix + (size_t)c * HW : dL_dpix_depth, W, H, tx0, ty0 + y, a, b);
                 uint8_t* base = smem + SM_BAUX;
                 const int kc = y * 2;
-                split_store(a, base + canon_off(c, kc, 8), base + canon_off(4 + c, kc, 8));
-                split_store(b, base + canon_off(c, kc + 1, 8), base + canon_off(4 + c, kc + 1, 8));
+                split_store(cur.b[0], base + canon_off(c, kc, 8), base + canon_off(4 + c, kc, 8));
+                split_store(cur.b[1], base + canon_off(c, kc + 1, 8), base + canon_off(4 + c, kc + 1, 8));
             }
         }
+        __syncthreads();  // s_tile (the next item) is visible
+        fetch(s_tile, nxt);  // in flight during this item's batches
 
         for (int q = 0; q < nbt; ++q) {
             const int cnt = min(TB, cnt_all - q * TB);
@@ -283,6 +310,7 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
             tc_fence_before();
             __syncthreads();  // TMEM, the operand tiles and this raw buffer are free again
         }
+        cur = nxt;
     }
     tc_fence_before();
     __syncthreads();
