@@ -83,8 +83,10 @@ preprocess_kernel(int P, int D, int M,
                   uint8_t* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
                   uint32_t* __restrict__ total_touched) {
     __shared__ float sV[16], sP[16];
+    __shared__ uint32_t s_touched, s_dmax;  // this block's share of R and of the largest depth bit pattern
     if (threadIdx.x < 16) sV[threadIdx.x] = view[threadIdx.x];
     else if (threadIdx.x < 32) sP[threadIdx.x - 16] = proj[threadIdx.x - 16];
+    else if (threadIdx.x == 32) { s_touched = 0; s_dmax = 0; }
     __syncthreads();
 
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -231,14 +233,21 @@ preprocess_kernel(int P, int D, int M,
     radii[idx] = out_radius;  // internal copy: key emission and the backward read this one
     if (radii_user != nullptr) radii_user[idx] = out_radius;
     tiles_touched[idx] = out_tiles;
-    {   // R = sum of tiles_touched without a scan pass: one atomic per converged group of threads
+    {   // R = sum of tiles_touched (and the depth bound of the sort keys) without a scan pass: warp-aggregated into shared
+        // memory, one pair of global atomics per block.  Threads past P have exited; the barrier covers the rest.
         namespace cg = cooperative_groups;
         auto grp = cg::coalesced_threads();
         const uint32_t sum = cg::reduce(grp, out_tiles, cg::plus<uint32_t>());
-        if (grp.thread_rank() == 0 && sum != 0) atomicAdd(total_touched, sum);
-        // largest depth bit pattern among the rendered Gaussians: bounds the key bits the sort has to cover
         const uint32_t dmax = cg::reduce(grp, out_tiles ? __float_as_uint(depth) : 0u, cg::greater<uint32_t>());
-        if (grp.thread_rank() == 0 && sum != 0) atomicMax(total_touched + 1, dmax);
+        if (grp.thread_rank() == 0 && sum != 0) {
+            atomicAdd(&s_touched, sum);
+            atomicMax(&s_dmax, dmax);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && s_touched != 0) {
+            atomicAdd(total_touched, s_touched);
+            atomicMax(total_touched + 1, s_dmax);
+        }
     }
     if (!live) return;
 

@@ -126,14 +126,14 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means, cons
     const bool stage_sh = shs != nullptr && row <= PB_ROW;
     const bool visible = idx < P && radii[idx] > 0;
     bool sh_written = false;  // does this thread's staged row hold data to flush?
+    bool sh_zero = false;     // ... or is its row to be zero-filled (culled Gaussian, write_zeros)?
     if (idx < P && !visible && write_zeros) {
         dL_dmeans[3 * idx + 0] = 0.f; dL_dmeans[3 * idx + 1] = 0.f; dL_dmeans[3 * idx + 2] = 0.f;
 #pragma unroll
         for (int i = 0; i < 6; ++i) dL_dcov[6 * (size_t)idx + i] = 0.f;
         if (shs != nullptr && !accumulate_sh) {
             if (stage_sh) {
-                for (int i = 0; i < row; ++i) s_sh[threadIdx.x][i] = 0.f;
-                sh_written = true;
+                sh_zero = true;  // the flush below writes the zero row without staging it
             } else {
                 for (int i = 0; i < row; ++i) dL_dsh[(size_t)idx * row + i] = 0.f;
             }
@@ -302,20 +302,21 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means, cons
         // warp-cooperative flush of the staged rows: lane-consecutive addresses in global memory
         __syncwarp();
         const int lane = threadIdx.x & 31, w0 = threadIdx.x & ~31;
-        const uint32_t wmask = __ballot_sync(0xffffffffu, sh_written);
-        const long long gbase = ((long long)blockIdx.x * blockDim.x + w0) * row;
+        const uint32_t dmask = __ballot_sync(0xffffffffu, sh_written), zmask = __ballot_sync(0xffffffffu, sh_zero);
+        const uint32_t wmask = dmask | zmask;
+        const long long g0 = (long long)blockIdx.x * blockDim.x + w0;  // first Gaussian of this warp
+        // element i = r * row + c of the warp's 32 x row block; (r, c) advance with i (no division in the loop)
+        int r = lane / row, c = lane - r * row;
         for (int i = lane; i < 32 * row; i += 32) {
-            const int r = i / row, c = i - r * row;
             if ((wmask >> r) & 1u) {
                 // split layout (dL_dsh_rest != NULL): coefficient 0 -> dL_dsh [P,1,3], the rest -> dL_dsh_rest [P,M-1,3]
-                float* dst = dL_dsh + gbase + i;
-                if (dL_dsh_rest != nullptr) {
-                    const long long gi = (long long)blockIdx.x * blockDim.x + w0 + r;
-                    dst = c < 3 ? dL_dsh + gi * 3 + c : dL_dsh_rest + gi * (row - 3) + (c - 3);
-                }
-                const float v = s_sh[w0 + r][c];
+                float* dst = dL_dsh + g0 * row + i;
+                if (dL_dsh_rest != nullptr) dst = c < 3 ? dL_dsh + (g0 + r) * 3 + c : dL_dsh_rest + (g0 + r) * (row - 3) + (c - 3);
+                const float v = ((dmask >> r) & 1u) ? s_sh[w0 + r][c] : 0.f;
                 *dst = accumulate_sh ? *dst + v : v;
             }
+            c += 32;
+            while (c >= row) { c -= row; ++r; }
         }
     }
 }
