@@ -411,12 +411,13 @@ class E2EPath:
             self._next = self._upload()
         window, ev = self._next
         cur.wait_event(ev)
-        self.copy_stream.wait_stream(cur)  # do not overwrite device inputs a still-running step may read
-        self._next = self._upload()
         for kf in window:  # tensors produced on the copy stream, consumed on the compute stream
             for t in (kf.camera.viewmatrix, kf.camera.projmatrix, kf.camera.campos, kf.gt_image, kf.gt_lf, kf.gt_depth):
                 t.record_stream(cur)
         loss = self.mapper.train_step(window, presharded=True)
+        # the next step's upload is queued while this step's kernels are still running (fresh allocations of the copy
+        # stream's own pool; record_stream above keeps this step's inputs alive until the compute stream is done with them)
+        self._next = self._upload()
         self.loss_host.copy_(loss.reshape(1), non_blocking=False)  # device -> host read of the step's result
         return float(self.loss_host[0])
 
