@@ -180,8 +180,9 @@ typedef struct lgs_geom_view {
 int lgs_view_binning(const char* binning_buffer, int R, lgs_binning_view* out);
 /* Binning algorithm (process-wide; set it before lgs_forward_stage1, not between stage1 and stage2):
  *   1 (default) the reference's single stable radix sort of all instances by (tile, depth bits)
- *               (rasterizer_impl.cu:304-309), over fewer key bits: depth bits are rebased to bits(0.2f) (the near
- *               cull) and bounded by the frame's largest depth, which preprocess accumulates;
+ *               (rasterizer_impl.cu:304-309), over 32-bit keys: depth bits are rebased to bits(0.2f) (the near cull)
+ *               and bounded by the frame's largest depth, which preprocess accumulates; the key keeps the tile id and
+ *               the top depth bits, and the rare runs of equal keys are put into (depth bits, index) order afterwards;
  *   0           tile-local: instances are counted and scattered per tile, every tile's list is sorted by
  *               (depth bits, Gaussian index) in shared memory -- no device-wide sort (experimental: slower than
  *               mode 1 at 640x480 / 1.4 M instances).

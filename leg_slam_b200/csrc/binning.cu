@@ -37,7 +37,10 @@ size_t sort_temp_bytes(int R) {
     size_t n = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, n, (uint64_t*)nullptr, (uint64_t*)nullptr,
                                     (uint32_t*)nullptr, (uint32_t*)nullptr, R);
-    return n;
+    size_t m = 0;  // the 32-bit key variant (launch_binning)
+    cub::DeviceRadixSort::SortPairs(nullptr, m, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (uint32_t*)nullptr, R);
+    return n > m ? n : m;
 }
 
 static int g_binning_mode = 1;  // 1 = the reference's single (tile|depth) radix sort (default), 0 = tile-local
@@ -336,6 +339,75 @@ tile_ranges_kernel(int L, const uint64_t* __restrict__ keys, uint2* __restrict__
     if (idx == L - 1) ranges[cur].y = L;
 }
 
+// ---- 32-bit keys (default when the depth bound is known) ---------------------------------------------------------
+// key32 = tile << q | (depth bits - bits(0.2f)) >> shift, q = what is left of 32 bits after the tile id (19 at 640x480).
+// Four radix passes over 8 B per instance instead of five over 12 B.  When shift > 0 the low depth bits are not in the
+// key: instances of one tile whose depths agree in the kept bits form a run (still in index order -- the sort is
+// stable); tile_ranges_fix_kernel puts every such run into (depth bits, index) order, which is exactly the order the
+// reference's full key produces.  Runs are rare and short (depths within 2^shift ulps of each other inside one tile).
+__global__ void __launch_bounds__(256)
+emit_keys32_kernel(int P, const GaussRec* __restrict__ rec, const uint32_t* __restrict__ offsets, const int* __restrict__ radii,
+                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, int tiles_x, int tiles_y, uint32_t depth_base,
+                   int shift, int q) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const int rad = radii[idx];
+    if (rad <= 0) return;
+    uint32_t off = (idx == 0) ? 0u : offsets[idx - 1];
+    const float4 q0 = rec[idx].q0;  // x, y, depth
+    const float rf = (float)rad;
+    const int x0 = min(tiles_x, max(0, (int)__fmul_rn(__fsub_rn(q0.x, rf), 0.125f)));
+    const int y0 = min(tiles_y, max(0, (int)__fmul_rn(__fsub_rn(q0.y, rf), 0.125f)));
+    const int x1 = min(tiles_x, max(0, (int)__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(q0.x, rf), 8.0f), -1.0f), 0.125f)));
+    const int y1 = min(tiles_y, max(0, (int)__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(q0.y, rf), 8.0f), -1.0f), 0.125f)));
+    const uint32_t dq = (__float_as_uint(q0.z) - depth_base) >> shift;
+    for (int y = y0; y < y1; ++y) {
+        for (int x = x0; x < x1; ++x) {
+            keys[off] = ((uint32_t)(y * tiles_x + x) << q) | dq;
+            vals[off] = (uint32_t)idx;
+            ++off;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+tile_ranges_fix_kernel(int L, const uint32_t* __restrict__ keys, uint32_t* __restrict__ point_list,
+                       const GaussRec* __restrict__ rec, uint2* __restrict__ ranges, int q, int shift) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= L) return;
+    const uint32_t key = keys[idx];
+    const uint32_t cur = key >> q;
+    const bool first = idx == 0 || keys[idx - 1] != key;
+    if (idx == 0) {
+        ranges[cur].x = 0;
+    } else {
+        const uint32_t prev = keys[idx - 1] >> q;
+        if (cur != prev) {
+            ranges[prev].y = idx;
+            ranges[cur].x = idx;
+        }
+    }
+    if (idx == L - 1) ranges[cur].y = L;
+    if (shift > 0 && first && idx + 1 < L && keys[idx + 1] == key) {
+        // this thread owns the run [idx, end): insertion sort by (depth bits, Gaussian index)
+        int end = idx + 2;
+        while (end < L && keys[end] == key) ++end;
+        for (int a = idx + 1; a < end; ++a) {
+            const uint32_t id_a = point_list[a];
+            const uint32_t d_a = __float_as_uint(rec[id_a].q0.z);
+            int b = a - 1;
+            while (b >= idx) {
+                const uint32_t id_b = point_list[b];
+                const uint32_t d_b = __float_as_uint(rec[id_b].q0.z);
+                if (d_b < d_a || (d_b == d_a && id_b < id_a)) break;
+                point_list[b + 1] = id_b;
+                --b;
+            }
+            point_list[b + 1] = id_a;
+        }
+    }
+}
+
 static int key_bits_for_tiles(uint32_t n) {
     // == getHigherMsb(n) of the reference for n >= 1: number of bits needed to write n
     int bits = 1;
@@ -380,8 +452,9 @@ int launch_binning(int P, int R, int W, int H, const GeomState& g, const int* ra
     if (R <= 0) return LGS_OK;
     // The reference sorts bits [0, 32 + msb(tiles)) of tile << 32 | depth bits (rasterizer_impl.cu:301-309).  Every
     // rendered Gaussian has depth > 0.2 (auxiliary.h:154), so depth bits - bits(0.2f) orders identically and, with the
-    // largest depth known from preprocess, needs fewer bits: 13 + 26 = 39 at 640x480 indoors, one radix pass less.
-    // With lgs_debug_keys(1) the reference's exact 64-bit keys are kept (parity tests compare them).
+    // largest depth known from preprocess, needs fewer bits: 13 + 26 = 39 at 640x480 indoors.  Default: 32-bit keys with
+    // the top depth bits + a fix-up of the rare equal-key runs (above); 64-bit compacted keys when the tile id needs
+    // more than 20 bits.  With lgs_debug_keys(1) the reference's exact 64-bit keys are kept (parity tests compare them).
     uint32_t depth_base = 0;
     int depth_bits = 32;
     const uint32_t kNear = 0x3e4ccccdu;  // bits of 0.2f
@@ -389,11 +462,29 @@ int launch_binning(int P, int R, int W, int H, const GeomState& g, const int* ra
         depth_base = kNear;
         depth_bits = key_bits_for_tiles(max_depth_bits - kNear);
     }
+    const int tile_bits = key_bits_for_tiles((uint32_t)tiles);
+    if (depth_base != 0 && tile_bits <= 20) {  // 32-bit keys: tile | as many depth bits as fit, runs fixed up afterwards
+        const int q = min(depth_bits, 32 - tile_bits), shift = depth_bits - q;
+        uint32_t* k32_unsorted = reinterpret_cast<uint32_t*>(b.keys_unsorted);  // the 64-bit key arrays hold the 32-bit keys
+        uint32_t* k32 = reinterpret_cast<uint32_t*>(b.keys);
+        emit_keys32_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g.rec, g.point_offsets, radii, k32_unsorted, b.vals_unsorted,
+                                                           tiles_x, tiles_y, depth_base, shift, q);
+        LGS_LAUNCH_CHECK();
+        prof_mark(PM_EMIT, s);
+        size_t n32 = b.sort_temp_bytes;
+        LGS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(b.sort_temp, n32, k32_unsorted, k32, b.vals_unsorted, b.point_list, R, 0,
+                                                     q + tile_bits, s));
+        prof_mark(PM_SORT, s);
+        tile_ranges_fix_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, k32, b.point_list, g.rec, im.ranges, q, shift);
+        LGS_LAUNCH_CHECK();
+        prof_mark(PM_RANGES, s);
+        return LGS_OK;
+    }
     emit_keys_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g.rec, g.point_offsets, radii,
                                                      b.keys_unsorted, b.vals_unsorted, tiles_x, tiles_y, depth_base, depth_bits);
     LGS_LAUNCH_CHECK();
     prof_mark(PM_EMIT, s);
-    const int end_bit = depth_bits + key_bits_for_tiles((uint32_t)tiles);
+    const int end_bit = depth_bits + tile_bits;
     size_t n = b.sort_temp_bytes;
     LGS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(b.sort_temp, n, b.keys_unsorted, b.keys,
                                                  b.vals_unsorted, b.point_list, R, 0, end_bit, s));

@@ -324,6 +324,26 @@ def test_compacted_sort_keys_give_the_same_lists(cfgB, dev):
     debug.binning_mode(1)
 
 
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_default_binning_without_debug_keys_small_cases(name, dev):
+    """The production path (32-bit keys + run fix-up, no key materialisation) on the small cases: same point_list,
+    ranges and images as with the reference's exact keys."""
+    from leg_slam_b200 import rasterize_points as rp, debug
+    cs = cases.make_case(name, dev)
+    debug.debug_keys(True)
+    R, c1, l1, d1, rad1, geom, binning, img = rp.rasterize_gaussians(*cases.fwd_args(cs))
+    pl = debug.binning_view(binning, R)["point_list"].clone()
+    rg = debug.image_view(img, cs["W"], cs["H"])["ranges"].clone()
+    debug.debug_keys(False)
+    R2, c2, l2, d2, rad2, geom2, binning2, img2 = rp.rasterize_gaussians(*cases.fwd_args(cs))
+    torch.cuda.synchronize()
+    debug.debug_keys(True)
+    assert R2 == R and torch.equal(rad1, rad2)
+    assert torch.equal(debug.binning_view(binning2, R2)["point_list"], pl)
+    assert torch.equal(debug.image_view(img2, cs["W"], cs["H"])["ranges"], rg)
+    assert torch.equal(c1, c2) and torch.equal(d1, d2)
+
+
 def test_fullsize_forward_idempotent_backward_linear(cfgB, dev):
     from leg_slam_b200 import rasterize_points as rp
     R, color, lf, depth, radii, geom, binning, img = cfgB["out"]
