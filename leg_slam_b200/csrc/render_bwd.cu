@@ -45,7 +45,7 @@
 namespace lgs {
 
 constexpr int BB = 32;       // Gaussians per TMA batch of the pixel kernel
-constexpr int BSTAGES = 3;   // its staging ring depth
+constexpr int BSTAGES = 2;   // its staging ring depth (2 x 9.7 KB: 8 CTAs per SM; 3 stages would allow only 7)
 constexpr int CB = 8;        // half-records per TMA batch of the channel kernel
 constexpr int CSTAGES = 4;   // its staging ring depth
 
