@@ -129,12 +129,10 @@ render_fwd_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
         const int k1 = 64 + t, j1 = k1 / 3, q1 = k1 - 3 * j1;  // float4 #(64 + t), t < 32
         const uint32_t ida = __shfl_sync(0xffffffffu, id_next, j0 & 31);
         const uint32_t idb = __shfl_sync(0xffffffffu, id_next, j1 & 31);
-        // j0 spans 0..21 over the two warps, j1 22..31: both within one warp's id_next lanes (every warp holds all 32 ids)
-        const float4 a = __ldg(r4 + (size_t)ida * 3 + q0);
-        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t < 32) c = __ldg(r4 + (size_t)idb * 3 + q1);
-        sts128(sb + TF_SM_REC + slot * TF_REC + t * 16, a);
-        if (t < 32) sts128(sb + TF_SM_REC + slot * TF_REC + (64 + t) * 16, c);
+        // every producer warp holds the batch's ids in its lanes (lane j = Gaussian j)
+        constexpr int NF4 = TF_B * 3;
+        if (t < NF4) sts128(sb + TF_SM_REC + slot * TF_REC + t * 16, __ldg(r4 + (size_t)ida * 3 + q0));
+        if (64 + t < NF4) sts128(sb + TF_SM_REC + slot * TF_REC + (64 + t) * 16, __ldg(r4 + (size_t)idb * 3 + q1));
     };
     if (warp >= 2) {
         load_ids(0);
@@ -258,7 +256,8 @@ render_fwd_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
 
     // ---- epilogue (forward.cu:377-391).  TMEM lane = A row: warps 0-1 hold the w_hi sums of pixel px, warps 2-3 the
     // w_lo sums.  Each side keeps 32 of the 64 columns and hands the other 32 over through shared memory.
-    float* xch = reinterpret_cast<float*>(smem + TF_SM_BHI);  // [64][64] floats = 16384 B = 2 * TF_B_BYTES
+    static_assert(TF_A_BYTES + 2 * TF_B_BYTES >= 64 * 64 * 4, "the exchange buffer overlays the operand tiles");
+    float* xch = reinterpret_cast<float*>(smem + TF_SM_A);  // [64][64] floats over the A and B tiles (all MMAs have completed)
     const uint32_t tb = tmem + ((uint32_t)(warp * 32) << 16);
     const int keep0 = warp < 2 ? 0 : 32;  // first column this thread finishes
     {
