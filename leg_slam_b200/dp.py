@@ -46,7 +46,14 @@ class FusedDPAdam:
         VP = ctypes.c_void_p * self.world
         self._gp = VP(*[int(p) for p in self.hg.buffer_ptrs])
         self._pp = VP(*[int(p) for p in self.hp.buffer_ptrs])
-        use_mc = os.environ.get("LGS_DP_NO_MULTIMEM", "0") != "1"
+        # multimem.ld_reduce makes every GPU of the group (the requester included) send its copy to the switch: each GPU
+        # ships its whole gradient buffer per step whatever G is.  That pays once the switch's reduction saves inbound
+        # traffic (G >= 4); with two GPUs plain peer loads / stores move a third less over the links (measured on 2
+        # B200s: exchange + Adam 0.35-0.40 ms with P2P, 0.61-0.69 ms with multimem; tools/prof_dp_step.py).
+        env = os.environ.get("LGS_DP_MULTIMEM", "")
+        use_mc = (self.world >= 4) if env == "" else (env == "1")
+        if os.environ.get("LGS_DP_NO_MULTIMEM", "0") == "1":
+            use_mc = False
         self.g_mc = int(getattr(self.hg, "multicast_ptr", 0) or 0) if use_mc else 0
         self.p_mc = int(getattr(self.hp, "multicast_ptr", 0) or 0) if use_mc else 0
         if not (self.g_mc and self.p_mc):
