@@ -41,38 +41,72 @@ __device__ __forceinline__ void mc_st(float* mc, float4 v) {
                  : "memory");
 }
 
+// Four 16-byte vectors per thread and iteration, every load issued before the first use: the peer / multicast loads
+// have NVLink latency (microseconds), so the number of requests in flight per SM decides the achieved link bandwidth.
+// WORLD > 0 unrolls the peer loop (2, 4, 8 ranks); WORLD = 0 is the generic loop.
+constexpr int DP_UNROLL = 4;
+
+template <bool MC, int WORLD>
 __global__ void __launch_bounds__(256)
 dp_adam_kernel(const __grid_constant__ DpTable tab, const float* __restrict__ grads_mc, float* __restrict__ params_mc,
                long long begin, long long end, float* __restrict__ p_local, float* __restrict__ m, float* __restrict__ v,
                float b1, float omb1, float b2, float omb2, float inv_bc2_sqrt, float eps) {
     const long long n4 = (end - begin) >> 2;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += (long long)gridDim.x * blockDim.x) {
-        const long long i = begin + 4 * k;
-        float4 g;
-        if (grads_mc != nullptr) {
-            g = mc_ld_reduce_add(grads_mc + i);  // in-switch reduction over all ranks
-        } else {
-            g = *reinterpret_cast<const float4*>(tab.grads[0] + i);
-            for (int r = 1; r < tab.world; ++r) {
-                const float4 x = *reinterpret_cast<const float4*>(tab.grads[r] + i);
-                g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+    const int world = WORLD > 0 ? WORLD : tab.world;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long k0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; k0 < n4; k0 += stride * DP_UNROLL) {
+        float4 g[DP_UNROLL], p[DP_UNROLL], mm[DP_UNROLL], vv[DP_UNROLL];
+#pragma unroll
+        for (int u = 0; u < DP_UNROLL; ++u) {
+            const long long k = k0 + u * stride;
+            if (k >= n4) continue;
+            const long long i = begin + 4 * k;
+            if (MC) {
+                g[u] = mc_ld_reduce_add(grads_mc + i);  // in-switch reduction over all ranks
+            } else {
+                g[u] = *reinterpret_cast<const float4*>(tab.grads[0] + i);
+            }
+            p[u] = *reinterpret_cast<const float4*>(p_local + i);
+            mm[u] = *reinterpret_cast<const float4*>(m + 4 * k);
+            vv[u] = *reinterpret_cast<const float4*>(v + 4 * k);
+        }
+        if (!MC) {  // peer gradients, fixed rank order (replicas stay bit-identical)
+#pragma unroll
+            for (int r = 1; r < (WORLD > 0 ? WORLD : DP_MAX_WORLD); ++r) {
+                if (r >= world) break;
+                float4 x[DP_UNROLL];
+#pragma unroll
+                for (int u = 0; u < DP_UNROLL; ++u) {
+                    const long long k = k0 + u * stride;
+                    x[u] = k < n4 ? *reinterpret_cast<const float4*>(tab.grads[r] + begin + 4 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < DP_UNROLL; ++u) { g[u].x += x[u].x; g[u].y += x[u].y; g[u].z += x[u].z; g[u].w += x[u].w; }
             }
         }
-        int t = 0;
-        while (t + 1 < tab.n_seg && i >= tab.seg_start[t + 1]) ++t;
-        const float ns = tab.neg_step[t];
-        float4 p = *reinterpret_cast<const float4*>(p_local + i);
-        float4 mm = *reinterpret_cast<const float4*>(m + 4 * k), vv = *reinterpret_cast<const float4*>(v + 4 * k);
-        adam_elem(p.x, g.x, mm.x, vv.x, b1, omb1, b2, omb2, inv_bc2_sqrt, eps, ns);
-        adam_elem(p.y, g.y, mm.y, vv.y, b1, omb1, b2, omb2, inv_bc2_sqrt, eps, ns);
-        adam_elem(p.z, g.z, mm.z, vv.z, b1, omb1, b2, omb2, inv_bc2_sqrt, eps, ns);
-        adam_elem(p.w, g.w, mm.w, vv.w, b1, omb1, b2, omb2, inv_bc2_sqrt, eps, ns);
-        *reinterpret_cast<float4*>(m + 4 * k) = mm;
-        *reinterpret_cast<float4*>(v + 4 * k) = vv;
-        if (params_mc != nullptr) {
-            mc_st(params_mc + i, p);  // switch broadcast to every rank, this one included
-        } else {
-            for (int r = 0; r < tab.world; ++r) *reinterpret_cast<float4*>(tab.params[r] + i) = p;
+#pragma unroll
+        for (int u = 0; u < DP_UNROLL; ++u) {
+            const long long k = k0 + u * stride;
+            if (k >= n4) continue;
+            const long long i = begin + 4 * k;
+            int t = 0;
+            while (t + 1 < tab.n_seg && i >= tab.seg_start[t + 1]) ++t;
+            const float ns = tab.neg_step[t];
+            adam_elem(p[u].x, g[u].x, mm[u].x, vv[u].x, b1, omb1, b2, omb2, inv_bc2_sqrt, eps, ns);
+            adam_elem(p[u].y, g[u].y, mm[u].y, vv[u].y, b1, omb1, b2, omb2, inv_bc2_sqrt, eps, ns);
+            adam_elem(p[u].z, g[u].z, mm[u].z, vv[u].z, b1, omb1, b2, omb2, inv_bc2_sqrt, eps, ns);
+            adam_elem(p[u].w, g[u].w, mm[u].w, vv[u].w, b1, omb1, b2, omb2, inv_bc2_sqrt, eps, ns);
+            *reinterpret_cast<float4*>(m + 4 * k) = mm[u];
+            *reinterpret_cast<float4*>(v + 4 * k) = vv[u];
+            if (MC) {
+                mc_st(params_mc + i, p[u]);  // switch broadcast to every rank, this one included
+            } else {
+#pragma unroll
+                for (int r = 0; r < (WORLD > 0 ? WORLD : DP_MAX_WORLD); ++r) {
+                    if (r >= world) break;
+                    *reinterpret_cast<float4*>(tab.params[r] + i) = p[u];
+                }
+            }
         }
     }
 }
@@ -105,11 +139,20 @@ extern "C" int lgs_dp_adam_shard(int n_seg, const int64_t* seg_start, const doub
     tab.n_seg = n_seg;
     tab.world = world;
     const long long n4 = (shard_end - shard_begin) >> 2;
-    const int grid = (int)((n4 + 255) / 256 < 148LL * 16 ? (n4 + 255) / 256 : 148LL * 16);
-    dp_adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tab, grads_mc, params_mc, shard_begin, shard_end, params_peers[rank],
-                                                           exp_avg_shard, exp_avg_sq_shard, (float)beta1, (float)(1.0 - beta1),
-                                                           (float)beta2, (float)(1.0 - beta2), 1.0f / (float)std::sqrt(bc2),
-                                                           (float)eps);
+    const long long want = (n4 + 256LL * DP_UNROLL - 1) / (256LL * DP_UNROLL);
+    const int grid = (int)(want < 148LL * 8 ? (want > 0 ? want : 1) : 148LL * 8);
+    const bool mc = grads_mc != nullptr && params_mc != nullptr;
+#define LGS_DP_LAUNCH(MCV, WV)                                                                                                  \
+    dp_adam_kernel<MCV, WV><<<grid, 256, 0, (cudaStream_t)stream>>>(tab, grads_mc, params_mc, shard_begin, shard_end,           \
+                                                                    params_peers[rank], exp_avg_shard, exp_avg_sq_shard,       \
+                                                                    (float)beta1, (float)(1.0 - beta1), (float)beta2,          \
+                                                                    (float)(1.0 - beta2), 1.0f / (float)std::sqrt(bc2), (float)eps)
+    if (mc) LGS_DP_LAUNCH(true, 0);
+    else if (world == 2) LGS_DP_LAUNCH(false, 2);
+    else if (world == 4) LGS_DP_LAUNCH(false, 4);
+    else if (world == 8) LGS_DP_LAUNCH(false, 8);
+    else LGS_DP_LAUNCH(false, 0);
+#undef LGS_DP_LAUNCH
     LGS_LAUNCH_CHECK();
     return LGS_OK;
 }
