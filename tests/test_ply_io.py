@@ -42,6 +42,28 @@ def test_restatement_roundtrip_and_header_cpu(tmp_path):
     np.testing.assert_array_equal(rec[:, 9 + 15], m["features_rest"][:, 0, 1])
 
 
+def test_column_table_and_header_parser_cpu(tmp_path):
+    """Host logic of leg_slam_b200.ply_io without a GPU: the column table is the reference's property order and the
+    header parser reads what the restated writer writes (plus the optimizer comments)."""
+    from leg_slam_b200 import ply_io
+    m = _model(5)
+    path = tmp_path / "h.ply"
+    PR.write_ply(path, m["xyz"], m["features_dc"], m["features_rest"], m["lang_feat"], m["opacity"], m["scaling"], m["rotation"])
+    with open(path, "rb") as f:
+        P, props, comments, off = ply_io.read_header(f)
+    cols = ply_io._columns(15, 64, False)
+    assert P == 5 and props == [c[0] for c in cols] and comments == {}
+    assert off == open(path, "rb").read().index(b"end_header\n") + 11
+    # f_rest_i is channel-major: property i holds coefficient i % 15 of channel i // 15 = element 3*(i%15) + i//15 of the row
+    assert cols[9 + 16] == ("f_rest_16", "features_rest", 3 * 1 + 1)
+    with_adam = ply_io._columns(15, 64, True)
+    assert len(with_adam) == 126 + 2 * 123 and with_adam[126][0] == "adam_m_0" and with_adam[-1] == ("adam_v_122", "v:rotation", 3)
+    bad = tmp_path / "bad.ply"
+    bad.write_bytes(b"ply\nformat ascii 1.0\nelement vertex 1\nproperty float x\nend_header\n0\n")
+    with open(bad, "rb") as f, pytest.raises(ValueError):
+        ply_io.read_header(f)
+
+
 @pytest.fixture(scope="module")
 def dev():
     if not torch.cuda.is_available():
