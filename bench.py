@@ -178,9 +178,11 @@ class KernelPath:
                     self.a[k] = view
                     off += P * n
                 self.flat = gflat
-                self.dp = dp_mod.FusedDPAdam(pflat, gflat, [P * n for _, n in self.order], [lrs[k] * 1e-3 for k, _ in self.order])
+                self.dp = dp_mod.FusedDPAdam(pflat, gflat, [P * n for _, n in self.order], [lrs[k] * 1e-3 for k, _ in self.order],
+                                            late_segment=[k for k, _ in self.order].index("lang_feats"))
                 self.dp_mode = "fused peer-memory reduce-scatter + Adam + all-gather (lgs_dp_adam_shard, " + \
-                               ("NVSwitch multimem" if self.dp.uses_multicast else "P2P loads/stores") + ")"
+                               ("NVSwitch multimem" if self.dp.uses_multicast else "P2P loads/stores") + \
+                               (", language-feature exchange overlapped with preprocess/binning on a side stream)" if self.dp.overlap else ")")
             except Exception as ex:  # symmetric memory unavailable on this box: NCCL path
                 self.dp = None
                 self.dp_mode += f" (symmetric memory unavailable: {type(ex).__name__})"

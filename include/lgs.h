@@ -226,11 +226,21 @@ int lgs_adam_multi(int n_tensors, float* const* params, const float* const* grad
  * rank (multimem.st on params_mc when non-NULL, else peer stores to params_peers[0..G)).
  * seg_start[0..n_seg] are the flat offsets of the parameter tensors (multiples of 4), lr[t] their rates.
  * grads_peers / params_peers are HOST arrays of device pointers into symmetric (peer-mapped) buffers; the
- * caller synchronises the ranks before (gradients complete) and after (parameters landed) the launch. */
+ * caller synchronises the ranks before (gradients complete) and after (parameters landed) the launch.
+ * max_ctas > 0 bounds the grid (a launch meant to run underneath other kernels on a side stream); 0 = whole GPU. */
 int lgs_dp_adam_shard(int n_seg, const int64_t* seg_start, const double* lr, int world, int rank,
                       const float* const* grads_peers, float* const* params_peers, const float* grads_mc,
                       float* params_mc, int64_t shard_begin, int64_t shard_end, float* exp_avg_shard,
-                      float* exp_avg_sq_shard, double beta1, double beta2, double eps, int step, void* stream);
+                      float* exp_avg_sq_shard, double beta1, double beta2, double eps, int step, int max_ctas,
+                      void* stream);
+
+/* Stream hooks of the CALLING HOST THREAD, for callers that overlap the exchange of the language-feature tensors (64 of
+ * the 123 floats per Gaussian) with the stages that never touch them.  Both are cudaEvent_t handles owned by the caller;
+ * NULL clears a hook.  While set: lgs_forward_stage2 makes its stream wait for `wait_before_render_fwd` after binning
+ * and before the render kernel (the only forward stage that reads lang_feat; reference forward.cu:261-392), and
+ * lgs_backward* records `record_after_render_bwd` on its stream after the render backward, when dL_dlang_feat is final
+ * and lang_feat is no longer read (preprocess backward follows; reference rasterizer_impl.cu:404-453). */
+int lgs_stream_hooks(void* wait_before_render_fwd, void* record_after_render_bwd);
 
 /* ---- activations  (reference src/gaussian_model.cpp:46-68) ---------------
  * forward : scales = exp(scaling) [P,3], rotations = normalize(rotation) [P,4], opacities =

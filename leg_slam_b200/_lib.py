@@ -57,7 +57,8 @@ SIGNATURES = {
     "lgs_bench_fma": (c_int, [c_int, c_int, c_void_p, c_void_p]),
     "lgs_adam_multi": (c_int, [c_int] + [c_void_p] * 6 + [c_double, c_double, c_double, c_int, c_void_p]),
     "lgs_dp_adam_shard": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int] + [c_void_p] * 4 + [c_int64, c_int64, c_void_p,
-                                  c_void_p, c_double, c_double, c_double, c_int, c_void_p]),
+                                  c_void_p, c_double, c_double, c_double, c_int, c_int, c_void_p]),
+    "lgs_stream_hooks": (c_int, [c_void_p, c_void_p]),
     "lgs_activations_fwd": (c_int, [c_int, c_int] + [c_void_p] * 10),
     "lgs_activations_bwd": (c_int, [c_int, c_int, c_int] + [c_void_p] * 13),
     "lgs_mapping_loss_scratch_bytes": (c_size_t, [c_int, c_int]),

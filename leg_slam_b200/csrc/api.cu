@@ -34,6 +34,14 @@ struct Stage1Note {
 };
 static thread_local Stage1Note g_stage1_note;
 
+// Stream hooks of the calling host thread (lgs_stream_hooks): lets a data-parallel caller overlap the exchange of the
+// language-feature parameters / gradients (52 % of the payload) with the stages that do not touch them.
+struct StreamHooks {
+    cudaEvent_t wait_before_render_fwd = nullptr;   // stage2 waits for it after binning, before the render kernel
+    cudaEvent_t record_after_render_bwd = nullptr;  // backward records it once dL_dlang_feat is final
+};
+static thread_local StreamHooks g_hooks;
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace lgs
@@ -167,6 +175,7 @@ int lgs_forward_stage2(int P, int W, int H, int R, const float* background, cons
     const uint32_t max_depth_bits = g_stage1_note.geom == geom_buffer ? g_stage1_note.max_depth_bits : 0xffffffffu;
     int st = launch_binning(P, R, W, H, g, g.internal_radii, b, im, max_depth_bits, s);
     if (st != LGS_OK) return st;
+    if (g_hooks.wait_before_render_fwd) LGS_CUDA_TRY(cudaStreamWaitEvent(s, g_hooks.wait_before_render_fwd, 0));
     st = launch_render_fwd(W, H, R, g, b, im, background, lang_feat, out_color, out_lang_feat, out_depth,
                            include_lang_feat != 0, s);
     prof_mark(PM_RENDER_FWD, s);
@@ -239,6 +248,7 @@ static int backward_impl(int P, int D, int M, int R, int W, int H, const float* 
         if (st != LGS_OK) return st;
     }
     prof_mark(PM_RENDER_BWD, s);
+    if (g_hooks.record_after_render_bwd) LGS_CUDA_TRY(cudaEventRecord(g_hooks.record_after_render_bwd, s));
     const float* cov3D = cov3D_precomp ? cov3D_precomp : g.cov3D;
     st = launch_preprocess_bwd(P, D, M, means3D, radii, shs, shs_rest, scales, rotations, scale_modifier, cov3D,
                                viewmatrix, projmatrix, cam_pos, W, H, tan_fovx, tan_fovy, g, dL_dmean2D,
@@ -285,6 +295,13 @@ int lgs_backward_split_sh(int P, int D, int M, int R, int W, int H, const float*
                          dL_dpix_depth, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dlang_feat, dL_ddepth, dL_dmean3D,
                          dL_dcov3D, dL_dfeatures_dc, M > 1 ? dL_dfeatures_rest : dL_dfeatures_dc, accumulate_sh, dL_dscale,
                          dL_drot, include_lang_feat, zero_outputs, bwd_scratch, stream);
+}
+
+// ---- stream hooks ----------------------------------------------------------------------
+int lgs_stream_hooks(void* wait_before_render_fwd, void* record_after_render_bwd) {
+    g_hooks.wait_before_render_fwd = (cudaEvent_t)wait_before_render_fwd;
+    g_hooks.record_after_render_bwd = (cudaEvent_t)record_after_render_bwd;
+    return LGS_OK;
 }
 
 // ---- per-stage timing ------------------------------------------------------------------

@@ -118,7 +118,8 @@ using namespace lgs;
 extern "C" int lgs_dp_adam_shard(int n_seg, const int64_t* seg_start, const double* lr, int world, int rank,
                                  const float* const* grads_peers, float* const* params_peers, const float* grads_mc,
                                  float* params_mc, int64_t shard_begin, int64_t shard_end, float* exp_avg_shard,
-                                 float* exp_avg_sq_shard, double beta1, double beta2, double eps, int step, void* stream) {
+                                 float* exp_avg_sq_shard, double beta1, double beta2, double eps, int step, int max_ctas,
+                                 void* stream) {
     if (n_seg < 1 || n_seg > DP_MAX_SEG || world < 1 || world > DP_MAX_WORLD || rank < 0 || rank >= world || step < 1)
         return LGS_ERR_INVALID_ARG;
     if (!seg_start || !lr || !grads_peers || !params_peers || !exp_avg_shard || !exp_avg_sq_shard) return LGS_ERR_INVALID_ARG;
@@ -140,7 +141,10 @@ extern "C" int lgs_dp_adam_shard(int n_seg, const int64_t* seg_start, const doub
     tab.world = world;
     const long long n4 = (shard_end - shard_begin) >> 2;
     const long long want = (n4 + 256LL * DP_UNROLL - 1) / (256LL * DP_UNROLL);
-    const int grid = (int)(want < 148LL * 8 ? (want > 0 ? want : 1) : 148LL * 8);
+    // max_ctas > 0 bounds the grid: a launch that runs underneath other kernels on a side stream must leave them SM slots
+    // (the default fills every thread slot of the GPU for the whole exchange)
+    const long long cap = max_ctas > 0 ? (long long)max_ctas : 148LL * 8;
+    const int grid = (int)(want < cap ? (want > 0 ? want : 1) : cap);
     const bool mc = grads_mc != nullptr && params_mc != nullptr;
 #define LGS_DP_LAUNCH(MCV, WV)                                                                                                  \
     dp_adam_kernel<MCV, WV><<<grid, 256, 0, (cudaStream_t)stream>>>(tab, grads_mc, params_mc, shard_begin, shard_end,           \

@@ -86,24 +86,9 @@ class Mapper:
         self._optimizer_factory = optimizer_factory
         world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.dp = None
+        self._dp_group = process_group
         if dp_mode == "fused" and world > 1 and params["xyz"].is_cuda and render_fn is None and fused:
-            from . import dp as dp_mod
-            dev0 = params["xyz"].device
-            n = sum(params[k].numel() for k in PARAM_ORDER)
-            pflat = dp_mod.symmetric_empty(n, dev0)
-            gflat = dp_mod.symmetric_empty(n, dev0)
-            gflat.zero_()
-            off, self.params = 0, {}
-            for k in PARAM_ORDER:
-                t = params[k].detach().contiguous()
-                view = pflat[off:off + t.numel()].view_as(t)
-                view.copy_(t)
-                self.params[k] = torch.nn.Parameter(view, requires_grad=False)
-                off += t.numel()
-            self.grads = FlatGrads(self.params, flat=gflat)
-            self.dp = dp_mod.FusedDPAdam(pflat, gflat, [params[k].numel() for k in PARAM_ORDER], [lrs[k] for k in PARAM_ORDER],
-                                         group=process_group)
-            self.optimizer = None
+            self._init_fused_dp({k: params[k].detach() for k in PARAM_ORDER})
         else:
             self.params = {k: torch.nn.Parameter(params[k].detach().clone().contiguous()) for k in PARAM_ORDER}
             groups = [dict(params=[self.params[k]], lr=lrs[k], name=k) for k in PARAM_ORDER]
@@ -131,6 +116,57 @@ class Mapper:
                 raise ValueError("track_densify_stats needs the fused path (CUDA tensors, our rasterizer)")
             from .densify import DensifyStats
             self.stats = DensifyStats(self.params["xyz"].shape[0], dev)
+
+    # -- fused data-parallel state: parameters + gradients in symmetric memory, Adam moments sharded (leg_slam_b200.dp)
+    def _init_fused_dp(self, tensors: dict, moments=None, step_count: int = 0):
+        """(Re)build the symmetric-memory parameter / gradient buffers and the sharded optimizer for `tensors`; collective
+        (every rank calls it with identical tensors).  Tensors start on 16-byte boundaries of the flat index space, as in
+        FlatGrads; `moments` = (exp_avg, exp_avg_sq) dicts of full tensors to carry over."""
+        from . import dp as dp_mod
+        if self.dp is not None:
+            self.dp.close()
+        dev0 = tensors["xyz"].device
+        sizes = [(tensors[k].numel() + 3) & ~3 for k in PARAM_ORDER]
+        n = sum(sizes)
+        pflat = dp_mod.symmetric_empty(n, dev0)
+        gflat = dp_mod.symmetric_empty(n, dev0)
+        pflat.zero_()
+        gflat.zero_()
+        off, self.params = 0, {}
+        for k, sz in zip(PARAM_ORDER, sizes):
+            t = tensors[k].contiguous()
+            view = pflat[off:off + t.numel()].view_as(t)
+            view.copy_(t)
+            self.params[k] = torch.nn.Parameter(view, requires_grad=False)
+            off += sz
+        self.grads = FlatGrads(self.params, flat=gflat)
+        torch.cuda.synchronize(dev0)
+        self.dp = dp_mod.FusedDPAdam(pflat, gflat, sizes, [self._lrs[k] for k in PARAM_ORDER], group=self._dp_group,
+                                     late_segment=PARAM_ORDER.index("lang_feat"))
+        self.optimizer = None
+        if moments is not None:
+            m = torch.zeros(n, dtype=torch.float32, device=dev0)
+            v = torch.zeros(n, dtype=torch.float32, device=dev0)
+            off = 0
+            for k, sz in zip(PARAM_ORDER, sizes):
+                m[off:off + tensors[k].numel()] = moments[0][k].reshape(-1)
+                v[off:off + tensors[k].numel()] = moments[1][k].reshape(-1)
+                off += sz
+            self.dp.load_moments(m, v, step_count)
+        else:
+            self.dp.step_count = int(step_count)
+
+    def _fused_dp_moments(self):
+        """Full (exp_avg, exp_avg_sq) dicts gathered from the ranks' shards, and the common step count."""
+        self.dp.flush()
+        m, v = self.dp.gather_moments()
+        md, vd, off = {}, {}, 0
+        for k in PARAM_ORDER:
+            t = self.params[k]
+            md[k] = m[off:off + t.numel()].view_as(t)
+            vd[k] = v[off:off + t.numel()].view_as(t)
+            off += (t.numel() + 3) & ~3
+        return md, vd, self.dp.step_count
 
     # -- activations exactly as the reference applies them each iteration (gaussian_model.cpp:46-68)
     def activated(self):
@@ -256,25 +292,31 @@ class Mapper:
         """The Gaussian set in the reference's .ply layout plus the Adam moments and step counts (leg_slam_b200.ply_io):
         loads in the reference as a plain model, resumes here with `load_checkpoint`."""
         from . import ply_io
-        if self.dp is not None:
-            raise NotImplementedError("dp_mode='fused' shards the Adam state over the ranks")
         p = {k: v.data for k, v in self.params.items()}
-        m, v, steps = {}, {}, {}
-        for k in PARAM_ORDER:
-            st = self.optimizer.state.get(self.params[k], {})
-            m[k] = st["exp_avg"] if "exp_avg" in st else torch.zeros_like(p[k])
-            v[k] = st["exp_avg_sq"] if "exp_avg_sq" in st else torch.zeros_like(p[k])
-            steps[k] = int(st.get("step", 0))
-        ply_io.save_ply(path, p, m, v, steps)
+        if self.dp is not None:  # collective: the shards of the Adam state are gathered; rank 0 writes the file
+            m, v, step = self._fused_dp_moments()
+            if self.rank == 0:
+                ply_io.save_ply(path, p, m, v, {k: step for k in PARAM_ORDER})
+            dist.barrier(group=self.pg)
+            return
+        m, v, steps = self._optimizer_moments(p)
+        ply_io.save_ply(path, p, m, v, {k: int(s) for k, s in steps.items()})
 
     def load_checkpoint(self, path):
         """Replace this mapper's Gaussian set and optimizer state by a checkpoint written by `save_checkpoint` (or by a
         plain reference .ply: fresh Adam state)."""
         from . import ply_io
-        if self.dp is not None:
-            raise NotImplementedError("dp_mode='fused' keeps parameters in symmetric memory")
         dev = self.params["xyz"].device
         p2, m2, v2, steps = ply_io.load_ply(path, dev, self.sh_degree)
+        if self.dp is not None:  # collective: every rank reads the same file
+            if m2 is not None and len({int(steps[k]) for k in PARAM_ORDER}) != 1:
+                raise ValueError("dp_mode='fused' keeps one Adam step count for all tensors")
+            self._init_fused_dp(p2, None if m2 is None else (m2, v2), 0 if m2 is None else int(steps[PARAM_ORDER[0]]))
+            self._fbuf = None
+            if self.stats is not None:
+                from .densify import DensifyStats
+                self.stats = DensifyStats(self.params["xyz"].shape[0], dev)
+            return
         self.params = {k: torch.nn.Parameter(p2[k]) for k in PARAM_ORDER}
         groups = [dict(params=[self.params[k]], lr=self._lrs[k], name=k) for k in PARAM_ORDER]
         self.optimizer = (self._optimizer_factory or (lambda g: FusedAdam(g, lr=0.0, eps=1e-15)))(groups)
@@ -287,6 +329,15 @@ class Mapper:
             from .densify import DensifyStats
             self.stats = DensifyStats(self.params["xyz"].shape[0], dev)
 
+    def _optimizer_moments(self, p):
+        m, v, steps = {}, {}, {}
+        for k in PARAM_ORDER:
+            st = self.optimizer.state.get(self.params[k], {})
+            m[k] = st["exp_avg"] if "exp_avg" in st else torch.zeros_like(p[k])
+            v[k] = st["exp_avg_sq"] if "exp_avg_sq" in st else torch.zeros_like(p[k])
+            steps[k] = st.get("step", 0)
+        return m, v, steps
+
     def densify_and_prune(self, max_grad, min_opacity, extent, max_screen_size, percent_dense=0.01, generator=None):
         """GaussianModel::densifyAndPrune (reference src/gaussian_model.cpp:806-824) on this mapper's Gaussian set: clone /
         split / prune in one fused gather (leg_slam_b200.densify), carrying the Adam moments and step counts over and
@@ -295,23 +346,25 @@ class Mapper:
         from . import densify as densify_mod
         if self.stats is None:
             raise ValueError("construct the Mapper with track_densify_stats=True")
-        if self.dp is not None:
-            raise NotImplementedError("dp_mode='fused' keeps parameters in symmetric memory: rebuild the Mapper from "
-                                      "densify.densify_and_prune's outputs instead")
         if self.world_size > 1:
             dist.all_reduce(self.stats.xyz_gradient_accum, op=dist.ReduceOp.SUM, group=self.pg)
             dist.all_reduce(self.stats.denom, op=dist.ReduceOp.SUM, group=self.pg)
             dist.all_reduce(self.stats.max_radii2D, op=dist.ReduceOp.MAX, group=self.pg)
         p = {k: v.data for k, v in self.params.items()}
-        m, v, steps = {}, {}, {}
-        for k in PARAM_ORDER:
-            st = self.optimizer.state.get(self.params[k], {})
-            m[k] = st["exp_avg"] if "exp_avg" in st else torch.zeros_like(p[k])
-            v[k] = st["exp_avg_sq"] if "exp_avg_sq" in st else torch.zeros_like(p[k])
-            steps[k] = st.get("step", 0)
+        if self.dp is not None:
+            m, v, step = self._fused_dp_moments()
+            steps = {k: step for k in PARAM_ORDER}
+        else:
+            m, v, steps = self._optimizer_moments(p)
         with torch.no_grad():
             p2, m2, v2, stats2, info = densify_mod.densify_and_prune(p, m, v, self.stats, max_grad, min_opacity, extent,
                                                                     max_screen_size, percent_dense, generator)
+        if self.dp is not None:  # new symmetric buffers for the new P; the moments are re-sharded
+            self._init_fused_dp(p2, (m2, v2), steps[PARAM_ORDER[0]])
+            self.stats = stats2
+            self._fbuf = None
+            torch.cuda.empty_cache()
+            return info
         self.params = {k: torch.nn.Parameter(p2[k]) for k in PARAM_ORDER}
         groups = [dict(params=[self.params[k]], lr=self._lrs[k], name=k) for k in PARAM_ORDER]
         self.optimizer = (self._optimizer_factory or (lambda g: FusedAdam(g, lr=0.0, eps=1e-15)))(groups)
@@ -336,12 +389,18 @@ class Mapper:
             with torch.no_grad():
                 total = self._train_views_fused(window, mine)  # overwrites the flat buffer: no memset needed
                 if self.dp is not None:
-                    self.dp.step()  # reduce-scatter + Adam + all-gather in one peer-memory kernel
+                    # reduce-scatter + Adam + all-gather in peer-memory kernels; with one local view the language-feature
+                    # gradient was written in place and is final when the render backward ends (exchange starts there)
+                    self.dp.step(late_ready_at_hook=len(mine) == 1)
                     return total
                 if self.world_size > 1:
                     dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.pg)
             self.optimizer.step()
             return total
+        if self.dp is not None:  # a rank without a view this iteration still takes part in the exchange
+            self.grads.zero_()
+            self.dp.step(late_ready_at_hook=False)
+            return torch.zeros((), device=self.grads.flat.device)
         self.grads.zero_()
         total = None
         for i in mine:

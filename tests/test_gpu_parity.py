@@ -656,7 +656,7 @@ def test_dp_adam_shard_kernel_single_rank(dev, oracle_mod):
         pp = (ctypes.c_void_p * 1)(p.data_ptr())
         for b, e in ((0, half), (half, n)):
             _lib.check(L.lgs_dp_adam_shard(len(sizes), seg, lr, 1, 0, gp, pp, None, None, b, e, m[b:].data_ptr(), v[b:].data_ptr(),
-                                           0.9, 0.999, 1e-15, step, torch.cuda.current_stream(dev).cuda_stream), "dp_adam")
+                                           0.9, 0.999, 1e-15, step, 0, torch.cuda.current_stream(dev).cuda_stream), "dp_adam")
         for t in range(len(sizes)):
             a, z = int(starts[t]), int(starts[t + 1])
             oracle_mod.adam(ref_p[a:z], gr.numpy()[a:z], ref_m[a:z], ref_v[a:z], lrs[t], step=step)

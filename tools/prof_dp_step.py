@@ -16,6 +16,7 @@ if __name__ == "__main__":
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     sc, cam, up = bench.make_workload(rank, world, dev)
+    os.environ["LGS_DP_OVERLAP"] = "0"  # this tool times the single-kernel exchange
     kp = bench.KernelPath(sc, cam, up, dev, world)
     for _ in range(5):
         kp.step()
@@ -44,7 +45,7 @@ if __name__ == "__main__":
         lr = (ctypes.c_double * len(d.lrs))(*d.lrs)
         _lib.check(L.lgs_dp_adam_shard(len(d.lrs), d._seg, lr, d.world, d.rank, d._gp, d._pp, ctypes.c_void_p(d.g_mc or None),
                                        ctypes.c_void_p(d.p_mc or None), d.begin, d.end, d.exp_avg.data_ptr(), d.exp_avg_sq.data_ptr(),
-                                       0.9, 0.999, 1e-15, d.step_count, torch.cuda.current_stream(dev).cuda_stream), "dp")
+                                       0.9, 0.999, 1e-15, d.step_count, 0, torch.cuda.current_stream(dev).cuda_stream), "dp")
         e3 = ev()
         kp.dp.hp.barrier(channel=1)
         e4 = ev()
