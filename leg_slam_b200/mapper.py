@@ -338,11 +338,14 @@ class Mapper:
             steps[k] = st.get("step", 0)
         return m, v, steps
 
-    def densify_and_prune(self, max_grad, min_opacity, extent, max_screen_size, percent_dense=0.01, generator=None):
+    def densify_and_prune(self, max_grad, min_opacity, extent, max_screen_size, percent_dense=0.01, generator=None,
+                          empty_cache: bool = False):
         """GaussianModel::densifyAndPrune (reference src/gaussian_model.cpp:806-824) on this mapper's Gaussian set: clone /
         split / prune in one fused gather (leg_slam_b200.densify), carrying the Adam moments and step counts over and
         rebuilding the flat gradient buffer.  With several ranks the statistics are summed (max for the radii) first and
-        every rank must pass a generator in the same state, so that the replicas stay identical."""
+        every rank must pass a generator in the same state, so that the replicas stay identical.
+        `empty_cache` repeats the reference's c10::cuda::CUDACachingAllocator::emptyCache() (:823); it is allocator
+        hygiene, not semantics, and costs up to 0.5 s of cudaFree / cudaMalloc at 3-6 M Gaussians, so it is off by default."""
         from . import densify as densify_mod
         if self.stats is None:
             raise ValueError("construct the Mapper with track_densify_stats=True")
@@ -363,7 +366,8 @@ class Mapper:
             self._init_fused_dp(p2, (m2, v2), steps[PARAM_ORDER[0]])
             self.stats = stats2
             self._fbuf = None
-            torch.cuda.empty_cache()
+            if empty_cache:
+                torch.cuda.empty_cache()
             return info
         self.params = {k: torch.nn.Parameter(p2[k]) for k in PARAM_ORDER}
         groups = [dict(params=[self.params[k]], lr=self._lrs[k], name=k) for k in PARAM_ORDER]
@@ -373,7 +377,8 @@ class Mapper:
         self.grads = FlatGrads(self.params)
         self.stats = stats2
         self._fbuf = None  # per-P work buffers
-        torch.cuda.empty_cache()  # c10::cuda::CUDACachingAllocator::emptyCache(), :823
+        if empty_cache:
+            torch.cuda.empty_cache()  # c10::cuda::CUDACachingAllocator::emptyCache(), :823
         return info
 
     def train_step(self, window: Sequence[Keyframe], presharded: bool = False):
