@@ -665,6 +665,64 @@ def test_dp_adam_shard_kernel_single_rank(dev, oracle_mod):
     np.testing.assert_array_equal(v.cpu().numpy().view(np.uint32), ref_v.view(np.uint32))
 
 
+def test_dp_adam_shard_grid_bound_is_bit_identical(dev):
+    """max_ctas only bounds the grid of lgs_dp_adam_shard (a launch that runs underneath other kernels): same bits."""
+    import ctypes
+    from leg_slam_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(92)
+    n = 4 * 70001
+    p0, gr = torch.randn(n, generator=g), torch.randn(n, generator=g) * 1e-3
+    seg = (ctypes.c_int64 * 3)(0, 4 * 30000, n)
+    lr = (ctypes.c_double * 2)(1e-3, 5e-2)
+    outs = []
+    for cap in (0, 1, 148 * 4):
+        p, m, v, gd = p0.clone().to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev), gr.to(dev)
+        gp, pp = (ctypes.c_void_p * 1)(gd.data_ptr()), (ctypes.c_void_p * 1)(p.data_ptr())
+        for step in (1, 2):
+            _lib.check(L.lgs_dp_adam_shard(2, seg, lr, 1, 0, gp, pp, None, None, 0, n, m.data_ptr(), v.data_ptr(), 0.9, 0.999, 1e-15,
+                                           step, cap, torch.cuda.current_stream(dev).cuda_stream), "dp_adam")
+        outs.append((p.cpu(), m.cpu(), v.cpu()))
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert torch.equal(a, b)
+
+
+def test_stream_hooks(dev):
+    """lgs_stream_hooks: the forward waits for the caller's event between binning and the render kernel, the backward records
+    the caller's event after the render backward; results are unchanged and NULL clears the hooks."""
+    import ctypes
+    from leg_slam_b200 import _lib, rasterize_points as rp
+    L = _lib.lib()
+    cs = cases.make_case("sh3_lf", dev)
+    base = rp.rasterize_gaussians(*cases.fwd_args(cs))
+    gbase = rp.rasterize_gaussians_backward(*cases.bwd_args(cs, base[4], base[5], base[0], base[6], base[7]))
+    side = torch.cuda.Stream(device=dev)
+    cur = torch.cuda.current_stream(dev)
+    ev_wait, ev_rec = torch.cuda.Event(), torch.cuda.Event()
+    ev_wait.record(cur)
+    ev_rec.record(cur)
+    torch.cuda.synchronize(dev)
+    try:
+        _lib.check(L.lgs_stream_hooks(ctypes.c_void_p(ev_wait.cuda_event), ctypes.c_void_p(ev_rec.cuda_event)), "hooks")
+        # the event the render kernel waits for is recorded behind a long busy kernel on another stream
+        with torch.cuda.stream(side):
+            torch.cuda._sleep(200_000_000)  # ~0.1 s
+            ev_wait.record(side)
+        out = rp.rasterize_gaussians(*cases.fwd_args(cs))
+        grads = rp.rasterize_gaussians_backward(*cases.bwd_args(cs, out[4], out[5], out[0], out[6], out[7]))
+        side.wait_event(ev_rec)  # the backward recorded it: waiting must not dead-lock and must complete
+        torch.cuda.synchronize(dev)
+        assert ev_rec.query()
+    finally:
+        _lib.check(L.lgs_stream_hooks(None, None), "hooks")
+    assert out[0] == base[0]
+    for a, b in zip(out[1:5], base[1:5]):
+        assert torch.equal(a, b)
+    for n, a, b in zip(cases.GRAD_NAMES, grads, gbase):
+        assert cases.rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-4, n
+
+
 def test_cosine_query(dev, oracle_mod):
     """Tensor-core kernel (tcgen05, 3xTF32) and the SIMT cross-check kernel against the fp64-accumulating oracle."""
     from leg_slam_b200 import cosine_query, relevance_scores

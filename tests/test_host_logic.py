@@ -103,3 +103,22 @@ def test_cov3d_precomp_helper_matches_oracle(oracle_mod):
     vis = f["radii"] > 0
     cov = cases.covariance_from_scale_rot(cs["scales"], cs["rotations"]).numpy()
     assert cases.rel_err(cov[vis], f["cov3D"][vis]) <= 1e-5
+
+
+def test_dp_range_partition_covers_the_flat_index_space_once():
+    """leg_slam_b200.dp._Range: the pieces of the flat index space (other tensors | early / late part of the language
+    features) sharded over the ranks are disjoint, 16-byte aligned and cover every index exactly once."""
+    from leg_slam_b200.dp import _Range
+    dev = torch.device("cpu")
+    for world in (1, 2, 3, 4, 8):
+        for pieces in ([(0, 123 * 40, 0)], [(0, 51 * 40, 0), (51 * 40, 51 * 40 + 1024, 1), (51 * 40 + 1024, 115 * 40, 2), (115 * 40, 123 * 40, 0)],
+                       [(0, 8, 0), (8, 12, 2), (12, 16, 0)]):
+            n = pieces[-1][1]
+            seen = np.zeros(n, np.int32)
+            for rank in range(world):
+                for b, e, ph in pieces:
+                    r = _Range(b, e, ph, world, rank, dev)
+                    assert r.sb % 4 == 0 and r.se % 4 == 0 and b <= r.sb <= r.se <= e
+                    assert r.exp_avg.numel() >= max(r.se - r.sb, 4) and r.exp_avg_sq.numel() == r.exp_avg.numel()
+                    seen[r.sb:r.se] += 1
+            assert (seen == 1).all(), (world, pieces)
