@@ -329,6 +329,24 @@ class Mapper:
             from .densify import DensifyStats
             self.stats = DensifyStats(self.params["xyz"].shape[0], dev)
 
+    def _release_state(self):
+        """Drop every reference this mapper holds to the current parameter / gradient / optimizer-state / work tensors, so
+        that their blocks return to the caching allocator now (by reference count) rather than at some later garbage
+        collection: the buffers of the next, slightly larger P then reuse them instead of costing a cudaMalloc each."""
+        if self.optimizer is not None:
+            self.optimizer.state.clear()
+            for g in self.optimizer.param_groups:
+                g["params"] = []
+            self.optimizer = None
+        for t in self.params.values():
+            t.grad = None
+        if self.grads is not None:
+            self.grads.views.clear()
+            self.grads.flat = None
+            self.grads = None
+        self._fbuf = None
+        self.stats = None
+
     def _optimizer_moments(self, p):
         m, v, steps = {}, {}, {}
         for k in PARAM_ORDER:
@@ -369,6 +387,8 @@ class Mapper:
             if empty_cache:
                 torch.cuda.empty_cache()
             return info
+        self._release_state()  # the old tensors go back to the allocator before the new gradient / work buffers are made
+        del p, m, v
         self.params = {k: torch.nn.Parameter(p2[k]) for k in PARAM_ORDER}
         groups = [dict(params=[self.params[k]], lr=self._lrs[k], name=k) for k in PARAM_ORDER]
         self.optimizer = (self._optimizer_factory or (lambda g: FusedAdam(g, lr=0.0, eps=1e-15)))(groups)

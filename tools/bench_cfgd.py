@@ -27,9 +27,18 @@ def main():
     ap.add_argument("--iters", type=int, default=300)
     ap.add_argument("--P", type=int, default=2_000_000)
     ap.add_argument("--ref-iters", type=int, default=20)
-    ap.add_argument("--grad-threshold", type=float, default=2e-6)
+    ap.add_argument("--grad-threshold", type=float, default=0.0,
+                    help="> 0: fixed densify_grad_threshold; 0: per round, the value that selects --grow-frac of the Gaussians")
+    ap.add_argument("--grow-frac", type=float, default=0.03)
+    ap.add_argument("--no-roundup", action="store_true")
+    ap.add_argument("--profile-densify", action="store_true", help="cProfile of every densify_and_prune call -> stderr")
+    ap.add_argument("--skip-ref", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
+    if not args.no_roundup:
+        # sizes rounded to 1/8 of a power of two: the buffers of the slightly larger P after a densification round fit the blocks
+        # the previous round released, so the caching allocator serves them without cudaMalloc (20-40 ms per GB on this box)
+        torch.cuda.memory._set_allocator_settings("roundup_power2_divisions:8")
     W, H = 1296, 968
     sc = synthetic.make_scene(args.P, seed=4, room=ROOM, device=dev)
     cams_host = synthetic.make_cameras(8, W, H, fx=1169.7, fy=1169.7, room=ROOM, seed=4)
@@ -40,7 +49,8 @@ def main():
     lrs = {k: v * bench.LR_SCALE for k, v in M.DEFAULT_LRS.items()}
     out = dict(config=f"cfgD: {args.P} Gaussians (ScanNet-shaped room {ROOM}), {W}x{H}, fx=fy=1169.7, SH degree 3, 64-D feature, "
                       f"8-keyframe window, 1 keyframe per iteration, densify/prune every 100 iterations "
-                      f"(grad threshold {args.grad_threshold}, min opacity 0.02, size threshold 20, extent 5.0)")
+                      f"(grad threshold {args.grad_threshold if args.grad_threshold > 0 else f'selecting {args.grow_frac:.0%} per round'}, "
+                      f"min opacity 0.02, size threshold 20, extent 5.0), allocator roundup_power2_divisions:8 = {not args.no_roundup}")
 
     m = M.Mapper(sc, lrs=lrs, sh_degree=3, track_densify_stats=True)
     for i in range(5):
@@ -59,7 +69,27 @@ def main():
             torch.cuda.synchronize()
             now = time.perf_counter()
             seg.append(dict(iters=f"{it - 99}..{it}", P=int(m.params["xyz"].shape[0]), ms_per_iter=(now - t_seg) * 1e3 / 100))
-            info = m.densify_and_prune(args.grad_threshold, 0.02, 5.0, 20, generator=gen)
+            thr = args.grad_threshold
+            if thr <= 0:  # the synthetic loss has no meaningful gradient scale: pick the threshold by the fraction it selects
+                avg = (m.stats.xyz_gradient_accum / m.stats.denom.clamp_min(1)).reshape(-1)
+                k = max(1, int(avg.numel() * (1.0 - args.grow_frac)))
+                thr = float(torch.kthvalue(avg, k).values)
+                torch.cuda.synchronize()
+                now = time.perf_counter()
+            if args.profile_densify:
+                import cProfile
+                import pstats
+                pr = cProfile.Profile()
+                pr.enable()
+            info = m.densify_and_prune(thr, 0.02, 5.0, 20, generator=gen)
+            if args.profile_densify:
+                torch.cuda.synchronize()
+                pr.disable()
+                print(f"---- densify at iteration {it}", file=sys.stderr)
+                pstats.Stats(pr, stream=sys.stderr).sort_stats("tottime").print_stats(8)
+            info["grad_threshold"] = thr
+            info["reserved_GB"] = round(torch.cuda.memory_reserved() / 1e9, 2)
+            info["allocated_GB"] = round(torch.cuda.memory_allocated() / 1e9, 2)
             torch.cuda.synchronize()
             t_seg = time.perf_counter()
             dens.append(dict(at_iter=it, ms=(t_seg - now) * 1e3, **info))
@@ -72,6 +102,9 @@ def main():
     torch.cuda.empty_cache()
 
     # reference arm: iterations only, at the initial P
+    if args.skip_ref:
+        print(json.dumps(out))
+        return
     try:
         bench.WIDTH, bench.HEIGHT = W, H
         e2e = bench.E2EPath(sc, cams_host[0], dev, 1, "reference", cams=cams_host[:1])
