@@ -405,7 +405,10 @@ class Mapper:
         """Render + back-propagate this rank's share of `window`, sum gradients over ranks, Adam.
         `window` is the iteration's global list of keyframes (every rank passes the same list and
         takes its round-robin share) unless `presharded`, in which case it already holds only this
-        rank's keyframes.  Returns the (detached) sum of this rank's view losses."""
+        rank's keyframes.  Returns the (detached) sum of this rank's view losses.
+        With dp_mode="fused" the language-feature part of the exchange may still be running on its side stream when this
+        returns; the next render forward waits for it by itself (lgs_stream_hooks), any OTHER reader of
+        `params["lang_feat"]` on the caller's stream calls `self.dp.flush()` first (checkpoints and densification do)."""
         mine = list(range(len(window))) if presharded else shard_views(len(window), self.rank, self.world_size)
         self.last_num_views = len(mine)
         if self.dp is None:
