@@ -93,6 +93,58 @@ def densify_and_prune(params, exp_avg, exp_avg_sq, stats, max_grad, min_opacity,
     return out_p, out_m, out_v, new_stats, info
 
 
+SH_C0 = 0.28209479177387814  # include/sh_utils.h:32
+
+
+def increase_pcd(params, exp_avg, exp_avg_sq, stats, new_points, new_colors, iteration, sh_degree=3):
+    """GaussianModel::increasePcd (tensor overload, src/gaussian_model.cpp:297-384): Gaussians for the new points of a
+    keyframe -- colour as the DC coefficient (RGB2SH), zero higher-order SH and language features, isotropic scale from
+    the mean squared distance to the 3 nearest new points (`ingest.distCUDA2`, clamped at 1e-7), identity rotation,
+    opacity inverse_sigmoid(0.1) -- appended to the 7 parameter tensors with zero Adam moments (densificationPostfix,
+    :653-727), the statistics reset at the new size.  Returns (new_params, new_exp_avg, new_exp_avg_sq, new_stats);
+    inputs are left untouched.  One allocation + two copies per tensor (no `cat` temporaries); the scale needs the k-NN
+    kernel, so there is no CPU path."""
+    from . import ingest
+    xyz = params["xyz"]
+    if not xyz.is_cuda or not new_points.is_cuda:
+        raise _lib.LgsError("leg_slam_b200 has no CPU path: tensors must live on a CUDA device")
+    if new_points.dim() != 2 or new_points.shape[1] != 3 or new_colors.shape != new_points.shape:
+        raise ValueError("new_points and new_colors must have dimensions (num_points, 3)")
+    n, P, dev = int(new_points.shape[0]), int(xyz.shape[0]), xyz.device
+    if n == 0:  # the reference returns before touching anything (:299-300)
+        return params, exp_avg, exp_avg_sq, stats
+    new_points = new_points.to(dev, torch.float32).contiguous()
+    n_coef = (sh_degree + 1) ** 2
+    if params["features_rest"].shape[1] != n_coef - 1:
+        raise ValueError("features_rest does not match sh_degree")
+    d2 = torch.clamp_min(ingest.distCUDA2(new_points.clone()), 0.0000001)
+    x = torch.full((n, 1), 0.1, dtype=torch.float32, device=dev)
+    new = dict(xyz=new_points,
+               features_dc=((new_colors.to(dev, torch.float32) - 0.5) / SH_C0).unsqueeze(1),        # [n,1,3]
+               features_rest=None, lang_feat=None,                                                   # zeros
+               opacity=torch.log(x / (1 - x)),
+               scaling=torch.log(torch.sqrt(d2)).unsqueeze(1).expand(n, 3),
+               rotation=None)                                                                        # (1,0,0,0)
+    out_p, out_m, out_v = {}, {}, {}
+    for k in PARAM_ORDER:
+        shape = (P + n,) + tuple(params[k].shape[1:])
+        out_p[k] = torch.empty(shape, dtype=torch.float32, device=dev)
+        out_p[k][:P].copy_(params[k])
+        if new[k] is None:
+            out_p[k][P:].zero_()
+        else:
+            out_p[k][P:].copy_(new[k])
+        for src, dst in ((exp_avg, out_m), (exp_avg_sq, out_v)):
+            dst[k] = torch.empty(shape, dtype=torch.float32, device=dev)
+            dst[k][:P].copy_(src[k])
+            dst[k][P:].zero_()
+    out_p["rotation"][P:, 0] = 1.0
+    new_stats = DensifyStats(P + n, dev)  # accum / denom / max_radii2D zeroed at the new size (:723-725)
+    new_stats.exist_since_iter[:P].copy_(stats.exist_since_iter)
+    new_stats.exist_since_iter[P:] = int(iteration)
+    return out_p, out_m, out_v, new_stats
+
+
 def reset_opacity(params, exp_avg, exp_avg_sq):
     """GaussianModel::resetOpacity (:567-575): inverse_sigmoid(min(sigmoid(opacity), 1)) -- the reference clamps against
     ones, i.e. not at all -- and zeroes the opacity's Adam moments (:577-595)."""

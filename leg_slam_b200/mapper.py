@@ -380,26 +380,71 @@ class Mapper:
         with torch.no_grad():
             p2, m2, v2, stats2, info = densify_mod.densify_and_prune(p, m, v, self.stats, max_grad, min_opacity, extent,
                                                                     max_screen_size, percent_dense, generator)
+        del p, m, v
+        self._rebind(p2, m2, v2, steps, stats2)
+        if empty_cache:
+            torch.cuda.empty_cache()  # c10::cuda::CUDACachingAllocator::emptyCache(), :823
+        return info
+
+    def _rebind(self, p2, m2, v2, steps, stats2):
+        """Make (p2, m2, v2, steps) this mapper's parameters and Adam state (the reference keeps step / exp_avg / exp_avg_sq
+        per group across its surgery, src/gaussian_model.cpp:683-699) and rebuild the per-P buffers."""
         if self.dp is not None:  # new symmetric buffers for the new P; the moments are re-sharded
             self._init_fused_dp(p2, (m2, v2), steps[PARAM_ORDER[0]])
             self.stats = stats2
             self._fbuf = None
-            if empty_cache:
-                torch.cuda.empty_cache()
-            return info
+            return
         self._release_state()  # the old tensors go back to the allocator before the new gradient / work buffers are made
-        del p, m, v
         self.params = {k: torch.nn.Parameter(p2[k]) for k in PARAM_ORDER}
         groups = [dict(params=[self.params[k]], lr=self._lrs[k], name=k) for k in PARAM_ORDER]
         self.optimizer = (self._optimizer_factory or (lambda g: FusedAdam(g, lr=0.0, eps=1e-15)))(groups)
-        for k in PARAM_ORDER:  # the reference keeps step / exp_avg / exp_avg_sq per group (:683-699)
+        for k in PARAM_ORDER:
             self.optimizer.state[self.params[k]] = dict(step=steps[k], exp_avg=m2[k], exp_avg_sq=v2[k])
         self.grads = FlatGrads(self.params)
         self.stats = stats2
         self._fbuf = None  # per-P work buffers
-        if empty_cache:
-            torch.cuda.empty_cache()  # c10::cuda::CUDACachingAllocator::emptyCache(), :823
-        return info
+
+    def _current_state(self):
+        """(params, exp_avg, exp_avg_sq, steps) as dicts of full tensors (the moment shards gathered under dp_mode='fused')."""
+        p = {k: v.data for k, v in self.params.items()}
+        if self.dp is not None:
+            m, v, step = self._fused_dp_moments()
+            return p, m, v, {k: step for k in PARAM_ORDER}
+        m, v, steps = self._optimizer_moments(p)
+        return p, m, v, steps
+
+    def increase_pcd(self, new_points, new_colors, iteration: int):
+        """GaussianModel::increasePcd (reference src/gaussian_model.cpp:297-384; called per new keyframe,
+        src/gaussian_mapper.cpp:873,974,1482): append Gaussians for `new_points` [n,3] / `new_colors` [n,3] with zero Adam
+        moments (leg_slam_b200.densify.increase_pcd).  With several ranks every rank passes the same points."""
+        from . import densify as densify_mod
+        if self.stats is None:
+            raise ValueError("construct the Mapper with track_densify_stats=True")
+        if int(new_points.shape[0]) == 0:
+            return 0
+        p, m, v, steps = self._current_state()
+        with torch.no_grad():
+            p2, m2, v2, stats2 = densify_mod.increase_pcd(p, m, v, self.stats, new_points, new_colors, iteration, self.sh_degree)
+        del p, m, v
+        self._rebind(p2, m2, v2, steps, stats2)
+        return int(new_points.shape[0])
+
+    def reset_opacity(self):
+        """GaussianModel::resetOpacity (:567-595; cadence src/gaussian_mapper.cpp:757-761): opacity through the reference's
+        (no-op) clamp, its Adam moments zeroed, step count kept."""
+        from . import densify as densify_mod
+        p, m, v, steps = self._current_state()
+        p, m, v = dict(p), dict(m), dict(v)
+        with torch.no_grad():
+            densify_mod.reset_opacity(p, m, v)
+        if self.dp is not None:
+            self._rebind(p, m, v, steps, self.stats)
+            return
+        self.params["opacity"].data.copy_(p["opacity"])
+        st = self.optimizer.state.get(self.params["opacity"])
+        if st:
+            st["exp_avg"].zero_()
+            st["exp_avg_sq"].zero_()
 
     def train_step(self, window: Sequence[Keyframe], presharded: bool = False):
         """Render + back-propagate this rank's share of `window`, sum gradients over ranks, Adam.

@@ -105,6 +105,32 @@ class Model:
             prune = torch.logical_or(torch.logical_or(prune, big_vs), big_ws)
         self.prune_points(prune)
 
+    # -- :297-384 increasePcd(tensor overload): Gaussians for the new points of a keyframe.  `dist2(points)` is distCUDA2
+    #    (third_party/simple-knn; oracle/ingest_ref.py restates it); RGB2SH = include/sh_utils.h:32,133-135
+    def increase_pcd(self, new_points, new_colors, iteration, dist2, max_sh_degree=3):
+        n = new_points.shape[0]
+        if n == 0:
+            return
+        dev = new_points.device
+        C0 = 0.28209479177387814
+        fused = (new_colors - 0.5) / C0
+        t = max_sh_degree + 1
+        features = torch.zeros(n, 3, t * t, dtype=torch.float32, device=dev)
+        features[:, 0:3, 0] = fused
+        features[:, 3:, 1:] = 0.0
+        lang = torch.zeros(n, self.p["lang_feat"].shape[1], dtype=torch.float32, device=dev)
+        d2 = torch.clamp_min(dist2(new_points.clone()), 0.0000001)
+        scales = torch.log(torch.sqrt(d2)).unsqueeze(1).repeat(1, 3)
+        rots = torch.zeros(n, 4, device=dev)
+        rots[:, 0] = 1
+        x = 0.1 * torch.ones(n, 1, dtype=torch.float32, device=dev)
+        opac = torch.log(x / (1 - x))
+        new_exist = torch.full((n,), iteration, dtype=torch.int32, device=dev)
+        new = dict(xyz=new_points, features_dc=features[:, :, 0:1].transpose(1, 2).contiguous(),
+                   features_rest=features[:, :, 1:].transpose(1, 2).contiguous(), lang_feat=lang.contiguous(),
+                   opacity=opac, scaling=scales, rotation=rots)
+        self.postfix(new, new_exist)
+
     # -- :567-595 (the clamp is against ones: a no-op; the moments ARE zeroed)
     def reset_opacity(self):
         op = torch.sigmoid(self.p["opacity"])

@@ -168,3 +168,95 @@ def test_mapper_densify_keeps_training(dev):
     for _ in range(2):
         l1 = mp.train_step(win)
     assert torch.isfinite(l1) and mp.stats.denom.shape == (P1, 1)
+
+
+def _new_points(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(n, 3, generator=g) * 2.0 - 1.0, torch.rand(n, 3, generator=g)
+
+
+def test_increase_pcd_restatement_invariants_cpu():
+    """GaussianModel::increasePcd as restated (oracle/densify_ref.py, reference src/gaussian_model.cpp:297-384): the new rows
+    carry the colour as DC coefficient, zero higher SH / language features, log-sqrt 3-NN scale, identity rotation, opacity
+    inverse_sigmoid(0.1), zero Adam moments; the old rows and moments are untouched; the statistics restart at the new size."""
+    import ingest_ref as IR
+    m = make_model(500, torch.device("cpu"), seed=5)
+    ref = clone_model(m)
+    pts, cols = _new_points(37, 6)
+    dist2 = lambda p: torch.from_numpy(IR.knn_mean_dist2(p.numpy()))  # noqa: E731
+    m.increase_pcd(pts, cols, 17, dist2)
+    P, n = 500, 37
+    for k in DR.PARAMS:
+        assert m.p[k].shape[0] == P + n and torch.equal(m.p[k][:P], ref.p[k])
+        assert torch.equal(m.m[k][:P], ref.m[k]) and torch.equal(m.v[k][:P], ref.v[k])
+        assert not m.m[k][P:].any() and not m.v[k][P:].any()
+    assert torch.equal(m.p["xyz"][P:], pts)
+    np.testing.assert_allclose(m.p["features_dc"][P:, 0].numpy() * 0.28209479177387814 + 0.5, cols.numpy(), atol=1e-6)
+    assert not m.p["features_rest"][P:].any() and not m.p["lang_feat"][P:].any()
+    assert torch.equal(m.p["rotation"][P:], torch.tensor([1.0, 0, 0, 0]).expand(n, 4))
+    np.testing.assert_allclose(torch.sigmoid(m.p["opacity"][P:]).numpy(), 0.1, atol=1e-6)
+    d2 = np.maximum(IR.knn_mean_dist2(pts.numpy()), 1e-7)
+    np.testing.assert_allclose(torch.exp(m.p["scaling"][P:]).numpy(), np.sqrt(d2)[:, None].repeat(3, 1), rtol=1e-5)
+    assert torch.equal(m.exist_since_iter[:P], ref.exist_since_iter) and (m.exist_since_iter[P:] == 17).all()
+    assert m.denom.shape == (P + n, 1) and not m.denom.any() and not m.xyz_gradient_accum.any() and not m.max_radii2D.any()
+    before = m.p["xyz"].shape[0]
+    m.increase_pcd(pts[:0], cols[:0], 18, dist2)  # no new points: nothing changes (:299-300)
+    assert m.p["xyz"].shape[0] == before
+
+
+@pytest.mark.gpu
+def test_increase_pcd_matches_restatement(dev):
+    """leg_slam_b200.densify.increase_pcd against the restatement (same distCUDA2 kernel for the scale): bit-exact."""
+    from leg_slam_b200 import densify as D, ingest
+    m = make_model(4000, dev, seed=8)
+    ref, orig = clone_model(m), clone_model(m)
+    pts, cols = _new_points(1234, 9)
+    pts, cols = pts.to(dev), cols.to(dev)
+    st = D.DensifyStats(4000, dev)
+    st.exist_since_iter = m.exist_since_iter.clone()
+    p2, m2, v2, st2 = D.increase_pcd(m.p, m.m, m.v, st, pts, cols, 23)
+    ref.increase_pcd(pts, cols, 23, ingest.distCUDA2)
+    for k in DR.PARAMS:
+        assert p2[k].is_contiguous() and torch.equal(p2[k], ref.p[k]), k
+        assert torch.equal(m2[k], ref.m[k]) and torch.equal(v2[k], ref.v[k]), k
+        assert torch.equal(m.p[k], orig.p[k]) and torch.equal(m.m[k], orig.m[k])  # inputs untouched
+    assert torch.equal(st2.exist_since_iter, ref.exist_since_iter)
+    assert st2.denom.shape == ref.denom.shape and not st2.denom.any() and not st2.max_radii2D.any()
+    same = D.increase_pcd(m.p, m.m, m.v, st, pts[:0], cols[:0], 24)
+    assert same[0] is m.p and same[3] is st
+    with pytest.raises(Exception, match="no CPU path"):
+        D.increase_pcd(m.p, m.m, m.v, st, pts.cpu(), cols.cpu(), 24)
+
+
+@pytest.mark.gpu
+def test_mapper_increase_pcd_and_reset_opacity(dev):
+    """A keyframe's new points join the Gaussian set between two mapping iterations: Adam state of the old rows and the step
+    counts carry over, the new rows start from zero moments, and training continues; resetOpacity zeroes the opacity moments."""
+    from leg_slam_b200 import mapper as M, synthetic
+    W, H = 96, 64
+    sc = synthetic.make_scene(5000, seed=63, mean_scale=0.06, device=dev)
+    cams = synthetic.make_cameras(2, W, H, seed=63)
+    g = torch.Generator().manual_seed(64)
+    win = [M.Keyframe(c.to(dev), torch.rand(3, H, W, generator=g).to(dev), torch.randn(64, 37, 37, generator=g).to(dev),
+                      (torch.rand(1, H, W, generator=g) * 3).to(dev)) for c in cams]
+    mp = M.Mapper(sc, sh_degree=3, track_densify_stats=True)
+    for _ in range(3):
+        mp.train_step(win)
+    P0 = mp.params["xyz"].shape[0]
+    xyz_before = mp.params["xyz"].detach().clone()
+    m_before = mp.optimizer.state[mp.params["xyz"]]["exp_avg"].clone()
+    pts, cols = _new_points(777, 65)
+    assert mp.increase_pcd(pts.to(dev) + torch.tensor([3.0, 2.0, 1.4], device=dev), cols.to(dev), iteration=3) == 777
+    P1 = mp.params["xyz"].shape[0]
+    assert P1 == P0 + 777 and torch.equal(mp.params["xyz"].detach()[:P0], xyz_before)
+    st = mp.optimizer.state[mp.params["xyz"]]
+    assert st["step"] == 3 and torch.equal(st["exp_avg"][:P0], m_before) and not st["exp_avg"][P0:].any()
+    assert (mp.stats.exist_since_iter[P0:] == 3).all() and mp.stats.denom.shape == (P1, 1) and not mp.stats.denom.any()
+    l1 = mp.train_step(win)
+    assert torch.isfinite(l1) and mp.optimizer.state[mp.params["xyz"]]["step"] == 4
+    op_before = torch.sigmoid(mp.params["opacity"].detach()).clone()
+    mp.reset_opacity()
+    so = mp.optimizer.state[mp.params["opacity"]]
+    assert not so["exp_avg"].any() and not so["exp_avg_sq"].any() and so["step"] == 4
+    np.testing.assert_allclose(torch.sigmoid(mp.params["opacity"].detach()).cpu().numpy(), op_before.cpu().numpy(), atol=1e-6)
+    assert torch.isfinite(mp.train_step(win))
