@@ -4,6 +4,8 @@
   leg_slam_b200/liblgs_host.so : CudaRasterizer::Rasterizer (include/cuda_rasterizer/rasterizer.h), no torch
   leg_slam_b200/_C.so          : libtorch RasterizeGaussiansCUDA / ...BackwardCUDA / markVisible
                                  (include/rasterize_points.h) + the pybind module `_C`
+  leg_slam_b200/_L2.so         : GaussianRasterizationSettings / GaussianRasterizerFunction / GaussianRasterizer
+                                 (include/gaussian_rasterizer.h) + the pybind module `_L2` for the tests
 
     python -m leg_slam_b200.build_host [--force]
 """
@@ -19,6 +21,7 @@ ROOT = os.path.dirname(PKG)
 HOST = os.path.join(PKG, "csrc", "host")
 LIB_HOST = os.path.join(PKG, "liblgs_host.so")
 LIB_C = os.path.join(PKG, "_C.so")
+LIB_L2 = os.path.join(PKG, "_L2.so")
 
 
 def _stale(target, deps):
@@ -49,6 +52,22 @@ def build(force=False, verbose=False):
                "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=1", "-I" + inc,
                "-I" + os.path.join(cuda, "include"), "-I" + sysconfig.get_paths()["include"]]
         cmd += ["-I" + p for p in ce.include_paths()] + srcs + ["-o", LIB_C, "-L" + PKG, "-llgs", "-Wl,-rpath,$ORIGIN"]
+        cmd += ["-L" + p for p in ce.library_paths()] + ["-L" + os.path.join(cuda, "lib64"), "-lc10", "-ltorch_cpu",
+                                                          "-ltorch", "-ltorch_python", "-lc10_cuda", "-ltorch_cuda",
+                                                          "-lcudart"]
+        cmd += ["-Wl,-rpath," + p for p in ce.library_paths()]
+        run(cmd)
+    # L2 in C++ (include/gaussian_rasterizer.h): autograd node + module, with its own pybind module for the tests
+    srcs2 = [os.path.join(HOST, "gaussian_rasterizer.cpp"), os.path.join(HOST, "rasterize_points.cpp"),
+             os.path.join(HOST, "l2_ext.cpp")]
+    if force or _stale(LIB_L2, srcs2 + hdrs + [os.path.join(inc, "gaussian_rasterizer.h")]):
+        import torch  # noqa: F401
+        from torch.utils import cpp_extension as ce
+        cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-DTORCH_EXTENSION_NAME=_L2",
+               "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=1", "-I" + inc,
+               "-I" + os.path.join(cuda, "include"), "-I" + sysconfig.get_paths()["include"]]
+        cmd += ["-I" + p for p in ce.include_paths()] + srcs2 + ["-o", LIB_L2, "-L" + PKG, "-llgs", "-Wl,-rpath,$ORIGIN"]
         cmd += ["-L" + p for p in ce.library_paths()] + ["-L" + os.path.join(cuda, "lib64"), "-lc10", "-ltorch_cpu",
                                                           "-ltorch", "-ltorch_python", "-lc10_cuda", "-ltorch_cuda",
                                                           "-lcudart"]

@@ -99,3 +99,32 @@ def test_l0_cpp_class_vs_oracle(host_libs, oracle_mod, tmp_path):
     assert cases.rel_err(depth, f["out_depth"]) <= 1e-4
     for n in cases.GRAD_NAMES:
         assert cases.rel_err(grads[n], g[n]) <= 1e-3, n
+
+
+def test_l2_cpp_module_validates_like_the_reference(host_libs):
+    """The C++ L2 layer (include/gaussian_rasterizer.h -> _L2.so): same two argument-validation messages as
+    GaussianRasterizer::forward (reference src/gaussian_rasterizer.cpp:196-206), raised before anything touches a device,
+    and CPU tensors are refused by L1 underneath."""
+    from leg_slam_b200 import _L2
+    cs = cases.make_case("sh3_lf")
+    rs = _L2.GaussianRasterizationSettings(cs["H"], cs["W"], cs["tanfovx"], cs["tanfovy"], cs["bg"], 1.0, cs["viewmatrix"],
+                                           cs["projmatrix"], cs["degree"], cs["campos"], False, True)
+    r = _L2.GaussianRasterizer(rs)
+    e = torch.empty(0)
+    m3, m2, op = cs["means3D"], torch.zeros_like(cs["means3D"]), cs["opacities"]
+
+    def call(has_shs, has_col, has_sc, has_rot, has_cov):
+        return r.forward(m3, m2, op, has_shs, has_col, True, has_sc, has_rot, has_cov, cs["shs"] if has_shs else e,
+                         m3 if has_col else e, cs["lang_feats"], cs["scales"] if has_sc else e,
+                         cs["rotations"] if has_rot else e, torch.zeros(cs["P"], 6) if has_cov else e)
+    for flags in ((False, False, True, True, False), (True, True, True, True, False)):
+        with pytest.raises(RuntimeError, match="SHs or precomputed colors"):
+            call(*flags)
+    for flags in ((True, False, True, False, False), (True, False, False, False, False), (True, False, True, True, True),
+                  (True, False, False, True, True)):
+        with pytest.raises(RuntimeError, match="scale/rotation pair or precomputed 3D covariance"):
+            call(*flags)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        call(True, False, True, True, False)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        r.markVisibleGaussians(m3)

@@ -1,0 +1,55 @@
+"""GPU parity of the C++ L2 layer (include/gaussian_rasterizer.h, _L2.so) against its Python twin
+(leg_slam_b200/rasterizer.py): forward outputs identical, the seven gradients within the gradient gate.
+
+NOT YET RUN ON A GPU: the layer was written after round 1's GPU budget was spent (its build, its argument validation and its
+CPU refusal are covered by tests/test_host_cpp.py on CPU).  Until it has been run once it only executes with
+LGS_RUN_UNVERIFIED=1, so that an untested test cannot turn the suite red; the file sorts last for the same reason."""
+import os
+
+import pytest
+import torch
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.skipif(os.environ.get("LGS_RUN_UNVERIFIED") != "1", reason="C++ L2 layer not yet verified on a GPU (set LGS_RUN_UNVERIFIED=1)")
+def test_l2_cpp_autograd_equals_python_wrapper():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from leg_slam_b200 import GaussianRasterizationSettings, GaussianRasterizer, build_host
+    build_host.build()
+    from leg_slam_b200 import _L2
+    dev = torch.device("cuda:0")
+    cs = cases.make_case("sh3_lf", dev)
+    e = torch.empty(0, device=dev)
+    g = torch.Generator().manual_seed(5)
+    gc, gl, gd = (torch.randn(c, cs["H"], cs["W"], generator=g).to(dev) for c in (3, 64, 1))
+    names = ("means3D", "opacities", "shs", "lang_feats", "scales", "rotations")
+
+    def leaves():
+        d = {k: cs[k].detach().clone().requires_grad_(True) for k in names}
+        d["means2D"] = torch.zeros_like(cs["means3D"]).requires_grad_(True)
+        return d
+
+    a = leaves()
+    rs = _L2.GaussianRasterizationSettings(cs["H"], cs["W"], cs["tanfovx"], cs["tanfovy"], cs["bg"], 1.0, cs["viewmatrix"],
+                                           cs["projmatrix"], cs["degree"], cs["campos"], False, True)
+    out_a = _L2.GaussianRasterizer(rs).forward(a["means3D"], a["means2D"], a["opacities"], True, False, True, True, True, False,
+                                               a["shs"], e, a["lang_feats"], a["scales"], a["rotations"], e)
+    ((out_a[0] * gc).sum() + (out_a[1] * gl).sum() + (out_a[2] * gd).sum()).backward()
+
+    b = leaves()
+    ps = GaussianRasterizationSettings(cs["H"], cs["W"], cs["tanfovx"], cs["tanfovy"], cs["bg"], 1.0, cs["viewmatrix"],
+                                       cs["projmatrix"], cs["degree"], cs["campos"], False, True)
+    out_b = GaussianRasterizer(ps)(b["means3D"], b["means2D"], b["opacities"], shs=b["shs"], lang_feats=b["lang_feats"],
+                                   scales=b["scales"], rotations=b["rotations"])
+    ((out_b[0] * gc).sum() + (out_b[1] * gl).sum() + (out_b[2] * gd).sum()).backward()
+
+    for x, y in zip(out_a, out_b):
+        assert torch.equal(x, y)
+    assert not out_a[3].requires_grad
+    for k in names + ("means2D",):
+        assert a[k].grad is not None and a[k].grad.shape == b[k].grad.shape, k
+        assert cases.rel_err(a[k].grad.cpu().numpy(), b[k].grad.cpu().numpy()) <= 1e-3, k
