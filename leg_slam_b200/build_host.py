@@ -5,7 +5,8 @@
   leg_slam_b200/_C.so          : libtorch RasterizeGaussiansCUDA / ...BackwardCUDA / markVisible
                                  (include/rasterize_points.h) + the pybind module `_C`
   leg_slam_b200/_L2.so         : GaussianRasterizationSettings / GaussianRasterizerFunction / GaussianRasterizer
-                                 (include/gaussian_rasterizer.h) + the pybind module `_L2` for the tests
+                                 (include/gaussian_rasterizer.h), LgsFusedAdam (include/lgs_adam.h) + the pybind module
+                                 `_L2` for the tests
 
     python -m leg_slam_b200.build_host [--force]
 """
@@ -59,15 +60,22 @@ def build(force=False, verbose=False):
         run(cmd)
     # L2 in C++ (include/gaussian_rasterizer.h): autograd node + module, with its own pybind module for the tests
     srcs2 = [os.path.join(HOST, "gaussian_rasterizer.cpp"), os.path.join(HOST, "rasterize_points.cpp"),
-             os.path.join(HOST, "l2_ext.cpp")]
-    if force or _stale(LIB_L2, srcs2 + hdrs + [os.path.join(inc, "gaussian_rasterizer.h")]):
+             os.path.join(HOST, "fused_adam.cpp"), os.path.join(HOST, "l2_ext.cpp")]
+    if force or _stale(LIB_L2, srcs2 + hdrs + [os.path.join(inc, "gaussian_rasterizer.h"), os.path.join(inc, "lgs_adam.h")]):
         import torch  # noqa: F401
         from torch.utils import cpp_extension as ce
         cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
-        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-DTORCH_EXTENSION_NAME=_L2",
-               "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=1", "-I" + inc,
-               "-I" + os.path.join(cuda, "include"), "-I" + sysconfig.get_paths()["include"]]
-        cmd += ["-I" + p for p in ce.include_paths()] + srcs2 + ["-o", LIB_L2, "-L" + PKG, "-llgs", "-Wl,-rpath,$ORIGIN"]
+        common = ["g++", "-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-DTORCH_EXTENSION_NAME=_L2",
+                  "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=1", "-I" + inc,
+                  "-I" + os.path.join(cuda, "include"), "-I" + sysconfig.get_paths()["include"]]
+        common += ["-I" + p for p in ce.include_paths()]
+        objdir = os.path.join(PKG, "build", "host")
+        os.makedirs(objdir, exist_ok=True)
+        objs = [os.path.join(objdir, os.path.basename(x)[:-4] + ".l2.o") for x in srcs2]
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=len(srcs2)) as ex:  # libtorch-heavy translation units: ~1 min each
+            list(ex.map(lambda so: run(common + ["-c", so[0], "-o", so[1]]), zip(srcs2, objs)))
+        cmd = ["g++", "-shared"] + objs + ["-o", LIB_L2, "-L" + PKG, "-llgs", "-Wl,-rpath,$ORIGIN"]
         cmd += ["-L" + p for p in ce.library_paths()] + ["-L" + os.path.join(cuda, "lib64"), "-lc10", "-ltorch_cpu",
                                                           "-ltorch", "-ltorch_python", "-lc10_cuda", "-ltorch_cuda",
                                                           "-lcudart"]

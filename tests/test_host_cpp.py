@@ -128,3 +128,16 @@ def test_l2_cpp_module_validates_like_the_reference(host_libs):
         call(True, False, True, True, False)
     with pytest.raises(RuntimeError, match="no CPU path"):
         r.markVisibleGaussians(m3)
+
+
+def test_cpp_fused_adam_refuses_cpu_and_checks_arguments(host_libs):
+    """LgsFusedAdam (include/lgs_adam.h, a torch::optim::Adam with a fused step): no CPU path, argument checks."""
+    from leg_slam_b200 import _L2
+    p = [torch.randn(10, 3), torch.randn(10, 1)]
+    g = [[torch.randn(10, 3), torch.randn(10, 1)]]
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        _L2.fused_adam_run(p, g, [1e-3, 5e-2], 1e-15)
+    with pytest.raises(RuntimeError, match="one learning rate per parameter"):
+        _L2.fused_adam_run(p, g, [1e-3], 1e-15)
+    with pytest.raises(RuntimeError, match="one gradient per parameter"):
+        _L2.fused_adam_run(p, [[g[0][0]]], [1e-3, 5e-2], 1e-15)

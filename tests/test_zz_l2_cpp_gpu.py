@@ -53,3 +53,34 @@ def test_l2_cpp_autograd_equals_python_wrapper():
     for k in names + ("means2D",):
         assert a[k].grad is not None and a[k].grad.shape == b[k].grad.shape, k
         assert cases.rel_err(a[k].grad.cpu().numpy(), b[k].grad.cpu().numpy()) <= 1e-3, k
+
+
+@pytest.mark.skipif(os.environ.get("LGS_RUN_UNVERIFIED") != "1", reason="C++ LgsFusedAdam not yet verified on a GPU (set LGS_RUN_UNVERIFIED=1)")
+def test_cpp_fused_adam_equals_torch_adam():
+    """LgsFusedAdam over the reference's group layout (one tensor per group, its learning rates, eps 1e-15) against
+    torch.optim.Adam: parameters <= 1e-6 relative after 3 steps, moments too, libtorch's step counts kept."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from leg_slam_b200 import build_host
+    build_host.build()
+    from leg_slam_b200 import _L2
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(12)
+    shapes = [(1000, 3), (1000, 1, 3), (1000, 15, 3), (1000, 64), (1000, 1), (1000, 3), (1000, 4)]
+    lrs = [3.2e-4, 2.5e-3, 1.25e-4, 1.5e-3, 0.05, 5e-3, 1e-3]
+    p0 = [torch.randn(s, generator=g) for s in shapes]
+    grads = [[torch.randn(s, generator=g) * 1e-2 for s in shapes] for _ in range(3)]
+    ours = [t.clone().to(dev) for t in p0]
+    out = _L2.fused_adam_run(ours, [[t.to(dev) for t in gs] for gs in grads], lrs, 1e-15)
+    ref = [torch.nn.Parameter(t.clone().to(dev)) for t in p0]
+    opt = torch.optim.Adam([dict(params=[t], lr=lr) for t, lr in zip(ref, lrs)], lr=0.0, eps=1e-15)
+    for gs in grads:
+        for t, gr in zip(ref, gs):
+            t.grad = gr.to(dev)
+        opt.step()
+    n = len(shapes)
+    assert out[-1].tolist() == [3] * n
+    for i in range(n):
+        assert cases.rel_err(ours[i].detach().cpu().numpy(), ref[i].detach().cpu().numpy()) <= 1e-6, i
+        assert cases.rel_err(out[i].cpu().numpy(), opt.state[ref[i]]["exp_avg"].cpu().numpy()) <= 1e-6, i
+        assert cases.rel_err(out[n + i].cpu().numpy(), opt.state[ref[i]]["exp_avg_sq"].cpu().numpy()) <= 1e-6, i
