@@ -68,6 +68,17 @@ def test_argument_validation_needs_no_gpu(built):
     assert L.lgs_cosine_query(0, 4, None, None, None, None) == 0
     assert L.lgs_cosine_query(4, 4, None, None, None, None) == 1
     assert L.lgs_mark_visible(0, None, None, None, None, None) == 0
+    # data-parallel pair: the hooks only store two handles; the exchange checks its table before touching a device
+    assert L.lgs_stream_hooks(None, None) == 0
+    seg = (ctypes.c_int64 * 2)(0, 8)
+    lr = (ctypes.c_double * 1)(1e-3)
+    ptrs = (ctypes.c_void_p * 1)(p.value)
+    common = (0.9, 0.999, 1e-15)
+    assert L.lgs_dp_adam_shard(0, seg, lr, 1, 0, ptrs, ptrs, None, None, 0, 8, p, p, *common, 1, 0, None) == 1      # n_seg < 1
+    assert L.lgs_dp_adam_shard(1, seg, lr, 1, 1, ptrs, ptrs, None, None, 0, 8, p, p, *common, 1, 0, None) == 1      # rank >= world
+    assert L.lgs_dp_adam_shard(1, seg, lr, 1, 0, ptrs, ptrs, None, None, 0, 8, p, p, *common, 0, 0, None) == 1      # step < 1
+    assert L.lgs_dp_adam_shard(1, seg, lr, 1, 0, ptrs, ptrs, None, None, 2, 8, p, p, *common, 1, 0, None) == 1      # shard not on 16 B
+    assert L.lgs_dp_adam_shard(1, seg, lr, 1, 0, ptrs, ptrs, None, None, 4, 4, p, p, *common, 1, 0, None) == 0      # empty shard
 
 
 def test_sass_is_sm100a_with_tma(built):
