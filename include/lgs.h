@@ -191,6 +191,12 @@ int lgs_view_binning(const char* binning_buffer, int R, lgs_binning_view* out);
  * uncompacted keys; mode 0 materialises them, keys_unsorted / values_unsorted in scatter order). */
 int lgs_binning_mode(int mode);
 int lgs_debug_keys(int on);
+/* EXPERIMENTAL, off by default, not yet measured: lgs_used_bits(1) makes the tensor-core forward record, per tile-list position
+ * and 32-pixel half of the tile, whether any pixel blended the instance (2 bytes per instance, overlaid on the unsorted key array
+ * of the binning buffer, which nothing reads after binning unless lgs_debug_keys(1) keeps the keys -- then the feature stays off),
+ * and the backward of that same forward (same binning buffer, same R, same host thread) skips the other halves on that byte
+ * instead of its conservative footprint test.  Results are unchanged by construction. */
+int lgs_used_bits(int on);
 int lgs_view_image(const char* image_buffer, int W, int H, lgs_image_view* out);
 int lgs_view_geom(const char* geom_buffer, int P, lgs_geom_view* out);
 

@@ -48,6 +48,7 @@ static int g_debug_keys = 0;    // tile-local mode: also materialise the 64-bit 
 void set_binning_mode(int m) { g_binning_mode = m; }
 int binning_mode() { return g_binning_mode; }
 void set_debug_keys(int on) { g_debug_keys = on; }
+int debug_keys_on() { return g_debug_keys; }
 
 GeomState geom_from_chunk(char* chunk, int P) {
     GeomState g;

@@ -114,7 +114,15 @@ int launch_render_fwd(int W, int H, int R, const GeomState& g, const BinningStat
                       bool include_lf, cudaStream_t s);
 int launch_render_fwd_tc(int W, int H, const GeomState& g, const BinningState& b, ImageState& im,
                          const float* background, const float* lang_feat, float* out_color,
-                         float* out_lang_feat, float* out_depth, cudaStream_t s);
+                         float* out_lang_feat, float* out_depth, cudaStream_t s, int R);
+// experimental (lgs_used_bits): per (list position, 32-pixel half) "blended somewhere" bytes written by the tensor-core
+// forward and read by the backward pixel kernel instead of its footprint cull.  begin_forward returns where the forward
+// writes them (NULL when off / debug keys kept) and remembers the binning buffer on the calling host thread; for_backward
+// returns them only for that same buffer and R (the backward of the forward that wrote them).
+void set_used_bits(int on);
+uint8_t* used_bits_begin_forward(const BinningState& b, int R);
+const uint8_t* used_bits_for_backward(const BinningState& b, int R);
+int debug_keys_on();
 int launch_render_bwd(int P, int W, int H, int R, const GeomState& g, const BinningState& b,
                       const ImageState& im, const float* background, const float* lang_feat,
                       const float* dL_dpix, const float* dL_dpix_lf, const float* dL_dpix_depth,

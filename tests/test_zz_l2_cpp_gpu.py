@@ -1,5 +1,5 @@
-"""GPU parity of the C++ L2 layer (include/gaussian_rasterizer.h, _L2.so) against its Python twin
-(leg_slam_b200/rasterizer.py): forward outputs identical, the seven gradients within the gradient gate.
+"""GPU tests of what was written after round 1's GPU budget was spent: the C++ L2 layer (include/gaussian_rasterizer.h, _L2.so)
+against its Python twin, the C++ LgsFusedAdam against torch.optim.Adam, and the experimental lgs_used_bits switch.
 
 NOT YET RUN ON A GPU: the layer was written after round 1's GPU budget was spent (its build, its argument validation and its
 CPU refusal are covered by tests/test_host_cpp.py on CPU).  Until it has been run once it only executes with
@@ -84,3 +84,30 @@ def test_cpp_fused_adam_equals_torch_adam():
         assert cases.rel_err(ours[i].detach().cpu().numpy(), ref[i].detach().cpu().numpy()) <= 1e-6, i
         assert cases.rel_err(out[i].cpu().numpy(), opt.state[ref[i]]["exp_avg"].cpu().numpy()) <= 1e-6, i
         assert cases.rel_err(out[n + i].cpu().numpy(), opt.state[ref[i]]["exp_avg_sq"].cpu().numpy()) <= 1e-6, i
+
+
+@pytest.mark.skipif(os.environ.get("LGS_RUN_UNVERIFIED") != "1", reason="lgs_used_bits not yet verified on a GPU (set LGS_RUN_UNVERIFIED=1)")
+def test_used_bits_leave_results_unchanged():
+    """lgs_used_bits(1) (experimental): the forward records which (list position, 32-pixel half) pairs blend somewhere and the
+    backward pixel kernel skips the rest on that byte instead of its footprint cull.  Forward outputs must be bit-identical and
+    the gradients equal up to the order of the global atomics; with the debug keys kept the feature must stay off."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from leg_slam_b200 import _lib, rasterize_points as rp
+    L = _lib.lib()
+    dev = torch.device("cuda:0")
+    for name in ("sh3_lf", "ragged_sh1", "dense_opaque"):  # dense_opaque: early termination, long lists
+        cs = cases.make_case(name, dev)
+        base = rp.rasterize_gaussians(*cases.fwd_args(cs))
+        gbase = rp.rasterize_gaussians_backward(*cases.bwd_args(cs, base[4], base[5], base[0], base[6], base[7]))
+        try:
+            _lib.check(L.lgs_used_bits(1), "lgs_used_bits")
+            out = rp.rasterize_gaussians(*cases.fwd_args(cs))
+            grads = rp.rasterize_gaussians_backward(*cases.bwd_args(cs, out[4], out[5], out[0], out[6], out[7]))
+        finally:
+            _lib.check(L.lgs_used_bits(0), "lgs_used_bits")
+        assert out[0] == base[0]
+        for a, b in zip(out[1:5], base[1:5]):
+            assert torch.equal(a, b)
+        for n, a, b in zip(cases.GRAD_NAMES, grads, gbase):
+            assert cases.rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5, (name, n)
