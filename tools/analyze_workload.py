@@ -39,6 +39,7 @@ def main():
     ncon = f["n_contrib"].reshape(H, W)
     m2d, co, pl, ranges = f["means2D"], f["conic_opacity"], f["point_list"], f["ranges"]
     tot = dict(R=0, R_cut=0, inst_unused=0, halves=0, halves_unused=0, halves_cull_pass=0, halves_cull_pass_unused=0,
+               halves_geometric=0,
                pairs_eval=0, pairs_eval_unused_inst=0, pairs_eval_unused_half=0, pairs_alpha_pass=0, pairs_blend=0)
     for ty in range(tiles_y):
         for tx in range(tiles_x):
@@ -81,6 +82,10 @@ def main():
                 ok = np.where(~(tau > 0), False, np.where(~(det > 0) | np.isnan(ex) | np.isnan(ey), True, box))
                 cull.append(ok)
             cull = np.stack(cull, axis=1)
+            # halves in which some pixel CENTRE passes the alpha tests, termination ignored: what an exact geometric cull
+            # (usable by the forward, which cannot know the termination in advance) would let through
+            geo = (power <= 0) & (alpha >= 1.0 / 255.0)
+            tot["halves_geometric"] += int(geo[:, :32].any(axis=1).sum() + geo[:, 32:].any(axis=1).sum())
             tot["halves_cull_pass"] += int(cull.sum())
             tot["halves_cull_pass_unused"] += int((cull & ~used_half).sum())
             assert not (used_half & ~cull).any()  # the cull never rejects a half that blends
@@ -98,6 +103,7 @@ def main():
                           instances_no_pixel=round(tot["inst_unused"] / max(tot["R_cut"], 1), 4),
                           halves_no_pixel=round(tot["halves_unused"] / max(tot["halves"], 1), 4),
                           halves_passing_the_kernels_cull=round(tot["halves_cull_pass"] / max(tot["halves"], 1), 4),
+                          halves_with_a_pixel_centre_inside_the_alpha_ellipse=round(tot["halves_geometric"] / max(tot["halves"], 1), 4),
                           halves_passing_the_cull_but_blending_nowhere=round(tot["halves_cull_pass_unused"] / max(tot["halves_cull_pass"], 1), 4),
                           evaluated_pairs_in_unused_instances=round(tot["pairs_eval_unused_inst"] / max(tot["pairs_eval"], 1), 4),
                           evaluated_pairs_in_unused_halves=round(tot["pairs_eval_unused_half"] / max(tot["pairs_eval"], 1), 4),
