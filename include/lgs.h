@@ -197,6 +197,10 @@ int lgs_debug_keys(int on);
  * and the backward of that same forward (same binning buffer, same R, same host thread) skips the other halves on that byte
  * instead of its conservative footprint test.  Results are unchanged by construction. */
 int lgs_used_bits(int on);
+/* EXPERIMENTAL, off by default, not yet measured: lgs_exact_cull(1) replaces the blend kernels' bounding-box footprint test
+ * by an exact ellipse-vs-pixel-rectangle test (17 % fewer (Gaussian, 32-pixel half) pairs evaluated at cfgB,
+ * tools/analyze_workload.py).  Conservative like the test it replaces: results are unchanged by construction. */
+int lgs_exact_cull(int on);
 int lgs_view_image(const char* image_buffer, int W, int H, lgs_image_view* out);
 int lgs_view_geom(const char* geom_buffer, int P, lgs_geom_view* out);
 

@@ -53,6 +53,7 @@ SIGNATURES = {
     "lgs_binning_mode": (c_int, [c_int]),
     "lgs_debug_keys": (c_int, [c_int]),
     "lgs_used_bits": (c_int, [c_int]),
+    "lgs_exact_cull": (c_int, [c_int]),
     "lgs_profile_enable": (c_int, [c_int]),
     "lgs_profile_read": (c_int, [ctypes.POINTER(c_float), c_int]),
     "lgs_bench_fma": (c_int, [c_int, c_int, c_void_p, c_void_p]),

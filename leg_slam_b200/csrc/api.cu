@@ -343,6 +343,10 @@ int lgs_used_bits(int on) {
     set_used_bits(on != 0);
     return LGS_OK;
 }
+int lgs_exact_cull(int on) {
+    set_exact_cull(on != 0);
+    return LGS_OK;
+}
 
 // ---- introspection ---------------------------------------------------------------------
 int lgs_view_binning(const char* binning_buffer, int R, lgs_binning_view* out) {

@@ -65,7 +65,8 @@ struct BwdStage {
 // USED_BITS (experimental, lgs_used_bits): the forward recorded per (list position, 32-pixel half) whether any pixel blended
 // the instance; a warp then skips the others on that byte instead of the conservative footprint test (exact: a pixel
 // contributes here iff it blended the instance in the forward).
-template <bool WITH_LF, bool USED_BITS = false>
+// EXACT_CULL (experimental, lgs_exact_cull): exact ellipse-vs-rectangle footprint test (common.cuh) when no bytes are there.
+template <bool WITH_LF, bool USED_BITS = false, bool EXACT_CULL = false>
 __global__ void __launch_bounds__(TILE_PIX)
 render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
                       const float* __restrict__ bg, const GaussRec* __restrict__ rec,
@@ -182,7 +183,8 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                 touch = used[(size_t)wrp * R + range.x + (uint32_t)(hi - lane)] != 0;
             } else {
                 const float4 t0 = S.rec[lane].q0, t1 = S.rec[lane].q1;
-                touch = footprint_touches(t0.x, t0.y, t1.x, t1.y, t1.z, t1.w, wx0, wx0 + 7.0f, wy0, wy0 + 3.0f);
+                touch = EXACT_CULL ? footprint_touches_exact(t0.x, t0.y, t1.x, t1.y, t1.z, t1.w, wx0, wx0 + 7.0f, wy0, wy0 + 3.0f)
+                                   : footprint_touches(t0.x, t0.y, t1.x, t1.y, t1.z, t1.w, wx0, wx0 + 7.0f, wy0, wy0 + 3.0f);
             }
         }
         const uint32_t vis = __ballot_sync(0xffffffffu, touch);
@@ -485,6 +487,11 @@ int launch_render_bwd(int P, int W, int H, int R, const GeomState& g, const Binn
             render_bwd_pix_kernel<true, true><<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, W, H, background, g.rec, lang_feat,
                                                                         im.final_T, im.n_contrib, im.tile_last, dL_dpix, dL_dpix_lf,
                                                                         dL_dpix_depth, hrec, hcount, work_counter, used, R);
+        else if (exact_cull_on())
+            render_bwd_pix_kernel<true, false, true><<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, W, H, background, g.rec,
+                                                                               lang_feat, im.final_T, im.n_contrib, im.tile_last,
+                                                                               dL_dpix, dL_dpix_lf, dL_dpix_depth, hrec, hcount,
+                                                                               work_counter, nullptr, 0);
         else
             render_bwd_pix_kernel<true><<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, W, H, background, g.rec, lang_feat,
                                                                   im.final_T, im.n_contrib, im.tile_last, dL_dpix, dL_dpix_lf,

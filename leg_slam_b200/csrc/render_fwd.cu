@@ -253,7 +253,10 @@ static bool env_simt_fwd() {
 static int g_used_bits = 0;
 static thread_local const void* g_used_for = nullptr;  // binning buffer whose unsorted-key array holds valid bytes
 static thread_local int g_used_R = 0;
+static int g_exact_cull = 0;
 void set_used_bits(int on) { g_used_bits = on; }
+void set_exact_cull(int on) { g_exact_cull = on; }
+int exact_cull_on() { return g_exact_cull; }
 uint8_t* used_bits_begin_forward(const BinningState& b, int R) {
     g_used_for = nullptr;
     if (!g_used_bits || debug_keys_on() || R <= 0) return nullptr;

@@ -54,7 +54,8 @@ constexpr int TF_CTAS = 6;                     // resident CTAs per SM (shared m
 // WRITE_USED (experimental, lgs_used_bits): additionally record, per list position and 32-pixel half of the tile, whether ANY
 // pixel of the half blended the instance -- used[half * R + position] = 0 / 1 -- so that the backward can skip the others
 // without evaluating them (tools/analyze_workload.py: 24.5 % of the halves that pass the footprint cull at cfgB).
-template <bool WRITE_USED>
+// EXACT_CULL (experimental, lgs_exact_cull): exact ellipse-vs-rectangle test instead of the bounding-box test (common.cuh).
+template <bool WRITE_USED, bool EXACT_CULL = false>
 __global__ void __launch_bounds__(TF_THREADS, TF_CTAS)
 render_fwd_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
                      const GaussRec* __restrict__ rec, const float* __restrict__ lang_feat,
@@ -169,7 +170,8 @@ render_fwd_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
             bool touch = false;
             if (lane < cnt) {
                 const float4 t0 = lds128(recs + lane * 48), t1 = lds128(recs + lane * 48 + 16);
-                touch = footprint_touches(t0.x, t0.y, t1.x, t1.y, t1.z, t1.w, wx0, wx0 + 7.0f, wy0, wy0 + 3.0f);
+                touch = EXACT_CULL ? footprint_touches_exact(t0.x, t0.y, t1.x, t1.y, t1.z, t1.w, wx0, wx0 + 7.0f, wy0, wy0 + 3.0f)
+                                   : footprint_touches(t0.x, t0.y, t1.x, t1.y, t1.z, t1.w, wx0, wx0 + 7.0f, wy0, wy0 + 3.0f);
             }
             vis = __ballot_sync(0xffffffffu, touch);
         }
@@ -312,24 +314,31 @@ int launch_render_fwd_tc(int W, int H, const GeomState& g, const BinningState& b
                          float* out_depth, cudaStream_t s, int R) {
     static bool configured = false;
     if (!configured) {
-        LGS_CUDA_TRY(cudaFuncSetAttribute(render_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SM_TOTAL));
-        LGS_CUDA_TRY(cudaFuncSetAttribute(render_fwd_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        LGS_CUDA_TRY(cudaFuncSetAttribute(render_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SM_TOTAL));
-        LGS_CUDA_TRY(cudaFuncSetAttribute(render_fwd_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+#define LGS_TF_CFG(K)                                                                                            \
+    LGS_CUDA_TRY(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SM_TOTAL));            \
+    LGS_CUDA_TRY(cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, 100))
+        LGS_TF_CFG((render_fwd_tc_kernel<false, false>));
+        LGS_TF_CFG((render_fwd_tc_kernel<true, false>));
+        LGS_TF_CFG((render_fwd_tc_kernel<false, true>));
+        LGS_TF_CFG((render_fwd_tc_kernel<true, true>));
+#undef LGS_TF_CFG
         configured = true;
     }
     const dim3 grid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE, 1);
     // the used bytes ([2][R]) overlay the unsorted key array (8 B / instance), which nothing reads after binning unless the
     // debug keys are kept for introspection
     uint8_t* used = used_bits_begin_forward(b, R);
-    if (used)
-        render_fwd_tc_kernel<true><<<grid, TF_THREADS, TF_SM_TOTAL, s>>>(im.ranges, b.point_list, W, H, g.rec, lang_feat, background,
-                                                                          im.final_T, im.n_contrib, im.tile_last, out_color,
-                                                                          out_lang_feat, out_depth, used, R);
-    else
-        render_fwd_tc_kernel<false><<<grid, TF_THREADS, TF_SM_TOTAL, s>>>(im.ranges, b.point_list, W, H, g.rec, lang_feat, background,
-                                                                           im.final_T, im.n_contrib, im.tile_last, out_color,
-                                                                           out_lang_feat, out_depth, nullptr, 0);
+    const bool exact = exact_cull_on() != 0;
+#define LGS_TF_LAUNCH(U, E)                                                                                                   \
+    render_fwd_tc_kernel<U, E><<<grid, TF_THREADS, TF_SM_TOTAL, s>>>(im.ranges, b.point_list, W, H, g.rec, lang_feat, background, \
+                                                                      im.final_T, im.n_contrib, im.tile_last, out_color,         \
+                                                                      out_lang_feat, out_depth, used, used ? R : 0)
+    if (used) {
+        if (exact) LGS_TF_LAUNCH(true, true); else LGS_TF_LAUNCH(true, false);
+    } else {
+        if (exact) LGS_TF_LAUNCH(false, true); else LGS_TF_LAUNCH(false, false);
+    }
+#undef LGS_TF_LAUNCH
     LGS_LAUNCH_CHECK();
     return LGS_OK;
 }

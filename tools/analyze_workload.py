@@ -39,7 +39,7 @@ def main():
     ncon = f["n_contrib"].reshape(H, W)
     m2d, co, pl, ranges = f["means2D"], f["conic_opacity"], f["point_list"], f["ranges"]
     tot = dict(R=0, R_cut=0, inst_unused=0, halves=0, halves_unused=0, halves_cull_pass=0, halves_cull_pass_unused=0,
-               halves_geometric=0,
+               halves_geometric=0, halves_exact_rect=0,
                pairs_eval=0, pairs_eval_unused_inst=0, pairs_eval_unused_half=0, pairs_alpha_pass=0, pairs_blend=0)
     for ty in range(tiles_y):
         for tx in range(tiles_x):
@@ -82,6 +82,32 @@ def main():
                 ok = np.where(~(tau > 0), False, np.where(~(det > 0) | np.isnan(ex) | np.isnan(ey), True, box))
                 cull.append(ok)
             cull = np.stack(cull, axis=1)
+            # exact continuous test (csrc/common.cuh footprint_touches_exact, same float32 expressions): minimum of the quadratic
+            # form over the warp's pixel rectangle -- 0 if the centre is inside, else the minimum over the four edges, each a
+            # clamped 1-D quadratic -- against the same threshold tau plus a magnitude-proportional rounding slack
+            f32 = np.float32
+            qa, qb, qc = c[:, 0].astype(f32), c[:, 1].astype(f32), c[:, 2].astype(f32)
+            with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+                tau32 = (np.log(f32(255.0) * c[:, 3].astype(f32)) * f32(1.01) + f32(0.01)).astype(f32)
+                det32 = qa * qc - qb * qb
+                nb_c, nb_a = -qb / qc, -qb / qa
+            for h in range(2):
+                X0, X1 = f32(tx * 8) - gx.astype(f32), f32(tx * 8 + 7.0) - gx.astype(f32)
+                Y0, Y1 = f32(ty * 8 + 4 * h) - gy.astype(f32), f32(ty * 8 + 4 * h + 3.0) - gy.astype(f32)
+                inside_c = (X0 <= 0) & (X1 >= 0) & (Y0 <= 0) & (Y1 >= 0)
+                qmin = np.full(len(ids), 3.0e38, f32)
+                with np.errstate(invalid="ignore", over="ignore"):
+                    for X, Y in ((X0, Y0), (X1, Y1)):
+                        dyv = np.minimum(np.maximum(nb_c * X, Y0), Y1)
+                        qmin = np.minimum(qmin, qa * X * X + f32(2.0) * qb * X * dyv + qc * dyv * dyv)
+                        dxv = np.minimum(np.maximum(nb_a * Y, X0), X1)
+                        qmin = np.minimum(qmin, qa * dxv * dxv + f32(2.0) * qb * dxv * Y + qc * Y * Y)
+                    mx, my = np.maximum(np.abs(X0), np.abs(X1)), np.maximum(np.abs(Y0), np.abs(Y1))
+                    slack = f32(2.0e-6) * (qa * mx * mx + f32(2.0) * np.abs(qb) * mx * my + qc * my * my)
+                    ok = inside_c | np.isnan(qmin) | (f32(0.5) * qmin <= tau32 + slack)
+                ok = np.where(~(tau32 > 0), False, np.where(~(det32 > 0) | ~(qa > 0) | ~(qc > 0), True, ok))
+                assert not (used_half[:, h] & ~ok).any()  # never rejects a half that blends
+                tot["halves_exact_rect"] += int(ok.sum())
             # halves in which some pixel CENTRE passes the alpha tests, termination ignored: what an exact geometric cull
             # (usable by the forward, which cannot know the termination in advance) would let through
             geo = (power <= 0) & (alpha >= 1.0 / 255.0)
@@ -104,6 +130,7 @@ def main():
                           halves_no_pixel=round(tot["halves_unused"] / max(tot["halves"], 1), 4),
                           halves_passing_the_kernels_cull=round(tot["halves_cull_pass"] / max(tot["halves"], 1), 4),
                           halves_with_a_pixel_centre_inside_the_alpha_ellipse=round(tot["halves_geometric"] / max(tot["halves"], 1), 4),
+                          halves_passing_an_exact_ellipse_vs_rectangle_test=round(tot["halves_exact_rect"] / max(tot["halves"], 1), 4),
                           halves_passing_the_cull_but_blending_nowhere=round(tot["halves_cull_pass_unused"] / max(tot["halves_cull_pass"], 1), 4),
                           evaluated_pairs_in_unused_instances=round(tot["pairs_eval_unused_inst"] / max(tot["pairs_eval"], 1), 4),
                           evaluated_pairs_in_unused_halves=round(tot["pairs_eval_unused_half"] / max(tot["pairs_eval"], 1), 4),
