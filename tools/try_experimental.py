@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""One GPU call that settles the two switches written at the end of round 1 (lgs_used_bits, lgs_exact_cull; include/lgs.h):
+for every combination it checks on cfgB that the forward images, final_T and n_contrib are bit-identical to the default path
+and the gradients equal up to atomic order, then times the per-kernel stages (bench.KernelPath.stage_times) and the whole step.
+Prints one JSON object.     python tools/try_experimental.py [--reps 30]"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from leg_slam_b200 import _lib, debug  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=30)
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    L = _lib.lib()
+    sc, cam, up = bench.make_workload(0, 1, dev)
+    kp = bench.KernelPath(sc, cam, up, dev, 1)
+
+    def run_once():
+        kp.flat.zero_()
+        kp.forward()
+        kp.backward()
+        torch.cuda.synchronize(dev)
+        iv = debug.image_view(kp.img, bench.WIDTH, bench.HEIGHT)
+        return dict(color=kp.out_color.clone(), lf=kp.out_lf.clone(), depth=kp.out_depth.clone(), final_T=iv["final_T"].clone(),
+                    n_contrib=iv["n_contrib"].clone(), grads=kp.flat.clone(), R=kp.R)
+
+    out = {}
+    base = None
+    for used, exact in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        _lib.check(L.lgs_used_bits(used), "lgs_used_bits")
+        _lib.check(L.lgs_exact_cull(exact), "lgs_exact_cull")
+        r = run_once()
+        row = {}
+        if base is None:
+            base = r
+        else:
+            row["forward_bit_identical"] = all(torch.equal(r[k], base[k]) for k in ("color", "lf", "depth", "final_T", "n_contrib"))
+            d = (r["grads"] - base["grads"]).abs().max() / base["grads"].abs().max()
+            row["grad_max_rel_diff"] = float(d)
+        for _ in range(5):
+            kp.step()
+        stage = kp.stage_times(args.reps)
+        row["stage_ms"] = {k: round(v, 4) for k, v in stage.items()}
+        row["step_ms"] = round(bench.timed(kp.step, 50, 10, 1, dev), 4)
+        out[f"used_bits={used},exact_cull={exact}"] = row
+    _lib.check(L.lgs_used_bits(0), "lgs_used_bits")
+    _lib.check(L.lgs_exact_cull(0), "lgs_exact_cull")
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
