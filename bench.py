@@ -259,16 +259,16 @@ class KernelPath:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
         self.adam()
 
-    # hand-written kernels per step: preprocess, emit_keys, tile_ranges, render_fwd, zero_grads, render_bwd_pix,
-    # render_bwd_chan, preprocess_bwd, adam (the CUB scan and radix-sort launches are library kernels, not counted)
-    KERNELS_PER_STEP = 9
+    # kernels per step, every one hand-written (no library launch is left on the path): preprocess, emit_keys, 3 radix passes,
+    # tile_ranges_fix, render_fwd, zero_grads, render_bwd_pix, render_bwd_chan, preprocess_bwd, adam
+    KERNELS_PER_STEP = 12
 
     def stage_times(self, reps=20):
         """Per-kernel device time (ms, mean over reps) from CUDA events on the launch stream."""
         L = self.L
         L.lgs_profile_enable(1)
-        acc = [0.0] * 11
-        buf = (ctypes.c_float * 10)()
+        acc = [0.0] * 10
+        buf = (ctypes.c_float * 9)()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(reps):
             self.forward()
@@ -277,12 +277,12 @@ class KernelPath:
             self.adam()
             e1.record()
             torch.cuda.synchronize(self.dev)
-            L.lgs_profile_read(buf, 10)
-            for i in range(10):
+            L.lgs_profile_read(buf, 9)
+            for i in range(9):
                 acc[i] += max(buf[i], 0.0)
-            acc[10] += e0.elapsed_time(e1)
+            acc[9] += e0.elapsed_time(e1)
         L.lgs_profile_enable(0)
-        names = ["preprocess", "scan", "emit_keys", "sort", "tile_ranges", "render_fwd", "zero_grads", "render_bwd_pix",
+        names = ["preprocess", "emit_keys", "sort", "tile_ranges", "render_fwd", "zero_grads", "render_bwd_pix",
                  "render_bwd_chan", "preprocess_bwd", "adam"]
         return {n: acc[i] / reps for i, n in enumerate(names)}
 
@@ -613,7 +613,7 @@ def main():
             fl = {}
         by = {"adam": 3444.0 * P_GAUSS,
               "preprocess": counts["P_visible"] * (44 + 12 * 16 + 75) + (P_GAUSS - counts["P_visible"]) * 20.0,
-              "preprocess_bwd": 536.0 * counts["P_visible"], "sort": 24.0 * counts["R"] * 6, "zero_grads": 304.0 * P_GAUSS}
+              "preprocess_bwd": 536.0 * counts["P_visible"], "sort": 16.0 * counts["R"] * 3, "zero_grads": 304.0 * P_GAUSS}
         kernels = {}
         for k, t in stage.items():
             ent = dict(ms=round(t, 4), share=round(t / sum(stage.values()), 4))
@@ -655,8 +655,8 @@ def main():
                     "h2d_bytes_per_step": int(H2D_BYTES_PER_VIEW * world), "d2h_bytes_per_step": 12 * world, "api": "leg_slam_b200.mapper.Mapper.train_step (fused activations + rasterizer + "
                                                     "fused loss + FusedAdam, all liblgs launches), inputs from pinned host memory"},
             "gpu_launches": KernelPath.KERNELS_PER_STEP * args.steps,
-            "gpu_launches_note": "hand-written kernels per step: preprocess, emit_keys, tile_ranges, render_fwd, zero_grads, "
-                                 "render_bwd_pix, render_bwd_chan, preprocess_bwd, adam; CUB scan (2) + radix sort (8) library launches not counted",
+            "gpu_launches_note": "kernels per step, all hand-written: preprocess, emit_keys, radix_pass x3, tile_ranges_fix, render_fwd, "
+                                 "zero_grads, render_bwd_pix, render_bwd_chan, preprocess_bwd, adam (no library launch on the path)",
             "clocks": clocks,
             "roofline": roof,
             "kernels": kernels,

@@ -66,14 +66,22 @@ size_t lgs_binning_bytes(int R);       /* replaces required<BinningState>(R)    
  * (Gaussian, tile) instances R = num_rendered, read back once per forward
  * (rasterizer_impl.cu:281-286).
  *
- * stage1 = FORWARD::preprocess + InclusiveSum (rasterizer_impl.cu:248-278):
- *   writes radii[P] (int32; pass NULL to use an internal array), fills geom_buffer,
- *   writes *num_rendered_host and synchronises `stream` once (the :282 readback).
- * stage2 = duplicateWithKeys + 64-bit radix sort on bits [0,32+msb(tiles)) +
- *   identifyTileRanges + renderCUDA (rasterizer_impl.cu:290-340):
+ * stage1 = FORWARD::preprocess (rasterizer_impl.cu:248-275):
+ *   writes radii[P] (int32; pass NULL to use an internal array), fills geom_buffer -- including a small device-side frame
+ *   header: R (accumulated by preprocess itself, so there is no scan over Gaussians), the frame's largest depth, status
+ *   flags -- then writes *num_rendered_host and synchronises `stream` once (the :282 readback).
+ *   num_rendered_host == NULL skips the read-back AND the synchronisation: R stays on the device, every later kernel
+ *   reads it there, and the caller hands stage2 / the backward the CAPACITY its binning buffer was sized for instead
+ *   (see lgs_forward_stage2; lgs_forward_status fetches R and the overflow flag whenever the caller next synchronises).
+ * stage2 = duplicateWithKeys + the tile|depth radix sort + identifyTileRanges + renderCUDA (rasterizer_impl.cu:290-340),
+ *   every kernel hand-written (csrc/binning.cu):
  *   out_color [3,H,W], out_lang_feat [64,H,W] (written only if include_lang_feat),
  *   out_depth [1,H,W]. Every pixel of the written outputs is written (no pre-zero
  *   needed).
+ *   R is the number of instances binning_buffer was sized for with lgs_binning_bytes(R): the value stage1 returned, or
+ *   any upper bound of it.  The same R must be passed to lgs_backward.  If the frame has more instances than R, the
+ *   surplus is dropped (memory-safe, images incomplete) and the overflow flag of lgs_forward_status is set.
+ *   Call stage2 once per stage1 (it consumes counters stage1 zeroed in the geometry buffer).
  */
 int lgs_forward_stage1(
     int P, int D, int M, int W, int H,
@@ -159,11 +167,15 @@ int lgs_mark_visible(int P, const float* means3D, const float* viewmatrix,
  *      ranges; reference layouts rasterizer_impl.h:33-63).  Returned pointers alias the
  *      caller's buffers. */
 typedef struct lgs_binning_view {
-    const uint64_t* keys_unsorted;   /* [R] tile<<32 | depth bits, emission order       */
-    const uint32_t* values_unsorted; /* [R] Gaussian index                              */
-    const uint64_t* keys_sorted;     /* [R]                                             */
-    const uint32_t* point_list;      /* [R] sorted Gaussian indices                     */
+    const uint32_t* point_list;      /* [R] sorted Gaussian indices (the reference's point_list)             */
+    const uint32_t* keys_sorted32;   /* [R] the production sort keys: tile << q | top depth bits             */
 } lgs_binning_view;
+typedef struct lgs_reference_keys_view {   /* the reference's BinningState arrays (rasterizer_impl.h:50-63)  */
+    const uint64_t* keys_unsorted;   /* [R] tile<<32 | depth bits, the reference's emission order            */
+    const uint32_t* values_unsorted; /* [R] Gaussian index                                                   */
+    const uint64_t* keys_sorted;     /* [R] read off point_list + ranges as this library computed them       */
+    const uint32_t* point_offsets;   /* [P] inclusive scan of tiles_touched (GeometryState::point_offsets)   */
+} lgs_reference_keys_view;
 typedef struct lgs_image_view {
     const uint32_t* ranges;          /* [tiles][2] (start,end) into point_list          */
     const float*    final_T;         /* [H*W]                                           */
@@ -173,42 +185,32 @@ typedef struct lgs_geom_view {
     const float*    records;         /* [P][12]: x,y,depth,idx bits | conic a,b,c, opacity | r,g,b,0 */
     const float*    cov3D;           /* [P][6]                                          */
     const uint32_t* tiles_touched;   /* [P]                                             */
-    const uint32_t* point_offsets;   /* [P] inclusive scan of tiles_touched (binning mode 1 only)  */
     const int32_t*  internal_radii;  /* [P]                                             */
     const uint8_t*  clamped;         /* [P] bit c set if colour channel c was clamped   */
 } lgs_geom_view;
 int lgs_view_binning(const char* binning_buffer, int R, lgs_binning_view* out);
-/* Binning algorithm (process-wide; set it before lgs_forward_stage1, not between stage1 and stage2):
- *   1 (default) the reference's single stable radix sort of all instances by (tile, depth bits)
- *               (rasterizer_impl.cu:304-309), over 32-bit keys: depth bits are rebased to bits(0.2f) (the near cull)
- *               and bounded by the frame's largest depth, which preprocess accumulates; the key keeps the tile id and
- *               the top depth bits, and the rare runs of equal keys are put into (depth bits, index) order afterwards;
- *   0           tile-local: instances are counted and scattered per tile, every tile's list is sorted by
- *               (depth bits, Gaussian index) in shared memory -- no device-wide sort (experimental: slower than
- *               mode 1 at 640x480 / 1.4 M instances).
- * point_list and ranges are bit-identical in both modes and to the reference.  The 64-bit key arrays of
- * lgs_binning_view hold the reference's exact keys only while lgs_debug_keys(1) is in effect (mode 1 then sorts the
- * uncompacted keys; mode 0 materialises them, keys_unsorted / values_unsorted in scatter order). */
-int lgs_binning_mode(int mode);
-int lgs_debug_keys(int on);
-/* EXPERIMENTAL, off by default, not yet measured: lgs_used_bits(1) makes the tensor-core forward record, per tile-list position
- * and 32-pixel half of the tile, whether any pixel blended the instance (2 bytes per instance, overlaid on the unsorted key array
- * of the binning buffer, which nothing reads after binning unless lgs_debug_keys(1) keeps the keys -- then the feature stays off),
- * and the backward of that same forward (same binning buffer, same R, same host thread) skips the other halves on that byte
- * instead of its conservative footprint test.  Results are unchanged by construction. */
-int lgs_used_bits(int on);
-/* EXPERIMENTAL, off by default, not yet measured: lgs_exact_cull(1) replaces the blend kernels' bounding-box footprint test
- * by an exact ellipse-vs-pixel-rectangle test (17 % fewer (Gaussian, 32-pixel half) pairs evaluated at cfgB,
- * tools/analyze_workload.py).  Conservative like the test it replaces: results are unchanged by construction. */
-int lgs_exact_cull(int on);
+/* Parity-test aid: re-express what a forward computed as the reference's key arrays.  The production path sorts 32-bit
+ * keys (tile id | the top depth bits, bounded by the frame's largest depth) emitted in no particular order and repairs the
+ * runs of equal keys afterwards; this call writes, into debug_buffer (lgs_debug_keys_bytes(P, R) bytes), the pairs
+ * duplicateWithKeys would have emitted in ITS order (Gaussian-major, y, x; rasterizer_impl.cu:70-111) and the sorted 64-bit
+ * key array that corresponds to this library's point_list and ranges.  If those equal the reference's arrays bit for bit,
+ * the lists do.  Never on the mapping path; no process-wide switch is involved. */
+size_t lgs_debug_keys_bytes(int P, int R);
+int lgs_debug_reference_keys(int P, int R, int W, int H, const char* geom_buffer, const char* binning_buffer,
+                             const char* image_buffer, char* debug_buffer, lgs_reference_keys_view* out, void* stream);
+/* The frame header of a geometry buffer, copied asynchronously on `stream` into status_host[0..3] (host memory, pinned for a
+ * truly asynchronous copy): [0] = R (instances of the frame), [1] = largest depth bit pattern of a rendered Gaussian,
+ * [2] = 1 if R exceeded the capacity stage2 was given, [3] = 1 if the sort gave up (never observed).  Valid once the
+ * caller has synchronised `stream`. */
+int lgs_forward_status(const char* geom_buffer, int P, unsigned int* status_host, void* stream);
 int lgs_view_image(const char* image_buffer, int W, int H, lgs_image_view* out);
 int lgs_view_geom(const char* geom_buffer, int P, lgs_geom_view* out);
 
-/* ---- optional per-stage timing (bench.py's roofline): when enabled, CUDA events are recorded
- *      on the launch stream between the kernels of stage1 / stage2 / backward.  After the caller
- *      has synchronised, lgs_profile_read fills ms[0..9] = preprocess, scan, emit_keys, sort,
- *      tile_ranges, render_fwd, zero_grads, render_bwd_pix, render_bwd_chan, preprocess_bwd
- *      (milliseconds, -1 if the stage did not run).  Not thread-safe; off by default. */
+/* ---- optional per-stage timing (bench.py's roofline) of the CALLING HOST THREAD: when enabled, CUDA events are recorded
+ *      on the launch stream between the kernels of this thread's stage1 / stage2 / backward calls.  After the caller
+ *      has synchronised, lgs_profile_read fills ms[0..8] = preprocess, emit_keys, sort (3 radix passes), tile_ranges,
+ *      render_fwd, zero_grads, render_bwd_pix, render_bwd_chan, preprocess_bwd (milliseconds, -1 if the stage did not
+ *      run).  State is thread-local: nothing here is shared between host threads.  Off by default. */
 int lgs_profile_enable(int on);
 int lgs_profile_read(float* ms, int n);
 

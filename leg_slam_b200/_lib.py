@@ -15,8 +15,12 @@ class LgsError(RuntimeError):
 
 
 class BinningView(ctypes.Structure):
-    _fields_ = [("keys_unsorted", c_void_p), ("values_unsorted", c_void_p),
-                ("keys_sorted", c_void_p), ("point_list", c_void_p)]
+    _fields_ = [("point_list", c_void_p), ("keys_sorted32", c_void_p)]
+
+
+class ReferenceKeysView(ctypes.Structure):
+    _fields_ = [("keys_unsorted", c_void_p), ("values_unsorted", c_void_p), ("keys_sorted", c_void_p),
+                ("point_offsets", c_void_p)]
 
 
 class ImageView(ctypes.Structure):
@@ -25,7 +29,7 @@ class ImageView(ctypes.Structure):
 
 class GeomView(ctypes.Structure):
     _fields_ = [("records", c_void_p), ("cov3D", c_void_p), ("tiles_touched", c_void_p),
-                ("point_offsets", c_void_p), ("internal_radii", c_void_p), ("clamped", c_void_p)]
+                ("internal_radii", c_void_p), ("clamped", c_void_p)]
 
 
 # symbol -> (restype, argtypes); the CPU test-suite checks every one of these is exported
@@ -50,10 +54,10 @@ SIGNATURES = {
     "lgs_view_binning": (c_int, [c_void_p, c_int, ctypes.POINTER(BinningView)]),
     "lgs_view_image": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(ImageView)]),
     "lgs_view_geom": (c_int, [c_void_p, c_int, ctypes.POINTER(GeomView)]),
-    "lgs_binning_mode": (c_int, [c_int]),
-    "lgs_debug_keys": (c_int, [c_int]),
-    "lgs_used_bits": (c_int, [c_int]),
-    "lgs_exact_cull": (c_int, [c_int]),
+    "lgs_debug_keys_bytes": (c_size_t, [c_int, c_int]),
+    "lgs_debug_reference_keys": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         ctypes.POINTER(ReferenceKeysView), c_void_p]),
+    "lgs_forward_status": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "lgs_profile_enable": (c_int, [c_int]),
     "lgs_profile_read": (c_int, [ctypes.POINTER(c_float), c_int]),
     "lgs_bench_fma": (c_int, [c_int, c_int, c_void_p, c_void_p]),

@@ -12,27 +12,23 @@ namespace lgs {
 static thread_local int g_last_cuda_error = 0;
 void set_last_cuda_error(cudaError_t e) { g_last_cuda_error = (int)e; }
 
-static bool g_prof = false;
-static cudaEvent_t g_ev[PM_COUNT];
-static bool g_ev_made = false;
-static bool g_ev_set[PM_COUNT];
-void prof_mark(int id, cudaStream_t s) {
-    if (!g_prof) return;
-    if (!g_ev_made) {
-        for (int i = 0; i < PM_COUNT; ++i) { cudaEventCreate(&g_ev[i]); g_ev_set[i] = false; }
-        g_ev_made = true;
-    }
-    cudaEventRecord(g_ev[id], s);
-    g_ev_set[id] = true;
-}
-
-// stage1 -> stage2 hand-off on the calling host thread: the depth bound that lets the sort skip key bits.  stage2
-// uses it only when it is called with the same geometry buffer; otherwise it sorts all 32 depth bits.
-struct Stage1Note {
-    const char* geom = nullptr;
-    uint32_t max_depth_bits = 0xffffffffu;
+// optional per-stage timing of the CALLING HOST THREAD (lgs_profile_enable): events recorded on the launch stream
+struct ProfState {
+    bool on = false, made = false;
+    cudaEvent_t ev[PM_COUNT];
+    bool set[PM_COUNT];
 };
-static thread_local Stage1Note g_stage1_note;
+static thread_local ProfState g_prof;
+void prof_mark(int id, cudaStream_t s) {
+    ProfState& p = g_prof;
+    if (!p.on) return;
+    if (!p.made) {
+        for (int i = 0; i < PM_COUNT; ++i) { cudaEventCreate(&p.ev[i]); p.set[i] = false; }
+        p.made = true;
+    }
+    cudaEventRecord(p.ev[id], s);
+    p.set[id] = true;
+}
 
 // Stream hooks of the calling host thread (lgs_stream_hooks): lets a data-parallel caller overlap the exchange of the
 // language-feature parameters / gradients (52 % of the payload) with the stages that do not touch them.
@@ -72,13 +68,12 @@ int lgs_abi_version(void) { return 1; }
 size_t lgs_geom_bytes(int P) {
     if (P < 0) return 0;
     GeomState g = geom_from_chunk(nullptr, P);
-    return (size_t)(reinterpret_cast<uintptr_t>(g.scan_temp) + g.scan_temp_bytes) + 256;
+    return (size_t)reinterpret_cast<uintptr_t>(g.end) + 256;
 }
 size_t lgs_image_bytes(int W, int H) {
     if (W < 0 || H < 0) return 0;
     ImageState im = image_from_chunk(nullptr, W, H);
-    const size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
-    return (size_t)(reinterpret_cast<uintptr_t>(im.tile_cursor + (tiles > 0 ? tiles : 1))) + 256;
+    return (size_t)reinterpret_cast<uintptr_t>(im.end) + 256;
 }
 size_t lgs_backward_scratch_bytes(int R, int W, int H) {
     return (R < 0 || W <= 0 || H <= 0) ? 0 : render_bwd_scratch_bytes(R, W, H);
@@ -86,7 +81,12 @@ size_t lgs_backward_scratch_bytes(int R, int W, int H) {
 size_t lgs_binning_bytes(int R) {
     if (R < 0) return 0;
     BinningState b = binning_from_chunk(nullptr, R);
-    return (size_t)(reinterpret_cast<uintptr_t>(b.sort_temp) + b.sort_temp_bytes) + 256;
+    return (size_t)reinterpret_cast<uintptr_t>(b.end) + 256;
+}
+size_t lgs_debug_keys_bytes(int P, int R) {
+    if (P < 0 || R < 0) return 0;
+    DebugKeys d = debug_keys_from_chunk(nullptr, P, R);
+    return (size_t)reinterpret_cast<uintptr_t>(d.end) + 256;
 }
 
 // ---- forward ---------------------------------------------------------------------------
@@ -97,8 +97,7 @@ static int forward_stage1_impl(int P, int D, int M, int W, int H, const float* m
                                const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered, char* geom_buffer,
                                int* radii, int* num_rendered_host, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    if (!num_rendered_host) return LGS_ERR_INVALID_ARG;
-    *num_rendered_host = 0;
+    if (num_rendered_host) *num_rendered_host = 0;
     if (P < 0 || W <= 0 || H <= 0 || D < 0 || D > 3) return LGS_ERR_INVALID_ARG;
     if (P == 0) return LGS_OK;
     if (!means3D || !opacities || !viewmatrix || !projmatrix || !geom_buffer) return LGS_ERR_INVALID_ARG;
@@ -116,17 +115,11 @@ static int forward_stage1_impl(int P, int D, int M, int W, int H, const float* m
                                tan_fovy, prefiltered, g, radii, s);
     if (st != LGS_OK) return st;
     prof_mark(PM_PREPROCESS, s);
-    st = launch_scan(P, g, s);
-    if (st != LGS_OK) return st;
-    prof_mark(PM_SCAN, s);
-    // the one readback of the forward (reference rasterizer_impl.cu:281-282)
+    if (!num_rendered_host) return LGS_OK;  // the caller keeps R on the device (lgs.h): no read-back, no synchronisation
+    // the one readback of the forward (reference rasterizer_impl.cu:281-282); R is accumulated by preprocess itself
     uint32_t R = 0;
-    uint32_t rd[2] = {0, 0};  // R, largest depth bit pattern of a rendered Gaussian (both accumulated by preprocess)
-    LGS_CUDA_TRY(cudaMemcpyAsync(rd, g.total_touched, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    LGS_CUDA_TRY(cudaMemcpyAsync(&R, g.hdr + HDR_R, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     LGS_CUDA_TRY(cudaStreamSynchronize(s));
-    R = rd[0];
-    g_stage1_note.geom = geom_buffer;
-    g_stage1_note.max_depth_bits = rd[1];
     *num_rendered_host = (int)R;
     return LGS_OK;
 }
@@ -172,8 +165,7 @@ int lgs_forward_stage2(int P, int W, int H, int R, const float* background, cons
     // radii for key emission: the internal copy is always written by stage1 when the
     // caller passed NULL; otherwise stage1 wrote the caller's array and mirrors it here.
     prof_mark(PM_S2_BEGIN, s);
-    const uint32_t max_depth_bits = g_stage1_note.geom == geom_buffer ? g_stage1_note.max_depth_bits : 0xffffffffu;
-    int st = launch_binning(P, R, W, H, g, g.internal_radii, b, im, max_depth_bits, s);
+    int st = launch_binning(P, R, W, H, g, g.internal_radii, b, im, s);
     if (st != LGS_OK) return st;
     if (g_hooks.wait_before_render_fwd) LGS_CUDA_TRY(cudaStreamWaitEvent(s, g_hooks.wait_before_render_fwd, 0));
     st = launch_render_fwd(W, H, R, g, b, im, background, lang_feat, out_color, out_lang_feat, out_depth,
@@ -306,45 +298,35 @@ int lgs_stream_hooks(void* wait_before_render_fwd, void* record_after_render_bwd
 
 // ---- per-stage timing ------------------------------------------------------------------
 int lgs_profile_enable(int on) {
-    g_prof = on != 0;
+    g_prof.on = on != 0;
     return LGS_OK;
 }
 int lgs_profile_read(float* ms, int n) {
-    // ms[0..9] = preprocess, scan, emit_keys(+memset), sort, tile_ranges, render_fwd, zero_grads,
-    //            render_bwd_pix, render_bwd_chan, preprocess_bwd of the most recent forward+backward; the
-    //            caller must have synchronised the stream.  Entries whose stage did not run are -1.
-    static const int a[10] = {PM_S1_BEGIN, PM_PREPROCESS, PM_S2_BEGIN, PM_EMIT, PM_SORT, PM_RANGES, PM_BWD_BEGIN,
-                              PM_ZERO, PM_RENDER_BWD_PIX, PM_RENDER_BWD};
-    static const int b[10] = {PM_PREPROCESS, PM_SCAN, PM_EMIT, PM_SORT, PM_RANGES, PM_RENDER_FWD, PM_ZERO,
-                              PM_RENDER_BWD_PIX, PM_RENDER_BWD, PM_PREPROCESS_BWD};
-    if (!ms || n < 10) return LGS_ERR_INVALID_ARG;
-    for (int i = 0; i < 10; ++i) {
+    // ms[0..8] = preprocess, emit_keys, sort, tile_ranges, render_fwd, zero_grads, render_bwd_pix, render_bwd_chan,
+    //            preprocess_bwd of this thread's most recent forward + backward; the caller must have synchronised the
+    //            stream.  Entries whose stage did not run are -1.
+    static const int a[9] = {PM_S1_BEGIN, PM_S2_BEGIN, PM_EMIT, PM_SORT, PM_RANGES, PM_BWD_BEGIN, PM_ZERO, PM_RENDER_BWD_PIX,
+                             PM_RENDER_BWD};
+    static const int b[9] = {PM_PREPROCESS, PM_EMIT, PM_SORT, PM_RANGES, PM_RENDER_FWD, PM_ZERO, PM_RENDER_BWD_PIX, PM_RENDER_BWD,
+                             PM_PREPROCESS_BWD};
+    if (!ms || n < 9) return LGS_ERR_INVALID_ARG;
+    const ProfState& p = g_prof;
+    for (int i = 0; i < 9; ++i) {
         ms[i] = -1.f;
-        if (g_ev_made && g_ev_set[a[i]] && g_ev_set[b[i]]) {
+        if (p.made && p.set[a[i]] && p.set[b[i]]) {
             float t = 0.f;
-            if (cudaEventElapsedTime(&t, g_ev[a[i]], g_ev[b[i]]) == cudaSuccess) ms[i] = t;
+            if (cudaEventElapsedTime(&t, p.ev[a[i]], p.ev[b[i]]) == cudaSuccess) ms[i] = t;
             else (void)cudaGetLastError();
         }
     }
     return LGS_OK;
 }
 
-// ---- binning mode / debug keys ---------------------------------------------------------
-int lgs_binning_mode(int mode) {
-    if (mode != 0 && mode != 1) return LGS_ERR_INVALID_ARG;
-    set_binning_mode(mode);
-    return LGS_OK;
-}
-int lgs_debug_keys(int on) {
-    set_debug_keys(on != 0);
-    return LGS_OK;
-}
-int lgs_used_bits(int on) {
-    set_used_bits(on != 0);
-    return LGS_OK;
-}
-int lgs_exact_cull(int on) {
-    set_exact_cull(on != 0);
+// ---- frame status (device-side header of the geometry buffer) ---------------------------
+int lgs_forward_status(const char* geom_buffer, int P, unsigned int* status_host, void* stream) {
+    if (!geom_buffer || !status_host || P < 0) return LGS_ERR_INVALID_ARG;
+    GeomState g = geom_from_chunk(const_cast<char*>(geom_buffer), P);
+    LGS_CUDA_TRY(cudaMemcpyAsync(status_host, g.hdr, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return LGS_OK;
 }
 
@@ -352,11 +334,23 @@ int lgs_exact_cull(int on) {
 int lgs_view_binning(const char* binning_buffer, int R, lgs_binning_view* out) {
     if (!out || R < 0) return LGS_ERR_INVALID_ARG;
     BinningState b = binning_from_chunk(const_cast<char*>(binning_buffer), R);
-    out->keys_unsorted = b.keys_unsorted;
-    out->values_unsorted = b.vals_unsorted;
-    out->keys_sorted = b.keys;
     out->point_list = b.point_list;
+    out->keys_sorted32 = b.keys[1];
     return LGS_OK;
+}
+int lgs_debug_reference_keys(int P, int R, int W, int H, const char* geom_buffer, const char* binning_buffer,
+                             const char* image_buffer, char* debug_buffer, lgs_reference_keys_view* out, void* stream) {
+    if (!out || P < 0 || R < 0 || W <= 0 || H <= 0 || !debug_buffer) return LGS_ERR_INVALID_ARG;
+    if ((P > 0 && !geom_buffer) || (R > 0 && !binning_buffer) || !image_buffer) return LGS_ERR_INVALID_ARG;
+    GeomState g = geom_from_chunk(const_cast<char*>(geom_buffer), P);
+    BinningState b = binning_from_chunk(const_cast<char*>(binning_buffer), R);
+    ImageState im = image_from_chunk(const_cast<char*>(image_buffer), W, H);
+    DebugKeys d = debug_keys_from_chunk(debug_buffer, P, R);
+    out->keys_unsorted = d.keys_unsorted;
+    out->values_unsorted = d.vals_unsorted;
+    out->keys_sorted = d.keys_sorted;
+    out->point_offsets = d.offsets;
+    return launch_debug_reference_keys(P, R, W, H, g, b, im, d, (cudaStream_t)stream);
 }
 int lgs_view_image(const char* image_buffer, int W, int H, lgs_image_view* out) {
     if (!out || W <= 0 || H <= 0) return LGS_ERR_INVALID_ARG;
@@ -372,7 +366,6 @@ int lgs_view_geom(const char* geom_buffer, int P, lgs_geom_view* out) {
     out->records = reinterpret_cast<const float*>(g.rec);
     out->cov3D = g.cov3D;
     out->tiles_touched = g.tiles_touched;
-    out->point_offsets = g.point_offsets;
     out->internal_radii = g.internal_radii;
     out->clamped = g.clamped;
     return LGS_OK;

@@ -25,33 +25,57 @@ struct __align__(16) GaussRec {
 static_assert(sizeof(GaussRec) == 48, "record must be 48 bytes");
 
 // ---- carved views of the three opaque buffers ------------------------------------
+// geometry-buffer header: everything the later kernels of a forward need to know about the frame, kept ON THE DEVICE
+// (zeroed by stage1 before preprocess; stage2 and the backward read it there, never through the host)
+enum GeomHeader {
+    HDR_R = 0,          // number of (Gaussian, tile) instances = sum of tiles_touched (accumulated by preprocess)
+    HDR_MAX_DEPTH = 1,  // largest depth bit pattern of a rendered Gaussian (bounds the sort keys)
+    HDR_OVERFLOW = 2,   // set by stage2 when HDR_R exceeds the capacity of the binning buffer it was given
+    HDR_ERROR = 3,      // set when a sort look-back gave up (never observed; the frame's lists are then incomplete)
+    HDR_CURSOR = 4,     // key emission: next free slot
+    HDR_TICKET = 5,     // [3] tile tickets of the three radix passes
+    HDR_WORDS = 16
+};
+constexpr int RS_BITS = 11;                 // radix digit width: passes over bits 0-10, 11-21, 22-31 of the 32-bit key
+constexpr int RS_BINS = 1 << RS_BITS;       // 2048
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 20;                // pairs per thread
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 5120 pairs per tile
+constexpr int RS_GROUP = 16;                // tiles per look-back group
+
 struct GeomState {
     GaussRec* rec;            // [P]
     float* cov3D;             // [P*6]
     uint32_t* tiles_touched;  // [P]
-    uint32_t* point_offsets;  // [P]
     int32_t* internal_radii;  // [P]
     uint8_t* clamped;         // [P] bit c = colour channel c clamped at 0
-    uint32_t* total_touched;  // [2] sum of tiles_touched (= R) and the largest depth bit pattern of a rendered Gaussian,
-                              //     accumulated by preprocess
-    char* scan_temp;          // CUB scan scratch
-    size_t scan_temp_bytes;
+    uint32_t* hdr;            // [HDR_WORDS] GeomHeader
+    uint32_t* hist;           // [3][RS_BINS] digit histograms of the sort keys (filled by key emission)
+    char* end;
 };
 struct ImageState {
     uint2* ranges;        // [tiles]
     float* final_T;       // [H*W]
     uint32_t* n_contrib;  // [H*W]
     uint32_t* tile_last;  // [tiles] max n_contrib over the tile's pixels (bwd skips the rest)
-    uint32_t* tile_count;   // [tiles] instances per tile (tile-local binning)
-    uint32_t* tile_cursor;  // [tiles] scatter cursor
+    char* end;
 };
 struct BinningState {
+    uint32_t* keys[2];      // [R] ping-pong: emitted keys in [0]; sorted keys in [1] after the three passes
+    uint32_t* vals[2];      // [R] ping-pong Gaussian indices
+    uint32_t* point_list;   // = vals[1]: sorted Gaussian indices
+    uint32_t* grp_stat;     // [3][groups][RS_BINS] look-back status of the tile groups (flag << 30 | count)
+    uint16_t* tile_agg;     // [3][tiles][RS_BINS]  per-tile digit counts (bit 15 = published)
+    uint32_t n_tiles_cap, n_groups_cap;
+    size_t status_bytes;
+    char* end;
+};
+struct DebugKeys {            // lgs_debug_reference_keys: the reference's arrays (rasterizer_impl.h:50-63)
     uint64_t* keys_unsorted;  // [R]
-    uint64_t* keys;           // [R]
+    uint64_t* keys_sorted;    // [R]
     uint32_t* vals_unsorted;  // [R]
-    uint32_t* point_list;     // [R]
-    char* sort_temp;
-    size_t sort_temp_bytes;
+    uint32_t* offsets;        // [P] inclusive scan of tiles_touched (the reference's point_offsets)
+    char* end;
 };
 
 template <typename T>
@@ -61,14 +85,10 @@ static inline void carve(char*& p, T*& out, size_t count, size_t align = 256) {
     p = reinterpret_cast<char*>(out + count);
 }
 
-size_t scan_temp_bytes(int P);
-size_t sort_temp_bytes(int R);
-void set_binning_mode(int m);
-int binning_mode();
-void set_debug_keys(int on);
 GeomState geom_from_chunk(char* chunk, int P);
 ImageState image_from_chunk(char* chunk, int W, int H);
 BinningState binning_from_chunk(char* chunk, int R);
+DebugKeys debug_keys_from_chunk(char* chunk, int P, int R);
 
 // ---- error plumbing ----------------------------------------------------------------
 void set_last_cuda_error(cudaError_t e);
@@ -83,7 +103,7 @@ void set_last_cuda_error(cudaError_t e);
 #define LGS_LAUNCH_CHECK() LGS_CUDA_TRY(cudaGetLastError())
 
 // ---- optional per-stage timing (lgs_profile_enable): CUDA events recorded on the launch stream
-enum ProfMark { PM_S1_BEGIN = 0, PM_PREPROCESS, PM_SCAN, PM_S2_BEGIN, PM_EMIT, PM_SORT, PM_RANGES, PM_RENDER_FWD,
+enum ProfMark { PM_S1_BEGIN = 0, PM_PREPROCESS, PM_S2_BEGIN, PM_EMIT, PM_SORT, PM_RANGES, PM_RENDER_FWD,
                 PM_BWD_BEGIN, PM_ZERO, PM_RENDER_BWD_PIX, PM_RENDER_BWD, PM_PREPROCESS_BWD, PM_COUNT };
 void prof_mark(int id, cudaStream_t s);
 
@@ -104,27 +124,18 @@ int launch_preprocess(int P, int D, int M, const float* means3D, const float* sh
                       GeomState& g, int* radii, cudaStream_t s);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix,
                         unsigned char* present, cudaStream_t s);
-int launch_scan(int P, GeomState& g, cudaStream_t s);
-// max_depth_bits: largest depth bit pattern among the rendered Gaussians, or 0xffffffff when unknown
+// R: the capacity the binning buffer was carved for (>= the frame's instance count, which the kernels read from g.hdr)
 int launch_binning(int P, int R, int W, int H, const GeomState& g, const int* radii,
-                   BinningState& b, ImageState& im, uint32_t max_depth_bits, cudaStream_t s);
+                   BinningState& b, ImageState& im, cudaStream_t s);
+int launch_debug_reference_keys(int P, int R, int W, int H, const GeomState& g, const BinningState& b, const ImageState& im,
+                                DebugKeys& d, cudaStream_t s);
 int launch_render_fwd(int W, int H, int R, const GeomState& g, const BinningState& b,
                       ImageState& im, const float* background, const float* lang_feat,
                       float* out_color, float* out_lang_feat, float* out_depth,
                       bool include_lf, cudaStream_t s);
 int launch_render_fwd_tc(int W, int H, const GeomState& g, const BinningState& b, ImageState& im,
                          const float* background, const float* lang_feat, float* out_color,
-                         float* out_lang_feat, float* out_depth, cudaStream_t s, int R);
-// experimental (lgs_used_bits): per (list position, 32-pixel half) "blended somewhere" bytes written by the tensor-core
-// forward and read by the backward pixel kernel instead of its footprint cull.  begin_forward returns where the forward
-// writes them (NULL when off / debug keys kept) and remembers the binning buffer on the calling host thread; for_backward
-// returns them only for that same buffer and R (the backward of the forward that wrote them).
-void set_used_bits(int on);
-void set_exact_cull(int on);
-int exact_cull_on();
-uint8_t* used_bits_begin_forward(const BinningState& b, int R);
-const uint8_t* used_bits_for_backward(const BinningState& b, int R);
-int debug_keys_on();
+                         float* out_lang_feat, float* out_depth, cudaStream_t s);
 int launch_render_bwd(int P, int W, int H, int R, const GeomState& g, const BinningState& b,
                       const ImageState& im, const float* background, const float* lang_feat,
                       const float* dL_dpix, const float* dL_dpix_lf, const float* dL_dpix_depth,
@@ -161,32 +172,18 @@ __device__ __forceinline__ float eval_power(float gx, float gy, float px, float 
     return __fmaf_rn(s, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, b)));
 }
 
-// Conservative footprint test of one Gaussian against a pixel rectangle [x0,x1] x [y0,y1] (pixel
-// centres): can ANY pixel in it pass the blend kernels' tests power <= 0 and alpha = o*exp(power) >=
-// 1/255?  alpha >= 1/255 needs 0.5 * d^T Q d <= tau = ln(255 o), whose bounding box has half-extents
-// sqrt(2 tau c / det Q), sqrt(2 tau a / det Q).  Inflated by 1 % + 0.01 px so that rounding can never
-// reject a pair the exact per-pixel test accepts; degenerate conics are reported as touching.
+// Conservative footprint test of one Gaussian against a pixel rectangle [x0,x1] x [y0,y1] (pixel centres): can ANY pixel in
+// it pass the blend kernels' tests power <= 0 and alpha = o*exp(power) >= 1/255?  alpha >= 1/255 needs 0.5 * d^T Q d <= tau =
+// ln(255 o).  The minimum of the quadratic form over the rectangle is 0 when the centre lies inside, otherwise the smallest
+// of the four edge minima, each a clamped 1-D quadratic.  tau is inflated by 1 % + 0.01 and the comparison gets a slack
+// proportional to the magnitude of the terms, so that the rounding of this evaluation and of the per-pixel one can never
+// reject a pair the exact per-pixel test accepts; degenerate conics are reported as touching.  (Round 1 used the bounding box
+// of the ellipse; this test lets 17 % fewer (Gaussian, 32-pixel half) pairs through at cfgB -- tools/analyze_workload.py --
+// with bit-identical images and gradients, profiles/r02_experimental_switches.json.)
 __device__ __forceinline__ bool footprint_touches(float gx, float gy, float a, float b, float c, float o, float x0,
                                                   float x1, float y0, float y1) {
     const float tau = __logf(255.0f * o) * 1.01f + 0.01f;
     if (!(tau > 0.f)) return !(tau <= 0.f);  // o < 1/255: nothing can pass; NaN: stay conservative
-    const float det = a * c - b * b;
-    if (!(det > 0.f)) return true;
-    const float k = 2.0f * tau / det;
-    const float ex = sqrtf(k * c) * 1.01f + 0.01f, ey = sqrtf(k * a) * 1.01f + 0.01f;
-    if (!(ex == ex) || !(ey == ey)) return true;
-    return (gx + ex >= x0) && (gx - ex <= x1) && (gy + ey >= y0) && (gy - ey <= y1);
-}
-
-// Exact version of the same question (experimental, lgs_exact_cull): the minimum of the quadratic form d^T Q d over the pixel
-// rectangle -- 0 when the centre lies inside, otherwise the smallest of the four edge minima, each a clamped 1-D quadratic --
-// against the same inflated threshold, plus a slack proportional to the magnitude of the terms so that the rounding of this
-// evaluation and of the per-pixel one can never reject a pair the exact per-pixel test accepts.  At cfgB it lets 17 % fewer
-// (Gaussian, 32-pixel half) pairs through than the bounding-box test (tools/analyze_workload.py).
-__device__ __forceinline__ bool footprint_touches_exact(float gx, float gy, float a, float b, float c, float o, float x0,
-                                                        float x1, float y0, float y1) {
-    const float tau = __logf(255.0f * o) * 1.01f + 0.01f;
-    if (!(tau > 0.f)) return !(tau <= 0.f);
     const float det = a * c - b * b;
     if (!(det > 0.f) || !(a > 0.f) || !(c > 0.f)) return true;
     const float X0 = x0 - gx, X1 = x1 - gx, Y0 = y0 - gy, Y1 = y1 - gy;  // the rectangle relative to the centre

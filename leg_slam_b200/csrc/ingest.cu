@@ -263,11 +263,8 @@ extern "C" int lgs_knn_mean_dist2(int P, const float* points, float* mean_dist2,
     LGS_LAUNCH_CHECK();
     const size_t smem = (size_t)n_boxes * 24;
     if (smem > 200 * 1024) return LGS_ERR_INVALID_ARG;  // > 8.7 M points: outside what a keyframe ingest produces
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 48 * 1024)  // per device and per launch: a cached "configured" size would be wrong on a process's second GPU
         LGS_CUDA_TRY(cudaFuncSetAttribute(knn_mean_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     knn_mean_dist_kernel<<<(P + 255) / 256, 256, smem, s>>>(P, n_boxes, sorted, boxes, mean_dist2);
     LGS_LAUNCH_CHECK();
     return LGS_OK;

@@ -245,8 +245,8 @@ preprocess_kernel(int P, int D, int M,
         }
         __syncthreads();
         if (threadIdx.x == 0 && s_touched != 0) {
-            atomicAdd(total_touched, s_touched);
-            atomicMax(total_touched + 1, s_dmax);
+            atomicAdd(total_touched + HDR_R, s_touched);
+            atomicMax(total_touched + HDR_MAX_DEPTH, s_dmax);
         }
     }
     if (!live) return;
@@ -338,12 +338,13 @@ int launch_preprocess(int P, int D, int M, const float* means3D, const float* sh
     const float focal_y = H / (2.0f * tan_fovy);  // rasterizer_impl.cu:224-225
     const float focal_x = W / (2.0f * tan_fovx);
     const int tiles_x = (W + TILE - 1) / TILE, tiles_y = (H + TILE - 1) / TILE;
-    LGS_CUDA_TRY(cudaMemsetAsync(g.total_touched, 0, 2 * sizeof(uint32_t), s));
+    // the frame header and the sort's digit histograms start from zero (one memset: they are contiguous)
+    LGS_CUDA_TRY(cudaMemsetAsync(g.hdr, 0, ((size_t)HDR_WORDS + 3 * RS_BINS) * sizeof(uint32_t), s));
     preprocess_kernel<<<(P + 255) / 256, 256, 0, s>>>(
         P, D, M, means3D, scales, scale_modifier, rotations, opacities, shs, shs_rest, cov3D_precomp,
         colors_precomp, viewmatrix, projmatrix, cam_pos, W, H, tan_fovx, tan_fovy, focal_x, focal_y,
         tiles_x, tiles_y, radii == g.internal_radii ? nullptr : radii, g.internal_radii, g.rec, g.cov3D,
-        g.clamped, g.tiles_touched, g.total_touched);
+        g.clamped, g.tiles_touched, g.hdr);
     LGS_LAUNCH_CHECK();
     return LGS_OK;
 }

@@ -197,14 +197,12 @@ cosine_tc_kernel(int P, int Q, int q0, int Qn, int N, int tmem_cols, int terms, 
 }
 
 int launch_cosine_tc(int P, int Q, const float* feats, const float* text, float* out, cudaStream_t s) {
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        LGS_CUDA_TRY(cudaGetDevice(&dev));
-        LGS_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        LGS_CUDA_TRY(cudaFuncSetAttribute(cosine_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          2 * QT_M * QT_K * 4 + 2 * 256 * QT_K * 4 + EPI_BYTES));
-    }
+    // per-device facts, looked up on every call (function attributes and the SM count belong to the current device)
+    int dev = 0, n_sm = 0;
+    LGS_CUDA_TRY(cudaGetDevice(&dev));
+    LGS_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    LGS_CUDA_TRY(cudaFuncSetAttribute(cosine_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      2 * QT_M * QT_K * 4 + 2 * 256 * QT_K * 4 + EPI_BYTES));
     const int ntiles = (P + QT_M - 1) / QT_M;
     static int terms = 0;
     if (terms == 0) {  // LGS_TC_TERMS=1: plain TF32 (one product per k-step) -- a timing experiment, not a product mode

@@ -62,11 +62,7 @@ struct BwdStage {
 // {Gaussian id, centre relative to the tile, w = alpha*T and t = G*dL/dalpha of the warp's 32
 // pixels} to that (tile, warp)'s contiguous stream in the scratch buffer.  Streams need no atomics:
 // each warp owns its stream and counts in a register; the count is stored once at the end.
-// USED_BITS (experimental, lgs_used_bits): the forward recorded per (list position, 32-pixel half) whether any pixel blended
-// the instance; a warp then skips the others on that byte instead of the conservative footprint test (exact: a pixel
-// contributes here iff it blended the instance in the forward).
-// EXACT_CULL (experimental, lgs_exact_cull): exact ellipse-vs-rectangle footprint test (common.cuh) when no bytes are there.
-template <bool WITH_LF, bool USED_BITS = false, bool EXACT_CULL = false>
+template <bool WITH_LF>
 __global__ void __launch_bounds__(TILE_PIX)
 render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
                       const float* __restrict__ bg, const GaussRec* __restrict__ rec,
@@ -74,8 +70,7 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                       const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ tile_last,
                       const float* __restrict__ dL_dpix, const float* __restrict__ dL_dpix_lf,
                       const float* __restrict__ dL_dpix_depth, float* __restrict__ hrec_buf,
-                      uint32_t* __restrict__ hrec_count, uint32_t* __restrict__ work_counter,
-                      const uint8_t* __restrict__ used, int R) {
+                      uint32_t* __restrict__ hrec_count, uint32_t* __restrict__ work_counter) {
     using Stage = BwdStage<WITH_LF>;
     __shared__ __align__(128) Stage stages[BSTAGES];
     __shared__ uint32_t s_ids[BSTAGES][BB];  // Gaussian ids of the batches in flight (batch b in slot b % BSTAGES)
@@ -176,16 +171,11 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         put_ids(b + BSTAGES);           // slot b % BSTAGES: read by issue(b) two barriers ago
         const Stage& S = stages[b % BSTAGES];
 
-        // lane j tests Gaussian j's opacity-aware bounding box against this warp's 8x4 pixels (common.cuh)
+        // lane j tests Gaussian j's alpha >= 1/255 ellipse against this warp's 8x4 pixels (common.cuh)
         bool touch = false;
         if (lane < cnt) {
-            if (USED_BITS) {  // slot `lane` of this batch is list position hi - lane
-                touch = used[(size_t)wrp * R + range.x + (uint32_t)(hi - lane)] != 0;
-            } else {
-                const float4 t0 = S.rec[lane].q0, t1 = S.rec[lane].q1;
-                touch = EXACT_CULL ? footprint_touches_exact(t0.x, t0.y, t1.x, t1.y, t1.z, t1.w, wx0, wx0 + 7.0f, wy0, wy0 + 3.0f)
-                                   : footprint_touches(t0.x, t0.y, t1.x, t1.y, t1.z, t1.w, wx0, wx0 + 7.0f, wy0, wy0 + 3.0f);
-            }
+            const float4 t0 = S.rec[lane].q0, t1 = S.rec[lane].q1;
+            touch = footprint_touches(t0.x, t0.y, t1.x, t1.y, t1.z, t1.w, wx0, wx0 + 7.0f, wy0, wy0 + 3.0f);
         }
         const uint32_t vis = __ballot_sync(0xffffffffu, touch);
 
@@ -482,20 +472,9 @@ int launch_render_bwd(int P, int W, int H, int R, const GeomState& g, const Binn
     uint32_t* hcount = reinterpret_cast<uint32_t*>(hrec + (size_t)2 * (R > 0 ? R : 1) * HREC_FLOATS);
     uint32_t* work_counter = hcount + 2 * (size_t)tiles;
     if (include_lf) {
-        const uint8_t* used = used_bits_for_backward(b, R);
-        if (used)
-            render_bwd_pix_kernel<true, true><<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, W, H, background, g.rec, lang_feat,
-                                                                        im.final_T, im.n_contrib, im.tile_last, dL_dpix, dL_dpix_lf,
-                                                                        dL_dpix_depth, hrec, hcount, work_counter, used, R);
-        else if (exact_cull_on())
-            render_bwd_pix_kernel<true, false, true><<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, W, H, background, g.rec,
-                                                                               lang_feat, im.final_T, im.n_contrib, im.tile_last,
-                                                                               dL_dpix, dL_dpix_lf, dL_dpix_depth, hrec, hcount,
-                                                                               work_counter, nullptr, 0);
-        else
-            render_bwd_pix_kernel<true><<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, W, H, background, g.rec, lang_feat,
-                                                                  im.final_T, im.n_contrib, im.tile_last, dL_dpix, dL_dpix_lf,
-                                                                  dL_dpix_depth, hrec, hcount, work_counter, nullptr, 0);
+        render_bwd_pix_kernel<true><<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, W, H, background, g.rec, lang_feat, im.final_T,
+                                                              im.n_contrib, im.tile_last, dL_dpix, dL_dpix_lf, dL_dpix_depth, hrec,
+                                                              hcount, work_counter);
         LGS_LAUNCH_CHECK();
         prof_mark(PM_RENDER_BWD_PIX, s);
         if (!env_simt_chan())
@@ -507,7 +486,7 @@ int launch_render_bwd(int P, int W, int H, int R, const GeomState& g, const Binn
     } else {
         render_bwd_pix_kernel<false><<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, W, H, background, g.rec, lang_feat,
                                                                im.final_T, im.n_contrib, im.tile_last, dL_dpix, dL_dpix_lf,
-                                                               dL_dpix_depth, hrec, hcount, work_counter, nullptr, 0);
+                                                               dL_dpix_depth, hrec, hcount, work_counter);
         LGS_LAUNCH_CHECK();
         prof_mark(PM_RENDER_BWD_PIX, s);
         render_bwd_chan_kernel<false><<<tiles, 32, 0, s>>>(im.ranges, W, H, (int)grid.x, dL_dpix, dL_dpix_lf, dL_dpix_depth,

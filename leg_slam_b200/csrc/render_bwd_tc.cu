@@ -324,13 +324,12 @@ int launch_render_bwd_chan_tc(int W, int H, const ImageState& im, const float* d
                               const float* dL_dpix_depth, const float* hrec, const uint32_t* hcount, uint32_t* work_counter,
                               float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
                               float* dL_dlang_feat, float* dL_ddepth, cudaStream_t s) {
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        LGS_CUDA_TRY(cudaGetDevice(&dev));
-        LGS_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        LGS_CUDA_TRY(cudaFuncSetAttribute(render_bwd_chan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    }
+    // per-device facts, looked up on every launch (function attributes and the SM count belong to the current device, so a
+    // process-wide "configured" flag would be wrong for the second GPU of a process)
+    int dev = 0, n_sm = 0;
+    LGS_CUDA_TRY(cudaGetDevice(&dev));
+    LGS_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    LGS_CUDA_TRY(cudaFuncSetAttribute(render_bwd_chan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     const int tiles_x = (W + TILE - 1) / TILE, tiles_y = (H + TILE - 1) / TILE;
     const int n_tiles = tiles_x * tiles_y;
     const int grid = 2 * n_tiles < TC_CTAS * n_sm ? 2 * n_tiles : TC_CTAS * n_sm;

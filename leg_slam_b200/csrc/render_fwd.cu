@@ -249,32 +249,12 @@ static bool env_simt_fwd() {
     return v == 1;
 }
 
-// ---- experimental "blended somewhere" bytes (common.cuh) -------------------------------------------------------------
-static int g_used_bits = 0;
-static thread_local const void* g_used_for = nullptr;  // binning buffer whose unsorted-key array holds valid bytes
-static thread_local int g_used_R = 0;
-static int g_exact_cull = 0;
-void set_used_bits(int on) { g_used_bits = on; }
-void set_exact_cull(int on) { g_exact_cull = on; }
-int exact_cull_on() { return g_exact_cull; }
-uint8_t* used_bits_begin_forward(const BinningState& b, int R) {
-    g_used_for = nullptr;
-    if (!g_used_bits || debug_keys_on() || R <= 0) return nullptr;
-    g_used_for = b.keys_unsorted;
-    g_used_R = R;
-    return reinterpret_cast<uint8_t*>(b.keys_unsorted);
-}
-const uint8_t* used_bits_for_backward(const BinningState& b, int R) {
-    if (!g_used_bits || g_used_for == nullptr || g_used_for != b.keys_unsorted || g_used_R != R) return nullptr;
-    return reinterpret_cast<const uint8_t*>(b.keys_unsorted);
-}
-
 int launch_render_fwd(int W, int H, int R, const GeomState& g, const BinningState& b, ImageState& im,
                       const float* background, const float* lang_feat, float* out_color,
                       float* out_lang_feat, float* out_depth, bool include_lf, cudaStream_t s) {
     if (include_lf && !env_simt_fwd())
-        return launch_render_fwd_tc(W, H, g, b, im, background, lang_feat, out_color, out_lang_feat, out_depth, s, R);
-    g_used_for = nullptr;  // the SIMT kernels do not write the bytes
+        return launch_render_fwd_tc(W, H, g, b, im, background, lang_feat, out_color, out_lang_feat, out_depth, s);
+    (void)R;
     const dim3 grid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE, 1);
     const bool tma = !env_no_tma();
 #define LGS_FWD_LAUNCH(LFV, TMAV)                                                                        \

@@ -51,17 +51,12 @@ constexpr int TF_SM_TOTAL = TF_SM_IDS + 2 * 128;     // 36096
 constexpr int TF_TMEM_COLS = 64;
 constexpr int TF_CTAS = 6;                     // resident CTAs per SM (shared memory and TMEM allow 6, registers <= 85)
 
-// WRITE_USED (experimental, lgs_used_bits): additionally record, per list position and 32-pixel half of the tile, whether ANY
-// pixel of the half blended the instance -- used[half * R + position] = 0 / 1 -- so that the backward can skip the others
-// without evaluating them (tools/analyze_workload.py: 24.5 % of the halves that pass the footprint cull at cfgB).
-// EXACT_CULL (experimental, lgs_exact_cull): exact ellipse-vs-rectangle test instead of the bounding-box test (common.cuh).
-template <bool WRITE_USED, bool EXACT_CULL = false>
 __global__ void __launch_bounds__(TF_THREADS, TF_CTAS)
 render_fwd_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H,
                      const GaussRec* __restrict__ rec, const float* __restrict__ lang_feat,
                      const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
                      uint32_t* __restrict__ tile_last, float* __restrict__ out_color, float* __restrict__ out_lf,
-                     float* __restrict__ out_depth, uint8_t* __restrict__ used, int R) {
+                     float* __restrict__ out_depth) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t mma_done;
     __shared__ uint32_t tmem_base_s;
@@ -166,12 +161,11 @@ render_fwd_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
 
         uint32_t vis = 0;
         if (warp < 2) {
-            // lane j tests Gaussian j's opacity-aware bounding box against this warp's 8x4 pixels (common.cuh)
+            // lane j tests Gaussian j's alpha >= 1/255 ellipse against this warp's 8x4 pixels (common.cuh)
             bool touch = false;
             if (lane < cnt) {
                 const float4 t0 = lds128(recs + lane * 48), t1 = lds128(recs + lane * 48 + 16);
-                touch = EXACT_CULL ? footprint_touches_exact(t0.x, t0.y, t1.x, t1.y, t1.z, t1.w, wx0, wx0 + 7.0f, wy0, wy0 + 3.0f)
-                                   : footprint_touches(t0.x, t0.y, t1.x, t1.y, t1.z, t1.w, wx0, wx0 + 7.0f, wy0, wy0 + 3.0f);
+                touch = footprint_touches(t0.x, t0.y, t1.x, t1.y, t1.z, t1.w, wx0, wx0 + 7.0f, wy0, wy0 + 3.0f);
             }
             vis = __ballot_sync(0xffffffffu, touch);
         }
@@ -183,7 +177,6 @@ render_fwd_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
         if (warp < 2) {
             // ---- alpha / T chain, 4 Gaussians (one 16-byte K-chunk of A) at a time
             const uint32_t arow = sb + TF_SM_A + px * 16;
-            uint32_t used_mask = 0;  // WRITE_USED: bit j = some pixel of this warp blended Gaussian j of the batch
 #pragma unroll 1
             for (int c = 0; c < TF_B / 4; ++c) {
                 const uint32_t m = (vis >> (4 * c)) & 15u;
@@ -212,9 +205,6 @@ render_fwd_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                         Dacc = fmaf(w, q0.z, Dacc);
                         T = act ? test_T : T;
                         last_contributor = act ? (uint32_t)(b * TF_B + 4 * c + u + 1) : last_contributor;  // 1-based list position
-                        if (WRITE_USED) {
-                            if (__any_sync(0xffffffffu, act)) used_mask |= 1u << (4 * c + u);  // m is warp-uniform
-                        }
                     }
                 }
                 const float4 w4 = make_float4(wv[0], wv[1], wv[2], wv[3]);
@@ -222,9 +212,6 @@ render_fwd_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                 split_trunc4(w4, h, l);
                 sts128(arow + c * TF_LBO_A, h);
                 sts128(arow + c * TF_LBO_A + 64 * 16, l);
-            }
-            if (WRITE_USED) {
-                if (lane < cnt) used[(size_t)(warp & 1) * R + range.x + b * TF_B + lane] = (uint8_t)((used_mask >> lane) & 1u);
             }
         } else {
             // ---- B tiles from the gathered registers: row t, one K-chunk per STS.128
@@ -311,34 +298,14 @@ render_fwd_tc_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
 
 int launch_render_fwd_tc(int W, int H, const GeomState& g, const BinningState& b, ImageState& im,
                          const float* background, const float* lang_feat, float* out_color, float* out_lang_feat,
-                         float* out_depth, cudaStream_t s, int R) {
-    static bool configured = false;
-    if (!configured) {
-#define LGS_TF_CFG(K)                                                                                            \
-    LGS_CUDA_TRY(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SM_TOTAL));            \
-    LGS_CUDA_TRY(cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, 100))
-        LGS_TF_CFG((render_fwd_tc_kernel<false, false>));
-        LGS_TF_CFG((render_fwd_tc_kernel<true, false>));
-        LGS_TF_CFG((render_fwd_tc_kernel<false, true>));
-        LGS_TF_CFG((render_fwd_tc_kernel<true, true>));
-#undef LGS_TF_CFG
-        configured = true;
-    }
+                         float* out_depth, cudaStream_t s) {
+    // function attributes are per device: set them on every launch (a cheap driver call) instead of caching "configured"
+    // in a process-wide flag, which would be wrong for the second GPU of a process
+    LGS_CUDA_TRY(cudaFuncSetAttribute(render_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TF_SM_TOTAL));
+    LGS_CUDA_TRY(cudaFuncSetAttribute(render_fwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     const dim3 grid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE, 1);
-    // the used bytes ([2][R]) overlay the unsorted key array (8 B / instance), which nothing reads after binning unless the
-    // debug keys are kept for introspection
-    uint8_t* used = used_bits_begin_forward(b, R);
-    const bool exact = exact_cull_on() != 0;
-#define LGS_TF_LAUNCH(U, E)                                                                                                   \
-    render_fwd_tc_kernel<U, E><<<grid, TF_THREADS, TF_SM_TOTAL, s>>>(im.ranges, b.point_list, W, H, g.rec, lang_feat, background, \
-                                                                      im.final_T, im.n_contrib, im.tile_last, out_color,         \
-                                                                      out_lang_feat, out_depth, used, used ? R : 0)
-    if (used) {
-        if (exact) LGS_TF_LAUNCH(true, true); else LGS_TF_LAUNCH(true, false);
-    } else {
-        if (exact) LGS_TF_LAUNCH(false, true); else LGS_TF_LAUNCH(false, false);
-    }
-#undef LGS_TF_LAUNCH
+    render_fwd_tc_kernel<<<grid, TF_THREADS, TF_SM_TOTAL, s>>>(im.ranges, b.point_list, W, H, g.rec, lang_feat, background, im.final_T,
+                                                               im.n_contrib, im.tile_last, out_color, out_lang_feat, out_depth);
     LGS_LAUNCH_CHECK();
     return LGS_OK;
 }

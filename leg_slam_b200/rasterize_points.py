@@ -56,13 +56,18 @@ def _f32c(t):
 
 def rasterize_gaussians(background, means3D, colors, lang_feat, opacity, scales, rotations, scale_modifier,
                         cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width,
-                        sh, degree, campos, prefiltered, include_lang_feat, sh_rest=None):
+                        sh, degree, campos, prefiltered, include_lang_feat, sh_rest=None, capacity=None, buffers=None):
     """-> (num_rendered, out_color[3,H,W], out_lang_feat[64,H,W], out_depth[1,H,W], radii[P] int32,
            geomBuffer, binningBuffer, imgBuffer)
 
     `sh_rest` (not in the reference signature): when given, `sh` is features_dc [P,1,3] and `sh_rest` is
     features_rest [P,M-1,3] -- the reference's two parameter tensors, read in place instead of their
-    per-iteration torch::cat (lgs_forward_stage1_split_sh)."""
+    per-iteration torch::cat (lgs_forward_stage1_split_sh).
+    `capacity` (not in the reference signature): when given, the forward runs WITHOUT the reference's blocking read-back of
+    num_rendered (rasterizer_impl.cu:281-282): the binning buffer is sized for `capacity` instances, R stays on the device,
+    and the returned num_rendered is `capacity` -- the value to hand to the backward.  `forward_status(geomBuffer, P)` fetches
+    the true R and the overflow flag asynchronously.  `buffers` = dict of caller-owned work buffers to reuse (geom, img,
+    binning; any missing or too small one is allocated and stored back)."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise ValueError("means3D must have dimensions (num_points, 3)")  # AT_ERROR, rasterize_points.cu:59-61
     L = _lib.lib()
@@ -91,9 +96,19 @@ def rasterize_gaussians(background, means3D, colors, lang_feat, opacity, scales,
     M = int(sh.size(1)) if sh is not None and sh.size(0) != 0 else 0
     s = _stream(means3D)
 
-    geom = torch.empty(L.lgs_geom_bytes(P), **byte)
-    img = torch.empty(L.lgs_image_bytes(W, H), **byte)
+    def _buf(name, nbytes):
+        if buffers is None:
+            return torch.empty(nbytes, **byte)
+        b = buffers.get(name)
+        if b is None or b.numel() < nbytes or b.device != dev:
+            b = torch.empty(nbytes, **byte)
+            buffers[name] = b
+        return b
+
+    geom = _buf("geom", L.lgs_geom_bytes(P))
+    img = _buf("img", L.lgs_image_bytes(W, H))
     R = ctypes.c_int(0)
+    Rref = None if capacity is not None else ctypes.byref(R)
     with torch.cuda.device(dev):
         if sh_rest is not None:
             sh_rest = _f32c(sh_rest)
@@ -102,20 +117,41 @@ def rasterize_gaussians(background, means3D, colors, lang_feat, opacity, scales,
                                                 ptr(scales), float(scale_modifier), ptr(rotations), ptr(cov3D_precomp),
                                                 ptr(viewmatrix), ptr(projmatrix), ptr(campos), float(tan_fovx),
                                                 float(tan_fovy), int(bool(prefiltered)), geom.data_ptr(), radii.data_ptr(),
-                                                ctypes.byref(R), s), "lgs_forward_stage1_split_sh")
+                                                Rref, s), "lgs_forward_stage1_split_sh")
         else:
             check(L.lgs_forward_stage1(P, int(degree), M, W, H, ptr(means3D), ptr(sh), ptr(colors), ptr(opacity),
                                        ptr(scales), float(scale_modifier), ptr(rotations), ptr(cov3D_precomp),
                                        ptr(viewmatrix), ptr(projmatrix), ptr(campos), float(tan_fovx), float(tan_fovy),
-                                       int(bool(prefiltered)), geom.data_ptr(), radii.data_ptr(), ctypes.byref(R), s),
+                                       int(bool(prefiltered)), geom.data_ptr(), radii.data_ptr(), Rref, s),
                   "lgs_forward_stage1")
-        # capacity rounded up so that consecutive iterations (R drifts slowly) reuse the same cached block
-        binning = torch.empty(L.lgs_binning_bytes(_round_up(R.value, 1 << 18)), **byte)
+        if capacity is not None:
+            R.value = int(capacity)
+            binning = _buf("binning", L.lgs_binning_bytes(R.value))
+        else:
+            # capacity rounded up so that consecutive iterations (R drifts slowly) reuse the same cached block
+            binning = _buf("binning", L.lgs_binning_bytes(_round_up(R.value, 1 << 18)))
         check(L.lgs_forward_stage2(P, W, H, R.value, ptr(background), ptr(lang_feat) if include_lf else None,
                                    geom.data_ptr(), binning.data_ptr(), img.data_ptr(), out_color.data_ptr(),
                                    out_lf.data_ptr(), out_depth.data_ptr(), int(include_lf), s),
               "lgs_forward_stage2")
     return R.value, out_color, out_lf, out_depth, radii, geom, binning, img
+
+
+_status_host = {}
+
+
+def forward_status(geomBuffer, P):
+    """-> pinned int32[4] = (R, largest depth bits, overflow, sort error) of the frame in `geomBuffer`, copied asynchronously on
+    the current stream (lgs_forward_status): valid after the caller's next synchronisation of that stream."""
+    dev = geomBuffer.device
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    st = _status_host.get(key)
+    if st is None:
+        st = torch.zeros(4, dtype=torch.int32).pin_memory()
+        _status_host[key] = st
+    with torch.cuda.device(dev):
+        check(_lib.lib().lgs_forward_status(geomBuffer.data_ptr(), int(P), st.data_ptr(), key[1]), "lgs_forward_status")
+    return st
 
 
 def backward_outputs(P, M, dev, include_lf, has_sh, has_scales):

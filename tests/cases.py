@@ -30,6 +30,35 @@ CASES = {
 }
 
 
+# BASELINE.json configurations at their stated sizes (cfgA / cfgB / cfgD; "ragged" = cfgB with an image
+# that is not a multiple of the 8x8 tile).  GPU-only: compared with the compiled reference side by side; cfgA also with the
+# CPU oracle.  scene seed 2 / 640x480 is the bench workload.
+BASELINE_CASES = {
+    "cfgA": dict(P=10_000, W=320, H=240, seed=1, room=(6.0, 4.0, 2.8), fx=None),
+    "cfgB": dict(P=500_000, W=640, H=480, seed=2, room=(6.0, 4.0, 2.8), fx=None),
+    "cfgB_ragged": dict(P=500_000, W=637, H=475, seed=2, room=(6.0, 4.0, 2.8), fx=320.0),
+    "cfgD": dict(P=2_000_000, W=1296, H=968, seed=4, room=(8.0, 6.0, 3.0), fx=1169.7),
+}
+
+
+def make_baseline_case(name, device="cpu"):
+    """Like make_case, for the BASELINE.json configurations: SH degree 3, scale/rotation, 64-D language features."""
+    c = BASELINE_CASES[name]
+    sc = synthetic.make_scene(c["P"], seed=c["seed"], room=c["room"])
+    a = synthetic.activate(sc)
+    cam = synthetic.make_cameras(1, c["W"], c["H"], fx=c["fx"], room=c["room"], seed=c["seed"])[0]
+    g = torch.Generator().manual_seed(c["seed"] + 100)
+    HW = c["H"] * c["W"]
+    empty = torch.empty(0)
+    out = dict(name=name, P=c["P"], W=c["W"], H=c["H"], degree=3, include_lf=True, bg=torch.zeros(3), means3D=a["means3D"],
+               opacities=a["opacities"], lang_feats=a["lang_feats"], viewmatrix=cam.viewmatrix, projmatrix=cam.projmatrix,
+               campos=cam.campos, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, scale_modifier=1.0,
+               dL_dcolor=torch.randn(3, c["H"], c["W"], generator=g) / HW, dL_dlf=torch.randn(64, c["H"], c["W"], generator=g) / HW,
+               dL_ddepth=torch.randn(1, c["H"], c["W"], generator=g) / HW, shs=a["shs"], colors_precomp=empty, scales=a["scales"],
+               rotations=a["rotations"], cov3D_precomp=empty)
+    return {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
+
+
 def covariance_from_scale_rot(scales, rots):
     """[P,6] upper triangle of (S R)^T (S R) with the reference's glm conventions (forward.cu:118-152),
     in float64 then rounded: used only to feed the cov3D_precomp path."""

@@ -23,45 +23,15 @@ def dev():
     return torch.device("cuda:0")
 
 
-@pytest.fixture(autouse=True)
-def _materialise_keys(dev):
-    """The binning keeps the reference's exact 64-bit keys only when asked (include/lgs.h lgs_debug_keys)."""
-    from leg_slam_b200 import debug
-    debug.debug_keys(True)
-    debug.binning_mode(1)
-    yield
-    debug.binning_mode(1)
-
-
-def _sorted_pairs(keys, vals):
-    """(key, value) pairs in lexicographic order: the emitted instance list as an order-free multiset."""
-    k, v = np.asarray(keys).view(np.uint64), np.asarray(vals).view(np.uint32)
-    o = np.lexsort((v, k))
-    return k[o], v[o]
-
-
-def assert_emitted_equal(ours, ref_keys, ref_vals, mode):
-    """Binning mode 1 emits in the reference's order (Gaussian-major): compare element-wise.  Mode 0 scatters them
-    per tile in any order: the same instances as a multiset."""
-    if mode == 1:
-        np.testing.assert_array_equal(ours["keys_unsorted"].view(np.uint64), np.asarray(ref_keys).view(np.uint64))
-        np.testing.assert_array_equal(ours["values_unsorted"].view(np.uint32), np.asarray(ref_vals).view(np.uint32))
-    else:
-        ak, av = _sorted_pairs(ours["keys_unsorted"], ours["values_unsorted"])
-        bk, bv = _sorted_pairs(ref_keys, ref_vals)
-        np.testing.assert_array_equal(ak, bk)
-        np.testing.assert_array_equal(av, bv)
-
-
-def run_ours(cs, mode=1):
+def run_ours(cs):
     from leg_slam_b200 import rasterize_points as rp, debug
-    debug.binning_mode(mode)
     R, color, lf, depth, radii, geom, binning, img = rp.rasterize_gaussians(*cases.fwd_args(cs))
     grads = rp.rasterize_gaussians_backward(*cases.bwd_args(cs, radii, geom, R, binning, img))
     torch.cuda.synchronize()
     P, W, H = cs["P"], cs["W"], cs["H"]
     n = lambda t: t.detach().cpu().numpy()  # noqa: E731
-    gv, bv, iv = debug.geom_view(geom, P), debug.binning_view(binning, R), debug.image_view(img, W, H)
+    # the reference's key arrays, re-expressed from what the production path (32-bit keys, own radix sort, run repair) computed
+    gv, bv, iv = debug.geom_view(geom, P), debug.reference_keys(geom, binning, img, P, R, W, H), debug.image_view(img, W, H)
     out = dict(num_rendered=R, radii=n(radii), out_color=n(color), out_lf=n(lf), out_depth=n(depth),
                records=n(gv["records"]), cov3D=n(gv["cov3D"]), tiles_touched=n(gv["tiles_touched"]),
                keys_unsorted=n(bv["keys_unsorted"]), values_unsorted=n(bv["values_unsorted"]),
@@ -72,11 +42,10 @@ def run_ours(cs, mode=1):
     return out
 
 
-@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("name", list(cases.CASES))
-def test_forward_backward_vs_oracle(name, mode, dev, oracle_mod):
+def test_forward_backward_vs_oracle(name, dev, oracle_mod):
     cs = cases.make_case(name, dev)
-    ours = run_ours(cs, mode)
+    ours = run_ours(cs)
     f = cases.oracle_forward(cases.make_case(name), oracle_mod)
     g = cases.oracle_backward(cases.make_case(name), f, oracle_mod)
     vis = f["radii"] > 0
@@ -86,7 +55,8 @@ def test_forward_backward_vs_oracle(name, mode, dev, oracle_mod):
     np.testing.assert_array_equal(ours["tiles_touched"].view(np.uint32), f["tiles_touched"])
     np.testing.assert_array_equal(ours["records"][vis, 2].view(np.uint32), f["depths"][vis].view(np.uint32))
     np.testing.assert_array_equal(ours["records"][vis, 0:2].copy().view(np.uint32), f["means2D"][vis].view(np.uint32))
-    assert_emitted_equal(ours, f["keys_unsorted"], f["values_unsorted"], mode)
+    np.testing.assert_array_equal(ours["keys_unsorted"].view(np.uint64), np.asarray(f["keys_unsorted"]).view(np.uint64))
+    np.testing.assert_array_equal(ours["values_unsorted"].view(np.uint32), np.asarray(f["values_unsorted"]).view(np.uint32))
     np.testing.assert_array_equal(ours["keys_sorted"].view(np.uint64), f["keys_sorted"])
     np.testing.assert_array_equal(ours["point_list"].view(np.uint32), f["point_list"])
     np.testing.assert_array_equal(ours["ranges"].view(np.uint32), f["ranges"])
@@ -107,17 +77,17 @@ def test_forward_backward_vs_oracle(name, mode, dev, oracle_mod):
         assert cases.rel_err(ours[gname], g[gname]) <= GRAD_TOL, gname
 
 
-@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("name", list(cases.CASES))
-def test_vs_reference_golden(name, mode, dev):
+def test_vs_reference_golden(name, dev):
     gd = golden(name)
     cs = cases.make_case(name, dev)
-    ours = run_ours(cs, mode)
+    ours = run_ours(cs)
     vis = gd["visible"]
     assert ours["num_rendered"] == int(gd["num_rendered"])
     for k in ("radii", "tiles_touched", "keys_sorted", "point_list", "ranges", "n_contrib"):
         np.testing.assert_array_equal(ours[k].view(gd[k].dtype), gd[k], err_msg=k)
-    assert_emitted_equal(ours, gd["keys_unsorted"], gd["values_unsorted"], mode)
+    np.testing.assert_array_equal(ours["keys_unsorted"].view(np.uint64), gd["keys_unsorted"].view(np.uint64))
+    np.testing.assert_array_equal(ours["values_unsorted"].view(np.uint32), gd["values_unsorted"].view(np.uint32))
     np.testing.assert_array_equal(ours["records"][vis, 2].view(np.uint32), gd["depths"][vis].view(np.uint32))
     np.testing.assert_array_equal(ours["records"][vis, 0:2].copy().view(np.uint32), gd["means2D"][vis].view(np.uint32))
     np.testing.assert_array_equal(ours["final_T"].view(np.uint32), gd["final_T"].view(np.uint32))
@@ -129,22 +99,24 @@ def test_vs_reference_golden(name, mode, dev):
         assert cases.rel_err(o, gd[gname]) <= GRAD_TOL, gname
 
 
-@pytest.mark.parametrize("name", ["sh3_lf", "dense_opaque"])
-def test_vs_compiled_reference_live(name, dev, ref_mod):
-    """Same call, same tensors, reference .so vs ours, side by side on this GPU."""
+def _compare_with_reference_live(cs, ref_mod, oracle_mod=None):
+    """Same call, same tensors, reference .so vs ours, side by side on this GPU: point_list, ranges, radii, n_contrib, final_T
+    and both 64-bit key arrays bit-equal; images <= 1e-4; the 9 gradients <= 1e-3."""
     import refbuf
     from leg_slam_b200 import rasterize_points as rp, debug
-    cs = cases.make_case(name, dev)
+    P, W, H = cs["P"], cs["W"], cs["H"]
     Rr, cr, lr, dr, radr, gr, br, ir = ref_mod.rasterize_gaussians(*cases.fwd_args(cs))
     Ro, co, lo, do, rado, go, bo, io = rp.rasterize_gaussians(*cases.fwd_args(cs))
     assert Rr == Ro
     assert torch.equal(radr, rado)
-    rb, ob = refbuf.ref_binning_view(br, Rr), debug.binning_view(bo, Ro)
-    assert torch.equal(rb["keys_sorted"], ob["keys_sorted"])
+    rb, ob = refbuf.ref_binning_view(br, Rr), debug.reference_keys(go, bo, io, P, Ro, W, H)
     assert torch.equal(rb["point_list"], ob["point_list"])
-    ri, oi = refbuf.ref_image_view(ir, cs["W"], cs["H"]), debug.image_view(io, cs["W"], cs["H"])
+    assert torch.equal(rb["keys_sorted"], ob["keys_sorted"])
+    assert torch.equal(rb["keys_unsorted"], ob["keys_unsorted"]) and torch.equal(rb["point_list_unsorted"], ob["values_unsorted"])
+    ri, oi = refbuf.ref_image_view(ir, W, H), debug.image_view(io, W, H)
     assert torch.equal(ri["ranges"], oi["ranges"])
     assert torch.equal(ri["n_contrib"], oi["n_contrib"])
+    assert torch.equal(ri["final_T"].view(torch.int32), oi["final_T"].view(torch.int32))
     n = lambda t: t.cpu().numpy()  # noqa: E731
     assert cases.rel_err(n(co), n(cr)) <= IMG_TOL and cases.rel_err(n(lo), n(lr)) <= IMG_TOL
     assert cases.rel_err(n(do), n(dr)) <= IMG_TOL
@@ -152,6 +124,57 @@ def test_vs_compiled_reference_live(name, dev, ref_mod):
     gour = rp.rasterize_gaussians_backward(*cases.bwd_args(cs, rado, go, Ro, bo, io))
     for gname, a, b in zip(cases.GRAD_NAMES, gour, gref):
         assert cases.rel_err(n(a), n(b)) <= GRAD_TOL, gname
+    return dict(R=Ro, color=co, lf=lo, depth=do, radii=rado, n_contrib=oi["n_contrib"], grads=gour)
+
+
+@pytest.mark.parametrize("name", ["sh3_lf", "dense_opaque"])
+def test_vs_compiled_reference_live(name, dev, ref_mod):
+    _compare_with_reference_live(cases.make_case(name, dev), ref_mod)
+
+
+@pytest.mark.parametrize("name", list(cases.BASELINE_CASES))
+def test_vs_compiled_reference_live_at_baseline_sizes(name, dev, ref_mod):
+    """BASELINE.json configs at their stated sizes against the unmodified reference on the same GPU: cfgA (10 k, 320x240),
+    cfgB (500 k, 640x480), a ragged cfgB (637x475: partial edge tiles) and cfgD (2 M, 1296x968: 19 602 tiles, 15-bit tile ids,
+    R ~ 3 M) -- the production binning path (32-bit keys, own 3-pass radix sort, run repair) and both blend kernels."""
+    _compare_with_reference_live(cases.make_baseline_case(name, dev), ref_mod)
+
+
+def test_cfgA_vs_cpu_oracle(dev, oracle_mod):
+    """BASELINE.json configs[0]: 10 k Gaussians, RGB + depth + 64-D feature forward / backward at 320x240, one view, against the
+    CPU golden (the C oracle)."""
+    cs = cases.make_baseline_case("cfgA", dev)
+    cpu = cases.make_baseline_case("cfgA")
+    ours = run_ours(cs)
+    f = cases.oracle_forward(cpu, oracle_mod)
+    g = cases.oracle_backward(cpu, f, oracle_mod)
+    assert ours["num_rendered"] == f["num_rendered"]
+    np.testing.assert_array_equal(ours["radii"], f["radii"])
+    np.testing.assert_array_equal(ours["keys_sorted"].view(np.uint64), f["keys_sorted"])
+    np.testing.assert_array_equal(ours["point_list"].view(np.uint32), f["point_list"])
+    np.testing.assert_array_equal(ours["ranges"].view(np.uint32), f["ranges"])
+    for k in ("out_color", "out_depth", "out_lf"):
+        assert cases.rel_err(ours[k], f[k]) <= IMG_TOL, k
+    assert (ours["n_contrib"].view(np.uint32) != f["n_contrib"]).mean() <= 1e-3
+    for gname in cases.GRAD_NAMES:
+        assert cases.rel_err(ours[gname], g[gname]) <= GRAD_TOL, gname
+
+
+def test_quantised_depths_long_runs_of_equal_keys(dev, ref_mod):
+    """Thousands of Gaussians at EXACTLY the same depth in one tile (what increasePcd from a quantised depth image of a
+    fronto-parallel wall produces when re-rendered from the same keyframe): the 32-bit sort keys are all equal inside a tile,
+    so the order comes entirely from the run repair (warp-cooperative for runs > 32).  Lists bit-equal to the reference."""
+    cs = cases.make_case("sh3_lf", dev)
+    P = cs["P"]
+    # put every Gaussian on three planes of constant view-space depth: depth = z_view, camera looks along view[:,2]
+    V = cs["viewmatrix"]  # column-major W2C: p_view = p_world @ V[:3,:3] + V[3,:3]
+    pv = cs["means3D"] @ V[:3, :3] + V[3, :3]
+    planes = torch.tensor([1.5, 2.25, 3.0], device=dev)
+    pv[:, 2] = planes[torch.arange(P, device=dev) % 3]
+    cs["means3D"] = ((pv - V[3, :3]) @ torch.linalg.inv(V[:3, :3])).contiguous()
+    out = _compare_with_reference_live(cs, ref_mod)
+    from leg_slam_b200 import debug
+    assert out["R"] > 0
 
 
 # ---------------------------------------------------------------------------- edge cases
@@ -259,9 +282,7 @@ def test_no_writes_outside_caller_buffers(dev):
 @pytest.fixture(scope="module")
 def cfgB(dev):
     """BASELINE.json configs[1]: 500k Gaussians, 640x480."""
-    from leg_slam_b200 import synthetic, rasterize_points as rp, debug
-    debug.debug_keys(True)  # module-scoped: runs before the function-scoped autouse fixture
-    debug.binning_mode(1)
+    from leg_slam_b200 import synthetic, rasterize_points as rp
     sc = synthetic.make_scene(500_000, seed=2, device=dev)
     cam = synthetic.make_cameras(1, 640, 480, seed=2)[0].to(dev)
     a = synthetic.activate(sc)
@@ -277,16 +298,19 @@ def test_fullsize_binning_properties(cfgB, dev):
     from leg_slam_b200 import debug
     R, color, lf, depth, radii, geom, binning, img = cfgB["out"]
     P, W, H = 500_000, 640, 480
-    gv, bv, iv = debug.geom_view(geom, P), debug.binning_view(binning, R), debug.image_view(img, W, H)
+    gv, bv, iv = debug.geom_view(geom, P), debug.reference_keys(geom, binning, img, P, R, W, H), debug.image_view(img, W, H)
     tt = gv["tiles_touched"].long()
-    assert int(tt.sum()) == R and torch.equal(gv["point_offsets"].long(), tt.cumsum(0))
+    assert int(tt.sum()) == R and torch.equal(bv["point_offsets"].long(), tt.cumsum(0))
     assert torch.equal(tt > 0, radii > 0)
     ks = bv["keys_sorted"]
     assert bool((ks[1:] >= ks[:-1]).all())  # sorted (keys are < 2^63, signed compare is fine)
+    # the production 32-bit keys are sorted too, and agree with the 64-bit ones on the tile
+    k32 = debug.binning_view(binning, R)["keys_sorted32"].long() & 0xffffffff
+    assert bool((k32[1:] >= k32[:-1]).all())
     # the sorted list is a permutation of the emitted list: checksum of checksums
     assert int(ks.sum()) == int(bv["keys_unsorted"].sum())
     assert int(bv["point_list"].long().sum()) == int(bv["values_unsorted"].long().sum())
-    # stability: equal keys keep emission order = ascending Gaussian index
+    # equal keys are in ascending Gaussian index (what the reference's stable sort of a Gaussian-major emission gives)
     same = ks[1:] == ks[:-1]
     pl = bv["point_list"].long()
     assert bool((pl[1:][same] > pl[:-1][same]).all())
@@ -303,45 +327,43 @@ def test_fullsize_binning_properties(cfgB, dev):
     assert bool((iv["n_contrib"].view(H, W).long() <= lens.view(H // 8, W // 8).repeat_interleave(8, 0).repeat_interleave(8, 1)).all())
 
 
-def test_compacted_sort_keys_give_the_same_lists(cfgB, dev):
-    """Without lgs_debug_keys the sort runs on rebased, bounded depth bits (fewer radix passes) and tile-local binning
-    sorts per tile: point_list and ranges must equal those of the reference's exact 64-bit keys."""
+def test_forward_without_readback_gives_the_same_frame(cfgB, dev):
+    """lgs_forward_stage1 with num_rendered_host == NULL leaves R on the device; stage2 and the backward then get the CAPACITY of
+    the binning buffer.  Same lists, same images, same gradients as the synchronous call; lgs_forward_status reports R; a
+    capacity below R sets the overflow flag and stays inside the buffers."""
     from leg_slam_b200 import rasterize_points as rp, debug
-    R, _c, _l, _d, radii, geom, binning, img = cfgB["out"]
+    R, color, lf, depth, radii, geom, binning, img = cfgB["out"]
     pl = debug.binning_view(binning, R)["point_list"].clone()
-    rg = debug.image_view(img, 640, 480)["ranges"].clone()
-    nc = debug.image_view(img, 640, 480)["n_contrib"].clone()
-    for mode in (1, 0):
-        debug.debug_keys(False)
-        debug.binning_mode(mode)
-        R2, _c2, _l2, _d2, radii2, geom2, binning2, img2 = rp.rasterize_gaussians(*cfgB["args"])
-        torch.cuda.synchronize()
-        assert R2 == R and torch.equal(radii2, radii)
-        assert torch.equal(debug.binning_view(binning2, R2)["point_list"], pl), mode
-        iv = debug.image_view(img2, 640, 480)
-        assert torch.equal(iv["ranges"], rg) and torch.equal(iv["n_contrib"], nc), mode
-    debug.debug_keys(True)
-    debug.binning_mode(1)
-
-
-@pytest.mark.parametrize("name", list(cases.CASES))
-def test_default_binning_without_debug_keys_small_cases(name, dev):
-    """The production path (32-bit keys + run fix-up, no key materialisation) on the small cases: same point_list,
-    ranges and images as with the reference's exact keys."""
-    from leg_slam_b200 import rasterize_points as rp, debug
-    cs = cases.make_case(name, dev)
-    debug.debug_keys(True)
-    R, c1, l1, d1, rad1, geom, binning, img = rp.rasterize_gaussians(*cases.fwd_args(cs))
-    pl = debug.binning_view(binning, R)["point_list"].clone()
-    rg = debug.image_view(img, cs["W"], cs["H"])["ranges"].clone()
-    debug.debug_keys(False)
-    R2, c2, l2, d2, rad2, geom2, binning2, img2 = rp.rasterize_gaussians(*cases.fwd_args(cs))
+    iv = debug.image_view(img, 640, 480)
+    rg, nc = iv["ranges"].clone(), iv["n_contrib"].clone()
+    cap = int(R * 1.37) + 999
+    R2, c2, l2, d2, radii2, geom2, binning2, img2 = rp.rasterize_gaussians(*cfgB["args"], capacity=cap)
+    assert R2 == cap
+    st = rp.forward_status(geom2, 500_000)
     torch.cuda.synchronize()
-    debug.debug_keys(True)
-    assert R2 == R and torch.equal(rad1, rad2)
-    assert torch.equal(debug.binning_view(binning2, R2)["point_list"], pl)
-    assert torch.equal(debug.image_view(img2, cs["W"], cs["H"])["ranges"], rg)
-    assert torch.equal(c1, c2) and torch.equal(d1, d2)
+    assert int(st[0]) == R and int(st[2]) == 0 and int(st[3]) == 0
+    assert torch.equal(radii2, radii) and torch.equal(c2, color) and torch.equal(l2, lf) and torch.equal(d2, depth)
+    assert torch.equal(debug.binning_view(binning2, cap)["point_list"][:R], pl)
+    iv2 = debug.image_view(img2, 640, 480)
+    assert torch.equal(iv2["ranges"], rg) and torch.equal(iv2["n_contrib"], nc)
+    a, cam, bg = cfgB["a"], cfgB["cam"], cfgB["bg"]
+    e = torch.empty(0, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(6)
+    dc, dl, dd = ((torch.randn(c, 480, 640, generator=g) / 307200).to(dev) for c in (3, 64, 1))
+
+    def bwd(rad, ge, Rx, bi, im):
+        return rp.rasterize_gaussians_backward(bg, a["means3D"], rad, e, a["lang_feats"], a["scales"], a["rotations"], 1.0, e,
+                                               cam.viewmatrix, cam.projmatrix, cam.tanfovx, cam.tanfovy, dc, dl, dd, a["shs"], 3,
+                                               cam.campos, ge, Rx, bi, im, True)
+    for name, x, y in zip(cases.GRAD_NAMES, bwd(radii, geom, R, binning, img), bwd(radii2, geom2, cap, binning2, img2)):
+        assert cases.rel_err(y.cpu().numpy(), x.cpu().numpy()) <= 1e-4, name  # same kernels, atomics reorder
+    # capacity too small: flagged, finite, nothing written outside (the guard test covers the buffers themselves)
+    small = R // 2
+    R3, c3, *_rest = rp.rasterize_gaussians(*cfgB["args"], capacity=small)
+    st3 = rp.forward_status(_rest[3], 500_000)
+    torch.cuda.synchronize()
+    assert int(st3[0]) == R and int(st3[2]) == 1
+    assert bool(torch.isfinite(c3).all())
 
 
 def test_fullsize_forward_idempotent_backward_linear(cfgB, dev):

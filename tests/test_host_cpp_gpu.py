@@ -1,10 +1,7 @@
-"""GPU tests of what was written after round 1's GPU budget was spent: the C++ L2 layer (include/gaussian_rasterizer.h, _L2.so)
-against its Python twin, the C++ LgsFusedAdam against torch.optim.Adam, and the experimental lgs_used_bits switch.
-
-NOT YET RUN ON A GPU: the layer was written after round 1's GPU budget was spent (its build, its argument validation and its
-CPU refusal are covered by tests/test_host_cpp.py on CPU).  Until it has been run once it only executes with
-LGS_RUN_UNVERIFIED=1, so that an untested test cannot turn the suite red; the file sorts last for the same reason."""
-import os
+"""GPU tests of the C++ host layers above the C ABI: the L2 autograd layer (include/gaussian_rasterizer.h, _L2.so) against
+its Python twin, and the C++ LgsFusedAdam (include/lgs_adam.h) against torch.optim.Adam.  (Their build, argument validation
+and CPU refusal are covered by tests/test_host_cpp.py on CPU.)  First run on a B200 in round 2:
+profiles/r02_unverified_tests_first_run.log."""
 
 import pytest
 import torch
@@ -14,7 +11,6 @@ import cases
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.skipif(os.environ.get("LGS_RUN_UNVERIFIED") != "1", reason="C++ L2 layer not yet verified on a GPU (set LGS_RUN_UNVERIFIED=1)")
 def test_l2_cpp_autograd_equals_python_wrapper():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
@@ -55,7 +51,6 @@ def test_l2_cpp_autograd_equals_python_wrapper():
         assert cases.rel_err(a[k].grad.cpu().numpy(), b[k].grad.cpu().numpy()) <= 1e-3, k
 
 
-@pytest.mark.skipif(os.environ.get("LGS_RUN_UNVERIFIED") != "1", reason="C++ LgsFusedAdam not yet verified on a GPU (set LGS_RUN_UNVERIFIED=1)")
 def test_cpp_fused_adam_equals_torch_adam():
     """LgsFusedAdam over the reference's group layout (one tensor per group, its learning rates, eps 1e-15) against
     torch.optim.Adam: parameters <= 1e-6 relative after 3 steps, moments too, libtorch's step counts kept."""
@@ -84,37 +79,3 @@ def test_cpp_fused_adam_equals_torch_adam():
         assert cases.rel_err(ours[i].detach().cpu().numpy(), ref[i].detach().cpu().numpy()) <= 1e-6, i
         assert cases.rel_err(out[i].cpu().numpy(), opt.state[ref[i]]["exp_avg"].cpu().numpy()) <= 1e-6, i
         assert cases.rel_err(out[n + i].cpu().numpy(), opt.state[ref[i]]["exp_avg_sq"].cpu().numpy()) <= 1e-6, i
-
-
-@pytest.mark.skipif(os.environ.get("LGS_RUN_UNVERIFIED") != "1", reason="lgs_used_bits / lgs_exact_cull not yet verified on a GPU (set LGS_RUN_UNVERIFIED=1)")
-@pytest.mark.parametrize("used_bits,exact_cull", [(1, 0), (0, 1), (1, 1)])
-def test_experimental_culls_leave_results_unchanged(used_bits, exact_cull):
-    """lgs_used_bits(1): the forward records which (list position, 32-pixel half) pairs blend somewhere and the backward pixel
-    kernel skips the rest on that byte instead of its footprint cull.  lgs_exact_cull(1): exact ellipse-vs-rectangle footprint
-    test instead of the bounding-box one.  Both only remove work that contributes nothing: forward outputs (incl. radii) must be
-    bit-identical and the gradients equal up to the order of the global atomics."""
-    if not torch.cuda.is_available():
-        pytest.skip("no CUDA device")
-    from leg_slam_b200 import _lib, debug, rasterize_points as rp
-    L = _lib.lib()
-    dev = torch.device("cuda:0")
-    for name in ("sh3_lf", "ragged_sh1", "dense_opaque"):  # dense_opaque: early termination, long lists
-        cs = cases.make_case(name, dev)
-        base = rp.rasterize_gaussians(*cases.fwd_args(cs))
-        iv0 = {k: v.clone() for k, v in debug.image_view(base[7], cs["W"], cs["H"]).items() if k in ("final_T", "n_contrib")}
-        gbase = rp.rasterize_gaussians_backward(*cases.bwd_args(cs, base[4], base[5], base[0], base[6], base[7]))
-        try:
-            _lib.check(L.lgs_used_bits(used_bits), "lgs_used_bits")
-            _lib.check(L.lgs_exact_cull(exact_cull), "lgs_exact_cull")
-            out = rp.rasterize_gaussians(*cases.fwd_args(cs))
-            iv1 = debug.image_view(out[7], cs["W"], cs["H"])
-            grads = rp.rasterize_gaussians_backward(*cases.bwd_args(cs, out[4], out[5], out[0], out[6], out[7]))
-        finally:
-            _lib.check(L.lgs_used_bits(0), "lgs_used_bits")
-            _lib.check(L.lgs_exact_cull(0), "lgs_exact_cull")
-        assert out[0] == base[0]
-        for a, b in zip(out[1:5], base[1:5]):
-            assert torch.equal(a, b)
-        assert torch.equal(iv1["final_T"], iv0["final_T"]) and torch.equal(iv1["n_contrib"], iv0["n_contrib"])
-        for n, a, b in zip(cases.GRAD_NAMES, grads, gbase):
-            assert cases.rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5, (name, n)
