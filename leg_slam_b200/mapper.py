@@ -37,6 +37,7 @@ class Keyframe(NamedTuple):
     gt_lf: torch.Tensor      # [64,h,w] encoder resolution (37x37 in the reference), resized per iteration
     gt_depth: torch.Tensor   # [1,H,W]
     mask: Optional[torch.Tensor] = None  # [3,H,W] undistortion mask (ones when absent)
+    kf_id: Optional[int] = None          # keyframe identity, when the caller has one (see Mapper: read-back-free forward)
 
 
 def shard_views(n_views: int, rank: int, world_size: int):
@@ -75,12 +76,17 @@ class Mapper:
                  process_group=None, optimizer_factory: Optional[Callable] = None,
                  render_fn: Optional[Callable] = None, faithful_loss_sign: bool = True,
                  use_cuda_graph: bool = True, fused: bool = True, dp_mode: str = "allreduce",
-                 track_densify_stats: bool = False):
+                 track_densify_stats: bool = False, async_forward: bool = True):
         """dp_mode: "allreduce" = NCCL all-reduce of the flat gradient, then Adam on every replica;
         "fused" = one peer-memory kernel per rank doing reduce-scatter + Adam-on-shard + all-gather
         (leg_slam_b200.dp.FusedDPAdam; needs world_size > 1, CUDA, P % 4 == 0).
         track_densify_stats: accumulate the densification statistics of every rendered view inside train_step
-        (GaussianModel::addDensificationStats, reference src/gaussian_mapper.cpp:737-744) for densify_and_prune."""
+        (GaussianModel::addDensificationStats, reference src/gaussian_mapper.cpp:737-744) for densify_and_prune.
+        async_forward: the fused path renders WITHOUT the reference's blocking read-back of num_rendered
+        (rasterizer_impl.cu:281-282): work buffers are sized for 1.5 x the largest instance count seen, R stays on the
+        device (include/lgs.h), and the host never waits inside an iteration.  The count is re-learnt with one synchronous
+        forward whenever it could jump -- the first step, a new `Keyframe.kf_id`, a changed number of Gaussians, a reported
+        overflow -- and every step's status comes back asynchronously (`last_num_rendered`, `overflow_steps`)."""
         lrs = dict(DEFAULT_LRS, **(lrs or {}))
         self._lrs = lrs
         self._optimizer_factory = optimizer_factory
@@ -111,6 +117,13 @@ class Mapper:
         self._fused_loss = fused_mod.FusedMappingLoss(faithful_sign=faithful_loss_sign) if self.fused else None
         self._fbuf = None
         self.stats = None
+        # read-back-free forward: capacity of the work buffers (instances), what justifies it, pending status copies
+        self.async_forward = bool(async_forward)
+        self._cap, self._cap_P, self._seen_kf = 0, -1, set()
+        self._work = {}
+        self._pending_status, self._status_pool = [], []
+        self.last_num_rendered = 0
+        self.overflow_steps = 0
         if track_densify_stats:
             if not self.fused:
                 raise ValueError("track_densify_stats needs the fused path (CUDA tensors, our rasterizer)")
@@ -261,10 +274,12 @@ class Mapper:
         for n_done, i in enumerate(mine):
             kf = window[i]
             cam = kf.camera
+            cap = self._forward_capacity(P, kf)
             R, color, lf, depth, radii, geom, binning, img = rp.rasterize_gaussians(
                 self.bg, a["means3D"], e, a["lang_feats"], a["opacities"], a["scales"], a["rotations"], 1.0, e,
                 cam.viewmatrix, cam.projmatrix, cam.tanfovx, cam.tanfovy, cam.height, cam.width, p["features_dc"],
-                self.sh_degree, cam.campos, False, True, sh_rest=p["features_rest"])
+                self.sh_degree, cam.campos, False, True, sh_rest=p["features_rest"], capacity=cap, buffers=self._work)
+            self._note_forward(P, kf, cap, R, geom)
             loss, gi, gl, gd = self._fused_loss(color, lf, depth, kf.gt_image, kf.gt_lf, kf.gt_depth, kf.mask)
             first = n_done == 0
             out = dict(fb["tmp"])
@@ -284,8 +299,55 @@ class Mapper:
                                       accumulate=not first)
             l0 = loss[0:1].clone().reshape(())
             total = l0 if total is None else total + l0
-            self.last_num_rendered = R
         return total
+
+    # -- read-back-free forward: capacity bookkeeping ------------------------------------------------------------------
+    def _forward_capacity(self, P, kf):
+        """None = render synchronously (learn R); otherwise the instance capacity to render with."""
+        self._drain_status()
+        if not self.async_forward or self._cap == 0 or self._cap_P != P or (kf.kf_id is not None and kf.kf_id not in self._seen_kf):
+            return None
+        return self._cap
+
+    def _note_forward(self, P, kf, cap, R, geom):
+        if kf.kf_id is not None:
+            self._seen_kf.add(kf.kf_id)
+        if cap is None:  # synchronous forward: R is exact
+            self.last_num_rendered = R
+            if self._cap_P != P:
+                self._cap = 0
+            self._cap = max(self._cap, int(R * 1.5) + 65536)
+            self._cap_P = P
+            return
+        if P == 0:
+            return
+        dev = geom.device
+        st = self._status_pool.pop() if self._status_pool else torch.zeros(4, dtype=torch.int32).pin_memory()
+        from . import _lib
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().lgs_forward_status(geom.data_ptr(), int(P), st.data_ptr(),
+                                                     torch.cuda.current_stream(dev).cuda_stream), "lgs_forward_status")
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+        self._pending_status.append((st, ev, cap))
+
+    def _drain_status(self):
+        """Consume the status copies whose events have completed: track R, grow the capacity ahead of need, and re-learn it
+        with a synchronous forward after an overflow (that frame's lists were incomplete: its update used partial gradients)."""
+        keep = []
+        for st, ev, cap in self._pending_status:
+            if not ev.query():
+                keep.append((st, ev, cap))
+                continue
+            R, overflow = int(st[0]), int(st[2])
+            self._status_pool.append(st)
+            self.last_num_rendered = R
+            if overflow:
+                self.overflow_steps += 1
+                self._cap = 0  # next forward is synchronous
+            elif self._cap and R > 0.8 * self._cap:
+                self._cap = int(R * 1.5) + 65536
+        self._pending_status = keep
 
     # -- .ply checkpoints (reference GaussianModel::savePly / loadPly, src/gaussian_model.cpp:854-1075; SURVEY.md 8f row 3)
     def save_checkpoint(self, path):
