@@ -497,6 +497,44 @@ class RefKernelPath:
         self.opt.step()
 
 
+# ------------------------------------------------------------------------------- cfgC (strong scaling)
+def cfgc_block(rank, world, device, steps=20, warmup=5):
+    """BASELINE.json configs[2]: Replica office0-shaped 1 M Gaussians, a FIXED window of 8 keyframes per mapping iteration,
+    data-parallel over the views: each of the N ranks renders and back-propagates 8 / N views against the replicated Gaussian
+    set, one exchange + Adam per iteration (leg_slam_b200.mapper.Mapper.train_step: fused activations, rasterizer, fused loss,
+    device-resident ground truth).  Total work is fixed, so the driver's per-N values of this block are STRONG scaling."""
+    from leg_slam_b200 import mapper as M, synthetic
+    P, K = 1_000_000, 8
+    sc = synthetic.make_scene(P, seed=3)
+    cams = synthetic.make_cameras(K, WIDTH, HEIGHT, seed=3)
+    g = torch.Generator().manual_seed(33)
+    win = [M.Keyframe(c.to(device), torch.rand(3, HEIGHT, WIDTH, generator=g).to(device),
+                      torch.randn(64, LF_LOWRES, LF_LOWRES, generator=g).to(device),
+                      (torch.rand(1, HEIGHT, WIDTH, generator=g) * 3.0).to(device), None, i) for i, c in enumerate(cams)]
+    params = {k: v.to(device) for k, v in sc.items()}
+    lrs = {k: v * LR_SCALE for k, v in M.DEFAULT_LRS.items()}
+    kw = dict(dp_mode="fused") if world > 1 else {}
+    try:
+        m = M.Mapper(params, lrs=lrs, sh_degree=SH_DEGREE, **kw)
+    except Exception:
+        m = M.Mapper(params, lrs=lrs, sh_degree=SH_DEGREE)
+    ms = timed(lambda _i: m.train_step(win), steps, warmup, world, device)
+    mode = "single GPU: 8 views accumulate, one fused Adam"
+    if world > 1:
+        mode = ("fused peer-memory reduce-scatter + Adam + all-gather (lgs_dp_adam_shard, " +
+                ("NVSwitch multimem" if m.dp.uses_multicast else "P2P loads/stores") + ")") if m.dp is not None else "NCCL all-reduce + fused Adam"
+    out = {"workload": "cfgC: Replica office0-shaped 1M Gaussians, 640x480, fixed 8-keyframe window per iteration, data-parallel over "
+                       "views (BASELINE.json configs[2])", "P": P, "views_per_iteration": K, "views_per_gpu": -(-K // world),
+           "n_gpus": world, "scaling": "strong", "ms_per_iteration": round(ms, 4), "views_per_s": round(K * 1000.0 / ms, 2),
+           "iterations_per_s": round(1000.0 / ms, 3), "steps": steps, "warmup": warmup, "exchange": mode,
+           "last_num_rendered": m.last_num_rendered, "overflow_steps": m.overflow_steps}
+    if m.dp is not None:
+        m.dp.close()
+    del m
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------ cpu baseline
 def cpu_baseline(sc, cam, up, target_seconds=12.0):
     """The CPU oracle (oracle/lgs_oracle.c, OpenMP over all host cores) on full cfgB mapping iterations:
@@ -564,6 +602,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfgc", action="store_true", help="skip the cfgC strong-scaling block (1 M Gaussians, 8-view window)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -598,6 +637,9 @@ def main():
     ms_e2e = timed(e2e.step, e2e_steps, max(3, args.warmup // 2), world, device)
     del e2e
     torch.cuda.empty_cache()
+    cfgc = None
+    if not args.no_cfgc:
+        cfgc = cfgc_block(rank, world, device)
 
     out = None
     if rank == 0:
@@ -678,6 +720,8 @@ def main():
                                     if n_blend else None),
             "fp32_fma_peak_tflops_measured": round(fma_peak, 2),
         }
+        if cfgc is not None:
+            out["cfgC"] = cfgc
         if cpu is not None:
             out["cpu_baseline"] = cpu
     if world > 1:

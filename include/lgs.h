@@ -346,6 +346,14 @@ int lgs_cosine_query(int P, int Q, const float* feats, const float* text, float*
 int lgs_cosine_query_simt(int P, int Q, const float* feats, const float* text, float* out,
                           void* stream);  /* fp32 SIMT cross-check of the same contraction */
 int lgs_minmax_invert(int64_t n, float* scores, float* scratch2, void* stream);
+/* Per-pixel variant (reference eval/find_objects_gaussians.py:323: F.cosine_similarity(rendered_lf, text[:,None,None], dim=0)):
+ * image is a rendered planar feature image [64,H,W] (HW = H*W), text [Q,64]; out [Q,H,W] with
+ * out[q][px] = <image[:,px], text_q> / (max(|image[:,px]|, 1e-8) * max(|text_q|, 1e-8))  (torch's cosine_similarity eps). */
+int lgs_cosine_image(int64_t HW, int Q, const float* image, const float* text, float* out, void* stream);
+/* Heat colours for "query, then heat-map render" (BASELINE.json configs[4]): colors[p] = blue -> red ramp of
+ * scores[p * stride] clamped to [0,1] (stride = Q selects one column of a [P,Q] score matrix); feed them to the forward as
+ * colors_precomp with include_lang_feat = 0, like the reference's recolouring of the queried Gaussians (:186-189). */
+int lgs_heat_colors(int P, const float* scores, int stride, float* colors, void* stream);
 
 #ifdef __cplusplus
 }

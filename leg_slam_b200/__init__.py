@@ -7,4 +7,4 @@ host-side mirror of the reference's Python/libtorch operator interface on top of
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians  # noqa: F401
 from .rasterize_points import mark_visible  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
-from .query import cosine_query, relevance_scores  # noqa: F401
+from .query import cosine_image, cosine_query, heat_colors, heatmap_render, relevance_scores  # noqa: F401

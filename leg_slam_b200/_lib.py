@@ -82,6 +82,8 @@ SIGNATURES = {
     "lgs_cosine_query": (c_int, [c_int, c_int] + [c_void_p] * 4),
     "lgs_cosine_query_simt": (c_int, [c_int, c_int] + [c_void_p] * 4),
     "lgs_minmax_invert": (c_int, [c_int64] + [c_void_p] * 3),
+    "lgs_cosine_image": (c_int, [c_int64, c_int] + [c_void_p] * 4),
+    "lgs_heat_colors": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -128,6 +128,55 @@ minmax_apply_kernel(long long n, float* __restrict__ s, const unsigned* __restri
         s[i] = 1.0f - (s[i] - lo) / range;
 }
 
+// ---- per-pixel query over a rendered feature image (reference eval/find_objects_gaussians.py:323) -------------------
+// dist[q][px] = F.cosine_similarity(rendered_lf [64,H,W], text_q [64,1,1], dim=0): dot / (max(|lf_px|, 1e-8) * max(|t_q|, 1e-8)).
+// Planar input, one pixel per thread, the 64 channel loads of a warp are 64 coalesced 128-byte rows; up to CI_Q text vectors
+// share one pass over the image (78.6 MB at 640x480).  HBM-bound: 256 B read + 4 Q B written per pixel.
+constexpr int CI_Q = 8;
+__global__ void __launch_bounds__(256)
+cosine_image_kernel(long long HW, int Q, const float* __restrict__ image, const float* __restrict__ text, float* __restrict__ out) {
+    __shared__ float s_t[CI_Q][LF];
+    __shared__ float s_inv[CI_Q];
+    for (int i = threadIdx.x; i < Q * LF; i += blockDim.x) s_t[i / LF][i % LF] = text[i];
+    __syncthreads();
+    if (threadIdx.x < Q) {
+        float n2 = 0.f;
+        for (int c = 0; c < LF; ++c) n2 = fmaf(s_t[threadIdx.x][c], s_t[threadIdx.x][c], n2);
+        s_inv[threadIdx.x] = 1.0f / fmaxf(sqrtf(n2), 1e-8f);
+    }
+    __syncthreads();
+    for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < HW; px += (long long)gridDim.x * blockDim.x) {
+        float dot[CI_Q];
+#pragma unroll
+        for (int q = 0; q < CI_Q; ++q) dot[q] = 0.f;
+        float n2 = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < LF; ++c) {
+            const float v = __ldcs(image + (size_t)c * HW + px);
+            n2 = fmaf(v, v, n2);
+#pragma unroll
+            for (int q = 0; q < CI_Q; ++q)
+                if (q < Q) dot[q] = fmaf(v, s_t[q][c], dot[q]);
+        }
+        const float inv = 1.0f / fmaxf(sqrtf(n2), 1e-8f);
+#pragma unroll
+        for (int q = 0; q < CI_Q; ++q)
+            if (q < Q) out[(size_t)q * HW + px] = dot[q] * inv * s_inv[q];
+    }
+}
+
+// ---- heat colours for the "query, then heat-map render" path (BASELINE.json configs[4]) --------------------------------
+// colours[p] = ramp(scores[p * stride]): blue (0) -> red (1), the colors_precomp input of a forward without SH / features.
+__global__ void __launch_bounds__(256)
+heat_colors_kernel(int P, const float* __restrict__ scores, int stride, float* __restrict__ colors) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float s = fminf(fmaxf(scores[(size_t)i * stride], 0.f), 1.f);
+    colors[3 * i + 0] = s;
+    colors[3 * i + 1] = 1.0f - fabsf(2.0f * s - 1.0f);
+    colors[3 * i + 2] = 1.0f - s;
+}
+
 }  // namespace lgs
 
 using namespace lgs;
@@ -173,6 +222,30 @@ extern "C" int lgs_minmax_invert(int64_t n, float* scores, float* scratch2, void
     minmax_init_kernel<<<1, 1, 0, s>>>(sc);
     minmax_reduce_kernel<<<grid, 256, 0, s>>>(n, scores, sc);
     minmax_apply_kernel<<<grid, 256, 0, s>>>(n, scores, sc);
+    LGS_LAUNCH_CHECK();
+    return LGS_OK;
+}
+
+// per-pixel cosine similarity of a planar [64,H,W] feature image against Q text vectors -> [Q,H,W]
+extern "C" int lgs_cosine_image(int64_t HW, int Q, const float* image, const float* text, float* out, void* stream) {
+    if (HW < 0 || Q < 0) return LGS_ERR_INVALID_ARG;
+    if (HW == 0 || Q == 0) return LGS_OK;
+    if (!image || !text || !out) return LGS_ERR_INVALID_ARG;
+    const long long blocks = (HW + 255) / 256;
+    const int grid = (int)(blocks < 148LL * 8 ? blocks : 148LL * 8);
+    for (int q0 = 0; q0 < Q; q0 += CI_Q) {
+        const int qn = Q - q0 < CI_Q ? Q - q0 : CI_Q;
+        cosine_image_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(HW, qn, image, text + (size_t)q0 * LF, out + (size_t)q0 * HW);
+        LGS_LAUNCH_CHECK();
+    }
+    return LGS_OK;
+}
+
+extern "C" int lgs_heat_colors(int P, const float* scores, int stride, float* colors, void* stream) {
+    if (P < 0 || stride < 1) return LGS_ERR_INVALID_ARG;
+    if (P == 0) return LGS_OK;
+    if (!scores || !colors) return LGS_ERR_INVALID_ARG;
+    heat_colors_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, scores, stride, colors);
     LGS_LAUNCH_CHECK();
     return LGS_OK;
 }

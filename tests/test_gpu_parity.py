@@ -778,3 +778,38 @@ def test_cosine_query(dev, oracle_mod):
     text2 = torch.randn(300, 64, generator=g)
     sim2 = cosine_query(feats[:1000].to(dev), text2.to(dev)).cpu().numpy()
     assert np.abs(sim2 - oracle_mod.cosine(feats[:1000].numpy(), text2.numpy())).max() <= 2e-6
+
+
+def test_per_pixel_cosine_query_and_heatmap_render(dev, ref_mod):
+    """The per-pixel query of the reference (eval/find_objects_gaussians.py:323) on a rendered feature image, against torch's
+    F.cosine_similarity in fp32 (tolerance 2e-6: same formula, different summation order) and a float64 numpy restatement; and
+    BASELINE.json configs[4] "query, then heat-map render": per-Gaussian relevance -> heat colours -> a forward through the
+    colors_precomp path, against the unmodified reference rasterizer given the same colours (1e-4)."""
+    from leg_slam_b200 import cosine_image, heat_colors, heatmap_render, rasterize_points as rp, relevance_scores, synthetic
+    cs = cases.make_case("ragged_sh1", dev)
+    _R, _c, lf, _d, *_ = rp.rasterize_gaussians(*cases.fwd_args(cs))
+    g = torch.Generator().manual_seed(77)
+    text = torch.randn(11, 64, generator=g).to(dev)
+    lf[:, 2, 3] = 0.0  # a zero feature vector exercises the eps clamp
+    got = cosine_image(lf, text)
+    ref = torch.stack([torch.nn.functional.cosine_similarity(lf, t[:, None, None], dim=0) for t in text])
+    assert got.shape == ref.shape == (11, cs["H"], cs["W"])
+    assert float((got - ref).abs().max()) <= 2e-6
+    a, t = lf.double().cpu().numpy().reshape(64, -1), text.double().cpu().numpy()
+    exact = (t @ a) / (np.maximum(np.linalg.norm(a, axis=0), 1e-8)[None] * np.maximum(np.linalg.norm(t, axis=1), 1e-8)[:, None])
+    assert np.abs(got.cpu().numpy().reshape(11, -1) - exact).max() <= 2e-6
+    assert torch.equal(cosine_image(lf, text[3]), got[3])
+    # heat-map render
+    cam = synthetic.make_cameras(1, cs["W"], cs["H"], seed=12)[0].to(dev)
+    heat, depth, radii, scores = heatmap_render(cs["means3D"], cs["opacities"], cs["scales"], cs["rotations"], cs["lang_feats"], text[0], cam)
+    assert torch.equal(scores, relevance_scores(cs["lang_feats"], text[0]))
+    colors = heat_colors(scores)
+    s = scores.clamp(0, 1)
+    assert torch.allclose(colors, torch.stack([s, 1 - (2 * s - 1).abs(), 1 - s], 1), atol=1e-6)
+    e = torch.empty(0, device=dev)
+    bg = torch.zeros(3, device=dev)
+    Rr, cr, _lr, dr, radr, *_ = ref_mod.rasterize_gaussians(bg, cs["means3D"], colors, e, cs["opacities"], cs["scales"], cs["rotations"], 1.0, e,
+                                                          cam.viewmatrix, cam.projmatrix, cam.tanfovx, cam.tanfovy, cs["H"], cs["W"], e, 0,
+                                                          cam.campos, False, False)
+    assert torch.equal(radr, radii)
+    assert cases.rel_err(heat.cpu().numpy(), cr.cpu().numpy()) <= IMG_TOL and cases.rel_err(depth.cpu().numpy(), dr.cpu().numpy()) <= IMG_TOL

@@ -10,7 +10,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
-from leg_slam_b200 import cosine_query, rasterize_points as rp, synthetic  # noqa: E402
+from leg_slam_b200 import cosine_image, cosine_query, heatmap_render, rasterize_points as rp, synthetic  # noqa: E402
 
 
 def t(fn, n=10, warm=3):
@@ -69,6 +69,16 @@ def main():
                                        ref_bwd_ms=t(lambda: ref.rasterize_gaussians_backward(*rb), 3, 1), ref_R=Rr)
     except Exception as ex:  # reference .so not shipped
         out["cfgD_2M_1296x968"]["ref"] = str(ex)
+    # cfgE end to end on the same 2M-Gaussian scene: query (one text embedding of the batch) -> min-max inversion -> heat colours
+    # -> forward through the colors_precomp path; and the per-pixel query on the rendered [64,H,W] feature image
+    text1 = torch.randn(64, generator=torch.Generator().manual_seed(3)).to(dev)
+    hm = lambda: heatmap_render(act["means3D"], act["opacities"], act["scales"], act["rotations"], act["lang_feats"], text1, cam)  # noqa: E731
+    out["cfgE_query_then_heatmap_render_2M_1296x968"] = dict(ms=t(hm, 5, 2))
+    t8 = torch.randn(8, 64, generator=torch.Generator().manual_seed(4)).to(dev)
+    ms_px = t(lambda: cosine_image(lf, t8), 10, 3)
+    ref_px = t(lambda: torch.stack([torch.nn.functional.cosine_similarity(lf, q[:, None, None], dim=0) for q in t8]), 5, 2)
+    out["per_pixel_cosine_1296x968_x8_queries"] = dict(ms=ms_px, torch_cosine_similarity_ms=ref_px,
+                                                       algorithmic_GBps=(256 + 32) * H * W / ms_px / 1e6)
     del sc, act, color, lf, depth, geom, binning, img
     torch.cuda.empty_cache()
     out.update(extra_rows(dev))

@@ -11,10 +11,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
-if __name__ == "__main__":
-    world, rank, local = bench.dist_setup(int(os.environ.get("WORLD_SIZE", "1")))
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
+def run(world, rank, dev, P, multimem):
+    bench.P_GAUSS = P
+    os.environ["LGS_DP_MULTIMEM"] = "1" if multimem else "0"
     sc, cam, up = bench.make_workload(rank, world, dev)
     os.environ["LGS_DP_OVERLAP"] = "0"  # this tool times the single-kernel exchange
     kp = bench.KernelPath(sc, cam, up, dev, world)
@@ -52,7 +51,19 @@ if __name__ == "__main__":
         torch.cuda.synchronize()
         for i, (a, b) in enumerate(((e0, e1), (e1, e2), (e2, e3), (e3, e4))):
             acc[i] += a.elapsed_time(b) / n
-    print(f"rank {rank}: fwd+bwd {acc[0]:.3f} ms | barrier {acc[1]:.3f} | exchange+Adam kernel {acc[2]:.3f} | barrier {acc[3]:.3f} | R={kp.R} "
+    print(f"P={P} rank {rank}: fwd+bwd {acc[0]:.3f} ms | barrier {acc[1]:.3f} | exchange+Adam kernel {acc[2]:.3f} | barrier {acc[3]:.3f} | "
           f"multicast={kp.dp.uses_multicast}", flush=True)
+    kp.dp.close()
+    del kp
+    torch.cuda.empty_cache()
     dist.barrier()
+
+
+if __name__ == "__main__":
+    world, rank, local = bench.dist_setup(int(os.environ.get("WORLD_SIZE", "1")))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    for P in (500_000, 1_000_000):
+        for mm in (True, False):
+            run(world, rank, dev, P, mm)
     dist.destroy_process_group()
