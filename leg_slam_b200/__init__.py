@@ -8,3 +8,4 @@ from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, raste
 from .rasterize_points import mark_visible  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .query import cosine_image, cosine_query, heat_colors, heatmap_render, relevance_scores  # noqa: F401
+from .renderer import GaussianModelView, GaussianPipelineParams, GaussianRenderer, KeyframeView  # noqa: F401

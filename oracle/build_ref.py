@@ -87,6 +87,44 @@ def build(force=False, verbose=True):
     return so
 
 
+LOSS_REF_INC = "/root/reference/include"
+LOSS_MOD = "ref_loss"
+LOSS_SO = os.path.join(OUT, LOSS_MOD + ".so")
+
+
+def build_loss(force=False, verbose=True):
+    """The UNMODIFIED reference loss (include/loss_utils.h: l1_loss, cosine_similarity, ssim, psnr -- header-only libtorch) behind
+    oracle/ref_loss_wrap.cpp, which also chains them as src/gaussian_mapper.cpp:707-721 does -> oracle/_ref/ref_loss.so (python
+    module `ref_loss`).  Oracle for SURVEY.md 8f row 2 (the fused loss); works on CPU and CUDA tensors.  Only flag added:
+    -DLANGUAGE_FEATURES_DIM=64 (the reference's CMakeLists.txt:4 defines it)."""
+    if os.path.exists(LOSS_SO) and not force:
+        return LOSS_SO
+    if not os.path.isdir(LOSS_REF_INC):
+        raise RuntimeError("reference tree not present (GPU box?) and no prebuilt " + LOSS_SO)
+    os.makedirs(OUT, exist_ok=True)
+    inc, lib = _torch_paths()
+    pyinc = sysconfig.get_paths()["include"]
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=" + LOSS_MOD, "-DTORCH_API_INCLUDE_EXTENSION_H",
+           "-D_GLIBCXX_USE_CXX11_ABI=1", "-DLANGUAGE_FEATURES_DIM=64", "-I" + LOSS_REF_INC, "-I" + pyinc] + ["-I" + p for p in inc] + \
+          [os.path.join(HERE, "ref_loss_wrap.cpp"), "-o", LOSS_SO] + ["-L" + p for p in lib] + \
+          ["-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python"] + ["-Wl,-rpath," + p for p in lib]
+    if verbose:
+        print("[build_ref]", " ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return LOSS_SO
+
+
+def load_loss():
+    import importlib.util
+    import torch  # noqa: F401
+    if not os.path.exists(LOSS_SO):
+        raise FileNotFoundError(LOSS_SO + " missing: run `python oracle/build_ref.py` where /root/reference exists")
+    spec = importlib.util.spec_from_file_location(LOSS_MOD, LOSS_SO)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 KNN_REF = "/root/reference/third_party/simple-knn"
 KNN_SO = os.path.join(OUT, "ref_simple_knn.so")
 
@@ -135,3 +173,4 @@ def load():
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
     print(build_knn(force="--force" in sys.argv))
+    print(build_loss(force="--force" in sys.argv))
