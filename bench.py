@@ -186,9 +186,11 @@ class KernelPath:
                     off += P * n
                 self.flat = gflat
                 self.dp = dp_mod.FusedDPAdam(pflat, gflat, [P * n for _, n in self.order], [lrs[k] * 1e-3 for k, _ in self.order],
-                                            late_segment=[k for k, _ in self.order].index("lang_feats"))
+                                            late_segment=[k for k, _ in self.order].index("lang_feats"),
+                                            rows=(P, [n for _, n in self.order]))
                 self.dp_mode = "fused peer-memory reduce-scatter + Adam + all-gather (lgs_dp_adam_shard, " + \
-                               ("NVSwitch multimem" if self.dp.uses_multicast else "P2P loads/stores") + \
+                               ("NVSwitch multimem" if self.dp.uses_multicast else
+                                ("P2P loads/stores, culled Gaussians' zero gradient rows skipped" if self.dp.sparse else "P2P loads/stores")) + \
                                (", language-feature exchange overlapped with preprocess/binning on a side stream)" if self.dp.overlap else ")")
             except Exception as ex:  # symmetric memory unavailable on this box: NCCL path
                 self.dp = None
@@ -259,6 +261,7 @@ class KernelPath:
         self.forward()
         self.backward()
         if self.dp is not None:
+            self.dp.mark_rows(self.radii, first=True)
             self.dp.step()
             return
         if self.world > 1:
@@ -522,7 +525,8 @@ def cfgc_block(rank, world, device, steps=20, warmup=5):
     mode = "single GPU: 8 views accumulate, one fused Adam"
     if world > 1:
         mode = ("fused peer-memory reduce-scatter + Adam + all-gather (lgs_dp_adam_shard, " +
-                ("NVSwitch multimem" if m.dp.uses_multicast else "P2P loads/stores") + ")") if m.dp is not None else "NCCL all-reduce + fused Adam"
+                ("NVSwitch multimem" if m.dp.uses_multicast else ("P2P loads/stores, culled Gaussians' zero gradient rows skipped" if m.dp.sparse
+                                                                  else "P2P loads/stores")) + ")") if m.dp is not None else "NCCL all-reduce + fused Adam"
     out = {"workload": "cfgC: Replica office0-shaped 1M Gaussians, 640x480, fixed 8-keyframe window per iteration, data-parallel over "
                        "views (BASELINE.json configs[2])", "P": P, "views_per_iteration": K, "views_per_gpu": -(-K // world),
            "n_gpus": world, "scaling": "strong", "ms_per_iteration": round(ms, 4), "views_per_s": round(K * 1000.0 / ms, 2),

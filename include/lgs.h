@@ -246,6 +246,24 @@ int lgs_dp_adam_shard(int n_seg, const int64_t* seg_start, const double* lr, int
                       float* exp_avg_sq_shard, double beta1, double beta2, double eps, int step, int max_ctas,
                       void* stream);
 
+/* Sparse variant of the P2P exchange (no multicast): every tensor t is [n_rows, row_len[t]] (one row per Gaussian) and
+ * row_mask[g] has bit r set when rank r's gradient row of Gaussian g can be non-zero, i.e. when r rendered g in one of its
+ * views -- a culled Gaussian's row is exactly +0.0 there (reference backward.cu / rasterize_points.cu:157-167 zero-fill), 60 % of
+ * the rows with one view per rank at cfgB.  A rank's copy of a 16-byte vector is loaded only if a Gaussian it touches has its
+ * bit set: same sums, bit for bit, fewer bytes over NVLink.  The masks come from the three helpers below: each rank marks
+ * its rendered Gaussians from `radii` (accumulating over its views), publishes the bytes to slot [rank] of every rank's table
+ * (symmetric memory, lgs_dp_rows_table_bytes each; peer stores), and -- after the caller's cross-rank barrier -- combines
+ * its local table into the bit mask. */
+int lgs_dp_adam_shard_sparse(int n_seg, const int64_t* seg_start, const double* lr, const int* row_len, int64_t n_rows,
+                             const uint16_t* row_mask, int world, int rank, const float* const* grads_peers,
+                             float* const* params_peers, int64_t shard_begin, int64_t shard_end, float* exp_avg_shard,
+                             float* exp_avg_sq_shard, double beta1, double beta2, double eps, int step, int max_ctas,
+                             void* stream);
+int lgs_dp_rows_mark(int P, const int* radii, unsigned char* vis, int accumulate, void* stream);
+size_t lgs_dp_rows_table_bytes(int P, int world);
+int lgs_dp_rows_publish(int P, int world, int rank, const unsigned char* vis, unsigned char* const* tables_peers, void* stream);
+int lgs_dp_rows_combine(int P, int world, const unsigned char* table, unsigned short* row_mask, void* stream);
+
 /* Stream hooks of the CALLING HOST THREAD, for callers that overlap the exchange of the language-feature tensors (64 of
  * the 123 floats per Gaussian) with the stages that never touch them.  Both are cudaEvent_t handles owned by the caller;
  * NULL clears a hook.  While set: lgs_forward_stage2 makes its stream wait for `wait_before_render_fwd` after binning

@@ -64,6 +64,12 @@ SIGNATURES = {
     "lgs_adam_multi": (c_int, [c_int] + [c_void_p] * 6 + [c_double, c_double, c_double, c_int, c_void_p]),
     "lgs_dp_adam_shard": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int] + [c_void_p] * 4 + [c_int64, c_int64, c_void_p,
                                   c_void_p, c_double, c_double, c_double, c_int, c_int, c_void_p]),
+    "lgs_dp_adam_shard_sparse": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                         c_int64, c_int64, c_void_p, c_void_p, c_double, c_double, c_double, c_int, c_int, c_void_p]),
+    "lgs_dp_rows_mark": (c_int, [c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "lgs_dp_rows_table_bytes": (c_size_t, [c_int, c_int]),
+    "lgs_dp_rows_publish": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "lgs_dp_rows_combine": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "lgs_stream_hooks": (c_int, [c_void_p, c_void_p]),
     "lgs_activations_fwd": (c_int, [c_int, c_int] + [c_void_p] * 10),
     "lgs_activations_bwd": (c_int, [c_int, c_int, c_int] + [c_void_p] * 13),

@@ -154,8 +154,10 @@ class Mapper:
             off += sz
         self.grads = FlatGrads(self.params, flat=gflat)
         torch.cuda.synchronize(dev0)
+        P = int(tensors["xyz"].shape[0])
         self.dp = dp_mod.FusedDPAdam(pflat, gflat, sizes, [self._lrs[k] for k in PARAM_ORDER], group=self._dp_group,
-                                     late_segment=PARAM_ORDER.index("lang_feat"))
+                                     late_segment=PARAM_ORDER.index("lang_feat"),
+                                     rows=(P, [tensors[k].numel() // max(P, 1) for k in PARAM_ORDER]) if P > 0 else None)
         self.optimizer = None
         if moments is not None:
             m = torch.zeros(n, dtype=torch.float32, device=dev0)
@@ -280,6 +282,8 @@ class Mapper:
                 cam.viewmatrix, cam.projmatrix, cam.tanfovx, cam.tanfovy, cam.height, cam.width, p["features_dc"],
                 self.sh_degree, cam.campos, False, True, sh_rest=p["features_rest"], capacity=cap, buffers=self._work)
             self._note_forward(P, kf, cap, R, geom)
+            if self.dp is not None:  # sparse gradient exchange: which rows of this rank's gradient can be non-zero
+                self.dp.mark_rows(radii, first=n_done == 0)
             loss, gi, gl, gd = self._fused_loss(color, lf, depth, kf.gt_image, kf.gt_lf, kf.gt_depth, kf.mask)
             first = n_done == 0
             out = dict(fb["tmp"])

@@ -6,8 +6,9 @@
 
 Part 1 -- the exchange kernel alone, no rendering, no atomics.  Every rank fills its symmetric gradient buffer with
 seeded values and runs `FusedDPAdam.step()` through (a) the P2P branch (peer loads / stores), (b) the NVSwitch multimem
-branch (multimem.ld_reduce / multimem.st; needs a multicast pointer), (c) each of them with the language-feature segment
-exchanged on the side stream (the overlapped schedule).  Required after every step and in every mode:
+branch (multimem.ld_reduce / multimem.st; needs a multicast pointer), (c) the SPARSE P2P branch (a rank's copy of a
+gradient row is loaded only where that rank reported the Gaussian as rendered; culled rows are exactly zero), each of them
+also with the language-feature segment exchanged on the side stream (the overlapped schedule).  Required after every step and in every mode:
   * parameters bit-identical on all ranks (replicas), Adam moments (gathered from the shards) too;
   * "exact" data set (gradients are small integers times 2^-12, so every partial sum is exact in fp32 whatever the
     order): parameters and both moments bit-equal to the CPU oracle's Adam on the sum, in EVERY mode -- hence bit-identical
@@ -59,8 +60,14 @@ def exchange_case(kind, P, world, steps):
                 t = torch.randint(-64, 65, (n,), generator=g).float() * (2.0 ** -12)
             else:
                 t = torch.randn(n, generator=g) * (10.0 ** torch.randint(-5, 0, (n,), generator=g).float())
-            t[torch.rand(n, generator=g) < 0.3] = 0.0  # culled Gaussians: exactly zero rows on some ranks
-            per_rank.append(t)
+            t[torch.rand(n, generator=g) < 0.1] = 0.0  # scattered exact zeros
+            # culled Gaussians: radii == 0 and an exactly zero row in every tensor of this rank's gradient (60 % of the rows)
+            radii = (torch.rand(P, generator=g) < 0.4).int() * torch.randint(1, 50, (P,), generator=g).int()
+            off = 0
+            for rl in ROW:
+                t[off:off + P * rl].view(P, rl)[radii == 0] = 0.0
+                off += P * rl
+            per_rank.append((t, radii))
         grads.append(per_rank)
     return p0, grads
 
@@ -72,8 +79,8 @@ def oracle_trajectory(p0, grads, P):
     starts = np.cumsum([0] + [P * r for r in ROW])
     traj = []
     for step, per_rank in enumerate(grads, start=1):
-        s = per_rank[0].clone()
-        for t in per_rank[1:]:
+        s = per_rank[0][0].clone()
+        for t, _radii in per_rank[1:]:
             s = s + t  # fp32, rank order
         sn = s.numpy()
         for i in range(len(ROW)):
@@ -99,9 +106,9 @@ def run_exchange(dev, rank, world, P, steps, result, fails):
     for kind in ("exact", "random"):
         p0, grads = exchange_case(kind, P, world, steps)
         traj, m_ref, v_ref = oracle_trajectory(p0, grads, P)
-        for mc in (False, True):
+        for mc, sparse in ((False, False), (True, False), (False, True)):
             for overlap in (False, True):
-                name = f"{kind}/{'multimem' if mc else 'p2p'}{'+overlap' if overlap else ''}"
+                name = f"{kind}/{'multimem' if mc else ('p2p-sparse' if sparse else 'p2p')}{'+overlap' if overlap else ''}"
                 os.environ["LGS_DP_MULTIMEM"] = "1" if mc else "0"
                 os.environ["LGS_DP_OVERLAP"] = "1" if overlap else "0"
                 pflat, gflat = dp_mod.symmetric_empty(n, dev), dp_mod.symmetric_empty(n, dev)
@@ -109,8 +116,10 @@ def run_exchange(dev, rank, world, P, steps, result, fails):
                 gflat.zero_()
                 torch.cuda.synchronize(dev)
                 dist.barrier()
-                opt = dp_mod.FusedDPAdam(pflat, gflat, sizes, list(LRS), late_segment=LATE if overlap else None)
-                row = dict(multicast=bool(opt.uses_multicast), overlap=bool(opt.overlap))
+                opt = dp_mod.FusedDPAdam(pflat, gflat, sizes, list(LRS), late_segment=LATE if overlap else None,
+                                         rows=(P, list(ROW)) if sparse else None)
+                row = dict(multicast=bool(opt.uses_multicast), overlap=bool(opt.overlap), sparse=bool(opt.sparse))
+                assert opt.sparse == sparse
                 if mc and not opt.uses_multicast:
                     row["skipped"] = "no multicast pointer on this fabric"
                     result[name] = row
@@ -118,7 +127,9 @@ def run_exchange(dev, rank, world, P, steps, result, fails):
                     continue
                 ok_rep, ok_oracle, worst = True, True, 0.0
                 for step in range(steps):
-                    gflat.copy_(grads[step][rank].to(dev))
+                    gflat.copy_(grads[step][rank][0].to(dev))
+                    if sparse:  # what the mapper reports after each of its views: the radii of that forward
+                        opt.mark_rows(grads[step][rank][1].to(dev), first=True)
                     opt.step(late_ready_at_hook=False)
                     opt.flush()
                     torch.cuda.synchronize(dev)
@@ -134,7 +145,7 @@ def run_exchange(dev, rank, world, P, steps, result, fails):
                 v_ok = np.array_equal(v.cpu().numpy().view(np.uint32), v_ref.view(np.uint32))
                 row.update(replicas_bit_identical=ok_rep, params_bit_equal_oracle=ok_oracle, max_rel_vs_oracle=worst,
                            exp_avg_bit_equal_oracle=m_ok, exp_avg_sq_bit_equal_oracle=v_ok)
-                need_bits = (kind == "exact") or not mc
+                need_bits = (kind == "exact") or not mc  # P2P (dense or sparse) sums in rank order; the switch in its own
                 if not ok_rep:
                     fails.append(f"{name}: replicas differ")
                 if need_bits and not (ok_oracle and m_ok and v_ok):
@@ -166,7 +177,7 @@ def run_kview(dev, rank, world, result, fails):
         ours = M.Mapper(sc, sh_degree=3, dp_mode="fused")
         assert ours.dp is not None
         name = f"kview/K={K}/G={world}"
-        row = dict(multicast=bool(ours.dp.uses_multicast), overlap=bool(ours.dp.overlap), views_per_rank=views_per_rank)
+        row = dict(multicast=bool(ours.dp.uses_multicast), overlap=bool(ours.dp.overlap), sparse=bool(ours.dp.sparse), views_per_rank=views_per_rank)
         # summed gradients: the local flat buffers, all-reduced on a copy (the fused step itself never materialises the sum)
         mine = M.shard_views(K, rank, world)
         with torch.no_grad():

@@ -39,4 +39,5 @@ def test_dp_exchange_and_kview_step_multirank(tmp_path):
     res = json.load(open(out))
     assert res["ok"] and res["world"] == n, res["failures"]
     ran = [k for k, v in res.items() if isinstance(v, dict) and "skipped" not in v]
-    assert any(k.startswith("exact/p2p") for k in ran) and any(k.startswith("kview/") for k in ran)
+    assert any(k.startswith("exact/p2p") for k in ran) and any(k.startswith("random/p2p-sparse") for k in ran)
+    assert any(k.startswith("kview/") for k in ran)
