@@ -219,7 +219,9 @@ static int backward_impl(int P, int D, int M, int R, int W, int H, const float* 
 
     int st;
     prof_mark(PM_BWD_BEGIN, s);
-    if (zero_outputs) {
+    // zero_outputs: the accumulated-into arrays are cleared by the render backward's pixel kernel as a side job (no separate
+    // memset launch); without instances there is no render backward, so clear them here
+    if (zero_outputs && R <= 0) {
         st = launch_zero_grads(P, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dlang_feat, dL_ddepth,
                                include_lang_feat != 0, s);
         if (st != LGS_OK) return st;
@@ -232,7 +234,7 @@ static int backward_impl(int P, int D, int M, int R, int W, int H, const float* 
         if (!scratch) LGS_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), render_bwd_scratch_bytes(R, W, H), s));
         st = launch_render_bwd(P, W, H, R, g, b, im, background, lang_feat, dL_dpix, dL_dpix_lf, dL_dpix_depth,
                                dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dlang_feat, dL_ddepth,
-                               include_lang_feat != 0, scratch, s);
+                               include_lang_feat != 0, scratch, zero_outputs != 0, s);
         if (!bwd_scratch) {
             cudaError_t e = cudaFreeAsync(scratch, s);
             if (st == LGS_OK && e != cudaSuccess) { set_last_cuda_error(e); st = LGS_ERR_CUDA; }

@@ -362,22 +362,30 @@ radix_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
             key[k] = valid ? __ldcs(keys_in + i) : 0xffffffffu;
             val[k] = valid ? __ldcs(vals_in + i) : 0u;
         }
-        // ---- rank inside the warp: running per-digit counts in shared memory, ties inside one row by lane
+        // ---- rank inside the warp: running per-digit counts in shared memory, ties inside one row by lane.  The 20 warp
+        // matches are independent of each other and of the counters: issue them all first (their latency overlaps), then walk
+        // the rows for the counter updates, whose read-modify-write chain through shared memory is the only serial part.
         uint16_t rank[RS_ITEMS];
         uint16_t* my_cnt = &s_wcnt[warp][0];
+        uint32_t peers[RS_ITEMS];
 #pragma unroll
         for (int k = 0; k < RS_ITEMS; ++k) {
             const bool valid = first + k * 32 < R;
             const uint32_t d = valid ? ((key[k] >> SHIFT) & MASK) : (0x10000u + lane);  // invalid lanes match nobody
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
-            const int leader = __ffs(peers) - 1;
+            peers[k] = __match_any_sync(0xffffffffu, d);
+        }
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; ++k) {
+            const bool valid = first + k * 32 < R;
+            const uint32_t d = (key[k] >> SHIFT) & MASK;
+            const int leader = __ffs(peers[k]) - 1;
             uint32_t old = 0;
             if (valid && lane == leader) {
                 old = my_cnt[d];
-                my_cnt[d] = (uint16_t)(old + __popc(peers));
+                my_cnt[d] = (uint16_t)(old + __popc(peers[k]));
             }
             old = __shfl_sync(0xffffffffu, old, leader);
-            rank[k] = (uint16_t)(old + __popc(peers & lt_mask));
+            rank[k] = (uint16_t)(old + __popc(peers[k] & lt_mask));
             __syncwarp();
         }
         __syncthreads();

@@ -140,7 +140,7 @@ int launch_render_bwd(int P, int W, int H, int R, const GeomState& g, const Binn
                       const ImageState& im, const float* background, const float* lang_feat,
                       const float* dL_dpix, const float* dL_dpix_lf, const float* dL_dpix_depth,
                       float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
-                      float* dL_dlang_feat, float* dL_ddepth, bool include_lf, char* scratch, cudaStream_t s);
+                      float* dL_dlang_feat, float* dL_ddepth, bool include_lf, char* scratch, bool zero_outputs, cudaStream_t s);
 size_t render_bwd_scratch_bytes(int R, int W, int H);
 int launch_render_bwd_chan_tc(int W, int H, const ImageState& im, const float* dL_dpix, const float* dL_dpix_lf,
                               const float* dL_dpix_depth, const float* hrec, const uint32_t* hcount, uint32_t* work_counter,

@@ -101,6 +101,31 @@ __device__ __forceinline__ V3 sh_backward(int deg, int M, const float* __restric
 constexpr int PB_THREADS = 128;
 constexpr int PB_ROW = 48;  // 16 SH coefficients x 3 channels
 
+// The warp's 32 staged rows (columns COL0 .. COL0 + ROWF - 1 of s_sh; rows without data are zeros) as ONE contiguous block of
+// 32 * ROWF floats in global memory, written (or accumulated into) with 16-byte accesses.  `dst` is 16-byte aligned because
+// the warp's first Gaussian index is a multiple of 32 and the tensors are.
+template <int ROWF, int COL0>
+__device__ __forceinline__ void flush_rows(float* __restrict__ dst, const float (*s_sh)[PB_ROW + 1], int w0, uint32_t dmask, int lane,
+                                           bool accumulate) {
+    static_assert((32 * ROWF) % 4 == 0, "block must be a whole number of 16-byte vectors");
+    constexpr int N4 = 32 * ROWF / 4;
+    for (int e4 = lane; e4 < N4; e4 += 32) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = 4 * e4 + j, r = e / ROWF, c = e - r * ROWF;  // compile-time divisor
+            v[j] = ((dmask >> r) & 1u) ? s_sh[w0 + r][COL0 + c] : 0.f;
+        }
+        float4* p = reinterpret_cast<float4*>(dst) + e4;
+        float4 o = make_float4(v[0], v[1], v[2], v[3]);
+        if (accumulate) {
+            const float4 old = *p;
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        *p = o;
+    }
+}
+
 __global__ void __launch_bounds__(PB_THREADS)
 preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means, const int* __restrict__ radii,
                       const float* __restrict__ shs, const float* __restrict__ shs_rest,
@@ -305,6 +330,17 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means, cons
         const uint32_t dmask = __ballot_sync(0xffffffffu, sh_written), zmask = __ballot_sync(0xffffffffu, sh_zero);
         const uint32_t wmask = dmask | zmask;
         const long long g0 = (long long)blockIdx.x * blockDim.x + w0;  // first Gaussian of this warp
+        const bool al16 = ((reinterpret_cast<uintptr_t>(dL_dsh) | reinterpret_cast<uintptr_t>(dL_dsh_rest)) & 15u) == 0;
+        if (wmask == 0xffffffffu && row == PB_ROW && al16) {
+            // every row of the warp's 32 x 48 block is written (the mapping configuration: SH degree 3, culled rows zero-filled):
+            // 16-byte stores over the contiguous block(s) -- 12 (concatenated) or 1 + 12 (split layout) iterations instead of 48
+            if (dL_dsh_rest == nullptr) flush_rows<PB_ROW, 0>(dL_dsh + g0 * PB_ROW, s_sh, w0, dmask, lane, accumulate_sh);
+            else {
+                flush_rows<3, 0>(dL_dsh + g0 * 3, s_sh, w0, dmask, lane, accumulate_sh);
+                flush_rows<PB_ROW - 3, 3>(dL_dsh_rest + g0 * (PB_ROW - 3), s_sh, w0, dmask, lane, accumulate_sh);
+            }
+            return;
+        }
         // element i = r * row + c of the warp's 32 x row block; (r, c) advance with i (no division in the loop)
         int r = lane / row, c = lane - r * row;
         for (int i = lane; i < 32 * row; i += 32) {

@@ -49,6 +49,17 @@ constexpr int BSTAGES = 2;   // its staging ring depth (2 x 9.7 KB: 8 CTAs per S
 constexpr int CB = 8;        // half-records per TMA batch of the channel kernel
 constexpr int CSTAGES = 4;   // its staging ring depth
 
+// gradient arrays for the pixel kernel to clear on behalf of the channel kernel (launch_render_bwd fills it)
+constexpr int ZT_MAX = 6;
+struct ZeroTargets {
+    float* ptr[ZT_MAX];        // 16-byte aligned array starts
+    size_t len16[ZT_MAX];      // whole 16-byte vectors in each
+    float* tail_ptr[ZT_MAX];   // the floats behind the last whole vector of each array ...
+    int tail_len[ZT_MAX];      // ... 0 to 3 of them
+    int n, n_tail;             // arrays; tail slots (4 per array)
+    size_t n16;                // total vectors
+};
+
 template <bool WITH_LF>
 struct BwdStage {
     GaussRec rec[BB];
@@ -70,7 +81,7 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                       const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ tile_last,
                       const float* __restrict__ dL_dpix, const float* __restrict__ dL_dpix_lf,
                       const float* __restrict__ dL_dpix_depth, float* __restrict__ hrec_buf,
-                      uint32_t* __restrict__ hrec_count, uint32_t* __restrict__ work_counter) {
+                      uint32_t* __restrict__ hrec_count, uint32_t* __restrict__ work_counter, const ZeroTargets zt) {
     using Stage = BwdStage<WITH_LF>;
     __shared__ __align__(128) Stage stages[BSTAGES];
     __shared__ uint32_t s_ids[BSTAGES][BB];  // Gaussian ids of the batches in flight (batch b in slot b % BSTAGES)
@@ -79,6 +90,25 @@ render_bwd_pix_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const int lane = tid & 31, wrp = tid >> 5;
     const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
     if (tile_id == 0 && tid == 0) *work_counter = 0;  // the tensor-core channel kernel's tile queue (next launch in stream order)
+    // Side job: clear the gradient arrays the CHANNEL kernel (the next launch) accumulates into.  This kernel never touches
+    // them, its stores are fire-and-forget underneath its own latency-bound work, and it saves the separate 152 MB memset
+    // launch (0.028 ms at cfgB) that the reference's caller does with torch::zeros (rasterize_points.cu:157-167).
+    if (zt.n16 > 0) {
+        const size_t gt = (size_t)tile_id * TILE_PIX + tid, T = (size_t)gridDim.x * gridDim.y * TILE_PIX;
+        // the first array (the feature gradients, 90 % of the bytes) with a plain strided loop, the small ones with a lookup
+        float4* const p0 = reinterpret_cast<float4*>(zt.ptr[0]);
+        const size_t n0 = zt.len16[0];
+#pragma unroll 4
+        for (size_t i = gt; i < n0; i += T) p0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (size_t i = gt; i < zt.n16 - n0; i += T) {
+            size_t k = i;
+            int a = 1;
+            while (a + 1 < zt.n && k >= zt.len16[a]) { k -= zt.len16[a]; ++a; }
+            reinterpret_cast<float4*>(zt.ptr[a])[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (size_t i = gt; i < (size_t)zt.n_tail; i += T)
+            if ((int)(i & 3) < zt.tail_len[i >> 2]) zt.tail_ptr[i >> 2][i & 3] = 0.f;
+    }
     const uint2 range = ranges[tile_id];
     const int n_all = (int)(range.y - range.x);
     const int n = min(n_all, (int)tile_last[tile_id]);  // entries behind tile_last touch no pixel
@@ -462,9 +492,35 @@ int launch_render_bwd(int P, int W, int H, int R, const GeomState& g, const Binn
                       const ImageState& im, const float* background, const float* lang_feat,
                       const float* dL_dpix, const float* dL_dpix_lf, const float* dL_dpix_depth,
                       float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
-                      float* dL_dlang_feat, float* dL_ddepth, bool include_lf, char* scratch, cudaStream_t s) {
-    (void)P;
+                      float* dL_dlang_feat, float* dL_ddepth, bool include_lf, char* scratch, bool zero_outputs, cudaStream_t s) {
     const dim3 grid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE, 1);
+    // the accumulated-into arrays are cleared by the pixel kernel itself (see there) when the caller asked for it
+    ZeroTargets zt;
+    zt.n = zt.n_tail = 0;
+    zt.n16 = 0;
+    if (zero_outputs) {
+        struct { float* p; size_t n; } arr[ZT_MAX] = {{include_lf ? dL_dlang_feat : nullptr, (size_t)P * LF}, {dL_dconic, (size_t)P * 4},
+                                                      {dL_dmean2D, (size_t)P * 3}, {dL_dcolor, (size_t)P * 3},
+                                                      {dL_dopacity, (size_t)P}, {dL_ddepth, (size_t)P}};
+        bool ok = true;
+        for (int a = 0; a < ZT_MAX; ++a)
+            if (arr[a].p && (reinterpret_cast<uintptr_t>(arr[a].p) & 15u)) ok = false;
+        if (!ok) {  // an unaligned array: the plain memset kernel
+            const int st = launch_zero_grads(P, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dlang_feat, dL_ddepth, include_lf, s);
+            if (st != LGS_OK) return st;
+        } else {
+            for (int a = 0; a < ZT_MAX; ++a) {
+                if (!arr[a].p) continue;
+                zt.ptr[zt.n] = arr[a].p;
+                zt.len16[zt.n] = arr[a].n / 4;
+                zt.n16 += arr[a].n / 4;
+                zt.tail_ptr[zt.n] = arr[a].p + (arr[a].n & ~(size_t)3);
+                zt.tail_len[zt.n] = (int)(arr[a].n & 3);
+                ++zt.n;
+            }
+            zt.n_tail = 4 * zt.n;
+        }
+    }
     const unsigned tiles = grid.x * grid.y;
     // scratch: [2R] half-records of 272 B (256-byte aligned base) followed by [tiles][2] record counts
     uintptr_t base = (reinterpret_cast<uintptr_t>(scratch) + 255) & ~(uintptr_t)255;
@@ -474,7 +530,7 @@ int launch_render_bwd(int P, int W, int H, int R, const GeomState& g, const Binn
     if (include_lf) {
         render_bwd_pix_kernel<true><<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, W, H, background, g.rec, lang_feat, im.final_T,
                                                               im.n_contrib, im.tile_last, dL_dpix, dL_dpix_lf, dL_dpix_depth, hrec,
-                                                              hcount, work_counter);
+                                                              hcount, work_counter, zt);
         LGS_LAUNCH_CHECK();
         prof_mark(PM_RENDER_BWD_PIX, s);
         if (!env_simt_chan())
@@ -486,7 +542,7 @@ int launch_render_bwd(int P, int W, int H, int R, const GeomState& g, const Binn
     } else {
         render_bwd_pix_kernel<false><<<grid, TILE_PIX, 0, s>>>(im.ranges, b.point_list, W, H, background, g.rec, lang_feat,
                                                                im.final_T, im.n_contrib, im.tile_last, dL_dpix, dL_dpix_lf,
-                                                               dL_dpix_depth, hrec, hcount, work_counter);
+                                                               dL_dpix_depth, hrec, hcount, work_counter, zt);
         LGS_LAUNCH_CHECK();
         prof_mark(PM_RENDER_BWD_PIX, s);
         render_bwd_chan_kernel<false><<<tiles, 32, 0, s>>>(im.ranges, W, H, (int)grid.x, dL_dpix, dL_dpix_lf, dL_dpix_depth,
