@@ -280,29 +280,37 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
                     red_add_f32(dL_dopacity + id, S0);
                     red_add_f32(dL_dmean2D + id * 3 + 0, gx * S0 - Su);
                     red_add_f32(dL_dmean2D + id * 3 + 1, gy * S0 - Sv);
-                    red_add_f32(dL_dconic + id * 4 + 0, Suu + gx * (gx * S0 - 2.f * Su));
-                    red_add_f32(dL_dconic + id * 4 + 1, Suv + gx * gy * S0 - gy * Su - gx * Sv);
-                    red_add_f32(dL_dconic + id * 4 + 3, Svv + gy * (gy * S0 - 2.f * Sv));
+                    red_add_v4_f32(dL_dconic + id * 4, Suu + gx * (gx * S0 - 2.f * Su), Suv + gx * gy * S0 - gy * Su - gx * Sv, 0.f,
+                                   Svv + gy * (gy * S0 - 2.f * Sv));  // slot 2 of the [2,2] conic gradient is unused: + 0
                 }
             }
             __syncthreads();
             {
                 const int ch = (warp & 1) * 32 + lane;
                 const float* rl = relay + (tid ^ 64) * RELAY_PITCH;  // the partner thread holds the other half of channel ch
-                float* outp = dL_dlang_feat + ch;
                 const int c0 = warp < 2 ? 0 : 32;  // first record column this thread finishes
+                float fin[32];                     // channel ch of records c0 .. c0 + 31
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const float4 o = *reinterpret_cast<const float4*>(rl + 4 * k);
                     const float o4[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int c = c0 + 4 * k + e;
-                        if (c < cnt) {
-                            const uint32_t id = __float_as_uint(*reinterpret_cast<const float*>(smem + SM_HDR + c * 16 + 12));
-                            const float mine = __uint_as_float(warp < 2 ? va[4 * k + e] : vb[4 * k + e]);
-                            red_add_f32(outp + (size_t)id * LF, mine + o4[e]);
-                        }
+                    for (int e = 0; e < 4; ++e) fin[4 * k + e] = __uint_as_float(warp < 2 ? va[4 * k + e] : vb[4 * k + e]) + o4[e];
+                }
+                // Two channels per reduction: neighbouring lanes (channels 2i, 2i + 1) trade halves of their 32 records, so that
+                // the even lane finishes records 0-15 and the odd lane records 16-31 of the PAIR with red.global.add.v2 -- a warp
+                // instruction still covers two contiguous 128-byte rows, and the L2 takes twice the floats per request
+                // (tools/micro/red_bench.cu: 1.46 against 0.75 T float-adds/s for this access pattern).
+                const bool odd = lane & 1;
+                float* outp = dL_dlang_feat + (ch & ~1);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float send = odd ? fin[c] : fin[16 + c];
+                    const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                    const int rc = c0 + (odd ? 16 + c : c);
+                    if (rc < cnt) {
+                        const uint32_t id = __float_as_uint(*reinterpret_cast<const float*>(smem + SM_HDR + rc * 16 + 12));
+                        red_add_v2_f32(outp + (size_t)id * LF, odd ? recv : fin[c], odd ? fin[16 + c] : recv);
                     }
                 }
             }
