@@ -269,8 +269,9 @@ class KernelPath:
         self.adam()
 
     # kernels per step, every one hand-written (no library launch is left on the path): preprocess, emit_keys, 3 radix passes,
-    # tile_ranges_fix, render_fwd, zero_grads, render_bwd_pix, render_bwd_chan, preprocess_bwd, adam
-    KERNELS_PER_STEP = 12
+    # tile_ranges_fix, render_fwd, render_bwd_pix (which also clears the accumulated-into gradient arrays), render_bwd_chan,
+    # preprocess_bwd, adam
+    KERNELS_PER_STEP = 11
 
     def stage_times(self, reps=20):
         """Per-kernel device time (ms, mean over reps) from CUDA events on the launch stream."""
@@ -682,8 +683,9 @@ def main():
             fl = {}
         by = {"adam": 3444.0 * P_GAUSS,
               "preprocess": counts["P_visible"] * (44 + 12 * 16 + 75) + (P_GAUSS - counts["P_visible"]) * 20.0,
-              "preprocess_bwd": 536.0 * counts["P_visible"], "sort": 16.0 * counts["R"] * 3, "zero_grads": 304.0 * P_GAUSS}
+              "preprocess_bwd": 536.0 * counts["P_visible"], "sort": 16.0 * counts["R"] * 3}
         kernels = {}
+        stage.pop("zero_grads", None)  # no longer a launch: the pixel kernel of the render backward clears the arrays
         for k, t in stage.items():
             ent = dict(ms=round(t, 4), share=round(t / sum(stage.values()), 4))
             if k in fl and t > 0:
@@ -725,7 +727,8 @@ def main():
                                                     "fused loss + FusedAdam, all liblgs launches), inputs from pinned host memory"},
             "gpu_launches": KernelPath.KERNELS_PER_STEP * args.steps,
             "gpu_launches_note": "kernels per step, all hand-written: preprocess, emit_keys, radix_pass x3, tile_ranges_fix, render_fwd, "
-                                 "zero_grads, render_bwd_pix, render_bwd_chan, preprocess_bwd, adam (no library launch on the path)",
+                                 "render_bwd_pix (also clears the gradient arrays), render_bwd_chan, preprocess_bwd, adam (no library "
+                                 "launch on the path)",
             "clocks": clocks,
             "roofline": roof,
             "kernels": kernels,
