@@ -79,3 +79,27 @@ def test_cpp_fused_adam_equals_torch_adam():
         assert cases.rel_err(ours[i].detach().cpu().numpy(), ref[i].detach().cpu().numpy()) <= 1e-6, i
         assert cases.rel_err(out[i].cpu().numpy(), opt.state[ref[i]]["exp_avg"].cpu().numpy()) <= 1e-6, i
         assert cases.rel_err(out[n + i].cpu().numpy(), opt.state[ref[i]]["exp_avg_sq"].cpu().numpy()) <= 1e-6, i
+
+
+def test_second_device_in_one_process():
+    """Kernel attributes (dynamic shared memory opt-in, SM count) belong to a device: a forward + backward + query on cuda:1
+    after the same on cuda:0, in ONE process, must work and agree (the one-time configuration used to be cached in
+    process-wide statics and applied to the first device only)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from leg_slam_b200 import cosine_query, rasterize_points as rp
+    outs = []
+    for d in (0, 1):
+        dev = torch.device("cuda", d)
+        cs = cases.make_case("sh3_lf", dev)
+        R, color, lf, depth, radii, geom, binning, img = rp.rasterize_gaussians(*cases.fwd_args(cs))
+        grads = rp.rasterize_gaussians_backward(*cases.bwd_args(cs, radii, geom, R, binning, img))
+        feats, text = cases.cosine_case()
+        sim = cosine_query(feats.to(dev), text.to(dev))
+        torch.cuda.synchronize(dev)
+        outs.append((R, color.cpu(), lf.cpu(), radii.cpu(), [g.cpu() for g in grads], sim.cpu()))
+    a, b = outs
+    assert a[0] == b[0] and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    assert torch.equal(a[5], b[5])
+    for x, y in zip(a[4], b[4]):
+        assert cases.rel_err(x.numpy(), y.numpy()) <= 1e-4  # atomics reorder between runs

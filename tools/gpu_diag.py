@@ -55,7 +55,7 @@ def run(P, W, H, seed=0, include_lf=True, timing=False):
     print("tiles_touched equal:", bool((vg["tiles_touched"] == og["tiles_touched"]).all()))
     if Rr == Ro and Rr > 0:
         vb = refbuf.ref_binning_view(br, Rr)
-        ob = debug.binning_view(bo, Ro)
+        ob = debug.reference_keys(go, bo, io, P, Ro, W, H)
         for k_ref, k_our in (("keys_unsorted", "keys_unsorted"), ("point_list_unsorted", "values_unsorted"),
                              ("keys_sorted", "keys_sorted"), ("point_list", "point_list")):
             print(f"{k_our} equal:", bool((vb[k_ref] == ob[k_our]).all()))
