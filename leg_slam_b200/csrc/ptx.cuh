@@ -18,16 +18,30 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Wait for the phase with the given parity to complete.  Bounded: a wait that lasts four seconds is a protocol error (a lost
+// arrival would otherwise hang the stream for good) and traps, which surfaces as a launch failure on the host.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint64_t t0 = 0;
+    for (uint32_t i = 1;; ++i) {
+        if (mbar_try_wait(bar, parity)) return;
+        if ((i & 1023u) == 0) {
+            uint64_t t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 4000000000ull) __trap();
+        }
+    }
 }
 
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).

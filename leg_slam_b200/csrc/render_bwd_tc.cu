@@ -19,12 +19,16 @@
 //   aux   D[64 x 8]    = W[64 x 32] * B_aux^T[32 x 8]         columns = {r,g,b,d}_hi, {r,g,b,d}_lo
 //   mom   D[64 x 8]    = T[64 x 32] * B_mom^T[32 x 8]         columns = 1,u,v,u^2,uv,v^2 (exact in TF32)
 //
-// Persistent CTAs (128 threads, 3 per SM) take (tile, pixel-warp half) work items from a counter.  Per batch of 64
-// records: one TMA bulk copy brings the raw records (re-issued for the next batch as soon as this one has been
-// split, so it flies during the MMAs and the epilogue), all threads split w/t into hi/lo tiles in the canonical
-// K-major layout, one thread issues 24 MMAs, and the four warps drain TMEM: hi-row and lo-row warps swap halves of
-// their record columns through shared memory (each sum is ONE red per record and channel, 32 reds per thread),
-// 16 lanes per warp finish colour / depth / moments.
+// Persistent CTAs of 256 threads, 2 per SM, take (tile, pixel-warp half) work items from a counter and run a two-stage
+// pipeline over batches of 64 records:
+//   front (warps 0-3)  TMA bulk copy of the raw records (two stages, requested one batch ahead -- across work items too),
+//                      split of w / t into hi / lo tiles in the canonical K-major layout, 24 MMAs issued by one thread into
+//                      one of two TMEM accumulator sets;
+//   drain (warps 4-7)  TMEM -> registers, hi-row and lo-row warps swap halves of their record columns through shared memory
+//                      (each sum is ONE red per record and channel pair, 16 red.v2 per thread), 16 lanes per warp finish
+//                      colour / depth / moments.
+// The drain of batch q runs under the copy + split + MMAs of batch q + 1 (mbarriers: raw_full, meta_ready, mma_done,
+// slot_free); round 1-2's kernel ran the two halves back to back in every CTA (21 % issue-slot utilisation).
 #include <cstdlib>
 #include "common.cuh"
 #include "ptx.cuh"
@@ -33,22 +37,26 @@
 namespace lgs {
 
 constexpr int TB = 64;             // half-records per batch
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 256;
+constexpr int TC_FRONT = 128;      // threads of the front half (and of the drain half)
 constexpr int HREC_BYTES = HREC_FLOATS * 4;
-constexpr int RAW_BYTES = TB * HREC_BYTES;         // 17408; also the relay [64 ch][68 floats]
+constexpr int RAW_BYTES = TB * HREC_BYTES;         // 17408
 constexpr int WT_TILE = TB * 32 * 4;               // 8192: one [64 rec x 32 px] TF32 tile
 constexpr int AMAIN_HALF = 128 * 32 * 4;           // 16384
-constexpr int SM_RAW = 0;
-constexpr int SM_WT = SM_RAW + RAW_BYTES;          // W_hi, W_lo, T_hi, T_lo
+constexpr int RELAY_PITCH = 36;                    // floats per thread in the drain's relay (16-byte aligned, spreads banks)
+constexpr int SM_RAW = 0;                          // two stages
+constexpr int SM_WT = SM_RAW + 2 * RAW_BYTES;      // W_hi, W_lo, T_hi, T_lo
 constexpr int SM_AMAIN = SM_WT + 4 * WT_TILE;      // [128 x 32]: the work item's half
 constexpr int SM_BAUX = SM_AMAIN + AMAIN_HALF;     // [8 x 32]
 constexpr int SM_BMOM = SM_BAUX + 1024;            // [2 halves][8 x 32]
-constexpr int SM_HDR = SM_BMOM + 2 * 1024;         // [64] float4 record headers of the current batch
-constexpr int SM_TOTAL = SM_HDR + TB * 16;         // 70656: three CTAs per SM
-constexpr int TC_CTAS = 3;
-constexpr int TMEM_COLS = 128;                     // main 0-63, aux 64-71, mom 72-79
-constexpr int RELAY_PITCH = 36;                    // floats per thread in the epilogue relay (16-byte aligned, spreads banks)
-static_assert(TC_THREADS * RELAY_PITCH * 4 <= 4 * WT_TILE, "relay must fit the operand tiles");
+constexpr int SM_HDR = SM_BMOM + 2 * 1024;         // [2 slots][64] float4 record headers
+constexpr int SM_RELAY = SM_HDR + 2 * TB * 16;     // [128 drain threads][36 floats]
+constexpr int SM_TOTAL = SM_RELAY + TC_FRONT * RELAY_PITCH * 4;  // 107520: two CTAs per SM
+constexpr int TC_CTAS = 2;
+constexpr int TMEM_SET = 128;                      // columns per accumulator set: main 0-63, aux 64-71, mom 72-79
+constexpr int TMEM_COLS = 2 * TMEM_SET;
+
+__device__ __forceinline__ void bar_named(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 // hi = x with the 13 low mantissa bits cleared (what kind::tf32 reads anyway), lo = x - hi (tc.cuh split_trunc4)
 __device__ __forceinline__ void split_store(const float4 x, uint8_t* hi, uint8_t* lo) {
@@ -84,17 +92,26 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
                           float* __restrict__ dL_dmean2D, float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity,
                           float* __restrict__ dL_dcolor, float* __restrict__ dL_dlang_feat, float* __restrict__ dL_ddepth) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t raw_full;
-    __shared__ __align__(8) uint64_t mma_done;
+    __shared__ __align__(8) uint64_t raw_full[2];    // the bulk copy of a raw stage has landed
+    __shared__ __align__(8) uint64_t meta_ready[2];  // headers + record count of a slot are written
+    __shared__ __align__(8) uint64_t mma_done[2];    // the MMAs of a slot have completed
+    __shared__ __align__(8) uint64_t slot_free[2];   // the drain is done with a slot (TMEM set, headers, count)
     __shared__ uint32_t tmem_base_s;
-    __shared__ int s_tile;
+    __shared__ int s_pop[2];                         // work-item ids popped two items ahead
+    __shared__ int s_cnt[2];
+    __shared__ __align__(16) uint32_t s_ids[2][TB];  // Gaussian ids of a slot's records
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const size_t HW = (size_t)H * W;
 
     if (tid == 0) {
-        mbar_init(&raw_full, 1);
-        mbar_init(&mma_done, 1);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&raw_full[i], 1);
+            mbar_init(&meta_ready[i], 1);
+            mbar_init(&mma_done[i], 1);
+            mbar_init(&slot_free[i], 4);  // one arrival per drain warp
+        }
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(&tmem_base_s, TMEM_COLS);
@@ -110,138 +127,200 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    const uint32_t idesc_main = make_idesc_tf32(128, TB);
-    const uint32_t idesc_aux = make_idesc_tf32(64, 8);
-    const uint32_t smem_base = smem_u32(smem);
-    const uint64_t dA_base = make_desc(smem_base + SM_AMAIN, 128 * 16, 128);
-    const uint64_t dWh_base = make_desc(smem_base + SM_WT, TB * 16, 128), dWl_base = make_desc(smem_base + SM_WT + WT_TILE, TB * 16, 128);
-    const uint64_t dTh_base = make_desc(smem_base + SM_WT + 2 * WT_TILE, TB * 16, 128);
-    const uint64_t dTl_base = make_desc(smem_base + SM_WT + 3 * WT_TILE, TB * 16, 128);
-    const uint64_t dBa_base = make_desc(smem_base + SM_BAUX, 128, 128), dBm_base = make_desc(smem_base + SM_BMOM, 128, 128);
 
-    uint32_t raw_phase = 0, mma_phase = 0;
+    if (warp < 4) {
+        // ============================================================ front: copy, split, MMA issue
+        const uint32_t idesc_main = make_idesc_tf32(128, TB);
+        const uint32_t idesc_aux = make_idesc_tf32(64, 8);
+        const uint32_t smem_base = smem_u32(smem);
+        const uint64_t dA_base = make_desc(smem_base + SM_AMAIN, 128 * 16, 128);
+        const uint64_t dWh_base = make_desc(smem_base + SM_WT, TB * 16, 128), dWl_base = make_desc(smem_base + SM_WT + WT_TILE, TB * 16, 128);
+        const uint64_t dTh_base = make_desc(smem_base + SM_WT + 2 * WT_TILE, TB * 16, 128);
+        const uint64_t dTl_base = make_desc(smem_base + SM_WT + 3 * WT_TILE, TB * 16, 128);
+        const uint64_t dBa_base = make_desc(smem_base + SM_BAUX, 128, 128), dBm_base = make_desc(smem_base + SM_BMOM, 128, 128);
 
-    // A work item's inputs -- its record count and range, and the half's upstream gradient rows -- are fetched ONE ITEM
-    // AHEAD into registers, so their global-memory round trips overlap the previous item's batches (they were 20 % of
-    // all warp samples when loaded at the start of the item, profiles/r01_chan_tc_v2_ncu.txt).
-    struct Item {
-        int id, cnt;
-        uint2 range;
-        float4 a[2][2];  // A_main rows of tasks tid, tid + 128
-        float4 b[2];     // B_aux row (threads 0..15)
-    };
-    auto fetch = [&](int id, Item& it) {
-        it.id = id;
-        it.cnt = 0;
-        if (id >= 2 * n_tiles) return;
-        const int tile = id >> 1, half = id & 1;
-        it.cnt = (int)hrec_count[id];
-        it.range = ranges[tile];
-        const uint32_t tx0 = (uint32_t)(tile % tiles_x) * TILE, ty0 = (uint32_t)(tile / tiles_x) * TILE + 4 * half;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {  // A_main: task = (row y, channel ch); consecutive lanes = consecutive channels
-            const int task = tid + TC_THREADS * i;
-            load_row8(dL_dpix_lf + (size_t)(task & 63) * HW, W, H, tx0, ty0 + (task >> 6), it.a[i][0], it.a[i][1]);
-        }
-        if (tid < 16) {  // B_aux: rows {r,g,b,d}
-            const int c = tid & 3;
-            load_row8(c < 3 ? dL_dpix + (size_t)c * HW : dL_dpix_depth, W, H, tx0, ty0 + (tid >> 2), it.b[0], it.b[1]);
-        }
-    };
-    if (tid == 0) s_tile = (int)atomicAdd(work_counter, 1u);
-    __syncthreads();
-    Item cur, nxt;
-    fetch(s_tile, cur);
-
-    for (;;) {
-        if (cur.id >= 2 * n_tiles) break;
-        __syncthreads();  // everyone has read s_tile (and finished the previous item)
-        if (tid == 0) s_tile = (int)atomicAdd(work_counter, 1u);
-        const int item = cur.id, tile = item >> 1, half = item & 1;
-        const int cnt_all = cur.cnt;
-        const uint2 range = cur.range;
-        const int n_all = (int)(range.y - range.x);
-        const int nbt = (cnt_all + TB - 1) / TB;
-        const float* stream = hrec_buf + ((size_t)2 * range.x + (size_t)half * n_all) * HREC_FLOATS;
-        (void)tile;
-
-        auto issue = [&](int q) {  // thread 0: bulk copy of the item's q-th batch into the raw buffer
-            const int cnt = min(TB, cnt_all - q * TB);
-            const uint32_t bytes = (uint32_t)cnt * HREC_BYTES;
-            mbar_arrive_expect_tx(&raw_full, bytes);
-            tma_bulk_g2s(smem + SM_RAW, stream + (size_t)q * TB * HREC_FLOATS, bytes, &raw_full);
+        // A work item's inputs are fetched AHEAD into registers, so that their global-memory round trips overlap earlier items'
+        // batches (items are short: 116 records = 2.3 batches on average at cfgB): record count and range two items ahead
+        // (the count decides the bulk copy that is requested during the previous item's last batch), the half's upstream
+        // gradient rows one item ahead.
+        struct Meta {
+            int id, cnt;
+            uint2 range;
         };
-        if (tid == 0 && cnt_all > 0) issue(0);
-
-        // ---- the half's upstream gradients as MMA operands (all earlier MMAs have completed: mma_done was waited on)
-        if (cnt_all > 0) {
+        struct Rows {
+            float4 a[2][2];  // A_main rows of tasks tid, tid + 128
+            float4 b[2];     // B_aux row (threads 0..15)
+        };
+        auto fetch_meta = [&](int id, Meta& m) {
+            m.id = id;
+            m.cnt = 0;
+            m.range = make_uint2(0u, 0u);
+            if (id >= 2 * n_tiles) return;
+            m.cnt = (int)hrec_count[id];
+            m.range = ranges[id >> 1];
+        };
+        auto fetch_rows = [&](int id, Rows& it) {
+            if (id >= 2 * n_tiles) return;
+            const int tile = id >> 1, half = id & 1;
+            const uint32_t tx0 = (uint32_t)(tile % tiles_x) * TILE, ty0 = (uint32_t)(tile / tiles_x) * TILE + 4 * half;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int task = tid + TC_THREADS * i;
-                const int y = task >> 6, ch = task & 63;
-                uint8_t* base = smem + SM_AMAIN;
-                const int kc = y * 2;
-                split_store(cur.a[i][0], base + canon_off(ch, kc, 128), base + canon_off(64 + ch, kc, 128));
-                split_store(cur.a[i][1], base + canon_off(ch, kc + 1, 128), base + canon_off(64 + ch, kc + 1, 128));
+            for (int i = 0; i < 2; ++i) {  // A_main: task = (row y, channel ch); consecutive lanes = consecutive channels
+                const int task = tid + TC_FRONT * i;
+                load_row8(dL_dpix_lf + (size_t)(task & 63) * HW, W, H, tx0, ty0 + (task >> 6), it.a[i][0], it.a[i][1]);
             }
-            if (tid < 16) {  // B_aux: rows {r,g,b,d}_hi, {r,g,b,d}_lo
-                const int c = tid & 3, y = tid >> 2;
-                uint8_t* base = smem + SM_BAUX;
-                const int kc = y * 2;
-                split_store(cur.b[0], base + canon_off(c, kc, 8), base + canon_off(4 + c, kc, 8));
-                split_store(cur.b[1], base + canon_off(c, kc + 1, 8), base + canon_off(4 + c, kc + 1, 8));
+            if (tid < 16) {  // B_aux: rows {r,g,b,d}
+                const int c = tid & 3;
+                load_row8(c < 3 ? dL_dpix + (size_t)c * HW : dL_dpix_depth, W, H, tx0, ty0 + (tid >> 2), it.b[0], it.b[1]);
             }
+        };
+        auto stream_of = [&](const Meta& it) {  // the item's half-record stream: the halves of a tile lie back to back
+            const size_t n_all = (size_t)(it.range.y - it.range.x);
+            return hrec_buf + ((size_t)2 * it.range.x + (size_t)(it.id & 1) * n_all) * HREC_FLOATS;
+        };
+        auto issue = [&](const float* src, int left, uint32_t stage) {  // thread 0: bulk copy of the next <= 64 records
+            const uint32_t bytes = (uint32_t)min(TB, left) * HREC_BYTES;
+            mbar_arrive_expect_tx(&raw_full[stage], bytes);
+            tma_bulk_g2s(smem + SM_RAW + stage * RAW_BYTES, src, bytes, &raw_full[stage]);
+        };
+        int popped = 0;  // thread 0: the id popped at the start of an item, published at its end (the atomic's round trip
+                         // then overlaps the item's batches instead of holding the other front warps at the barrier)
+        if (tid == 0) {
+            const int first = (int)atomicAdd(work_counter, 3u);
+            s_pop[0] = first;
+            s_pop[1] = first + 1;
+            popped = first + 2;
         }
-        __syncthreads();  // s_tile (the next item) is visible
-        fetch(s_tile, nxt);  // in flight during this item's batches
+        bar_named(1, TC_FRONT);
+        Meta cur, nxt, nn;  // items i, i + 1, i + 2
+        Rows cur_rows, nxt_rows;
+        fetch_meta(s_pop[0], cur);
+        fetch_rows(cur.id, cur_rows);
+        fetch_meta(s_pop[1], nxt);
+        bar_named(1, TC_FRONT);        // both ids have been read: the ring may be rewritten
+        if (tid == 0) s_pop[0] = popped;
+        uint32_t q = 0;                // batches this CTA has started: batch q uses raw stage / slot q & 1
+        bool first_in_flight = false;  // the item's first batch was requested during the previous item's last batch
+        int pop_slot = 0;
 
-        for (int q = 0; q < nbt; ++q) {
-            const int cnt = min(TB, cnt_all - q * TB);
-            uint8_t* raw = smem + SM_RAW;
-            mbar_wait(&raw_full, raw_phase);
-            raw_phase ^= 1u;
+        for (;;) {
+            if (cur.id >= 2 * n_tiles) break;
+            if (tid == 0) popped = (int)atomicAdd(work_counter, 1u);  // item i + 3, used from the end of this item on
+            const int half = cur.id & 1;
+            const int cnt_all = cur.cnt;
+            const int nbt = (cnt_all + TB - 1) / TB;
+            const float* stream = stream_of(cur);
+            // the stage of batch q was last read by the split of batch q - 2: free
+            if (tid == 0 && cnt_all > 0 && !first_in_flight) issue(stream, cnt_all, q & 1u);
+            bar_named(1, TC_FRONT);  // the id published at the end of the previous item is visible
+            fetch_meta(s_pop[pop_slot], nn);  // item i + 2: in flight during this item's and the next item's batches
+            fetch_rows(nxt.id, nxt_rows);     // in flight during this item's batches
+            pop_slot ^= 1;
 
-            // ---- split w / t into TF32 hi / lo tiles, canonical K-major [64 rec][32 px]
-            {
-                const int r = tid & 63, cb = tid >> 6;
-                if (tid < TB) *reinterpret_cast<float4*>(smem + SM_HDR + tid * 16) = *reinterpret_cast<const float4*>(raw + tid * HREC_BYTES);
+            for (int j = 0; j < nbt; ++j, ++q) {
+                const uint32_t s = q & 1u, use = q >> 1;
+                const int cnt = min(TB, cnt_all - j * TB);
+                // ---- request the batch after this one (of this item, or the first of the next): its stage was read by the
+                // split of batch q - 1, which every front thread has left (barrier below)
+                if (tid == 0) {
+                    if (j + 1 < nbt) issue(stream + (size_t)(j + 1) * TB * HREC_FLOATS, cnt_all - (j + 1) * TB, s ^ 1u);
+                    else if (nxt.cnt > 0) issue(stream_of(nxt), nxt.cnt, s ^ 1u);
+                }
+                // ---- the operand tiles are free once the previous batch's MMAs have completed
+                if (q > 0) {
+                    mbar_wait(&mma_done[s ^ 1u], ((q - 1) >> 1) & 1u);
+                    tc_fence_after();
+                }
+                if (j == 0) {  // the half's upstream gradients as MMA operands
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int c16 = cb + 2 * i;  // 0-7: w chunks, 8-15: t chunks
-                    const float4 x = *reinterpret_cast<const float4*>(raw + r * HREC_BYTES + 16 + c16 * 16);
-                    uint8_t* t = smem + SM_WT + (c16 >> 3) * 2 * WT_TILE + (c16 & 7) * (TB * 16) + r * 16;
-                    split_store(x, t, t + WT_TILE);
+                    for (int i = 0; i < 2; ++i) {
+                        const int task = tid + TC_FRONT * i;
+                        const int y = task >> 6, ch = task & 63;
+                        uint8_t* base = smem + SM_AMAIN;
+                        const int kc = y * 2;
+                        split_store(cur_rows.a[i][0], base + canon_off(ch, kc, 128), base + canon_off(64 + ch, kc, 128));
+                        split_store(cur_rows.a[i][1], base + canon_off(ch, kc + 1, 128), base + canon_off(64 + ch, kc + 1, 128));
+                    }
+                    if (tid < 16) {  // B_aux: rows {r,g,b,d}_hi, {r,g,b,d}_lo
+                        const int c = tid & 3, y = tid >> 2;
+                        uint8_t* base = smem + SM_BAUX;
+                        const int kc = y * 2;
+                        split_store(cur_rows.b[0], base + canon_off(c, kc, 8), base + canon_off(4 + c, kc, 8));
+                        split_store(cur_rows.b[1], base + canon_off(c, kc + 1, 8), base + canon_off(4 + c, kc + 1, 8));
+                    }
+                }
+                // ---- slot s (TMEM set, headers, count) is free once the drain has finished batch q - 2
+                if (q >= 2) mbar_wait(&slot_free[s], (use - 1) & 1u);
+                mbar_wait(&raw_full[s], use & 1u);
+
+                // ---- split w / t into TF32 hi / lo tiles, canonical K-major [64 rec][32 px]
+                {
+                    const uint8_t* raw = smem + SM_RAW + s * RAW_BYTES;
+                    const int r = tid & 63, cb = tid >> 6;
+                    if (tid < TB) *reinterpret_cast<float4*>(smem + SM_HDR + s * (TB * 16) + tid * 16) = *reinterpret_cast<const float4*>(raw + tid * HREC_BYTES);
+                    if (tid < TB) s_ids[s][tid] = *reinterpret_cast<const uint32_t*>(raw + tid * HREC_BYTES + 12);
+                    if (tid == 0) s_cnt[s] = cnt;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int c16 = cb + 2 * i;  // 0-7: w chunks, 8-15: t chunks
+                        const float4 x = *reinterpret_cast<const float4*>(raw + r * HREC_BYTES + 16 + c16 * 16);
+                        uint8_t* t = smem + SM_WT + (c16 >> 3) * 2 * WT_TILE + (c16 & 7) * (TB * 16) + r * 16;
+                        split_store(x, t, t + WT_TILE);
+                    }
+                }
+                fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+                bar_named(1, TC_FRONT);
+
+                if (tid == 0) {
+                    mbar_arrive(&meta_ready[s]);  // headers + count of slot s (release; the barrier above made them this thread's)
+                    tc_fence_after();
+                    const uint32_t acc_set = tmem + s * TMEM_SET;
+                    // descriptors differ between k-steps (and halves) only in the 14-bit start-address field (16-byte units)
+                    const uint64_t dBm0 = dBm_base + (uint64_t)(half * (1024 >> 4));
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {  // K = 8 pixels per instruction = two 16-byte chunks
+                        const uint32_t acc = ks > 0 ? 1u : 0u;
+                        const uint64_t kA = (uint64_t)(ks * ((2 * 128 * 16) >> 4)), kW = (uint64_t)(ks * ((2 * TB * 16) >> 4));
+                        const uint64_t kB = (uint64_t)(ks * ((2 * 128) >> 4));
+                        umma_tf32(acc_set + 0, dA_base + kA, dWh_base + kW, idesc_main, acc);
+                        umma_tf32(acc_set + 0, dA_base + kA, dWl_base + kW, idesc_main, 1u);
+                        umma_tf32(acc_set + 64, dWh_base + kW, dBa_base + kB, idesc_aux, acc);
+                        umma_tf32(acc_set + 64, dWl_base + kW, dBa_base + kB, idesc_aux, 1u);
+                        umma_tf32(acc_set + 72, dTh_base + kW, dBm0 + kB, idesc_aux, acc);
+                        umma_tf32(acc_set + 72, dTl_base + kW, dBm0 + kB, idesc_aux, 1u);
+                    }
+                    umma_commit(&mma_done[s]);
                 }
             }
-            fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
-            __syncthreads();
-
-            if (tid == 0) {
-                if (q + 1 < nbt) issue(q + 1);  // every thread has read the raw records: refill during the MMAs + epilogue
-                tc_fence_after();
-                // descriptors differ between k-steps (and halves) only in the 14-bit start-address field (16-byte units)
-                const uint64_t dA0 = dA_base, dBa0 = dBa_base;
-                const uint64_t dBm0 = dBm_base + (uint64_t)(half * (1024 >> 4));
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {  // K = 8 pixels per instruction = two 16-byte chunks
-                    const uint32_t acc = ks > 0 ? 1u : 0u;
-                    const uint64_t kA = (uint64_t)(ks * ((2 * 128 * 16) >> 4)), kW = (uint64_t)(ks * ((2 * TB * 16) >> 4));
-                    const uint64_t kB = (uint64_t)(ks * ((2 * 128) >> 4));
-                    umma_tf32(tmem + 0, dA0 + kA, dWh_base + kW, idesc_main, acc);
-                    umma_tf32(tmem + 0, dA0 + kA, dWl_base + kW, idesc_main, 1u);
-                    umma_tf32(tmem + 64, dWh_base + kW, dBa0 + kB, idesc_aux, acc);
-                    umma_tf32(tmem + 64, dWl_base + kW, dBa0 + kB, idesc_aux, 1u);
-                    umma_tf32(tmem + 72, dTh_base + kW, dBm0 + kB, idesc_aux, acc);
-                    umma_tf32(tmem + 72, dTl_base + kW, dBm0 + kB, idesc_aux, 1u);
-                }
-                umma_commit(&mma_done);
-            }
-            mbar_wait(&mma_done, mma_phase);
-            mma_phase ^= 1u;
+            first_in_flight = nbt > 0 && nxt.cnt > 0;
+            cur = nxt;
+            cur_rows = nxt_rows;
+            nxt = nn;
+            // s_pop[pop_slot] was last read after the barrier at the start of the PREVIOUS item, which every front thread
+            // has left (it passed this item's barrier); the next item's barrier publishes the new id
+            if (tid == 0) s_pop[pop_slot] = popped;
+        }
+        // ---- no more work: tell the drain (a count of -1 in the next slot, once the drain has left it)
+        if (tid == 0) {
+            const uint32_t s = q & 1u;
+            if (q >= 2) mbar_wait(&slot_free[s], ((q >> 1) - 1) & 1u);
+            s_cnt[s] = -1;
+            mbar_arrive(&meta_ready[s]);
+        }
+    } else {
+        // ============================================================ drain: TMEM -> reductions
+        const int dt = tid - TC_FRONT, dw = warp - 4;  // dw = TMEM lane quadrant (warp % 4)
+        float* relay = reinterpret_cast<float*>(smem + SM_RELAY);
+        for (uint32_t q = 0;; ++q) {
+            const uint32_t s = q & 1u, par = (q >> 1) & 1u;
+            mbar_wait(&meta_ready[s], par);
+            const int cnt = *reinterpret_cast<volatile int*>(&s_cnt[s]);
+            if (cnt < 0) break;
+            const uint8_t* hdr = smem + SM_HDR + s * (TB * 16);
+            mbar_wait(&mma_done[s], par);
             tc_fence_after();
 
-            // ---- drain TMEM.  Warp w reads TMEM lanes 32*(w%4) .. +31.
-            const uint32_t tb = tmem + ((uint32_t)(warp * 32) << 16);
+            // Warp dw reads TMEM lanes 32 * dw .. + 31 of accumulator set s.
+            const uint32_t tb = tmem + ((uint32_t)(dw * 32) << 16) + s * TMEM_SET;
             uint32_t va[32], vb[32], ax[8], mo[8];
             tmem_ld32(tb + 0, va);
             tmem_ld32(tb + 32, vb);
@@ -250,12 +329,10 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
             tmem_ld_wait();
             // Channel ch's sum is (g_hi row, warps 0-1) + (g_lo row, warps 2-3).  Each side hands the other half of its
             // 64 record columns over through shared memory and finishes its own half: warps 0-1 records 0-31, warps
-            // 2-3 records 32-63 -- 32 red.global.add per thread, all four warps busy.  The W/T operand tiles are free
-            // (the MMAs have completed) and serve as the relay: [128 threads][36 floats].
-            float* relay = reinterpret_cast<float*>(smem + SM_WT);
+            // 2-3 records 32-63.  Partners are thread dt and dt ^ 64: the two warps of a pair meet on their own barrier.
             {
-                float* rl = relay + tid * RELAY_PITCH;
-                if (warp < 2) {
+                float* rl = relay + dt * RELAY_PITCH;
+                if (dw < 2) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(rl + 4 * k) = make_uint4(vb[4 * k], vb[4 * k + 1], vb[4 * k + 2], vb[4 * k + 3]);
                 } else {
@@ -263,11 +340,12 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
                     for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(rl + 4 * k) = make_uint4(va[4 * k], va[4 * k + 1], va[4 * k + 2], va[4 * k + 3]);
                 }
             }
+            bar_named(2 + (dw & 1), 64);
             // colour / depth / moments: the M = 64 accumulators keep record 16*w + l on lane l < 16 of warp w
             if (lane < 16) {
-                const int r = 16 * warp + lane;
+                const int r = 16 * dw + lane;
                 if (r < cnt) {
-                    const float4 hd = *reinterpret_cast<const float4*>(smem + SM_HDR + r * 16);
+                    const float4 hd = *reinterpret_cast<const float4*>(hdr + r * 16);
                     const size_t id = (size_t)__float_as_uint(hd.w);
                     const float gx = hd.x, gy = hd.y;
                     red_add_f32(dL_dcolor + id * 3 + 0, __uint_as_float(ax[0]) + __uint_as_float(ax[4]));
@@ -284,41 +362,44 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
                                    Svv + gy * (gy * S0 - 2.f * Sv));  // slot 2 of the [2,2] conic gradient is unused: + 0
                 }
             }
-            __syncthreads();
             {
-                const int ch = (warp & 1) * 32 + lane;
-                const float* rl = relay + (tid ^ 64) * RELAY_PITCH;  // the partner thread holds the other half of channel ch
-                const int c0 = warp < 2 ? 0 : 32;  // first record column this thread finishes
+                const int ch = (dw & 1) * 32 + lane;
+                const float* rl = relay + (dt ^ 64) * RELAY_PITCH;  // the partner thread holds the other half of channel ch
+                const int c0 = dw < 2 ? 0 : 32;    // first record column this thread finishes
                 float fin[32];                     // channel ch of records c0 .. c0 + 31
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const float4 o = *reinterpret_cast<const float4*>(rl + 4 * k);
                     const float o4[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) fin[4 * k + e] = __uint_as_float(warp < 2 ? va[4 * k + e] : vb[4 * k + e]) + o4[e];
+                    for (int e = 0; e < 4; ++e) fin[4 * k + e] = __uint_as_float(dw < 2 ? va[4 * k + e] : vb[4 * k + e]) + o4[e];
                 }
+                bar_named(2 + (dw & 1), 64);  // both partners have read: the relay rows may be rewritten (next batch)
                 // Two channels per reduction: neighbouring lanes (channels 2i, 2i + 1) trade halves of their 32 records, so that
                 // the even lane finishes records 0-15 and the odd lane records 16-31 of the PAIR with red.global.add.v2 -- a warp
                 // instruction still covers two contiguous 128-byte rows, and the L2 takes twice the floats per request
                 // (tools/micro/red_bench.cu: 1.46 against 0.75 T float-adds/s for this access pattern).
                 const bool odd = lane & 1;
                 float* outp = dL_dlang_feat + (ch & ~1);
+                const int rc0 = c0 + (odd ? 16 : 0);
+                // the 16 ids up front (the reductions are compiler barriers: a load between them would wait out its latency)
+                uint32_t idq[16];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(&s_ids[s][rc0 + 4 * k]);
+                    idq[4 * k] = v.x; idq[4 * k + 1] = v.y; idq[4 * k + 2] = v.z; idq[4 * k + 3] = v.w;
+                }
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     const float send = odd ? fin[c] : fin[16 + c];
                     const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-                    const int rc = c0 + (odd ? 16 + c : c);
-                    if (rc < cnt) {
-                        const uint32_t id = __float_as_uint(*reinterpret_cast<const float*>(smem + SM_HDR + rc * 16 + 12));
-                        red_add_v2_f32(outp + (size_t)id * LF, odd ? recv : fin[c], odd ? fin[16 + c] : recv);
-                    }
+                    if (rc0 + c < cnt) red_add_v2_f32(outp + (size_t)idq[c] * LF, odd ? recv : fin[c], odd ? fin[16 + c] : recv);
                 }
             }
-            fence_proxy_async();
             tc_fence_before();
-            __syncthreads();  // TMEM, the operand tiles and this raw buffer are free again
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&slot_free[s]);  // this warp is done with TMEM set s, its headers and its count
         }
-        cur = nxt;
     }
     tc_fence_before();
     __syncthreads();
