@@ -109,7 +109,7 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
         for (int i = 0; i < 2; ++i) {
             mbar_init(&raw_full[i], 1);
             mbar_init(&meta_ready[i], 1);
-            mbar_init(&mma_done[i], 1);
+            mbar_init(&mma_done[i], 3);   // one commit per issuing thread (main / colour+depth / moments)
             mbar_init(&slot_free[i], 4);  // one arrival per drain warp
         }
         mbar_fence_init();
@@ -270,8 +270,10 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
                 fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
                 bar_named(1, TC_FRONT);
 
-                if (tid == 0) {
-                    mbar_arrive(&meta_ready[s]);  // headers + count of slot s (release; the barrier above made them this thread's)
+                // Three threads (lane 0 of warps 0-2) issue the batch's 24 MMAs -- eight each, one commit each: the issue is a
+                // few hundred single-thread instructions (descriptors through uniform registers) on the front's critical path
+                if (lane == 0 && warp < 3) {
+                    if (warp == 0) mbar_arrive(&meta_ready[s]);  // headers + count of slot s (release; the barrier above made them this thread's)
                     tc_fence_after();
                     const uint32_t acc_set = tmem + s * TMEM_SET;
                     // descriptors differ between k-steps (and halves) only in the 14-bit start-address field (16-byte units)
@@ -281,12 +283,16 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
                         const uint32_t acc = ks > 0 ? 1u : 0u;
                         const uint64_t kA = (uint64_t)(ks * ((2 * 128 * 16) >> 4)), kW = (uint64_t)(ks * ((2 * TB * 16) >> 4));
                         const uint64_t kB = (uint64_t)(ks * ((2 * 128) >> 4));
-                        umma_tf32(acc_set + 0, dA_base + kA, dWh_base + kW, idesc_main, acc);
-                        umma_tf32(acc_set + 0, dA_base + kA, dWl_base + kW, idesc_main, 1u);
-                        umma_tf32(acc_set + 64, dWh_base + kW, dBa_base + kB, idesc_aux, acc);
-                        umma_tf32(acc_set + 64, dWl_base + kW, dBa_base + kB, idesc_aux, 1u);
-                        umma_tf32(acc_set + 72, dTh_base + kW, dBm0 + kB, idesc_aux, acc);
-                        umma_tf32(acc_set + 72, dTl_base + kW, dBm0 + kB, idesc_aux, 1u);
+                        if (warp == 0) {
+                            umma_tf32(acc_set + 0, dA_base + kA, dWh_base + kW, idesc_main, acc);
+                            umma_tf32(acc_set + 0, dA_base + kA, dWl_base + kW, idesc_main, 1u);
+                        } else if (warp == 1) {
+                            umma_tf32(acc_set + 64, dWh_base + kW, dBa_base + kB, idesc_aux, acc);
+                            umma_tf32(acc_set + 64, dWl_base + kW, dBa_base + kB, idesc_aux, 1u);
+                        } else {
+                            umma_tf32(acc_set + 72, dTh_base + kW, dBm0 + kB, idesc_aux, acc);
+                            umma_tf32(acc_set + 72, dTl_base + kW, dBm0 + kB, idesc_aux, 1u);
+                        }
                     }
                     umma_commit(&mma_done[s]);
                 }
