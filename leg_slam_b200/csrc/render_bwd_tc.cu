@@ -12,7 +12,9 @@
 // operands split into hi + lo parts (hi = the 19 bits kind::tf32 reads, lo = the exact remainder) so the result
 // keeps fp32-level accuracy:
 //
-//   main  D[128 x 64]  = A_main[128 x 32] * W^T[32 x 64]      rows 0-63 = g_hi[ch], rows 64-127 = g_lo[ch];
+//   main  D[128 x 64]  = A_main[128 x 32] * W^T[32 x 64]      rows 0-63 = g_hi[ch], rows 64-127 = g_lo[ch]; A_main is
+//                                                             constant over a work item and lives in TENSOR MEMORY
+//                                                             (written once per item with tcgen05.st);
 //                                                             two MMAs per k-step (W_hi, W_lo) give all four
 //                                                             hi/lo products; TMEM lane = channel, so one
 //                                                             warp's red.global.add covers 128 contiguous bytes
@@ -42,19 +44,22 @@ constexpr int TC_FRONT = 128;      // threads of the front half (and of the drai
 constexpr int HREC_BYTES = HREC_FLOATS * 4;
 constexpr int RAW_BYTES = TB * HREC_BYTES;         // 17408
 constexpr int WT_TILE = TB * 32 * 4;               // 8192: one [64 rec x 32 px] TF32 tile
-constexpr int AMAIN_HALF = 128 * 32 * 4;           // 16384
 constexpr int RELAY_PITCH = 36;                    // floats per thread in the drain's relay (16-byte aligned, spreads banks)
 constexpr int SM_RAW = 0;                          // two stages
 constexpr int SM_WT = SM_RAW + 2 * RAW_BYTES;      // W_hi, W_lo, T_hi, T_lo
-constexpr int SM_AMAIN = SM_WT + 4 * WT_TILE;      // [128 x 32]: the work item's half
-constexpr int SM_BAUX = SM_AMAIN + AMAIN_HALF;     // [8 x 32]
+constexpr int SM_BAUX = SM_WT + 4 * WT_TILE;       // [8 x 32]
 constexpr int SM_BMOM = SM_BAUX + 1024;            // [2 halves][8 x 32]
 constexpr int SM_HDR = SM_BMOM + 2 * 1024;         // [2 slots][64] float4 record headers
 constexpr int SM_RELAY = SM_HDR + 2 * TB * 16;     // [128 drain threads][36 floats]
-constexpr int SM_TOTAL = SM_RELAY + TC_FRONT * RELAY_PITCH * 4;  // 107520: two CTAs per SM
+constexpr int SM_TOTAL = SM_RELAY + TC_FRONT * RELAY_PITCH * 4;  // 91136: two CTAs per SM
 constexpr int TC_CTAS = 2;
-constexpr int TMEM_SET = 128;                      // columns per accumulator set: main 0-63, aux 64-71, mom 72-79
-constexpr int TMEM_COLS = 2 * TMEM_SET;
+// tensor memory, 256 columns: two accumulator sets (main [128 x 64] + colour/depth [64 x 8] + moments [64 x 8]) and the work
+// item's A operand [128 x 32] (rows 0-63 g_hi[ch], rows 64-127 g_lo[ch]; one column per pixel of the half)
+constexpr int TM_MAIN = 0;      // + 64 * set
+constexpr int TM_AUX = 128;     // + 16 * set
+constexpr int TM_MOM = 136;     // + 16 * set
+constexpr int TM_A = 192;
+constexpr int TMEM_COLS = 256;
 
 __device__ __forceinline__ void bar_named(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
@@ -133,7 +138,6 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
         const uint32_t idesc_main = make_idesc_tf32(128, TB);
         const uint32_t idesc_aux = make_idesc_tf32(64, 8);
         const uint32_t smem_base = smem_u32(smem);
-        const uint64_t dA_base = make_desc(smem_base + SM_AMAIN, 128 * 16, 128);
         const uint64_t dWh_base = make_desc(smem_base + SM_WT, TB * 16, 128), dWl_base = make_desc(smem_base + SM_WT + WT_TILE, TB * 16, 128);
         const uint64_t dTh_base = make_desc(smem_base + SM_WT + 2 * WT_TILE, TB * 16, 128);
         const uint64_t dTl_base = make_desc(smem_base + SM_WT + 3 * WT_TILE, TB * 16, 128);
@@ -148,7 +152,7 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
             uint2 range;
         };
         struct Rows {
-            float4 a[2][2];  // A_main rows of tasks tid, tid + 128
+            float4 a[4][2];  // this thread's A_main row: channel tid & 63 over the half's 4 x 8 pixels
             float4 b[2];     // B_aux row (threads 0..15)
         };
         auto fetch_meta = [&](int id, Meta& m) {
@@ -164,10 +168,8 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
             const int tile = id >> 1, half = id & 1;
             const uint32_t tx0 = (uint32_t)(tile % tiles_x) * TILE, ty0 = (uint32_t)(tile / tiles_x) * TILE + 4 * half;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {  // A_main: task = (row y, channel ch); consecutive lanes = consecutive channels
-                const int task = tid + TC_FRONT * i;
-                load_row8(dL_dpix_lf + (size_t)(task & 63) * HW, W, H, tx0, ty0 + (task >> 6), it.a[i][0], it.a[i][1]);
-            }
+            for (int y = 0; y < 4; ++y)  // consecutive lanes = consecutive channels (planes); 32 contiguous bytes per lane and row
+                load_row8(dL_dpix_lf + (size_t)(tid & 63) * HW, W, H, tx0, ty0 + y, it.a[y][0], it.a[y][1]);
             if (tid < 16) {  // B_aux: rows {r,g,b,d}
                 const int c = tid & 3;
                 load_row8(c < 3 ? dL_dpix + (size_t)c * HW : dL_dpix_depth, W, H, tx0, ty0 + (tid >> 2), it.b[0], it.b[1]);
@@ -231,15 +233,23 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
                     tc_fence_after();
                 }
                 if (j == 0) {  // the half's upstream gradients as MMA operands
+                    // A_main into tensor memory: this thread's row (TMEM lane tid) is channel tid & 63, hi part for rows 0-63,
+                    // lo part for rows 64-127; column k = pixel k of the half
+                    uint32_t arow[32];
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int task = tid + TC_FRONT * i;
-                        const int y = task >> 6, ch = task & 63;
-                        uint8_t* base = smem + SM_AMAIN;
-                        const int kc = y * 2;
-                        split_store(cur_rows.a[i][0], base + canon_off(ch, kc, 128), base + canon_off(64 + ch, kc, 128));
-                        split_store(cur_rows.a[i][1], base + canon_off(ch, kc + 1, 128), base + canon_off(64 + ch, kc + 1, 128));
+                    for (int y = 0; y < 4; ++y) {
+                        float4 h0, l0, h1, l1;
+                        split_trunc4(cur_rows.a[y][0], h0, l0);
+                        split_trunc4(cur_rows.a[y][1], h1, l1);
+                        const float4 p0 = tid < 64 ? h0 : l0, p1 = tid < 64 ? h1 : l1;
+                        arow[8 * y + 0] = __float_as_uint(p0.x); arow[8 * y + 1] = __float_as_uint(p0.y);
+                        arow[8 * y + 2] = __float_as_uint(p0.z); arow[8 * y + 3] = __float_as_uint(p0.w);
+                        arow[8 * y + 4] = __float_as_uint(p1.x); arow[8 * y + 5] = __float_as_uint(p1.y);
+                        arow[8 * y + 6] = __float_as_uint(p1.z); arow[8 * y + 7] = __float_as_uint(p1.w);
                     }
+                    tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + TM_A, arow);
+                    tmem_st_wait();
+                    tc_fence_before();  // ordered before the MMAs through the barrier below
                     if (tid < 16) {  // B_aux: rows {r,g,b,d}_hi, {r,g,b,d}_lo
                         const int c = tid & 3, y = tid >> 2;
                         uint8_t* base = smem + SM_BAUX;
@@ -275,23 +285,22 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
                 if (lane == 0 && warp < 3) {
                     if (warp == 0) mbar_arrive(&meta_ready[s]);  // headers + count of slot s (release; the barrier above made them this thread's)
                     tc_fence_after();
-                    const uint32_t acc_set = tmem + s * TMEM_SET;
                     // descriptors differ between k-steps (and halves) only in the 14-bit start-address field (16-byte units)
                     const uint64_t dBm0 = dBm_base + (uint64_t)(half * (1024 >> 4));
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {  // K = 8 pixels per instruction = two 16-byte chunks
+                    for (int ks = 0; ks < 4; ++ks) {  // K = 8 pixels per instruction = two 16-byte chunks = 8 TMEM columns of A
                         const uint32_t acc = ks > 0 ? 1u : 0u;
-                        const uint64_t kA = (uint64_t)(ks * ((2 * 128 * 16) >> 4)), kW = (uint64_t)(ks * ((2 * TB * 16) >> 4));
+                        const uint64_t kW = (uint64_t)(ks * ((2 * TB * 16) >> 4));
                         const uint64_t kB = (uint64_t)(ks * ((2 * 128) >> 4));
                         if (warp == 0) {
-                            umma_tf32(acc_set + 0, dA_base + kA, dWh_base + kW, idesc_main, acc);
-                            umma_tf32(acc_set + 0, dA_base + kA, dWl_base + kW, idesc_main, 1u);
+                            umma_tf32_ts(tmem + TM_MAIN + 64 * s, tmem + TM_A + 8 * ks, dWh_base + kW, idesc_main, acc);
+                            umma_tf32_ts(tmem + TM_MAIN + 64 * s, tmem + TM_A + 8 * ks, dWl_base + kW, idesc_main, 1u);
                         } else if (warp == 1) {
-                            umma_tf32(acc_set + 64, dWh_base + kW, dBa_base + kB, idesc_aux, acc);
-                            umma_tf32(acc_set + 64, dWl_base + kW, dBa_base + kB, idesc_aux, 1u);
+                            umma_tf32(tmem + TM_AUX + 16 * s, dWh_base + kW, dBa_base + kB, idesc_aux, acc);
+                            umma_tf32(tmem + TM_AUX + 16 * s, dWl_base + kW, dBa_base + kB, idesc_aux, 1u);
                         } else {
-                            umma_tf32(acc_set + 72, dTh_base + kW, dBm0 + kB, idesc_aux, acc);
-                            umma_tf32(acc_set + 72, dTl_base + kW, dBm0 + kB, idesc_aux, 1u);
+                            umma_tf32(tmem + TM_MOM + 16 * s, dTh_base + kW, dBm0 + kB, idesc_aux, acc);
+                            umma_tf32(tmem + TM_MOM + 16 * s, dTl_base + kW, dBm0 + kB, idesc_aux, 1u);
                         }
                     }
                     umma_commit(&mma_done[s]);
@@ -326,12 +335,12 @@ render_bwd_chan_tc_kernel(const uint2* __restrict__ ranges, int W, int H, int ti
             tc_fence_after();
 
             // Warp dw reads TMEM lanes 32 * dw .. + 31 of accumulator set s.
-            const uint32_t tb = tmem + ((uint32_t)(dw * 32) << 16) + s * TMEM_SET;
+            const uint32_t tb = tmem + ((uint32_t)(dw * 32) << 16);
             uint32_t va[32], vb[32], ax[8], mo[8];
-            tmem_ld32(tb + 0, va);
-            tmem_ld32(tb + 32, vb);
-            tmem_ld8(tb + 64, ax);
-            tmem_ld8(tb + 72, mo);
+            tmem_ld32(tb + TM_MAIN + 64 * s, va);
+            tmem_ld32(tb + TM_MAIN + 64 * s + 32, vb);
+            tmem_ld8(tb + TM_AUX + 16 * s, ax);
+            tmem_ld8(tb + TM_MOM + 16 * s, mo);
             tmem_ld_wait();
             // Channel ch's sum is (g_hi row, warps 0-1) + (g_lo row, warps 2-3).  Each side hands the other half of its
             // 64 record columns over through shared memory and finishes its own half: warps 0-1 records 0-31, warps
