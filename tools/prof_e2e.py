@@ -17,7 +17,10 @@ import bench  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--tiny", action="store_true", help="2000 Gaussians at 64x48: the device work vanishes, what is left is the host's cost per step")
     args = ap.parse_args()
+    if args.tiny:
+        bench.P_GAUSS, bench.WIDTH, bench.HEIGHT = 2000, 64, 48
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
     sc, cam, up = bench.make_workload(0, 1, dev)
