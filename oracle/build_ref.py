@@ -125,6 +125,78 @@ def load_loss():
     return mod
 
 
+UTILS_MOD = "ref_utils"
+UTILS_SO = os.path.join(OUT, UTILS_MOD + ".so")
+
+
+def build_utils(force=False, verbose=True):
+    """The UNMODIFIED reference helper headers include/general_utils.h (inverse_sigmoid, build_rotation) and include/sh_utils.h
+    (eval_sh, RGB2SH, SH2RGB) -- header-only libtorch -- behind oracle/ref_utils_wrap.cpp -> oracle/_ref/ref_utils.so (python
+    module `ref_utils`).  Pins the numeric helpers of SURVEY.md 8f rows 1 and 4 and of the GaussianRenderer counterpart."""
+    if os.path.exists(UTILS_SO) and not force:
+        return UTILS_SO
+    if not os.path.isdir(LOSS_REF_INC):
+        raise RuntimeError("reference tree not present (GPU box?) and no prebuilt " + UTILS_SO)
+    os.makedirs(OUT, exist_ok=True)
+    inc, lib = _torch_paths()
+    pyinc = sysconfig.get_paths()["include"]
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=" + UTILS_MOD, "-DTORCH_API_INCLUDE_EXTENSION_H",
+           "-D_GLIBCXX_USE_CXX11_ABI=1", "-I" + LOSS_REF_INC, "-I" + pyinc] + ["-I" + p for p in inc] + \
+          [os.path.join(HERE, "ref_utils_wrap.cpp"), "-o", UTILS_SO] + ["-L" + p for p in lib] + \
+          ["-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python"] + ["-Wl,-rpath," + p for p in lib]
+    if verbose:
+        print("[build_ref]", " ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return UTILS_SO
+
+
+def load_utils():
+    import importlib.util
+    import torch  # noqa: F401
+    if not os.path.exists(UTILS_SO):
+        raise FileNotFoundError(UTILS_SO + " missing: run `python oracle/build_ref.py` where /root/reference exists")
+    spec = importlib.util.spec_from_file_location(UTILS_MOD, UTILS_SO)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+PLY_REF = "/root/reference/third_party/tinyply"
+PLY_SO = os.path.join(OUT, "ref_ply.so")
+
+
+def build_ply(force=False, verbose=True):
+    """The UNMODIFIED reference .ply library (third_party/tinyply/tinyply.cpp + tinyply.h, plain C++) + our C entry points
+    oracle/ref_ply_wrap.cpp, which issue savePly's / loadPly's tinyply calls -> oracle/_ref/ref_ply.so (ctypes, CPU only).
+    Oracle for SURVEY.md 8f row 3 (.ply checkpoints)."""
+    if os.path.exists(PLY_SO) and not force:
+        return PLY_SO
+    if not os.path.isdir(PLY_REF):
+        raise RuntimeError("reference tree not present (GPU box?) and no prebuilt " + PLY_SO)
+    os.makedirs(OUT, exist_ok=True)
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I" + PLY_REF, os.path.join(PLY_REF, "tinyply.cpp"),
+           os.path.join(HERE, "ref_ply_wrap.cpp"), "-o", PLY_SO]
+    if verbose:
+        print("[build_ref]", " ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return PLY_SO
+
+
+def load_ply():
+    import ctypes
+    if not os.path.exists(PLY_SO):
+        raise FileNotFoundError(PLY_SO + " missing: run `python oracle/build_ref.py` where /root/reference exists")
+    lib = ctypes.CDLL(PLY_SO)
+    fp = ctypes.c_void_p
+    lib.ref_ply_write.restype = ctypes.c_int
+    lib.ref_ply_write.argtypes = [ctypes.c_char_p] + [ctypes.c_int] * 4 + [fp] * 8
+    lib.ref_ply_count.restype = ctypes.c_longlong
+    lib.ref_ply_count.argtypes = [ctypes.c_char_p]
+    lib.ref_ply_read.restype = ctypes.c_int
+    lib.ref_ply_read.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int] + [fp] * 7
+    return lib
+
+
 KNN_REF = "/root/reference/third_party/simple-knn"
 KNN_SO = os.path.join(OUT, "ref_simple_knn.so")
 
@@ -174,3 +246,5 @@ if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
     print(build_knn(force="--force" in sys.argv))
     print(build_loss(force="--force" in sys.argv))
+    print(build_ply(force="--force" in sys.argv))
+    print(build_utils(force="--force" in sys.argv))

@@ -6,11 +6,29 @@ resetOpacity :567-575 / replaceTensorToOptimizer :577-595, general_utils.h:25-53
 and the max_radii2D update of src/gaussian_mapper.cpp:739-742.  Runs on CPU or CUDA tensors.  Only tests/ may
 import it (the package never does).
 
-Parity unpinned: the reference's GaussianModel needs Eigen / OpenCV / Sophus / tinyply, none of which exist in this
-image, so it cannot be compiled here and it ships no fixtures for this path.  This restatement is checked by
-construction (same libtorch ops in the same order) and by its own invariants (tests/test_densify.py).
+Parity partly pinned: the reference's GaussianModel cannot be compiled here (gaussian_model.h pulls in Sophus -> Eigen and
+OpenCV, neither exists in this image) and it ships no fixtures for this path, so the SEQUENCE of tensor operations below is a
+restatement checked by construction (same libtorch ops in the same order) and by its own invariants (tests/test_densify.py).
+Its numeric helpers -- inverse_sigmoid, build_rotation -- are held bit-identical to the unmodified reference header
+(include/general_utils.h compiled into oracle/_ref/ref_utils.so; tests/test_reference_utils.py).
 """
 import torch
+
+
+# The two helpers below are pinned against the UNMODIFIED reference header (oracle/_ref/ref_utils.so,
+# tests/test_reference_utils.py): bit-identical on the same device.
+def inverse_sigmoid(x):
+    """general_utils::inverse_sigmoid (include/general_utils.h:25-27)."""
+    return torch.log(x / (1 - x))
+
+
+def build_rotation(r):
+    """general_utils::build_rotation (include/general_utils.h:29-60): quaternion (r, x, y, z), normalised here, -> [n, 3, 3]."""
+    q = r / torch.sqrt(r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1] + r[:, 2] * r[:, 2] + r[:, 3] * r[:, 3]).unsqueeze(1)
+    r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    return torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                        2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                        2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], dim=1).view(-1, 3, 3)
 
 PARAMS = ("xyz", "features_dc", "features_rest", "lang_feat", "opacity", "scaling", "rotation")
 
@@ -78,12 +96,7 @@ class Model:
         sel = torch.logical_and(sel, self._scale().max(dim=1).values > self.percent_dense * extent)
         stds = self._scale()[sel].repeat(N, 1)
         samples = normal01(stds.shape[0]) * stds
-        q = self.p["rotation"][sel]
-        q = q / torch.sqrt((q * q).sum(dim=1, keepdim=True))
-        r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
-        R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
-                         2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
-                         2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], dim=1).view(-1, 3, 3).repeat(N, 1, 1)
+        R = build_rotation(self.p["rotation"][sel]).repeat(N, 1, 1)
         new = {k: self.p[k][sel].repeat(*([N] + [1] * (self.p[k].dim() - 1))) for k in PARAMS}
         new["xyz"] = torch.bmm(R, samples.unsqueeze(-1)).squeeze(-1) + self.p["xyz"][sel].repeat(N, 1)
         new["scaling"] = torch.log(self._scale()[sel].repeat(N, 1) / (0.8 * N))
@@ -124,7 +137,7 @@ class Model:
         rots = torch.zeros(n, 4, device=dev)
         rots[:, 0] = 1
         x = 0.1 * torch.ones(n, 1, dtype=torch.float32, device=dev)
-        opac = torch.log(x / (1 - x))
+        opac = inverse_sigmoid(x)
         new_exist = torch.full((n,), iteration, dtype=torch.int32, device=dev)
         new = dict(xyz=new_points, features_dc=features[:, :, 0:1].transpose(1, 2).contiguous(),
                    features_rest=features[:, :, 1:].transpose(1, 2).contiguous(), lang_feat=lang.contiguous(),
@@ -135,6 +148,6 @@ class Model:
     def reset_opacity(self):
         op = torch.sigmoid(self.p["opacity"])
         x = torch.min(op, torch.ones_like(op * 0.01))
-        self.p["opacity"] = torch.log(x / (1 - x))
+        self.p["opacity"] = inverse_sigmoid(x)
         self.m["opacity"] = torch.zeros_like(self.p["opacity"])
         self.v["opacity"] = torch.zeros_like(self.p["opacity"])

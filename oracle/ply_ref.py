@@ -4,8 +4,11 @@ write_ply follows GaussianModel::savePly (/root/reference/src/gaussian_model.cpp
 transpose(1,2).flatten(1) of f_dc / f_rest, zero normals) with tinyply's binary writer (header lines `property float
 <name>`, little-endian float32 records).  read_ply follows the reference's Python reader
 (/root/reference/eval/gaussian_model.py:58-111: properties looked up BY NAME, f_rest reshaped (P, 3, K) then
-transposed).  Parity unpinned: tinyply is not vendored in /root/reference (third_party is fetched by its build
-scripts), plyfile is not installed here, and the reference holds no .ply fixture."""
+transposed).  PINNED (tests/test_ply_io.py::test_restatement_pinned_by_the_reference_tinyply_cpu): the file written here is
+byte-identical to the one the reference's own tinyply (third_party/tinyply, compiled unmodified into oracle/_ref/ref_ply.so)
+writes for savePly's call sequence, and the reference's reader -- tinyply with loadPly's property requests and reshapes
+(gaussian_model.cpp:882-956) -- returns the same tensors.  What stays restated is the sequence of tinyply calls itself
+(oracle/ref_ply_wrap.cpp, cited line by line): GaussianModel cannot be compiled here (Eigen / OpenCV / Sophus)."""
 import numpy as np
 
 

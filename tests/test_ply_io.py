@@ -42,6 +42,65 @@ def test_restatement_roundtrip_and_header_cpu(tmp_path):
     np.testing.assert_array_equal(rec[:, 9 + 15], m["features_rest"][:, 0, 1])
 
 
+@pytest.fixture(scope="module")
+def ref_ply():
+    """The reference's own tinyply behind savePly's / loadPly's call sequence (oracle/ref_ply_wrap.cpp -> oracle/_ref/ref_ply.so)."""
+    import build_ref
+    try:
+        if os.path.isdir(build_ref.PLY_REF):
+            build_ref.build_ply(verbose=False)
+        return build_ref.load_ply()
+    except FileNotFoundError as e:
+        pytest.skip(str(e))
+
+
+def _ptr(a):
+    import ctypes
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _ref_write(lib, path, m):
+    P = m["xyz"].shape[0]
+    dc = np.ascontiguousarray(np.transpose(m["features_dc"], (0, 2, 1)).reshape(P, -1))      # savePly: transpose(1,2).flatten(1)
+    rest = np.ascontiguousarray(np.transpose(m["features_rest"], (0, 2, 1)).reshape(P, -1))
+    normals = np.zeros_like(m["xyz"])
+    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (m["xyz"], normals, dc, rest, m["lang_feat"], m["opacity"], m["scaling"],
+                                                                m["rotation"])]
+    assert lib.ref_ply_write(str(path).encode(), P, dc.shape[1], rest.shape[1], m["lang_feat"].shape[1], *[_ptr(a) for a in arrs]) == 0
+
+
+def _ref_read(lib, path, max_sh_degree=3, n_lf=64):
+    """loadPly's requests through tinyply, then its from_blob(...).transpose(1, 2) (gaussian_model.cpp:946-956)."""
+    P = int(lib.ref_ply_count(str(path).encode()))
+    assert P >= 0
+    n_rest = ((max_sh_degree + 1) ** 2 - 1) * 3
+    z = lambda *s: np.zeros(s, np.float32)  # noqa: E731
+    xyz, dc, rest, lf, op, sc, rot = z(P, 3), z(P, 3), z(P, n_rest), z(P, n_lf), z(P, 1), z(P, 3), z(P, 4)
+    assert lib.ref_ply_read(str(path).encode(), max_sh_degree, n_lf, *[_ptr(a) for a in (xyz, dc, rest, lf, op, sc, rot)]) == 0
+    return dict(xyz=xyz, features_dc=np.ascontiguousarray(dc.reshape(P, 3, 1).transpose(0, 2, 1)),
+                features_rest=np.ascontiguousarray(rest.reshape(P, 3, n_rest // 3).transpose(0, 2, 1)), lang_feat=lf, opacity=op,
+                scaling=sc, rotation=rot)
+
+
+@pytest.mark.parametrize("P", [1, 37, 5003])
+def test_restatement_pinned_by_the_reference_tinyply_cpu(tmp_path, ref_ply, P):
+    """SURVEY.md 8f row 3 oracle pin: the numpy restatement (oracle/ply_ref.py) writes, byte for byte, the file the reference's
+    own tinyply writes for savePly's call sequence, and the reference's reader (tinyply + loadPly's property requests and
+    reshapes) returns exactly the tensors that went in -- from either file."""
+    m = _model(P, seed=P)
+    a, b = tmp_path / "restated.ply", tmp_path / "tinyply.ply"
+    PR.write_ply(a, m["xyz"], m["features_dc"], m["features_rest"], m["lang_feat"], m["opacity"], m["scaling"], m["rotation"])
+    _ref_write(ref_ply, b, m)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    for path in (a, b):
+        back = _ref_read(ref_ply, path)
+        for k in m:
+            np.testing.assert_array_equal(back[k], m[k], err_msg=k)
+    restated = PR.read_ply(b)   # and the restated reader agrees with the reference's on the reference-written file
+    for k in m:
+        np.testing.assert_array_equal(restated[k], m[k], err_msg=k)
+
+
 def test_column_table_and_header_parser_cpu(tmp_path):
     """Host logic of leg_slam_b200.ply_io without a GPU: the column table is the reference's property order and the
     header parser reads what the restated writer writes (plus the optimizer comments)."""
@@ -72,7 +131,7 @@ def dev():
 
 
 @pytest.mark.gpu
-def test_save_matches_reference_format_and_loads_back(tmp_path, dev):
+def test_save_matches_reference_format_and_loads_back(tmp_path, dev, ref_ply):
     from leg_slam_b200 import ply_io
     m = _model(5003, seed=2)
     t = {k: torch.from_numpy(v).to(dev) for k, v in m.items()}
@@ -80,7 +139,11 @@ def test_save_matches_reference_format_and_loads_back(tmp_path, dev):
     ply_io.save_ply(ours, t)
     PR.write_ply(ref, m["xyz"], m["features_dc"], m["features_rest"], m["lang_feat"], m["opacity"], m["scaling"], m["rotation"])
     assert open(ours, "rb").read() == open(ref, "rb").read()      # byte-identical files
-    back = PR.read_ply(ours)                                      # the reference's reader logic on our file
+    _ref_write(ref_ply, tmp_path / "tinyply.ply", m)              # ... and identical to what the reference's tinyply writes
+    assert open(ours, "rb").read() == open(tmp_path / "tinyply.ply", "rb").read()
+    for k, v in _ref_read(ref_ply, ours).items():                 # the reference's reader (tinyply + loadPly's requests) on our file
+        np.testing.assert_array_equal(v, m[k], err_msg=k)
+    back = PR.read_ply(ours)                                      # the reference's Python reader logic on our file
     for k in m:
         np.testing.assert_array_equal(back[k], m[k], err_msg=k)
     params, ea, eas, steps = ply_io.load_ply(ref, dev)            # our loader on a reference-format file
@@ -90,7 +153,7 @@ def test_save_matches_reference_format_and_loads_back(tmp_path, dev):
 
 
 @pytest.mark.gpu
-def test_checkpoint_with_optimizer_state_resumes(tmp_path, dev):
+def test_checkpoint_with_optimizer_state_resumes(tmp_path, dev, ref_ply):
     from leg_slam_b200 import ply_io
     m = _model(1201, seed=4)
     t = {k: torch.from_numpy(v).to(dev) for k, v in m.items()}
@@ -103,6 +166,8 @@ def test_checkpoint_with_optimizer_state_resumes(tmp_path, dev):
     back = PR.read_ply(path)   # still a valid reference-format file: extra properties are ignored by name lookup
     for k in m:
         np.testing.assert_array_equal(back[k], m[k], err_msg=k)
+    for k, v in _ref_read(ref_ply, path).items():   # the reference's tinyply skips the comments and the extra properties too
+        np.testing.assert_array_equal(v, m[k], err_msg=k)
     p2, ea2, eas2, steps2 = ply_io.load_ply(path, dev)
     assert steps2 == steps
     for k in t:
