@@ -177,6 +177,34 @@ def test_quantised_depths_long_runs_of_equal_keys(dev, ref_mod):
     assert out["R"] > 0
 
 
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 128, 129, 257, 700])
+def test_translucent_stack_hits_the_channel_kernels_batch_boundaries(n, dev, ref_mod):
+    """n translucent Gaussians stacked over the same few tiles, none terminating the pixel: every (tile, half) work item of
+    the backward's channel kernel then holds about n half-records -- below, at and just above its 64-record batches, up to a
+    dozen batches in one item -- and a 24 x 16 image gives fewer work items than resident CTAs.  Whole forward + backward
+    against the compiled reference."""
+    cs = cases.make_case("sh3_lf", dev)
+    g = torch.Generator().manual_seed(900 + n)
+    V = cs["viewmatrix"]  # p_view = p_world @ V[:3,:3] + V[3,:3]
+    W, H = 24, 16
+    pv = torch.zeros(n, 3)
+    pv[:, 0] = (torch.rand(n, generator=g) - 0.5) * 0.6          # spread over the middle tiles (fx = W / 2 = 12 px per unit at z = 1)
+    pv[:, 1] = (torch.rand(n, generator=g) - 0.5) * 0.4
+    pv[:, 2] = 2.0 + torch.rand(n, generator=g)                  # depths 2 .. 3
+    pv = pv.to(dev)
+    cs.update(P=n, W=W, H=H, means3D=((pv - V[3, :3]) @ torch.linalg.inv(V[:3, :3])).contiguous(),
+              opacities=torch.full((n, 1), 0.012, device=dev),  # alpha <= 0.012 >= 1/255 near the centre: 0.988^700 > 1e-4, nobody stops
+              scales=(0.25 + 0.2 * torch.rand(n, 3, generator=g)).to(dev), rotations=torch.nn.functional.normalize(
+                  torch.randn(n, 4, generator=g), dim=1).to(dev),
+              shs=(torch.randn(n, 16, 3, generator=g) * 0.3).to(dev), lang_feats=torch.randn(n, 64, generator=g).to(dev),
+              dL_dcolor=(torch.randn(3, H, W, generator=g) / (H * W)).to(dev), dL_dlf=(torch.randn(64, H, W, generator=g) / (H * W)).to(dev),
+              dL_ddepth=(torch.randn(1, H, W, generator=g) / (H * W)).to(dev))
+    # same intrinsics family as the case (FoV 90 degrees): only the image size changes
+    out = _compare_with_reference_live(cs, ref_mod)
+    assert out["R"] >= n  # every Gaussian lands in at least one tile
+    assert int(out["n_contrib"].max()) >= min(n, 60)
+
+
 # ---------------------------------------------------------------------------- edge cases
 def test_empty_and_all_culled(dev):
     from leg_slam_b200 import rasterize_points as rp
