@@ -24,13 +24,15 @@
 // Persistent CTAs of 256 threads, 2 per SM, take (tile, pixel-warp half) work items from a counter and run a two-stage
 // pipeline over batches of 64 records:
 //   front (warps 0-3)  TMA bulk copy of the raw records (two stages, requested one batch ahead -- across work items too),
-//                      split of w / t into hi / lo tiles in the canonical K-major layout, 24 MMAs issued by one thread into
-//                      one of two TMEM accumulator sets;
+//                      split of w / t into hi / lo tiles in the canonical K-major layout, 24 MMAs issued by three threads
+//                      (main / colour + depth / moments) into one of two TMEM accumulator sets;
 //   drain (warps 4-7)  TMEM -> registers, hi-row and lo-row warps swap halves of their record columns through shared memory
 //                      (each sum is ONE red per record and channel pair, 16 red.v2 per thread), 16 lanes per warp finish
 //                      colour / depth / moments.
 // The drain of batch q runs under the copy + split + MMAs of batch q + 1 (mbarriers: raw_full, meta_ready, mma_done,
-// slot_free); round 1-2's kernel ran the two halves back to back in every CTA (21 % issue-slot utilisation).
+// slot_free; every wait is bounded, ptx.cuh); the earlier kernel ran the two halves back to back in every CTA (21 % issue-slot
+// utilisation).  What bounds it now is the SM's L1TEX data pipe: shared-memory traffic of the split and the relay, the tensor
+// core's operand reads and the global reductions all pass through it (profiles/r02_step_ncu.txt).
 #include <cstdlib>
 #include "common.cuh"
 #include "ptx.cuh"
