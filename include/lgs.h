@@ -343,6 +343,29 @@ int lgs_transform_points(int P, const float* points, const float* transformmatri
 size_t lgs_knn_scratch_bytes(int P);
 int lgs_knn_mean_dist2(int P, const float* points, float* mean_dist2, char* scratch, void* stream);
 
+/* ---- neighbours of the path that call into it or feed it (widening per SURVEY.md 8b "who calls it") -----------
+ * lgs_scale_transform_mark_visible: scaleAndTransformThenMarkVisiblePoints (src/operate_points.cu:52-70,96-140; a caller of
+ *   markVisible, used by the loop-closure correction): rows i with not_transformed_mask[i] && unstable_mask[i] && view-z of
+ *   points[i] > 0.2 get  points[i] <- T * (scale * points[i]),  rots[i] <- quaternion of T[:3,:3] * R(rots[i]) (w,x,y,z; not
+ *   normalised),  not_transformed_mask[i] <- 0, IN PLACE; *num_transformed (device int) is incremented by the number of such
+ *   rows.  faithful_rot_store != 0 stores the rotation row as the reference does, (w, x, z, 0)
+ *   (cuda_rasterizer/operate_points.h:169-178 writes z to offset 2 twice, never offset 3); 0 stores (w, x, y, z).
+ *   Matrices 4x4 as the reference indexes them (pose tensors stored transposed).  rots 16-byte aligned.
+ * lgs_inactive_geo_densify: monocularPinholeInactiveGeoDensifyBySearchingNeighborhoodKeypoints (src/stereo_vision.cu:63-133,
+ *   164-212): N keypoints (kps_pixel [N,2], kps_has3D bool bytes, kps_point_local [N,3]); a keypoint without a 3D point takes the
+ *   depth of the nearest keypoint that has one (squared pixel distance <= max_pixel_dist, ties to the lowest index) and is
+ *   reprojected with it; rows ending with z > 0 are written in order to out_points / out_colors [<= N,3], their number to
+ *   *out_count (device int).  colors: the image buffer the reference indexes at trunc(v * width + u) + {0,1,2}; offsets
+ *   outside [0, colors_len) read as zero.  scratch: lgs_inactive_geo_scratch_bytes(N).  kps_pixel 8-byte aligned. */
+int lgs_scale_transform_mark_visible(int P, float scale, float* points, float* rots, unsigned char* not_transformed_mask,
+                                     const unsigned char* unstable_mask, const float* transformmatrix, const float* viewmatrix,
+                                     int faithful_rot_store, int* num_transformed, void* stream);
+size_t lgs_inactive_geo_scratch_bytes(int N);
+int lgs_inactive_geo_densify(int N, int width, float fx, float fy, float cx, float cy, float max_pixel_dist,
+                             const float* kps_pixel, const unsigned char* kps_has3D, const float* kps_point_local,
+                             const float* colors, long long colors_len, float* out_points, float* out_colors, int* out_count,
+                             char* scratch, void* stream);
+
 /* ---- .ply checkpoint records (reference GaussianModel::savePly / loadPly,
  *      src/gaussian_model.cpp:854-1075) ------------------------------------------------------------------
  * block is the [P][C] float32 vertex block exactly as it lies in a binary_little_endian .ply.  Column c holds element

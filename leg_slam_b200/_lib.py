@@ -83,6 +83,9 @@ SIGNATURES = {
     "lgs_transform_points": (c_int, [c_int] + [c_void_p] * 4),
     "lgs_knn_scratch_bytes": (c_size_t, [c_int]),
     "lgs_knn_mean_dist2": (c_int, [c_int] + [c_void_p] * 4),
+    "lgs_scale_transform_mark_visible": (c_int, [c_int, c_float] + [c_void_p] * 6 + [c_int, c_void_p, c_void_p]),
+    "lgs_inactive_geo_scratch_bytes": (c_size_t, [c_int]),
+    "lgs_inactive_geo_densify": (c_int, [c_int, c_int] + [c_float] * 5 + [c_void_p] * 4 + [ctypes.c_longlong] + [c_void_p] * 5),
     "lgs_ply_pack": (c_int, [ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lgs_ply_unpack": (c_int, [ctypes.c_longlong, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lgs_cosine_query": (c_int, [c_int, c_int] + [c_void_p] * 4),

@@ -269,3 +269,260 @@ extern "C" int lgs_knn_mean_dist2(int P, const float* points, float* mean_dist2,
     LGS_LAUNCH_CHECK();
     return LGS_OK;
 }
+
+namespace lgs {
+
+// ================================ loop-closure correction of the visible Gaussians ====================================
+// scaleAndTransformThenMarkVisiblePoints (reference src/operate_points.cu:52-70,96-140, device helpers
+// cuda_rasterizer/operate_points.h:54-179): the Gaussians a corrected keyframe sees (markVisible), that are still
+// flagged "not transformed" and "unstable", get   point <- T * (scale * point),   rotation <- quaternion of T[:3,:3] * R(q).
+// The reference runs markVisible, two logical_ands, a sum().item(), two zero-filled temporaries, one kernel and six
+// boolean-index gathers / scatters; here it is ONE kernel that updates the rows in place (every thread owns its row) and
+// counts the selected rows with one atomic per warp.
+//
+// As shipped, the reference stores the new quaternion's z at offset 2 twice and never writes offset 3
+// (operate_points.h:169-178) into a zero-filled temporary whose whole rows are then copied back: a corrected row reads
+// (w, x, z, 0).  `faithful_rot_store` = 1 reproduces that ("do not fix silently"), 0 stores
+// (w, x, y, z).
+__global__ void __launch_bounds__(256)
+scale_transform_visible_kernel(int P, float scale, float* __restrict__ points, float* __restrict__ rots,
+                               unsigned char* __restrict__ not_transformed, const unsigned char* __restrict__ unstable,
+                               const float* __restrict__ T, const float* __restrict__ view, int faithful_rot_store,
+                               int* __restrict__ num_transformed) {
+    __shared__ float m[16], vw[16];
+    if (threadIdx.x < 16) {
+        m[threadIdx.x] = T[threadIdx.x];
+        vw[threadIdx.x] = view[threadIdx.x];
+    }
+    __syncthreads();
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    bool sel = false;
+    if (idx < P && not_transformed[idx] && unstable[idx]) {
+        const float x = points[3 * (size_t)idx], y = points[3 * (size_t)idx + 1], z = points[3 * (size_t)idx + 2];
+        // markVisible on the ORIGINAL point: view-space z > 0.2 (auxiliary.h:139-164; same expression as lgs_mark_visible)
+        const float depth = __fadd_rn(vw[14], __fmaf_rn(z, vw[10], __fmaf_rn(x, vw[2], __fmul_rn(y, vw[6]))));
+        sel = !(depth <= 0.2f);
+        if (sel) {
+            const float sx = __fmul_rn(x, scale), sy = __fmul_rn(y, scale), sz = __fmul_rn(z, scale);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)  // transformPoint4x3 (auxiliary.h:58-66)
+                points[3 * (size_t)idx + r] = __fadd_rn(m[12 + r], __fmaf_rn(sz, m[8 + r], __fmaf_rn(sx, m[r], __fmul_rn(sy, m[4 + r]))));
+            // rotation matrix of the stored (w, x, y, z) quaternion, NOT normalised (operate_points.h:59-87)
+            const float qw = rots[4 * (size_t)idx], qx = rots[4 * (size_t)idx + 1], qy = rots[4 * (size_t)idx + 2], qz = rots[4 * (size_t)idx + 3];
+            // Every product sum below is spelled out with the fused multiply-adds nvcc gives the reference's statement of
+            // these formulas (read off its SASS, like the transforms above): the rotation rows then come out bit-identical.
+            const float tx = __fadd_rn(qx, qx), ty = __fadd_rn(qy, qy), tz = __fadd_rn(qz, qz);
+            const float twx = __fmul_rn(tx, qw), twy = __fmul_rn(ty, qw), twz = __fmul_rn(tz, qw);
+            const float tyy = __fmul_rn(ty, qy), tzz = __fmul_rn(tz, qz);
+            float R0[3][3];
+            R0[0][0] = __fsub_rn(1.0f, __fadd_rn(tyy, tzz));
+            R0[1][1] = __fsub_rn(1.0f, __fmaf_rn(qx, tx, tzz));
+            R0[2][2] = __fsub_rn(1.0f, __fmaf_rn(qx, tx, tyy));
+            R0[0][1] = __fmaf_rn(qx, ty, -twz); R0[1][0] = __fmaf_rn(qx, ty, twz);
+            R0[0][2] = __fmaf_rn(qx, tz, twy);  R0[2][0] = __fmaf_rn(qx, tz, -twy);
+            R0[1][2] = __fmaf_rn(qy, tz, -twx); R0[2][1] = __fmaf_rn(qy, tz, twx);
+            float R[3][3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)  // T[:3,:3] * R0 with T stored transposed (:90-99): middle product first ...
+                    R[i][j] = __fmaf_rn(R0[2][j], m[8 + i], __fmaf_rn(R0[0][j], m[i], __fmul_rn(R0[1][j], m[4 + i])));
+            // ... except the first element, which the reference build starts from its first product
+            R[0][0] = __fmaf_rn(R0[2][0], m[8], __fmaf_rn(R0[1][0], m[4], __fmul_rn(R0[0][0], m[0])));
+            // matrix -> quaternion, Shoemake's branches (:101-147)
+            float ow, ox, oy, oz;
+            float t = __fadd_rn(__fadd_rn(R[0][0], R[1][1]), R[2][2]);
+            if (t > 0.0f) {
+                t = __fsqrt_rn(__fadd_rn(t, 1.0f));
+                ow = __fmul_rn(0.5f, t);
+                t = __fdiv_rn(0.5f, t);
+                ox = __fmul_rn(__fsub_rn(R[2][1], R[1][2]), t);
+                oy = __fmul_rn(__fsub_rn(R[0][2], R[2][0]), t);
+                oz = __fmul_rn(__fsub_rn(R[1][0], R[0][1]), t);
+            } else {
+                int i = 0;
+                if (R[1][1] > R[0][0]) i = 1;
+                if (R[2][2] > (i == 0 ? R[0][0] : R[1][1])) i = 2;
+                // the three cyclic cases written out (register-resident matrix: no dynamic indexing)
+                float rii, rjj, rkk, rkj, rjk, rji, rij, rki, rik;
+                if (i == 0)      { rii = R[0][0]; rjj = R[1][1]; rkk = R[2][2]; rkj = R[2][1]; rjk = R[1][2]; rji = R[1][0]; rij = R[0][1]; rki = R[2][0]; rik = R[0][2]; }
+                else if (i == 1) { rii = R[1][1]; rjj = R[2][2]; rkk = R[0][0]; rkj = R[0][2]; rjk = R[2][0]; rji = R[2][1]; rij = R[1][2]; rki = R[0][1]; rik = R[1][0]; }
+                else             { rii = R[2][2]; rjj = R[0][0]; rkk = R[1][1]; rkj = R[1][0]; rjk = R[0][1]; rji = R[0][2]; rij = R[2][0]; rki = R[1][2]; rik = R[2][1]; }
+                t = __fsqrt_rn(__fadd_rn(__fsub_rn(__fsub_rn(rii, rjj), rkk), 1.0f));
+                const float ci = __fmul_rn(0.5f, t);
+                t = __fdiv_rn(0.5f, t);
+                ow = __fmul_rn(__fsub_rn(rkj, rjk), t);
+                const float cj = __fmul_rn(__fadd_rn(rji, rij), t), ck = __fmul_rn(__fadd_rn(rki, rik), t);
+                ox = i == 0 ? ci : (i == 1 ? ck : cj);
+                oy = i == 0 ? cj : (i == 1 ? ci : ck);
+                oz = i == 0 ? ck : (i == 1 ? cj : ci);
+            }
+            float4 o = faithful_rot_store ? make_float4(ow, ox, oz, 0.0f) : make_float4(ow, ox, oy, oz);
+            *reinterpret_cast<float4*>(rots + 4 * (size_t)idx) = o;
+            not_transformed[idx] = 0;
+        }
+    }
+    const unsigned n = __popc(__ballot_sync(0xffffffffu, sel));
+    if ((threadIdx.x & 31) == 0 && n > 0) atomicAdd(num_transformed, (int)n);
+}
+
+}  // namespace lgs
+
+extern "C" int lgs_scale_transform_mark_visible(int P, float scale, float* points, float* rots, unsigned char* not_transformed_mask,
+                                                const unsigned char* unstable_mask, const float* transformmatrix,
+                                                const float* viewmatrix, int faithful_rot_store, int* num_transformed,
+                                                void* stream) {
+    if (P < 0) return LGS_ERR_INVALID_ARG;
+    if (P == 0) return LGS_OK;
+    if (!points || !rots || !not_transformed_mask || !unstable_mask || !transformmatrix || !viewmatrix || !num_transformed)
+        return LGS_ERR_INVALID_ARG;
+    if (reinterpret_cast<uintptr_t>(rots) & 15u) return LGS_ERR_INVALID_ARG;  // rows are stored as float4
+    scale_transform_visible_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        P, scale, points, rots, not_transformed_mask, unstable_mask, transformmatrix, viewmatrix, faithful_rot_store, num_transformed);
+    LGS_LAUNCH_CHECK();
+    return LGS_OK;
+}
+
+namespace lgs {
+
+// ================================ inactive-geometry densification (monocular keypoints) ===============================
+// monocularPinholeInactiveGeoDensifyBySearchingNeighborhoodKeypoints (reference src/stereo_vision.cu:63-133,164-212):
+// a keypoint without a 3D point borrows the depth of the nearest keypoint (in pixels) that has one and is reprojected
+// with it; keypoints that end with a positive depth are returned, in order, with their colours.  The reference runs one
+// thread per keypoint over ALL keypoints in global memory and compacts with a boolean index on the host side; here the
+// candidates stream through shared memory in tiles (visited in index order, so distance ties resolve to the lowest
+// index exactly as in the sequential loop) and a second, single-CTA kernel compacts in order and leaves the count on the
+// device.  Semantics kept as shipped: `max_pixel_dist` bounds the SQUARED distance (:105-108); the colour triple is read
+// at float offset v * width + u, truncated, WITHOUT a factor of three (:81,88-90,125-127); u, v are truncated to integers
+// for the reprojection (cuda_rasterizer/stereo_vision.h:41-55).  Offsets outside `colors` (undefined behaviour in the
+// reference) read as zero.
+constexpr int IGD_TILE = 256;
+
+__global__ void __launch_bounds__(IGD_TILE)
+inactive_geo_search_kernel(int N, int width, float fx, float fy, float cx, float cy, float max_pixel_dist,
+                           const float2* __restrict__ pixels, const unsigned char* __restrict__ has3D,
+                           const float* __restrict__ point3D, const float* __restrict__ colors, long long colors_len,
+                           float* __restrict__ res_p, float* __restrict__ res_c, unsigned char* __restrict__ keep) {
+    __shared__ float4 cand[IGD_TILE];  // u, v, z, has3D
+    const int idx = blockIdx.x * IGD_TILE + threadIdx.x;
+    const bool live = idx < N;
+    float2 px = make_float2(0.f, 0.f);
+    bool has = false;
+    if (live) {
+        px = pixels[idx];
+        has = has3D[idx] != 0;
+    }
+    float min_dist = FLT_MAX, depth = -1.0f;
+    for (int base = 0; base < N; base += IGD_TILE) {
+        const int j = base + threadIdx.x;
+        __syncthreads();
+        if (j < N) {
+            const float2 q = pixels[j];
+            cand[threadIdx.x] = make_float4(q.x, q.y, point3D[3 * (size_t)j + 2], has3D[j] ? 1.0f : 0.0f);
+        }
+        __syncthreads();
+        if (live && !has) {
+            const int cnt = min(IGD_TILE, N - base);
+            for (int k = 0; k < cnt; ++k) {
+                const float4 c = cand[k];
+                const float du = __fsub_rn(px.x, c.x), dv = __fsub_rn(px.y, c.y);
+                const float dist = __fmaf_rn(du, du, __fmul_rn(dv, dv));  // the association the reference compiles to
+                const bool ok = c.w != 0.0f && (base + k) != idx && !(dist > max_pixel_dist) && !(dist >= min_dist);
+                min_dist = ok ? dist : min_dist;
+                depth = ok ? c.z : depth;
+            }
+        }
+    }
+    if (!live) return;
+    float3 p = make_float3(0.f, 0.f, -1.0f), c = make_float3(0.f, 0.f, 0.f);
+    const bool with_point = has || depth > 0.0f;
+    if (with_point) {
+        if (has) {
+            p = make_float3(point3D[3 * (size_t)idx], point3D[3 * (size_t)idx + 1], point3D[3 * (size_t)idx + 2]);
+        } else {
+            const int ui = (int)px.x, vi = (int)px.y;
+            p.x = __fdiv_rn(__fmul_rn(__fsub_rn((float)ui, cx), depth), fx);
+            p.y = __fdiv_rn(__fmul_rn(__fsub_rn((float)vi, cy), depth), fy);
+            p.z = depth;
+        }
+        const long long off = (long long)(int)__fmaf_rn(px.y, (float)width, px.x);
+        if (off >= 0 && off + 2 < colors_len) c = make_float3(colors[off], colors[off + 1], colors[off + 2]);
+    }
+    res_p[3 * (size_t)idx] = p.x; res_p[3 * (size_t)idx + 1] = p.y; res_p[3 * (size_t)idx + 2] = p.z;
+    res_c[3 * (size_t)idx] = c.x; res_c[3 * (size_t)idx + 1] = c.y; res_c[3 * (size_t)idx + 2] = c.z;
+    keep[idx] = p.z > 0.0f ? 1 : 0;  // stereo_vision.cu:203-206
+}
+
+// order-preserving compaction by ONE CTA (keypoints per frame are thousands, not millions): chunks of 1024 rows, ballot +
+// warp prefix inside the chunk, a running base across chunks
+__global__ void __launch_bounds__(1024)
+inactive_geo_compact_kernel(int N, const float* __restrict__ res_p, const float* __restrict__ res_c,
+                            const unsigned char* __restrict__ keep, float* __restrict__ out_p, float* __restrict__ out_c,
+                            int* __restrict__ count) {
+    __shared__ int warp_cnt[32];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int start = 0; start < N; start += 1024) {
+        const int i = start + threadIdx.x;
+        const bool k = i < N && keep[i] != 0;
+        const unsigned b = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) warp_cnt[warp] = __popc(b);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 32; ++w) {
+            const int c = warp_cnt[w];
+            before += w < warp ? c : 0;
+            total += c;
+        }
+        const int base = s_base;
+        if (k) {
+            const size_t o = (size_t)(base + before + __popc(b & ((1u << lane) - 1u)));
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                out_p[3 * o + r] = res_p[3 * (size_t)i + r];
+                out_c[3 * o + r] = res_c[3 * (size_t)i + r];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = base + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = s_base;
+}
+
+}  // namespace lgs
+
+extern "C" size_t lgs_inactive_geo_scratch_bytes(int N) {
+    if (N <= 0) return 0;
+    return (size_t)N * 25 + 256;  // [N,3] points, [N,3] colours, [N] flags
+}
+
+extern "C" int lgs_inactive_geo_densify(int N, int width, float fx, float fy, float cx, float cy, float max_pixel_dist,
+                                        const float* kps_pixel, const unsigned char* kps_has3D, const float* kps_point_local,
+                                        const float* colors, long long colors_len, float* out_points, float* out_colors,
+                                        int* out_count, char* scratch, void* stream) {
+    if (N < 0 || width <= 0) return LGS_ERR_INVALID_ARG;
+    if (!out_count) return LGS_ERR_INVALID_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (N == 0) {
+        LGS_CUDA_TRY(cudaMemsetAsync(out_count, 0, sizeof(int), s));
+        return LGS_OK;
+    }
+    if (!kps_pixel || !kps_has3D || !kps_point_local || !colors || colors_len < 0 || !out_points || !out_colors || !scratch)
+        return LGS_ERR_INVALID_ARG;
+    if (reinterpret_cast<uintptr_t>(kps_pixel) & 7u) return LGS_ERR_INVALID_ARG;  // rows are read as float2
+    char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(scratch) + 15) & ~(uintptr_t)15);
+    float* res_p = reinterpret_cast<float*>(p); p += (size_t)N * 12;
+    float* res_c = reinterpret_cast<float*>(p); p += (size_t)N * 12;
+    unsigned char* keep = reinterpret_cast<unsigned char*>(p);
+    inactive_geo_search_kernel<<<(N + IGD_TILE - 1) / IGD_TILE, IGD_TILE, 0, s>>>(
+        N, width, fx, fy, cx, cy, max_pixel_dist, reinterpret_cast<const float2*>(kps_pixel), kps_has3D, kps_point_local, colors,
+        colors_len, res_p, res_c, keep);
+    LGS_LAUNCH_CHECK();
+    inactive_geo_compact_kernel<<<1, 1024, 0, s>>>(N, res_p, res_c, keep, out_points, out_colors, out_count);
+    LGS_LAUNCH_CHECK();
+    return LGS_OK;
+}

@@ -229,6 +229,89 @@ def load_knn():
     return lib
 
 
+GEO_REF = "/root/reference"
+GEO_MOD = "ref_geometry"
+GEO_SO = os.path.join(OUT, GEO_MOD + ".so")
+
+
+def _geometry_cmds(force):
+    inc, _ = _torch_paths()
+    pyinc = sysconfig.get_paths()["include"]
+    glm = os.path.join(REF, "third_party", "glm")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    common = ["-D_GLIBCXX_USE_CXX11_ABI=1", "-DLANGUAGE_FEATURES_DIM=64", "-I" + GEO_REF, "-I" + os.path.join(GEO_REF, "include"),
+              "-I" + glm, "-I" + pyinc] + ["-I" + p for p in inc]
+    nvcc = [os.path.join(cuda, "bin", "nvcc"), "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-gencode",
+            "arch=compute_100,code=sm_100", "-include", "cstdint"] + common + ["-c"]
+    cxx = ["g++", "-O2", "-std=c++17", "-fPIC", "-DTORCH_EXTENSION_NAME=" + GEO_MOD, "-DTORCH_API_INCLUDE_EXTENSION_H",
+           "-I" + os.path.join(cuda, "include")] + common + ["-c"]
+    jobs, objs = [], []
+    for f in ("stereo_vision.cu", "operate_points.cu"):
+        o = os.path.join(OUT, "geo_" + f + ".o")
+        objs.append(o)
+        src = os.path.join(GEO_REF, "src", f)
+        if force or not os.path.exists(o) or os.path.getmtime(o) < os.path.getmtime(src):
+            jobs.append(nvcc + [src, "-o", o])
+    o = os.path.join(OUT, "ref_geometry_wrap.cpp.o")
+    objs.append(o)
+    jobs.append(cxx + [os.path.join(HERE, "ref_geometry_wrap.cpp"), "-o", o])
+    return jobs, objs
+
+
+def build_geometry_objects(force=False, verbose=True):
+    """Compile step of build_geometry (independent of build(): can run beside it)."""
+    if os.path.exists(GEO_SO) and not force:
+        return
+    if not os.path.isdir(os.path.join(GEO_REF, "src")):
+        raise RuntimeError("reference tree not present (GPU box?) and no prebuilt " + GEO_SO)
+    os.makedirs(OUT, exist_ok=True)
+    jobs, _ = _geometry_cmds(force)
+
+    def run(cmd):
+        if verbose:
+            print("[build_ref]", " ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+
+    with ThreadPoolExecutor(max_workers=3) as ex:
+        list(ex.map(run, jobs))
+
+
+def build_geometry(force=False, verbose=True):
+    """The UNMODIFIED reference geometry operators src/stereo_vision.cu (reprojectDepthPinhole,
+    monocularPinholeInactiveGeoDensifyBySearchingNeighborhoodKeypoints) and src/operate_points.cu (transformPoints,
+    scaleAndTransformThenMarkVisiblePoints), compiled where they lie for sm_100 and linked with the reference rasterizer
+    objects of build() (markVisible) behind oracle/ref_geometry_wrap.cpp -> oracle/_ref/ref_geometry.so (python module
+    `ref_geometry`).  Oracle for SURVEY.md 8f row 4 and the two neighbouring operators (tests/test_ingest.py).  Both .cu
+    files include <torch/torch.h>, so nvcc needs ~5 minutes for them (compiled in parallel)."""
+    if os.path.exists(GEO_SO) and not force:
+        return GEO_SO
+    build_geometry_objects(force, verbose)
+    ras_objs = [os.path.join(OUT, f) for f in ("forward.cu.o", "backward.cu.o", "rasterizer_impl.cu.o", "rasterize_points.cu.o")]
+    if not all(os.path.exists(o) for o in ras_objs):
+        build(force=True, verbose=verbose)
+    _, lib = _torch_paths()
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    _, objs = _geometry_cmds(False)
+    cmd = ["g++", "-shared", "-o", GEO_SO] + objs + ras_objs + ["-L" + p for p in lib] + \
+          ["-L" + os.path.join(cuda, "lib64"), "-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python", "-lc10_cuda", "-ltorch_cuda",
+           "-lcudart"] + ["-Wl,-rpath," + p for p in lib]
+    if verbose:
+        print("[build_ref]", " ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return GEO_SO
+
+
+def load_geometry():
+    import importlib.util
+    import torch  # noqa: F401
+    if not os.path.exists(GEO_SO):
+        raise FileNotFoundError(GEO_SO + " missing: run `python oracle/build_ref.py` where /root/reference exists")
+    spec = importlib.util.spec_from_file_location(GEO_MOD, GEO_SO)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def load():
     """Import the prebuilt module (after `import torch`)."""
     import importlib.util
@@ -248,3 +331,4 @@ if __name__ == "__main__":
     print(build_loss(force="--force" in sys.argv))
     print(build_ply(force="--force" in sys.argv))
     print(build_utils(force="--force" in sys.argv))
+    print(build_geometry(force="--force" in sys.argv))
