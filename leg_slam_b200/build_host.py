@@ -3,7 +3,10 @@
 
   leg_slam_b200/liblgs_host.so : CudaRasterizer::Rasterizer (include/cuda_rasterizer/rasterizer.h), no torch
   leg_slam_b200/_C.so          : libtorch RasterizeGaussiansCUDA / ...BackwardCUDA / markVisible
-                                 (include/rasterize_points.h) + the pybind module `_C`
+                                 (include/rasterize_points.h), the geometry operators transformPoints /
+                                 scaleAndTransformThenMarkVisiblePoints / reprojectDepthPinhole /
+                                 monocularPinholeInactiveGeoDensify... / distCUDA2 (include/operate_points.h,
+                                 stereo_vision.h, spatial.h) + the pybind module `_C`
   leg_slam_b200/_L2.so         : GaussianRasterizationSettings / GaussianRasterizerFunction / GaussianRasterizer
                                  (include/gaussian_rasterizer.h), LgsFusedAdam (include/lgs_adam.h) + the pybind module
                                  `_L2` for the tests
@@ -34,6 +37,7 @@ def build(force=False, verbose=False):
     inc = os.path.join(ROOT, "include")
     hdrs = [os.path.join(inc, "lgs.h"), os.path.join(inc, "cuda_rasterizer", "rasterizer.h"),
             os.path.join(inc, "rasterize_points.h")]
+    geo_hdrs = [os.path.join(inc, h) for h in ("operate_points.h", "stereo_vision.h", "spatial.h")]
 
     def run(cmd):
         if verbose:
@@ -44,8 +48,8 @@ def build(force=False, verbose=False):
     if force or _stale(LIB_HOST, [src0] + hdrs):
         run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I" + inc, src0, "-o", LIB_HOST, "-L" + PKG, "-llgs",
              "-Wl,-rpath,$ORIGIN"])
-    srcs = [os.path.join(HOST, "rasterize_points.cpp"), os.path.join(HOST, "ext.cpp")]
-    if force or _stale(LIB_C, srcs + hdrs):
+    srcs = [os.path.join(HOST, "rasterize_points.cpp"), os.path.join(HOST, "geometry_ops.cpp"), os.path.join(HOST, "ext.cpp")]
+    if force or _stale(LIB_C, srcs + hdrs + geo_hdrs):
         import torch  # noqa: F401
         from torch.utils import cpp_extension as ce
         cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")

@@ -141,3 +141,43 @@ def test_cpp_fused_adam_refuses_cpu_and_checks_arguments(host_libs):
         _L2.fused_adam_run(p, g, [1e-3], 1e-15)
     with pytest.raises(RuntimeError, match="one gradient per parameter"):
         _L2.fused_adam_run(p, [[g[0][0]]], [1e-3, 5e-2], 1e-15)
+
+
+def test_l1_geometry_operators_validate_like_the_reference(host_libs):
+    """include/operate_points.h / stereo_vision.h / spatial.h on liblgs (csrc/host/geometry_ops.cpp, bound in `_C` for the
+    tests): the reference's AT_ERROR messages (src/operate_points.cu:62-64,106-118, src/stereo_vision.cu:140-142,175-180),
+    its empty-input behaviour, and no CPU path."""
+    from leg_slam_b200 import _C
+    out = subprocess.run(["nm", "-D", "--defined-only", "-C", os.path.join(ROOT, "leg_slam_b200", "_C.so")],
+                         capture_output=True, text=True).stdout
+    for sym in ("transformPoints(at::Tensor&, at::Tensor&)", "scaleAndTransformThenMarkVisiblePoints(", "reprojectDepthPinhole(",
+                "monocularPinholeInactiveGeoDensifyBySearchingNeighborhoodKeypoints(", "distCUDA2(at::Tensor const&)"):
+        assert sym in out, sym
+    I = torch.eye(4)
+    ones = torch.ones(5, dtype=torch.bool)
+    with pytest.raises(RuntimeError, match=r"points must have dimensions \(num_points, 3\)"):
+        _C.transform_points(torch.zeros(5, 2), I)
+    with pytest.raises(RuntimeError, match=r"points must have dimensions \(num_points, 3\)"):
+        _C.scale_and_transform_then_mark_visible(torch.zeros(5, 2), torch.zeros(5, 4), ones, ones, I, I, I, 0, 1.0)
+    with pytest.raises(RuntimeError, match=r"points_mask must have dimensions \(num_points\)"):
+        _C.scale_and_transform_then_mark_visible(torch.zeros(5, 3), torch.zeros(5, 4), ones[:4], ones, I, I, I, 0, 1.0)
+    with pytest.raises(RuntimeError, match=r"points must have dimensions \(num_points\)"):
+        _C.reproject_depth_pinhole(torch.zeros(5, 2), ones, [1.0, 1.0, 0.0, 0.0], 5)
+    with pytest.raises(RuntimeError, match=r"kps_pixel must have dimensions \(num_points, 2\)"):
+        _C.inactive_geo_densify(torch.zeros(5, 3), ones, torch.zeros(5, 3), torch.zeros(100), 1.0, [1.0, 1.0, 0.0, 0.0], 8)
+    with pytest.raises(RuntimeError, match=r"kps_has3D must have dimensions \(num_points\)"):
+        _C.inactive_geo_densify(torch.zeros(5, 2), ones[:, None], torch.zeros(5, 3), torch.zeros(100), 1.0, [1.0, 1.0, 0.0, 0.0], 8)
+    with pytest.raises(RuntimeError, match=r"kps_point_local must have dimensions \(num_points, 3\)"):
+        _C.inactive_geo_densify(torch.zeros(5, 2), ones, torch.zeros(5, 2), torch.zeros(100), 1.0, [1.0, 1.0, 0.0, 0.0], 8)
+    for call in (lambda: _C.transform_points(torch.zeros(5, 3), I),
+                 lambda: _C.scale_and_transform_then_mark_visible(torch.zeros(5, 3), torch.zeros(5, 4), ones, ones, I, I, I, 0, 1.0),
+                 lambda: _C.reproject_depth_pinhole(torch.zeros(5), ones, [1.0, 1.0, 0.0, 0.0], 5),
+                 lambda: _C.inactive_geo_densify(torch.zeros(5, 2), ones, torch.zeros(5, 3), torch.zeros(100), 1.0, [1.0, 1.0, 0.0, 0.0], 8),
+                 lambda: _C.dist_cuda2(torch.zeros(5, 3))):
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            call()
+    # empty inputs never reach a device (the reference skips its launches for P == 0 / N == 0)
+    e3 = torch.zeros(0, 3)
+    assert _C.transform_points(e3, I).shape == (0, 3)
+    assert _C.scale_and_transform_then_mark_visible(e3, torch.zeros(0, 4), ones[:0], ones[:0], I, I, I, 7, 1.0) == 7
+    assert _C.dist_cuda2(e3).shape == (0,)

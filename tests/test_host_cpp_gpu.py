@@ -103,3 +103,69 @@ def test_second_device_in_one_process():
     assert torch.equal(a[5], b[5])
     for x, y in zip(a[4], b[4]):
         assert cases.rel_err(x.numpy(), y.numpy()) <= 1e-4  # atomics reorder between runs
+
+
+def test_cpp_geometry_operators_equal_the_compiled_reference():
+    """The libtorch geometry operators with the reference's signatures (include/operate_points.h, stereo_vision.h, spatial.h;
+    csrc/host/geometry_ops.cpp through `_C`) against the unmodified reference operators (oracle/_ref/ref_geometry.so,
+    ref_simple_knn.so), call for call: rebinding, in-place updates, counts and outputs bit-identical."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import build_ref
+    import test_ingest as TI
+    from leg_slam_b200 import build_host
+    build_host.build()
+    from leg_slam_b200 import _C
+    try:
+        ref = build_ref.load_geometry()
+        knn = build_ref.load_knn()
+    except FileNotFoundError as ex:
+        pytest.skip(str(ex))
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(21)
+    # depth image -> camera points -> world points
+    W, H = 320, 240
+    depth = (torch.rand(W * H, generator=g) * 4 + 0.2).to(dev)
+    mask = (torch.rand(W * H, generator=g) > 0.25).to(dev)
+    intr = [300.0, 301.0, 159.5, 119.5]
+    pa, pb = _C.reproject_depth_pinhole(depth, mask, intr, W), ref.reproject_depth_pinhole(depth, mask, intr, W)
+    assert torch.equal(pa, pb)
+    T = TI._pose(g).to(dev)
+    wa, wb = _C.transform_points(pa, T), ref.transform_points(pb.clone(), T)
+    assert torch.equal(wa, wb) and wa.data_ptr() != pa.data_ptr()
+    # k-NN scale initialisation
+    sub = wa[mask][:20000].contiguous()
+    da = _C.dist_cuda2(sub)
+    db = torch.zeros(sub.shape[0], device=dev)
+    torch.cuda.synchronize()
+    assert knn.ref_simple_knn(sub.shape[0], sub.data_ptr(), db.data_ptr()) == 0
+    assert torch.equal(da, db)
+    # loop-closure correction, in place, on contiguous tensors and on a strided view (staged and copied back)
+    pts, rots, nt, un = TI._loop_closure_case(30000, 77)
+    view, proj = TI._pose(g, t=(0.1, 0.2, 0.5)).to(dev), torch.eye(4, device=dev)
+    a = [t.clone().to(dev) for t in (pts, rots, nt, un)]
+    b = [t.clone().to(dev) for t in (pts, rots, nt, un)]
+    na = _C.scale_and_transform_then_mark_visible(a[0], a[1], a[2], a[3], T, view, proj, 3, 1.05)
+    nb = ref.scale_and_transform_then_mark_visible(b[0], b[1], b[2], b[3], T, view, proj, 3, 1.05)
+    assert na == nb and 3 < na < 30003
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    wide = torch.zeros(30000, 6, device=dev)
+    wide[:, :3] = pts.to(dev)
+    c = [wide[:, :3], rots.clone().to(dev), nt.clone().to(dev), un.clone().to(dev)]
+    assert not c[0].is_contiguous()
+    nc = _C.scale_and_transform_then_mark_visible(c[0], c[1], c[2], c[3], T, view, proj, 3, 1.05)
+    assert nc == nb and torch.equal(wide[:, :3], b[0]) and torch.equal(c[1], b[1]) and torch.equal(c[2], b[2])
+    assert float(wide[:, 3:].abs().max()) == 0.0
+    # inactive-geometry densification
+    px, has, p3, colors = [t.to(dev) for t in TI._keypoint_case(3000, 640, 480, 5)]
+    kin = [600.0, 600.0, 319.5, 239.5]
+    ra = _C.inactive_geo_densify(px, has, p3, colors, 400.0, kin, 640)
+    rb = ref.inactive_geo_densify(px, has, p3, colors, 400.0, kin, 640)
+    assert 0 < ra[0].shape[0] < 3000
+    assert torch.equal(ra[0], rb[0]) and torch.equal(ra[1], rb[1])
+    e = _C.inactive_geo_densify(px[:0], has[:0], p3[:0], colors, 400.0, kin, 640)
+    assert e[0] is None and e[1] is None  # undefined tensors, like the reference
