@@ -204,11 +204,8 @@ int launch_cosine_tc(int P, int Q, const float* feats, const float* text, float*
     LGS_CUDA_TRY(cudaFuncSetAttribute(cosine_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       2 * QT_M * QT_K * 4 + 2 * 256 * QT_K * 4 + EPI_BYTES));
     const int ntiles = (P + QT_M - 1) / QT_M;
-    static int terms = 0;
-    if (terms == 0) {  // LGS_TC_TERMS=1: plain TF32 (one product per k-step) -- a timing experiment, not a product mode
-        const char* e = getenv("LGS_TC_TERMS");
-        terms = (e && e[0] == '1') ? 1 : 3;
-    }
+    const int terms = 3;  // hi*hi + hi*lo + lo*hi: fp32-level accuracy (a one-term plain-TF32 mode existed as a timing
+                          // experiment behind an environment variable; removed -- the product has one precision)
     for (int q0 = 0; q0 < Q; q0 += 256) {
         const int Qn = Q - q0 < 256 ? Q - q0 : 256;
         const int N = (Qn + 15) & ~15;  // M = 128 needs N % 16 == 0

@@ -512,6 +512,42 @@ class Mapper:
             st["exp_avg"].zero_()
             st["exp_avg_sq"].zero_()
 
+    def scaled_transform_visible_points_of_keyframe(self, point_not_transformed_flags, diff_pose, kf_world_view_transform,
+                                                    kf_full_proj_transform, kf_creation_iter: int,
+                                                    stable_num_iter_existence: int, num_transformed: int = 0, scale: float = 1.0):
+        """GaussianModel::scaledTransformVisiblePointsOfKeyframe (reference src/gaussian_model.cpp:422-481; called under the
+        render mutex when a loop closure moved a keyframe, src/gaussian_mapper.cpp:924-945): the Gaussians that keyframe sees,
+        that are younger than `stable_num_iter_existence` iterations relative to it and not yet transformed, are moved by
+        `diff_pose` (one fused kernel, leg_slam_b200.ingest), then xyz and rotation are put back into the optimizer with zeroed
+        Adam moments and their step counts kept (replaceTensorToOptimizer, :577-595).  As in the reference the rotation
+        parameter becomes the ACTIVATED (normalised) rotation for every Gaussian, and corrected rows carry the shipped
+        (w, x, z, 0) layout.  `point_not_transformed_flags` [P] bool is updated in place; returns the updated counter."""
+        from . import ingest
+        if self.stats is None:
+            raise ValueError("construct the Mapper with track_densify_stats=True (exist_since_iter_ lives with the statistics)")
+        p, m, v, steps = self._current_state()
+        p, m, v = dict(p), dict(m), dict(v)
+        with torch.no_grad():
+            points = p["xyz"].detach().clone()
+            rots = torch.nn.functional.normalize(p["rotation"].detach())  # getRotationActivation, gaussian_model.cpp:50-52
+            unstable = torch.abs(self.stats.exist_since_iter - int(kf_creation_iter)) < int(stable_num_iter_existence)
+            n = ingest.scaleAndTransformThenMarkVisiblePoints(points, rots, point_not_transformed_flags, unstable, diff_pose,
+                                                              kf_world_view_transform, kf_full_proj_transform,
+                                                              num_transformed, scale)
+            p["xyz"], p["rotation"] = points, rots
+            for k in ("xyz", "rotation"):
+                m[k], v[k] = torch.zeros_like(p[k]), torch.zeros_like(p[k])
+        if self.dp is not None:
+            self._rebind(p, m, v, steps, self.stats)
+            return n
+        for k in ("xyz", "rotation"):
+            self.params[k].data.copy_(p[k])
+            st = self.optimizer.state.get(self.params[k])
+            if st:
+                st["exp_avg"].zero_()
+                st["exp_avg_sq"].zero_()
+        return n
+
     def train_step(self, window: Sequence[Keyframe], presharded: bool = False):
         """Render + back-propagate this rank's share of `window`, sum gradients over ranks, Adam.
         `window` is the iteration's global list of keyframes (every rank passes the same list and

@@ -260,3 +260,55 @@ def test_mapper_increase_pcd_and_reset_opacity(dev):
     assert not so["exp_avg"].any() and not so["exp_avg_sq"].any() and so["step"] == 4
     np.testing.assert_allclose(torch.sigmoid(mp.params["opacity"].detach()).cpu().numpy(), op_before.cpu().numpy(), atol=1e-6)
     assert torch.isfinite(mp.train_step(win))
+
+
+@pytest.mark.gpu
+def test_mapper_loop_closure_correction(dev):
+    """GaussianModel::scaledTransformVisiblePointsOfKeyframe on the mapper (reference src/gaussian_model.cpp:422-481): the rows
+    the unmodified reference operator selects and moves (oracle/_ref/ref_geometry.so on clones of the same tensors) are the
+    rows the mapper's parameters end with; every rotation row is the activated one; xyz / rotation moments are zeroed, their
+    step counts and every other tensor's Adam state are untouched; training continues."""
+    import build_ref
+    from leg_slam_b200 import mapper as M, synthetic
+    try:
+        ref = build_ref.load_geometry()
+    except FileNotFoundError as ex:
+        pytest.skip(str(ex))
+    W, H = 96, 64
+    sc = synthetic.make_scene(6000, seed=71, mean_scale=0.06, device=dev)
+    cams = [c.to(dev) for c in synthetic.make_cameras(2, W, H, seed=71)]
+    g = torch.Generator().manual_seed(72)
+    win = [M.Keyframe(c, torch.rand(3, H, W, generator=g).to(dev), torch.randn(64, 37, 37, generator=g).to(dev),
+                      (torch.rand(1, H, W, generator=g) * 3).to(dev)) for c in cams]
+    mp = M.Mapper(sc, sh_degree=3, track_densify_stats=True)
+    for _ in range(3):
+        mp.train_step(win)
+    P = mp.params["xyz"].shape[0]
+    mp.stats.exist_since_iter.copy_(torch.randint(0, 40, (P,), generator=g).to(dev))  # ages relative to the keyframe
+    flags = (torch.rand(P, generator=g) > 0.2).to(dev)
+    diff = torch.eye(4)
+    diff[:3, :3] = torch.tensor([[0.9998, -0.02, 0.0], [0.02, 0.9998, 0.0], [0.0, 0.0, 1.0]])
+    diff[:3, 3] = torch.tensor([0.05, -0.02, 0.01])
+    diff_t = diff.t().contiguous().to(dev)  # pose tensors are stored transposed (src/gaussian_mapper.cpp:931-933)
+    cam = cams[0]
+    # the reference's sequence on clones: activation, unstable flags, the unmodified operator
+    r_pts = mp.params["xyz"].detach().clone()
+    r_rots = torch.nn.functional.normalize(mp.params["rotation"].detach())
+    r_flags = flags.clone()
+    r_unstable = torch.abs(mp.stats.exist_since_iter - 17) < 15
+    n_ref = ref.scale_and_transform_then_mark_visible(r_pts, r_rots, r_flags, r_unstable, diff_t, cam.viewmatrix, cam.projmatrix, 2, 1.03)
+    lf_m = mp.optimizer.state[mp.params["lang_feat"]]["exp_avg"].clone()
+    assert mp.optimizer.state[mp.params["xyz"]]["exp_avg"].any()
+    n = mp.scaled_transform_visible_points_of_keyframe(flags, diff_t, cam.viewmatrix, cam.projmatrix, 17, 15, 2, 1.03)
+    assert n == n_ref and 2 < n < P + 2
+    assert torch.equal(flags, r_flags)
+    assert torch.equal(mp.params["xyz"].detach(), r_pts) and torch.equal(mp.params["rotation"].detach(), r_rots)
+    for k in ("xyz", "rotation"):
+        st = mp.optimizer.state[mp.params[k]]
+        assert st["step"] == 3 and not st["exp_avg"].any() and not st["exp_avg_sq"].any()
+    st = mp.optimizer.state[mp.params["lang_feat"]]
+    assert st["step"] == 3 and torch.equal(st["exp_avg"], lf_m)
+    assert torch.isfinite(mp.train_step(win)) and mp.optimizer.state[mp.params["xyz"]]["step"] == 4
+    plain = M.Mapper(sc, sh_degree=3)
+    with pytest.raises(ValueError, match="track_densify_stats"):
+        plain.scaled_transform_visible_points_of_keyframe(flags, diff_t, cam.viewmatrix, cam.projmatrix, 17, 15)
