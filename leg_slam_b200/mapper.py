@@ -31,6 +31,35 @@ DEFAULT_LRS = dict(xyz=3.2e-4, features_dc=2.5e-3, features_rest=2.5e-3 / 20.0, 
                    scaling=5e-3, rotation=1e-3)
 
 
+class ExponLr:
+    """GaussianModel::exponLrFunc (reference src/gaussian_model.cpp:1143-1157) with the constants trainingSetup stores for it
+    (:513-517: lr_init / lr_final already multiplied by spatial_lr_scale): log-linear interpolation from lr_init at step 0 to
+    lr_final at max_steps, times an optional sine-eased delay factor.  Evaluated in float32 like the reference (logf, expf,
+    sinf on float operands)."""
+
+    def __init__(self, lr_init, lr_final, lr_delay_mult=1.0, max_steps=1_000_000, lr_delay_steps=0):
+        import numpy as np
+        self._np = np
+        f = np.float32
+        self.lr_init, self.lr_final, self.lr_delay_mult = f(lr_init), f(lr_final), f(lr_delay_mult)
+        self.max_steps, self.lr_delay_steps = int(max_steps), int(lr_delay_steps)
+
+    def __call__(self, step: int) -> float:
+        np = self._np
+        f = np.float32
+        if step < 0 or (self.lr_init == 0 and self.lr_final == 0):
+            return 0.0
+        if self.lr_delay_steps > 0:
+            x = min(max(f(step) / f(self.lr_delay_steps), f(0)), f(1))
+            delay = self.lr_delay_mult + (f(1) - self.lr_delay_mult) * np.sin(f(np.pi / 2) * x, dtype=np.float32)
+        else:
+            delay = f(1)
+        t = min(max(f(step) / f(self.max_steps), f(0)), f(1))
+        log_lerp = np.exp(np.log(self.lr_init, dtype=np.float32) * (f(1) - t) + np.log(self.lr_final, dtype=np.float32) * t,
+                          dtype=np.float32)
+        return float(f(delay) * log_lerp)
+
+
 class Keyframe(NamedTuple):
     camera: Camera
     gt_image: torch.Tensor   # [3,H,W]
@@ -100,7 +129,9 @@ class Mapper:
             groups = [dict(params=[self.params[k]], lr=lrs[k], name=k) for k in PARAM_ORDER]
             self.optimizer = (optimizer_factory or (lambda g: FusedAdam(g, lr=0.0, eps=1e-15)))(groups)
             self.grads = FlatGrads(self.params)
-        self.sh_degree = sh_degree
+        self.sh_degree = sh_degree          # active_sh_degree_: what the rasterizer evaluates
+        self.max_sh_degree = sh_degree      # max_sh_degree_: what features_rest can hold (set_sh_degree clamps to it)
+        self.xyz_lr_schedule = None         # ExponLr, installed by set_position_lr_schedule
         self.pg = process_group
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
@@ -511,6 +542,62 @@ class Mapper:
         if st:
             st["exp_avg"].zero_()
             st["exp_avg_sq"].zero_()
+
+    # -- per-iteration settings the reference applies at the top of trainForOneIteration (src/gaussian_mapper.cpp:662-683) ----
+    def _set_lr(self, name, lr):
+        self._lrs[name] = float(lr)  # also what a later densify / load rebuilds the optimizer with
+        i = PARAM_ORDER.index(name)
+        if self.dp is not None:
+            self.dp.lrs[i] = float(lr)
+        else:
+            self.optimizer.param_groups[i]["lr"] = float(lr)
+
+    def learning_rate(self, name) -> float:
+        return self._lrs[name]
+
+    def set_position_lr_schedule(self, position_lr_init, position_lr_final, position_lr_delay_mult=0.01,
+                                 position_lr_max_steps=30_000, spatial_lr_scale=1.0):
+        """The xyz part of GaussianModel::trainingSetup (reference src/gaussian_model.cpp:493,513-517): start at
+        position_lr_init * spatial_lr_scale and remember the decay's constants (defaults: include/gaussian_parameters.h:60-63;
+        lr_delay_steps_ stays 0 in the reference, so the delay factor is inactive)."""
+        self.spatial_lr_scale = float(spatial_lr_scale)
+        self.xyz_lr_schedule = ExponLr(float(position_lr_init) * self.spatial_lr_scale, float(position_lr_final) * self.spatial_lr_scale,
+                                       position_lr_delay_mult, position_lr_max_steps)
+        self._set_lr("xyz", float(position_lr_init) * self.spatial_lr_scale)
+
+    def update_learning_rate(self, step: int) -> float:
+        """GaussianModel::updateLearningRate (:520-530): the xyz group's learning rate for this iteration."""
+        if self.xyz_lr_schedule is None:
+            raise ValueError("call set_position_lr_schedule first")
+        lr = self.xyz_lr_schedule(int(step))
+        self._set_lr("xyz", lr)
+        return lr
+
+    def set_position_learning_rate(self, position_lr):   # :542-544
+        self._set_lr("xyz", float(position_lr) * getattr(self, "spatial_lr_scale", 1.0))
+
+    def set_feature_learning_rate(self, feature_lr):     # :546-549 -- the rest coefficients run at a twentieth
+        self._set_lr("features_dc", feature_lr)
+        self._set_lr("features_rest", float(feature_lr) / 20.0)
+
+    def set_language_feature_learning_rate(self, lr):    # :551-553
+        self._set_lr("lang_feat", lr)
+
+    def set_opacity_learning_rate(self, lr):             # :555-557
+        self._set_lr("opacity", lr)
+
+    def set_scaling_learning_rate(self, lr):             # :559-561
+        self._set_lr("scaling", lr)
+
+    def set_rotation_learning_rate(self, lr):            # :563-565
+        self._set_lr("rotation", lr)
+
+    def one_up_sh_degree(self):                          # GaussianModel::oneUpShDegree, :100-103
+        if self.sh_degree < self.max_sh_degree:
+            self.sh_degree += 1
+
+    def set_sh_degree(self, sh: int):                    # GaussianModel::setShDegree, :105-107
+        self.sh_degree = min(int(sh), self.max_sh_degree)
 
     def scaled_transform_visible_points_of_keyframe(self, point_not_transformed_flags, diff_pose, kf_world_view_transform,
                                                     kf_full_proj_transform, kf_creation_iter: int,

@@ -626,6 +626,23 @@ void oracle_cosine(int P, int Q, const float* feats, const float* text, float* o
     }
 }
 
+/* GaussianModel::exponLrFunc (reference src/gaussian_model.cpp:1143-1157): the xyz learning rate of an iteration, in float
+ * with libm's float functions exactly as the compiled reference evaluates it (std::log / std::exp / std::sin on floats,
+ * M_PI_2f32, std::clamp). */
+float oracle_expon_lr(int step, float lr_init, float lr_final, float lr_delay_mult, int lr_delay_steps, int max_steps) {
+    if (step < 0 || (lr_init == 0.0f && lr_final == 0.0f)) return 0.0f;
+    float delay_rate = 1.0f;
+    if (lr_delay_steps > 0) {
+        float x = (float)step / lr_delay_steps;
+        x = x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x);
+        delay_rate = lr_delay_mult + (1.0f - lr_delay_mult) * sinf(1.57079632679489661923f * x);
+    }
+    float t = (float)step / max_steps;
+    t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
+    const float log_lerp = expf(logf(lr_init) * (1 - t) + logf(lr_final) * t);
+    return delay_rate * log_lerp;
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -35,6 +35,8 @@ def lib():
         _lib.oracle_num_rendered.restype = ctypes.c_int64
         _lib.oracle_render_fwd.restype = ctypes.c_int64
         _lib.oracle_num_threads.restype = ctypes.c_int
+        _lib.oracle_expon_lr.restype = ctypes.c_float
+        _lib.oracle_expon_lr.argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int]
     return _lib
 
 
@@ -154,3 +156,8 @@ def mark_visible(means3D, viewmatrix):
     out = np.zeros(means3D.shape[0], np.uint8)
     lib().oracle_mark_visible(I(means3D.shape[0]), _p(means3D), _p(viewmatrix), _p(out))
     return out.astype(bool)
+
+
+def expon_lr(step, lr_init, lr_final, lr_delay_mult=1.0, lr_delay_steps=0, max_steps=1_000_000):
+    return float(lib().oracle_expon_lr(int(step), float(lr_init), float(lr_final), float(lr_delay_mult), int(lr_delay_steps),
+                                       int(max_steps)))

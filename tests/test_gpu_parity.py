@@ -523,6 +523,54 @@ def test_mapper_step_matches_reference_rasterizer_and_torch_adam(dev, ref_mod):
             assert (d > 0.05 * step).mean() <= 2e-3, (k, float(d.max()), step)
 
 
+def test_mapper_sh_degree_and_lr_schedule_follow_reference(dev, ref_mod):
+    """The per-iteration settings of trainForOneIteration (reference src/gaussian_mapper.cpp:662-683): the active SH degree
+    grows from 0 (setShDegree / oneUpShDegree) and the xyz learning rate follows exponLrFunc; ours (fused path + FusedAdam)
+    against the compiled reference rasterizer + torch.optim.Adam under the same schedule.  Coefficients above the active
+    degree receive no gradient, so Adam leaves them exactly where they were."""
+    import bench
+    from leg_slam_b200 import mapper as M
+    sc, win = _mapper_window(dev)
+
+    class _Shim(bench.E2EPath):
+        def __init__(self):
+            self.mapper = None
+    shim = _Shim()
+    refm = M.Mapper(sc, sh_degree=3, use_cuda_graph=False, optimizer_factory=lambda g: torch.optim.Adam(g, lr=0.0, eps=1e-15))
+    shim.mapper = refm
+    refm.render_fn = shim._ref_render_fn()
+    ours = M.Mapper(sc, sh_degree=3)
+    assert ours.fused
+    rest0 = sc["features_rest"].clone()
+    xyz_lrs = []
+    try:
+        for m in (ours, refm):
+            m.set_position_lr_schedule(3.2e-4, 3.2e-6, 0.01, 6, spatial_lr_scale=2.0)
+            m.set_sh_degree(0)
+        for it in range(6):
+            if it > 0 and it % 2 == 0:
+                ours.one_up_sh_degree(), refm.one_up_sh_degree()
+            assert ours.sh_degree == it // 2
+            bench.SH_DEGREE = refm.sh_degree  # the reference arm's autograd glue reads the degree from the bench module
+            xyz_lrs.append(ours.update_learning_rate(it))
+            assert refm.update_learning_rate(it) == xyz_lrs[-1]
+            lo, lr = ours.train_step(win), refm.train_step(win)
+            assert abs(float(lo) - float(lr)) <= 2e-4 * abs(float(lr)), (it, float(lo), float(lr))
+            n_active = (ours.sh_degree + 1) ** 2 - 1  # rest coefficients the rasterizer reads
+            for m in (ours, refm):
+                assert torch.equal(m.params["features_rest"].detach()[:, n_active:], rest0[:, n_active:]), (it, n_active)
+            if n_active:
+                assert not torch.equal(ours.params["features_rest"].detach()[:, :n_active], rest0[:, :n_active])
+    finally:
+        bench.SH_DEGREE = 3
+    assert xyz_lrs[0] > xyz_lrs[-1] > 6.4e-6 and abs(xyz_lrs[0] - 6.4e-4) < 1e-9
+    for k in M.PARAM_ORDER:
+        r = refm.params[k].detach().cpu().numpy()
+        step = sum(xyz_lrs) if k == "xyz" else 6 * M.DEFAULT_LRS[k]
+        d = np.abs(ours.params[k].detach().cpu().numpy() - r)
+        assert (d > 0.05 * step).mean() <= 3e-3, (k, float(d.max()), step)
+
+
 def test_psnr_after_n_iterations_matches_reference(dev, ref_mod):
     """north_star gate: PSNR after N mapping iterations within 0.05 dB of the reference trajectory.  Same seeded
     scene, same ground truth (rendered by the reference from a perturbed copy of the scene), same loss; ours =

@@ -122,3 +122,55 @@ def test_dp_range_partition_covers_the_flat_index_space_once():
                     assert r.exp_avg.numel() >= max(r.se - r.sb, 4) and r.exp_avg_sq.numel() == r.exp_avg.numel()
                     seen[r.sb:r.se] += 1
             assert (seen == 1).all(), (world, pieces)
+
+
+def test_position_lr_schedule_matches_the_c_statement(oracle_mod):
+    """Mapper's ExponLr against the float / libm statement of GaussianModel::exponLrFunc (reference
+    src/gaussian_model.cpp:1143-1157) in the C oracle, plus the closed-form ends: lr_init at step 0, lr_final from max_steps
+    on, the geometric mean half way, 0 for a negative step, and the delay factor's ends when it is enabled."""
+    from leg_slam_b200.mapper import ExponLr
+    init, final = 1.6e-4 * 5.3, 1.6e-6 * 5.3
+    e = ExponLr(init, final, 0.01, 30_000)
+    for step in (0, 1, 17, 999, 15_000, 29_999, 30_000, 31_000, 10 ** 6):
+        ref = oracle_mod.expon_lr(step, init, final, 0.01, 0, 30_000)
+        assert abs(e(step) - ref) <= 1.2e-7 * ref, (step, e(step), ref)  # one float ulp: numpy's and libm's logf / expf
+    assert abs(e(0) - init) <= 3e-7 * init and abs(e(30_000) - final) <= 3e-7 * final and e(45_000) == e(30_000)
+    assert abs(e(15_000) - math.sqrt(init * final)) <= 1e-6 * math.sqrt(init * final)
+    assert e(-1) == 0.0 and ExponLr(0.0, 0.0)(5) == 0.0
+    vals = [e(s) for s in range(0, 30_001, 1000)]
+    assert all(a > b for a, b in zip(vals, vals[1:]))
+    d = ExponLr(1e-2, 1e-4, 0.01, 1000, lr_delay_steps=100)
+    for step in (0, 1, 50, 99, 100, 500):
+        ref = oracle_mod.expon_lr(step, 1e-2, 1e-4, 0.01, 100, 1000)
+        assert abs(d(step) - ref) <= 2.4e-7 * ref, (step, d(step), ref)
+    assert abs(d(0) - 1e-4) <= 1e-10
+
+
+def test_mapper_per_iteration_settings():
+    """What trainForOneIteration sets before it renders (reference src/gaussian_mapper.cpp:662-683 on
+    src/gaussian_model.cpp:100-107,520-565): learning rates reach the optimizer's groups (feature_rest at a twentieth, xyz
+    times spatial_lr_scale), the xyz schedule, and the active SH degree clamps at the model's."""
+    from leg_slam_b200 import mapper as M
+    sc = synthetic.make_scene(50, seed=3)
+    mp = M.Mapper(sc, sh_degree=3)
+    lr_of = lambda k: mp.optimizer.param_groups[M.PARAM_ORDER.index(k)]["lr"]  # noqa: E731
+    assert lr_of("xyz") == M.DEFAULT_LRS["xyz"]
+    mp.set_position_lr_schedule(1.6e-4, 1.6e-6, 0.01, 30_000, spatial_lr_scale=5.0)
+    assert abs(lr_of("xyz") - 8e-4) < 1e-12
+    assert mp.update_learning_rate(30_000) == lr_of("xyz") and abs(lr_of("xyz") - 8e-6) < 1e-11
+    mp.set_position_learning_rate(2e-4)
+    assert abs(lr_of("xyz") - 1e-3) < 1e-12 and mp.learning_rate("xyz") == lr_of("xyz")
+    mp.set_feature_learning_rate(2.5e-3)
+    assert lr_of("features_dc") == 2.5e-3 and lr_of("features_rest") == 2.5e-3 / 20.0
+    mp.set_language_feature_learning_rate(1e-3), mp.set_opacity_learning_rate(0.04), mp.set_scaling_learning_rate(4e-3)
+    mp.set_rotation_learning_rate(2e-3)
+    assert [lr_of(k) for k in ("lang_feat", "opacity", "scaling", "rotation")] == [1e-3, 0.04, 4e-3, 2e-3]
+    with pytest.raises(ValueError, match="set_position_lr_schedule"):
+        M.Mapper(sc, sh_degree=3).update_learning_rate(1)
+    mp.set_sh_degree(0)
+    assert mp.sh_degree == 0
+    for want in (1, 2, 3, 3):
+        mp.one_up_sh_degree()
+        assert mp.sh_degree == want
+    mp.set_sh_degree(7)
+    assert mp.sh_degree == 3 and mp.max_sh_degree == 3
