@@ -93,7 +93,8 @@ def densify_and_prune(params, exp_avg, exp_avg_sq, stats, max_grad, min_opacity,
     return out_p, out_m, out_v, new_stats, info
 
 
-SH_C0 = 0.28209479177387814  # include/sh_utils.h:32
+SH_C0 = 0.282094806432724  # include/sh_utils.h:32 `const float C0 = 0.28209479177387814f`: the float32 value (a CUDA tensor /
+# scalar multiplies by the scalar's reciprocal, so the double literal would give a last-bit-different DC coefficient)
 
 
 def increase_pcd(params, exp_avg, exp_avg_sq, stats, new_points, new_colors, iteration, sh_degree=3):
@@ -143,6 +144,33 @@ def increase_pcd(params, exp_avg, exp_avg_sq, stats, new_points, new_colors, ite
     new_stats.exist_since_iter[:P].copy_(stats.exist_since_iter)
     new_stats.exist_since_iter[P:] = int(iteration)
     return out_p, out_m, out_v, new_stats
+
+
+def create_from_pcd(points, colors, lang_feats=None, sh_degree=3):
+    """GaussianModel::createFromPcd (reference src/gaussian_model.cpp:109-194) on tensors: the initial Gaussian set of a point
+    cloud -- colour as the DC coefficient (RGB2SH), zero higher-order SH, the points' language features (zeros when the cloud
+    carries none), isotropic log-scale from the mean squared distance to the 3 nearest points (`ingest.distCUDA2`, clamped
+    at 1e-7), identity rotation, opacity inverse_sigmoid(0.1).  Returns (params, stats): the 7 parameter tensors in the
+    mapper's layout and fresh statistics with exist_since_iter = 0.  The scale needs the k-NN kernel: no CPU path."""
+    from . import ingest
+    if not points.is_cuda:
+        raise _lib.LgsError("leg_slam_b200 has no CPU path: tensors must live on a CUDA device")
+    if points.dim() != 2 or points.shape[1] != 3 or colors.shape != points.shape:
+        raise ValueError("points and colors must have dimensions (num_points, 3)")
+    n, dev = int(points.shape[0]), points.device
+    if lang_feats is not None and tuple(lang_feats.shape) != (n, 64):
+        raise ValueError("lang_feats must have dimensions (num_points, 64)")
+    f = dict(dtype=torch.float32, device=dev)
+    xyz = points.to(**f).contiguous().clone()
+    d2 = torch.clamp_min(ingest.distCUDA2(xyz.clone()), 0.0000001)
+    x = torch.full((n, 1), 0.1, **f)
+    rot = torch.zeros(n, 4, **f)
+    rot[:, 0] = 1.0
+    params = dict(xyz=xyz, features_dc=((colors.to(**f) - 0.5) / SH_C0).unsqueeze(1).contiguous(),
+                  features_rest=torch.zeros(n, (sh_degree + 1) ** 2 - 1, 3, **f),
+                  lang_feat=torch.zeros(n, 64, **f) if lang_feats is None else lang_feats.to(**f).contiguous().clone(),
+                  opacity=torch.log(x / (1 - x)), scaling=torch.log(torch.sqrt(d2)).unsqueeze(1).repeat(1, 3), rotation=rot)
+    return params, DensifyStats(n, dev)
 
 
 def reset_opacity(params, exp_avg, exp_avg_sq):

@@ -599,6 +599,29 @@ class Mapper:
     def set_sh_degree(self, sh: int):                    # GaussianModel::setShDegree, :105-107
         self.sh_degree = min(int(sh), self.max_sh_degree)
 
+    def apply_scaled_transformation(self, s: float, T):
+        """GaussianModel::applyScaledTransformation (reference src/gaussian_model.cpp:387-405; the map-wide correction after
+        a scale / pose change of the tracker): xyz <- T (s * xyz) with `T` [4,4] stored transposed like the reference's pose
+        tensors, and -- as shipped -- the LOG-scale parameter multiplied by s (:403), then xyz and scaling go back into the
+        optimizer with zeroed moments and kept step counts (scaledTransformationPostfix, :407-420)."""
+        from . import ingest
+        p, m, v, steps = self._current_state()
+        p, m, v = dict(p), dict(m), dict(v)
+        with torch.no_grad():
+            p["xyz"] = ingest.transformPoints(p["xyz"].detach() * float(s), T)
+            p["scaling"] = p["scaling"].detach() * float(s)
+            for k in ("xyz", "scaling"):
+                m[k], v[k] = torch.zeros_like(p[k]), torch.zeros_like(p[k])
+        if self.dp is not None:
+            self._rebind(p, m, v, steps, self.stats)
+            return
+        for k in ("xyz", "scaling"):
+            self.params[k].data.copy_(p[k])
+            st = self.optimizer.state.get(self.params[k])
+            if st:
+                st["exp_avg"].zero_()
+                st["exp_avg_sq"].zero_()
+
     def scaled_transform_visible_points_of_keyframe(self, point_not_transformed_flags, diff_pose, kf_world_view_transform,
                                                     kf_full_proj_transform, kf_creation_iter: int,
                                                     stable_num_iter_existence: int, num_transformed: int = 0, scale: float = 1.0):

@@ -125,7 +125,7 @@ class Model:
         if n == 0:
             return
         dev = new_points.device
-        C0 = 0.28209479177387814
+        C0 = 0.282094806432724  # `const float C0 = 0.28209479177387814f` (sh_utils.h:32) as the float it is
         fused = (new_colors - 0.5) / C0
         t = max_sh_degree + 1
         features = torch.zeros(n, 3, t * t, dtype=torch.float32, device=dev)

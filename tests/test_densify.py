@@ -222,6 +222,11 @@ def test_increase_pcd_matches_restatement(dev):
         assert torch.equal(m.p[k], orig.p[k]) and torch.equal(m.m[k], orig.m[k])  # inputs untouched
     assert torch.equal(st2.exist_since_iter, ref.exist_since_iter)
     assert st2.denom.shape == ref.denom.shape and not st2.denom.any() and not st2.max_radii2D.any()
+    try:  # the DC coefficient against the reference's own RGB2SH (unmodified include/sh_utils.h) on the same device
+        import build_ref
+        assert torch.equal(p2["features_dc"][4000:, 0], build_ref.load_utils().RGB2SH(cols))
+    except FileNotFoundError:
+        pass
     same = D.increase_pcd(m.p, m.m, m.v, st, pts[:0], cols[:0], 24)
     assert same[0] is m.p and same[3] is st
     with pytest.raises(Exception, match="no CPU path"):
@@ -312,3 +317,62 @@ def test_mapper_loop_closure_correction(dev):
     plain = M.Mapper(sc, sh_degree=3)
     with pytest.raises(ValueError, match="track_densify_stats"):
         plain.scaled_transform_visible_points_of_keyframe(flags, diff_t, cam.viewmatrix, cam.projmatrix, 17, 15)
+
+
+@pytest.mark.gpu
+def test_create_from_pcd_and_scaled_transformation(dev):
+    """GaussianModel::createFromPcd (reference src/gaussian_model.cpp:109-194) against the same composition of the
+    reference's own pieces -- RGB2SH and inverse_sigmoid from its unmodified headers (oracle/_ref/ref_utils.so), simple-knn
+    (ref_simple_knn.so) -- and applyScaledTransformation (:387-420) against transformPoints of the unmodified
+    src/operate_points.cu (ref_geometry.so); the created model trains."""
+    import build_ref
+    from leg_slam_b200 import densify as D, mapper as M, synthetic
+    try:
+        ru, knn, geo = build_ref.load_utils(), build_ref.load_knn(), build_ref.load_geometry()
+    except FileNotFoundError as ex:
+        pytest.skip(str(ex))
+    g = torch.Generator().manual_seed(91)
+    n = 4000
+    pts = (torch.rand(n, 3, generator=g) * torch.tensor([6.0, 4.0, 2.8])).to(dev)
+    cols = torch.rand(n, 3, generator=g).to(dev)
+    lfs = torch.randn(n, 64, generator=g).to(dev)
+    params, stats = D.create_from_pcd(pts, cols, lfs, sh_degree=3)
+    assert [tuple(params[k].shape) for k in M.PARAM_ORDER] == [(n, 3), (n, 1, 3), (n, 15, 3), (n, 64), (n, 1), (n, 3), (n, 4)]
+    assert torch.equal(params["xyz"], pts) and params["xyz"].data_ptr() != pts.data_ptr()
+    assert torch.equal(params["features_dc"][:, 0], ru.RGB2SH(cols)) and not params["features_rest"].any()
+    assert torch.equal(params["lang_feat"], lfs)
+    assert torch.equal(params["opacity"], ru.inverse_sigmoid(torch.full((n, 1), 0.1, device=dev)))
+    d2 = torch.zeros(n, device=dev)
+    torch.cuda.synchronize()
+    assert knn.ref_simple_knn(n, pts.contiguous().data_ptr(), d2.data_ptr()) == 0
+    want = torch.log(torch.sqrt(torch.clamp_min(d2, 0.0000001)))
+    assert torch.equal(params["scaling"], want[:, None].repeat(1, 3))
+    assert torch.equal(params["rotation"], torch.tensor([1.0, 0, 0, 0], device=dev).repeat(n, 1))
+    assert not stats.exist_since_iter.any() and stats.denom.shape == (n, 1)
+    nolf, _ = D.create_from_pcd(pts, cols, None, sh_degree=3)
+    assert not nolf["lang_feat"].any()
+    with pytest.raises(ValueError, match="num_points, 3"):
+        D.create_from_pcd(pts, cols[:, :2])
+    with pytest.raises(Exception, match="no CPU path"):
+        D.create_from_pcd(pts.cpu(), cols.cpu())
+    # the created model maps; then the map-wide scaled transformation
+    W, H = 96, 64
+    cams = [c.to(dev) for c in synthetic.make_cameras(2, W, H, seed=92)]
+    win = [M.Keyframe(c, torch.rand(3, H, W, generator=g).to(dev), torch.randn(64, 37, 37, generator=g).to(dev),
+                      (torch.rand(1, H, W, generator=g) * 3).to(dev)) for c in cams]
+    params["xyz"] = params["xyz"] - torch.tensor([3.0, 2.0, 1.4], device=dev)  # the synthetic cameras orbit the origin
+    mp = M.Mapper(params, sh_degree=3, track_densify_stats=True)
+    for _ in range(2):
+        assert torch.isfinite(mp.train_step(win))
+    import test_ingest as TI
+    T = TI._pose(g).to(dev)
+    xyz0, sc0 = mp.params["xyz"].detach().clone(), mp.params["scaling"].detach().clone()
+    op_m = mp.optimizer.state[mp.params["opacity"]]["exp_avg"].clone()
+    mp.apply_scaled_transformation(1.25, T)
+    assert torch.equal(mp.params["xyz"].detach(), geo.transform_points(xyz0 * 1.25, T))
+    assert torch.equal(mp.params["scaling"].detach(), sc0 * 1.25)
+    for k in ("xyz", "scaling"):
+        st = mp.optimizer.state[mp.params[k]]
+        assert st["step"] == 2 and not st["exp_avg"].any() and not st["exp_avg_sq"].any()
+    assert torch.equal(mp.optimizer.state[mp.params["opacity"]]["exp_avg"], op_m)
+    assert torch.isfinite(mp.train_step(win))
