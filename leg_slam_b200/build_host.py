@@ -8,8 +8,8 @@
                                  monocularPinholeInactiveGeoDensify... / distCUDA2 (include/operate_points.h,
                                  stereo_vision.h, spatial.h) + the pybind module `_C`
   leg_slam_b200/_L2.so         : GaussianRasterizationSettings / GaussianRasterizerFunction / GaussianRasterizer
-                                 (include/gaussian_rasterizer.h), LgsFusedAdam (include/lgs_adam.h) + the pybind module
-                                 `_L2` for the tests
+                                 (include/gaussian_rasterizer.h), LgsFusedAdam (include/lgs_adam.h), GaussianModel
+                                 (include/gaussian_model.h) + the pybind module `_L2` for the tests
 
     python -m leg_slam_b200.build_host [--force]
 """
@@ -64,8 +64,10 @@ def build(force=False, verbose=False):
         run(cmd)
     # L2 in C++ (include/gaussian_rasterizer.h): autograd node + module, with its own pybind module for the tests
     srcs2 = [os.path.join(HOST, "gaussian_rasterizer.cpp"), os.path.join(HOST, "rasterize_points.cpp"),
-             os.path.join(HOST, "fused_adam.cpp"), os.path.join(HOST, "l2_ext.cpp")]
-    if force or _stale(LIB_L2, srcs2 + hdrs + [os.path.join(inc, "gaussian_rasterizer.h"), os.path.join(inc, "lgs_adam.h")]):
+             os.path.join(HOST, "fused_adam.cpp"), os.path.join(HOST, "geometry_ops.cpp"), os.path.join(HOST, "gaussian_model.cpp"),
+             os.path.join(HOST, "l2_ext.cpp")]
+    if force or _stale(LIB_L2, srcs2 + hdrs + geo_hdrs + [os.path.join(inc, "gaussian_rasterizer.h"), os.path.join(inc, "lgs_adam.h"),
+                                                          os.path.join(inc, "gaussian_model.h")]):
         import torch  # noqa: F401
         from torch.utils import cpp_extension as ce
         cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")

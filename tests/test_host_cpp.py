@@ -181,3 +181,75 @@ def test_l1_geometry_operators_validate_like_the_reference(host_libs):
     assert _C.transform_points(e3, I).shape == (0, 3)
     assert _C.scale_and_transform_then_mark_visible(e3, torch.zeros(0, 4), ones[:0], ones[:0], I, I, I, 7, 1.0) == 7
     assert _C.dist_cuda2(e3).shape == (0,)
+
+
+def test_cpp_gaussian_model_settings_and_surgery_cpu(host_libs, oracle_mod):
+    """GaussianModel in C++ (include/gaussian_model.h, _L2.so): SH-degree bookkeeping, trainingSetup's seven groups and rates,
+    the xyz schedule bit-identical to the libm statement of exponLrFunc in the C oracle, the rate setters, and the
+    optimizer-state surgery that is plain libtorch (prunePoints, resetOpacity) on CPU tensors; everything that needs a
+    kernel refuses CPU tensors."""
+    from leg_slam_b200 import _L2
+    g = _L2.GaussianModel(3)
+    assert (g.active_sh_degree_, g.max_sh_degree_) == (0, 3)
+    for want in (1, 2, 3, 3):
+        g.oneUpShDegree()
+        assert g.active_sh_degree_ == want
+    g.setShDegree(7)
+    assert g.active_sh_degree_ == 3
+    g.setShDegree(1)
+    assert g.active_sh_degree_ == 1
+    gen = torch.Generator().manual_seed(1)
+    n = 12
+    g.xyz_, g.features_dc_, g.features_rest_ = torch.randn(n, 3, generator=gen), torch.randn(n, 1, 3, generator=gen), torch.randn(n, 15, 3, generator=gen)
+    g.language_features_, g.opacity_ = torch.randn(n, 64, generator=gen), torch.randn(n, 1, generator=gen)
+    g.scaling_, g.rotation_ = torch.randn(n, 3, generator=gen), torch.randn(n, 4, generator=gen)
+    for name in ("xyz_", "features_dc_", "features_rest_", "language_features_", "opacity_", "scaling_", "rotation_"):
+        setattr(g, name, getattr(g, name).requires_grad_())  # leaves, as createFromPcd leaves them
+    g.exist_since_iter_ = torch.arange(n, dtype=torch.int32)
+    g.max_radii2D_ = torch.zeros(n)
+    g.spatial_lr_scale_ = 5.3
+    a = _L2.GaussianOptimizationParams()
+    assert abs(a.position_lr_init_ - 1.6e-4) < 1e-10 and a.position_lr_max_steps_ == 30_000
+    g.trainingSetup(a)
+    assert g.params_are_the_optimizers()
+    f32 = np.float32
+    init, final = float(f32(1.6e-4) * f32(5.3)), float(f32(1.6e-6) * f32(5.3))
+    want = [init, float(f32(2.5e-3)), float(f32(2.5e-3)) / 20.0, float(f32(1.5e-3)), float(f32(0.05)), float(f32(5e-3)), float(f32(1e-3))]
+    assert [g.learning_rate(i) for i in range(7)] == want
+    assert g.xyz_gradient_accum_.shape == (n, 1) and g.denom_.shape == (n, 1)
+    for step in (0, 1, 17, 999, 15_000, 29_999, 30_000, 31_000, -1):
+        ref = oracle_mod.expon_lr(step, init, final, 0.01, 0, 30_000)
+        assert g.updateLearningRate(step) == ref and g.learning_rate(0) == ref, step
+    g.setPositionLearningRate(2e-4)
+    assert g.learning_rate(0) == float(f32(2e-4) * f32(5.3))
+    g.setFeatureLearningRate(1e-3)
+    assert g.learning_rate(1) == float(f32(1e-3)) and g.learning_rate(2) == float(f32(1e-3)) / 20.0
+    g.setLanguageFeatureLearningRate(2e-3), g.setOpacityLearningRate(0.04), g.setScalingLearningRate(4e-3), g.setRotationLearningRate(2e-3)
+    assert [g.learning_rate(i) for i in (3, 4, 5, 6)] == [float(f32(v)) for v in (2e-3, 0.04, 4e-3, 2e-3)]
+    assert g.adam_state(0)[0] == -1  # no step yet: no state
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        g.step([torch.zeros_like(t) for t in (g.xyz_, g.features_dc_, g.features_rest_, g.language_features_, g.opacity_, g.scaling_, g.rotation_)])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        g.densifyAndPrune(1e-3, 0.005, 5.0, 20)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        g.createFromPcd(torch.zeros(4, 3), torch.zeros(4, 3), torch.empty(0), 1.0)
+    # libtorch-only surgery
+    op = g.opacity_.detach().clone()
+    g.resetOpacity()
+    assert torch.allclose(torch.sigmoid(g.opacity_.detach()), torch.sigmoid(op), atol=1e-6) and g.params_are_the_optimizers()
+    mask = torch.zeros(n, dtype=torch.bool)
+    mask[[1, 5, 6]] = True
+    xyz = g.xyz_.detach().clone()
+    g.prunePoints(mask)
+    assert torch.equal(g.xyz_.detach(), xyz[~mask]) and g.rotation_.shape == (n - 3, 4) and g.params_are_the_optimizers()
+    assert g.exist_since_iter_.tolist() == [i for i in range(n) if i not in (1, 5, 6)] and g.denom_.shape == (n - 3, 1)
+    cov = g.getCovarianceActivation(1)
+    q = torch.nn.functional.normalize(g.rotation_.detach())
+    r, x, y, z = q.unbind(1)
+    R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y), 2 * (x * y + r * z), 1 - 2 * (x * x + z * z),
+                     2 * (y * z - r * x), 2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], 1).view(-1, 3, 3)
+    L = R @ torch.diag_embed(torch.exp(g.scaling_.detach()))
+    S = L @ L.transpose(1, 2)
+    want_cov = torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], 1)
+    assert torch.allclose(cov, want_cov, rtol=1e-5, atol=1e-6)
+    assert torch.equal(g.getFeatures(), torch.cat([g.features_dc_, g.features_rest_], 1))

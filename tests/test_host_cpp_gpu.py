@@ -169,3 +169,116 @@ def test_cpp_geometry_operators_equal_the_compiled_reference():
     assert torch.equal(ra[0], rb[0]) and torch.equal(ra[1], rb[1])
     e = _C.inactive_geo_densify(px[:0], has[:0], p3[:0], colors, 400.0, kin, 640)
     assert e[0] is None and e[1] is None  # undefined tensors, like the reference
+
+
+def test_cpp_gaussian_model_equals_the_python_mapper_side():
+    """GaussianModel in C++ (include/gaussian_model.h, _L2.so) against the Python statements of the same reference methods
+    (leg_slam_b200.densify / ingest / optim, each already held to the reference), on the same tensors: createFromPcd, Adam
+    steps through optimizer_ (LgsFusedAdam), addDensificationStats, densifyAndPrune (same generator state), increasePcd,
+    resetOpacity, the loop-closure correction (against the unmodified reference operator) and applyScaledTransformation."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import test_ingest as TI
+    from leg_slam_b200 import FusedAdam, build_host, densify as D, ingest
+    build_host.build()
+    from leg_slam_b200 import _L2
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(31)
+    n = 6000
+    pts = ((torch.rand(n, 3, generator=gen) - 0.5) * torch.tensor([6.0, 4.0, 2.8])).to(dev)
+    cols, lfs = torch.rand(n, 3, generator=gen).to(dev), torch.randn(n, 64, generator=gen).to(dev)
+    names = ("xyz_", "features_dc_", "features_rest_", "language_features_", "opacity_", "scaling_", "rotation_")
+    cur = lambda g: [getattr(g, k).detach() for k in names]  # noqa: E731
+
+    g = _L2.GaussianModel(3)
+    g.createFromPcd(pts, cols, lfs, 2.0)
+    py, stats = D.create_from_pcd(pts, cols, lfs, sh_degree=3)
+    for a, k in zip(cur(g), D.PARAM_ORDER):
+        assert torch.equal(a, py[k]), k
+    assert not g.exist_since_iter_.any() and g.max_radii2D_.shape == (n,)
+    args = _L2.GaussianOptimizationParams()
+    g.trainingSetup(args)
+    assert g.params_are_the_optimizers() and abs(g.learning_rate(0) - 3.2e-4) < 1e-9
+    # three optimizer steps on seeded gradients: LgsFusedAdam behind optimizer_ vs the Python FusedAdam, same kernel
+    ps = [torch.nn.Parameter(py[k].clone()) for k in D.PARAM_ORDER]
+    opt = FusedAdam([dict(params=[p], lr=g.learning_rate(i)) for i, p in enumerate(ps)], lr=0.0, eps=1e-15)
+    for s in range(3):
+        grads = [(torch.randn(p.shape, generator=gen) * 0.01).to(dev) for p in ps]
+        g.step([x.clone() for x in grads])
+        for p, x in zip(ps, grads):
+            p.grad = x
+        opt.step()
+    for i, (a, p) in enumerate(zip(cur(g), ps)):
+        st = g.adam_state(i)
+        assert torch.equal(a, p.detach()) and st[0] == 3, i
+        assert torch.equal(st[1], opt.state[p]["exp_avg"]) and torch.equal(st[2], opt.state[p]["exp_avg_sq"]), i
+    # statistics of two "views"
+    for s in range(2):
+        vs = torch.zeros(n, 3, device=dev, requires_grad=True)
+        vs.grad = (torch.randn(n, 3, generator=gen) * 4e-4).to(dev)
+        filt = (torch.rand(n, generator=gen) > 0.4).to(dev)
+        g.addDensificationStats(vs, filt)
+        stats.xyz_gradient_accum[filt] += vs.grad[filt, :2].norm(dim=-1, keepdim=True)
+        stats.denom[filt] += 1
+    assert torch.equal(g.xyz_gradient_accum_, stats.xyz_gradient_accum) and torch.equal(g.denom_, stats.denom)
+    g.exist_since_iter_ = torch.randint(0, 30, (n,), generator=gen).to(torch.int32).to(dev)
+    stats.exist_since_iter = g.exist_since_iter_.clone()
+    # densifyAndPrune: same classification, same gather, same normal draws
+    p_now = {k: a.clone() for k, a in zip(D.PARAM_ORDER, cur(g))}
+    m_now = {k: g.adam_state(i)[1].clone() for i, k in enumerate(D.PARAM_ORDER)}
+    v_now = {k: g.adam_state(i)[2].clone() for i, k in enumerate(D.PARAM_ORDER)}
+    torch.manual_seed(77)
+    g.densifyAndPrune(6e-4, 0.1, 20.0, 20)
+    torch.manual_seed(77)
+    p2, m2, v2, st2, info = D.densify_and_prune(p_now, m_now, v_now, stats, 6e-4, 0.1, 20.0, 20, percent_dense=g.percentDense())
+    assert info["cloned"] > 0 and info["split_selected"] > 0 and 0 < info["kept"] < n and info["new_P"] != n, info
+    for i, (a, k) in enumerate(zip(cur(g), D.PARAM_ORDER)):
+        st = g.adam_state(i)
+        assert torch.equal(a, p2[k]) and torch.equal(st[1], m2[k]) and torch.equal(st[2], v2[k]) and st[0] == 3, k
+    assert torch.equal(g.exist_since_iter_, st2.exist_since_iter) and g.params_are_the_optimizers()
+    P1 = info["new_P"]
+    assert g.denom_.shape == (P1, 1) and not g.denom_.any() and not g.xyz_gradient_accum_.any() and g.max_radii2D_.shape == (P1,)
+    # a keyframe's new points
+    newp = ((torch.rand(500, 3, generator=gen) - 0.5) * 3).to(dev)
+    newc = torch.rand(500, 3, generator=gen).to(dev)
+    g.increasePcd(newp, newc, 42)
+    p3, m3, v3, st3 = D.increase_pcd(p2, m2, v2, st2, newp, newc, 42)
+    for i, (a, k) in enumerate(zip(cur(g), D.PARAM_ORDER)):
+        st = g.adam_state(i)
+        assert torch.equal(a, p3[k]) and torch.equal(st[1], m3[k]) and torch.equal(st[2], v3[k]) and st[0] == 3, k
+    assert torch.equal(g.exist_since_iter_, st3.exist_since_iter) and (g.exist_since_iter_[P1:] == 42).all()
+    # resetOpacity
+    D.reset_opacity(p3, m3, v3)
+    g.resetOpacity()
+    st = g.adam_state(4)
+    assert torch.equal(g.opacity_.detach(), p3["opacity"]) and st[0] == 3 and not st[1].any() and not st[2].any()
+    # loop closure: the reference's sequence with its unmodified operator on clones
+    import build_ref
+    try:
+        ref = build_ref.load_geometry()
+    except FileNotFoundError as ex:
+        pytest.skip(str(ex))
+    P2 = g.xyz_.shape[0]
+    flags = (torch.rand(P2, generator=gen) > 0.2).to(dev)
+    T = TI._pose(gen).to(dev)
+    view, proj = TI._pose(gen, t=(0.1, 0.2, 0.5)).to(dev), torch.eye(4, device=dev)
+    r_pts, r_rots, r_flags = g.xyz_.detach().clone(), torch.nn.functional.normalize(g.rotation_.detach()), flags.clone()
+    r_un = torch.abs(g.exist_since_iter_ - 17) < 15
+    n_ref = ref.scale_and_transform_then_mark_visible(r_pts, r_rots, r_flags, r_un, T, view, proj, 4, 1.02)
+    sc_before = g.adam_state(5)[1].clone()
+    assert g.scaledTransformVisiblePointsOfKeyframe(flags, T, view, proj, 17, 15, 4, 1.02) == n_ref and 4 < n_ref < P2 + 4
+    assert torch.equal(flags, r_flags) and torch.equal(g.xyz_.detach(), r_pts) and torch.equal(g.rotation_.detach(), r_rots)
+    for i in (0, 6):
+        st = g.adam_state(i)
+        assert st[0] == 3 and not st[1].any() and not st[2].any()
+    assert torch.equal(g.adam_state(5)[1], sc_before) and g.params_are_the_optimizers()
+    # map-wide scaled transformation
+    xyz0, sc0 = g.xyz_.detach().clone(), g.scaling_.detach().clone()
+    g.applyScaledTransformation(1.25, T)
+    assert torch.equal(g.xyz_.detach(), ingest.transformPoints(xyz0 * 1.25, T)) and torch.equal(g.scaling_.detach(), sc0 * 1.25)
+    assert not g.adam_state(5)[1].any() and g.adam_state(5)[0] == 3 and g.params_are_the_optimizers()
+    g.step([torch.zeros_like(a) for a in cur(g)])
+    assert g.adam_state(0)[0] == 4
