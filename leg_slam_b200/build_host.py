@@ -65,9 +65,10 @@ def build(force=False, verbose=False):
     # L2 in C++ (include/gaussian_rasterizer.h): autograd node + module, with its own pybind module for the tests
     srcs2 = [os.path.join(HOST, "gaussian_rasterizer.cpp"), os.path.join(HOST, "rasterize_points.cpp"),
              os.path.join(HOST, "fused_adam.cpp"), os.path.join(HOST, "geometry_ops.cpp"), os.path.join(HOST, "gaussian_model.cpp"),
-             os.path.join(HOST, "l2_ext.cpp")]
+             os.path.join(HOST, "gaussian_renderer.cpp"), os.path.join(HOST, "l2_ext.cpp")]
     if force or _stale(LIB_L2, srcs2 + hdrs + geo_hdrs + [os.path.join(inc, "gaussian_rasterizer.h"), os.path.join(inc, "lgs_adam.h"),
-                                                          os.path.join(inc, "gaussian_model.h")]):
+                                                          os.path.join(inc, "gaussian_model.h"), os.path.join(inc, "gaussian_renderer.h"),
+                                                          os.path.join(inc, "gaussian_keyframe.h")]):
         import torch  # noqa: F401
         from torch.utils import cpp_extension as ce
         cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")

@@ -4,6 +4,7 @@
 
 #include "gaussian_model.h"
 #include "gaussian_rasterizer.h"
+#include "gaussian_renderer.h"
 #include "lgs_adam.h"
 
 namespace {
@@ -76,7 +77,30 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         .def_readwrite("scaling_lr_", &GaussianOptimizationParams::scaling_lr_)
         .def_readwrite("rotation_lr_", &GaussianOptimizationParams::rotation_lr_)
         .def_readwrite("percent_dense_", &GaussianOptimizationParams::percent_dense_);
-    pybind11::class_<GaussianModel>(m, "GaussianModel")
+    pybind11::class_<GaussianKeyframe, std::shared_ptr<GaussianKeyframe>>(m, "GaussianKeyframe")
+        .def(pybind11::init<>())
+        .def_readwrite("FoVx_", &GaussianKeyframe::FoVx_)
+        .def_readwrite("FoVy_", &GaussianKeyframe::FoVy_)
+        .def_readwrite("image_height_", &GaussianKeyframe::image_height_)
+        .def_readwrite("image_width_", &GaussianKeyframe::image_width_)
+        .def_readwrite("world_view_transform_", &GaussianKeyframe::world_view_transform_)
+        .def_readwrite("full_proj_transform_", &GaussianKeyframe::full_proj_transform_)
+        .def_readwrite("camera_center_", &GaussianKeyframe::camera_center_)
+        .def_readwrite("language_features_", &GaussianKeyframe::language_features_);
+    pybind11::class_<GaussianPipelineParams>(m, "GaussianPipelineParams")
+        .def(pybind11::init<bool, bool>(), pybind11::arg("convert_SHs") = false, pybind11::arg("compute_cov3D") = false);
+    m.def("render", [](std::shared_ptr<GaussianKeyframe> cam, int H, int W, std::shared_ptr<GaussianModel> g, GaussianPipelineParams pipe,
+                       torch::Tensor bg, torch::Tensor override_color, float scaling_modifier, bool use_override, bool include_lf) {
+        return GaussianRenderer::render(cam, H, W, g, pipe, bg, override_color, scaling_modifier, use_override, include_lf);
+    });
+    m.def("mapping_iteration_backward", [](std::shared_ptr<GaussianModel> g, std::shared_ptr<GaussianKeyframe> cam,
+                                           GaussianPipelineParams pipe, torch::Tensor bg, torch::Tensor gt_image, torch::Tensor gt_depth,
+                                           torch::Tensor mask, float lambda_dssim, bool stats) {
+        pybind11::gil_scoped_release no_gil;  // the autograd engine must not be entered with the GIL held
+        return mappingIterationBackward(g, cam, pipe, bg, gt_image, gt_depth, mask, lambda_dssim, stats);
+    });
+    m.def("mapping_iteration_step", &mappingIterationStep);
+    pybind11::class_<GaussianModel, std::shared_ptr<GaussianModel>>(m, "GaussianModel")
         .def(pybind11::init<int>())
         .def("getScalingActivation", &GaussianModel::getScalingActivation)
         .def("getRotationActivation", &GaussianModel::getRotationActivation)

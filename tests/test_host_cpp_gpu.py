@@ -282,3 +282,87 @@ def test_cpp_gaussian_model_equals_the_python_mapper_side():
     assert not g.adam_state(5)[1].any() and g.adam_state(5)[0] == 3 and g.params_are_the_optimizers()
     g.step([torch.zeros_like(a) for a in cur(g)])
     assert g.adam_state(0)[0] == 4
+
+
+def _cpp_model_from_scene(_L2, sc, lrs=None):
+    g = _L2.GaussianModel(3)
+    for name, k in (("xyz_", "xyz"), ("features_dc_", "features_dc"), ("features_rest_", "features_rest"),
+                    ("language_features_", "lang_feat"), ("opacity_", "opacity"), ("scaling_", "scaling"), ("rotation_", "rotation")):
+        setattr(g, name, sc[k].detach().clone().contiguous().requires_grad_())
+    P = sc["xyz"].shape[0]
+    g.exist_since_iter_ = torch.zeros(P, dtype=torch.int32, device=sc["xyz"].device)
+    g.max_radii2D_ = torch.zeros(P, device=sc["xyz"].device)
+    g.spatial_lr_scale_ = 1.0
+    a = _L2.GaussianOptimizationParams()
+    a.position_lr_init_ = 3.2e-4  # leg_slam_b200.mapper.DEFAULT_LRS (the reference's Replica configuration)
+    g.trainingSetup(a)
+    g.setShDegree(3)
+    return g
+
+
+def _cpp_keyframe(_L2, kf):
+    import math
+    k = _L2.GaussianKeyframe()
+    c = kf.camera
+    k.FoVx_, k.FoVy_ = 2.0 * math.atan(c.tanfovx), 2.0 * math.atan(c.tanfovy)
+    k.image_height_, k.image_width_ = c.height, c.width
+    k.world_view_transform_, k.full_proj_transform_, k.camera_center_ = c.viewmatrix, c.projmatrix, c.campos
+    k.language_features_ = kf.gt_lf
+    return k
+
+
+def test_cpp_renderer_and_mapping_iteration():
+    """GaussianRenderer::render in C++ (include/gaussian_renderer.h) against the Python statement of the same function on the
+    same model -- all input selections (SHs / SH -> RGB outside / override colour; scaling + rotation / precomputed covariance)
+    -- and three mapping iterations through mappingIterationBackward + mappingIterationStep (render, fused loss, autograd
+    through the C++ rasterizer node, densification statistics, LgsFusedAdam) against the Python mapper's fused path."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import numpy as np
+    from leg_slam_b200 import build_host, mapper as M, renderer as R, synthetic
+    build_host.build()
+    from leg_slam_b200 import _L2
+    dev = torch.device("cuda:0")
+    W, H = 96, 64
+    sc = synthetic.make_scene(4000, seed=51, mean_scale=0.06, device=dev)
+    cams = synthetic.make_cameras(2, W, H, seed=51)
+    gen = torch.Generator().manual_seed(52)
+    win = [M.Keyframe(c.to(dev), torch.rand(3, H, W, generator=gen).to(dev), torch.randn(64, 37, 37, generator=gen).to(dev),
+                      (torch.rand(1, H, W, generator=gen) * 3).to(dev)) for c in cams]
+    g = _cpp_model_from_scene(_L2, sc)
+    kfs = [_cpp_keyframe(_L2, kf) for kf in win]
+    bg = torch.zeros(3, device=dev)
+    none = torch.empty(0, device=dev)
+    pyview = R.GaussianModelView({k: sc[k] for k in M.PARAM_ORDER}, sh_degree=3)
+    override = torch.rand(4000, 3, generator=gen).to(dev)
+    with torch.no_grad():
+        for conv, cov, use_override in ((False, False, False), (True, False, False), (False, True, False), (False, False, True)):
+            a = _L2.render(kfs[0], H, W, g, _L2.GaussianPipelineParams(conv, cov), bg, override if use_override else none, 1.0,
+                           use_override, True)
+            b = R.GaussianRenderer.render(R.KeyframeView(win[0].camera), H, W, pyview, R.GaussianPipelineParams(conv, cov), bg,
+                                          override if use_override else None, 1.0, use_override, True)
+            assert torch.equal(a[5], b[5]) and torch.equal(a[4], b[4]), (conv, cov, use_override)
+            for x, y in zip(a[:3], b[:3]):
+                assert float((x - y).abs().max()) <= 1e-5 * max(1.0, float(y.abs().max())), (conv, cov, use_override)
+            assert a[3].shape == (4000, 3) and not a[3].any()
+    # three iterations, one keyframe each
+    ours = M.Mapper(sc, sh_degree=3, track_densify_stats=True)
+    pipe = _L2.GaussianPipelineParams()
+    mask = torch.empty(0, device=dev)
+    for it in range(3):
+        kf = win[it % 2]
+        l_cpp = _L2.mapping_iteration_backward(g, kfs[it % 2], pipe, bg, kf.gt_image, kf.gt_depth, mask, 0.2, True)
+        _L2.mapping_iteration_step(g)
+        l_py = ours.train_step([kf])
+        assert abs(float(l_cpp) - float(l_py)) <= 1e-4 * abs(float(l_py)), (it, float(l_cpp), float(l_py))
+    assert g.xyz_.grad is None  # zero_grad(true)
+    cur = [getattr(g, n).detach() for n in ("xyz_", "features_dc_", "features_rest_", "language_features_", "opacity_", "scaling_",
+                                            "rotation_")]
+    for a, k in zip(cur, M.PARAM_ORDER):
+        d = np.abs(a.cpu().numpy() - ours.params[k].detach().cpu().numpy())
+        step = 3 * M.DEFAULT_LRS[k]
+        assert (d > 0.05 * step).mean() <= 2e-3, (k, float(d.max()), step)
+        assert g.adam_state(M.PARAM_ORDER.index(k))[0] == 3
+    assert torch.equal(g.denom_, ours.stats.denom) and torch.equal(g.max_radii2D_, ours.stats.max_radii2D)
+    ga, pa = g.xyz_gradient_accum_.cpu().numpy(), ours.stats.xyz_gradient_accum.cpu().numpy()
+    assert np.abs(ga - pa).max() <= 2e-3 * np.abs(pa).max()
