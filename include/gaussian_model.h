@@ -17,13 +17,19 @@
  *
  * Signatures that name Eigen / Sophus / colmap-style types (absent from this image) take tensors instead and say so:
  * createFromPcd(points, colors, lang_feats, spatial_lr_scale) for the std::map<point3D_id_t, Point3D> overload,
- * applyScaledTransformation(s, T) with T the pose tensor stored transposed for the Sophus::SE3f overload.  Not here:
- * densifyAndClone / densifyAndSplit as separate steps (fused into densifyAndPrune), loadPly / savePly (tinyply;
- * leg_slam_b200.ply_io writes and reads the same files) and saveSparsePointsPly.
+ * applyScaledTransformation(s, T) with T the pose tensor stored transposed for the Sophus::SE3f overload.
+ *   checkpoints              savePly / loadPly (:854-1075) without tinyply: the same binary_little_endian file (property
+ *                            order x y z nx ny nz f_dc_* f_rest_* lf_* opacity scale_* rot_*, SH stored channel-major), the
+ *                            interleaving on the GPU (lgs_ply_pack / lgs_ply_unpack); loadPly also restores the language
+ *                            features (the reference's loader drops them) and, with savePly(path, true), the Adam state rides
+ *                            along as extra properties (adam_m_* / adam_v_*, step counts as header comments) -- the format of
+ *                            leg_slam_b200.ply_io, byte for byte.
+ * Not here: densifyAndClone / densifyAndSplit as separate steps (fused into densifyAndPrune) and saveSparsePointsPly.
  */
 #pragma once
 #include <torch/torch.h>
 
+#include <filesystem>
 #include <memory>
 #include <vector>
 
@@ -93,6 +99,9 @@ public:
                               torch::Tensor &new_rotation, torch::Tensor &new_exist_since_iter);
     void densifyAndPrune(float max_grad, float min_opacity, float extent, int max_screen_size);
     void addDensificationStats(torch::Tensor &viewspace_point_tensor, torch::Tensor &update_filter);
+
+    void loadPly(std::filesystem::path ply_path);
+    void savePly(std::filesystem::path result_path, bool with_optimizer_state = false);
 
     float percentDense();
     void setPercentDense(const float percent_dense);

@@ -13,6 +13,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <fstream>
+#include <map>
 #include <sstream>
 #include <string>
 
@@ -420,3 +422,168 @@ void GaussianModel::addDensificationStats(torch::Tensor& viewspace_point_tensor,
 
 float GaussianModel::percentDense() { return percent_dense_; }
 void GaussianModel::setPercentDense(const float percent_dense) { percent_dense_ = percent_dense; }
+
+// ---- checkpoints (:854-1075; file format of leg_slam_b200/ply_io.py = what tinyply writes for the reference)
+namespace {
+struct PlyColumn {
+    std::string name;
+    int tensor;  // index into the tensor list handed to the kernel, -1 = no tensor (normals: zeros / skipped)
+    int elem;
+};
+const char* const kGroupNames[7] = {"xyz", "features_dc", "features_rest", "lang_feat", "opacity", "scaling", "rotation"};
+
+// tensors 0-6 = the parameters in optimizer order, 7-13 = exp_avg, 14-20 = exp_avg_sq
+std::vector<PlyColumn> ply_columns(int n_rest, int n_lf, bool with_adam) {
+    std::vector<PlyColumn> c = {{"x", 0, 0}, {"y", 0, 1}, {"z", 0, 2}, {"nx", -1, 0}, {"ny", -1, 0}, {"nz", -1, 0}};
+    for (int k = 0; k < 3; ++k) c.push_back({"f_dc_" + std::to_string(k), 1, k});
+    for (int i = 0; i < 3 * n_rest; ++i) c.push_back({"f_rest_" + std::to_string(i), 2, 3 * (i % n_rest) + i / n_rest});  // channel-major
+    for (int i = 0; i < n_lf; ++i) c.push_back({"lf_" + std::to_string(i), 3, i});
+    c.push_back({"opacity", 4, 0});
+    for (int i = 0; i < 3; ++i) c.push_back({"scale_" + std::to_string(i), 5, i});
+    for (int i = 0; i < 4; ++i) c.push_back({"rot_" + std::to_string(i), 6, i});
+    if (with_adam) {
+        const int rows[7] = {3, 3, 3 * n_rest, n_lf, 1, 3, 4};
+        for (int which = 0; which < 2; ++which) {
+            int i = 0;
+            for (int t = 0; t < 7; ++t)
+                for (int e = 0; e < rows[t]; ++e) c.push_back({std::string(which ? "adam_v_" : "adam_m_") + std::to_string(i++), 7 + 7 * which + t, e});
+        }
+    }
+    return c;
+}
+
+void ply_run(bool pack, int64_t P, const std::vector<PlyColumn>& cols, std::vector<torch::Tensor>& tensors, torch::Tensor& block) {
+    const c10::cuda::CUDAGuard guard(block.device());
+    std::vector<int> col_t, col_e, rows;
+    for (auto& c : cols) {
+        col_t.push_back(c.tensor >= 0 && c.tensor < (int)tensors.size() && tensors[c.tensor].defined() ? c.tensor : -1);
+        col_e.push_back(c.elem);
+    }
+    std::vector<float*> ptrs;
+    for (auto& t : tensors) {
+        ptrs.push_back(t.defined() ? t.data_ptr<float>() : nullptr);
+        rows.push_back(t.defined() && P > 0 ? (int)(t.numel() / P) : 1);
+    }
+    auto i32 = torch::TensorOptions().dtype(torch::kInt32);
+    torch::Tensor d_t = torch::tensor(col_t, i32).to(block.device()), d_e = torch::tensor(col_e, i32).to(block.device());
+    const int st = pack ? lgs_ply_pack(P, (int)cols.size(), d_t.data_ptr<int>(), d_e.data_ptr<int>(), (int)ptrs.size(), ptrs.data(),
+                                       rows.data(), block.data_ptr<float>(), stream())
+                        : lgs_ply_unpack(P, (int)cols.size(), d_t.data_ptr<int>(), d_e.data_ptr<int>(), (int)ptrs.size(), ptrs.data(),
+                                         rows.data(), block.data_ptr<float>(), stream());
+    check(st, pack ? "lgs_ply_pack" : "lgs_ply_unpack");
+}
+}  // namespace
+
+void GaussianModel::savePly(std::filesystem::path result_path, bool with_optimizer_state) {
+    torch::NoGradGuard no_grad;
+    TORCH_CHECK(xyz_.is_cuda(), "leg_slam_b200 has no CPU path: tensors must live on a CUDA device");
+    const int64_t P = xyz_.size(0);
+    const int n_rest = (int)features_rest_.size(1), n_lf = (int)language_features_.size(1);
+    std::vector<torch::Tensor> tensors;
+    for (int i = 0; i < 7; ++i) tensors.push_back(param(i).detach().contiguous());
+    std::vector<int64_t> steps(7, 0);
+    const bool with_adam = with_optimizer_state && optimizer_ != nullptr;
+    if (with_adam) {
+        for (int which = 0; which < 2; ++which)
+            for (int i = 0; i < 7; ++i) {
+                auto* st = find_state(*optimizer_, optimizer_->param_groups()[i].params()[0]);
+                steps[i] = st ? st->step() : 0;
+                tensors.push_back(st ? (which ? st->exp_avg_sq() : st->exp_avg()).contiguous() : torch::zeros_like(tensors[i]));
+            }
+    }
+    auto cols = ply_columns(n_rest, n_lf, with_adam);
+    torch::Tensor block = torch::empty({P, (int64_t)cols.size()}, xyz_.options().dtype(torch::kFloat32));
+    ply_run(true, P, cols, tensors, block);
+    torch::Tensor host = block.cpu();
+    std::ofstream f(result_path, std::ios::binary);
+    TORCH_CHECK(f.good(), "cannot open ", result_path.string(), " for writing");
+    std::ostringstream h;
+    h << "ply\nformat binary_little_endian 1.0\n";
+    if (with_adam)
+        for (int i = 0; i < 7; ++i) h << "comment lgs_adam_step " << kGroupNames[i] << " " << steps[i] << "\n";
+    h << "element vertex " << P << "\n";
+    for (auto& c : cols) h << "property float " << c.name << "\n";
+    h << "end_header\n";
+    const std::string hs = h.str();
+    f.write(hs.data(), (std::streamsize)hs.size());
+    f.write(reinterpret_cast<const char*>(host.data_ptr<float>()), (std::streamsize)(host.numel() * sizeof(float)));
+    TORCH_CHECK(f.good(), "write to ", result_path.string(), " failed");
+}
+
+void GaussianModel::loadPly(std::filesystem::path ply_path) {
+    torch::NoGradGuard no_grad;
+    std::ifstream f(ply_path, std::ios::binary);
+    TORCH_CHECK(f.good(), "cannot open ", ply_path.string());
+    std::string line;
+    std::getline(f, line);
+    TORCH_CHECK(line.rfind("ply", 0) == 0, "not a ply file");
+    int64_t P = -1;
+    bool in_vertex = false;
+    std::vector<std::string> props;
+    std::map<std::string, int64_t> step_of;
+    for (;;) {
+        TORCH_CHECK((bool)std::getline(f, line), "ply header not terminated");
+        std::istringstream ss(line);
+        std::string tok, a, b, c;
+        ss >> tok;
+        if (tok == "format") {
+            ss >> a;
+            TORCH_CHECK(a == "binary_little_endian", "only binary_little_endian ply files are supported");
+        } else if (tok == "comment") {
+            ss >> a >> b >> c;
+            if (a == "lgs_adam_step" && !c.empty()) step_of[b] = std::stoll(c);
+        } else if (tok == "element") {
+            ss >> a >> b;
+            in_vertex = a == "vertex";
+            if (in_vertex) P = std::stoll(b);
+        } else if (tok == "property" && in_vertex) {
+            ss >> a >> b;
+            TORCH_CHECK(a == "float" || a == "float32", "property ", b, ": only float32 vertex properties are supported");
+            props.push_back(b);
+        } else if (tok == "end_header") {
+            break;
+        }
+    }
+    TORCH_CHECK(P >= 0, "ply file has no vertex element");
+    const int n_rest = (max_sh_degree_ + 1) * (max_sh_degree_ + 1) - 1;
+    int n_have = 0, n_lf = 0;
+    bool with_adam = false;
+    for (auto& p : props) {
+        n_have += p.rfind("f_rest_", 0) == 0;
+        n_lf += p.rfind("lf_", 0) == 0;
+        with_adam = with_adam || p.rfind("adam_m_", 0) == 0;
+    }
+    TORCH_CHECK(n_have == 3 * n_rest, "file holds ", n_have, " f_rest properties, max_sh_degree=", max_sh_degree_, " needs ", 3 * n_rest);
+    torch::Tensor host = torch::empty({P, (int64_t)props.size()}, torch::kFloat32);
+    f.read(reinterpret_cast<char*>(host.data_ptr<float>()), (std::streamsize)(host.numel() * sizeof(float)));
+    TORCH_CHECK(f.gcount() == (std::streamsize)(host.numel() * sizeof(float)), "ply file is shorter than its header says");
+    std::map<std::string, PlyColumn> want;
+    for (auto& c : ply_columns(n_rest, n_lf, with_adam)) want[c.name] = c;
+    std::vector<PlyColumn> cols;
+    for (auto& p : props) {  // unknown properties are skipped, like the reference does
+        auto it = want.find(p);
+        cols.push_back(it == want.end() ? PlyColumn{p, -1, 0} : it->second);
+    }
+    auto f32 = torch::TensorOptions().dtype(torch::kFloat32).device(torch::kCUDA);
+    const std::vector<std::vector<int64_t>> shapes = {{P, 3}, {P, 1, 3}, {P, n_rest, 3}, {P, n_lf}, {P, 1}, {P, 3}, {P, 4}};
+    std::vector<torch::Tensor> tensors;
+    for (int rep = 0; rep < (with_adam ? 3 : 1); ++rep)
+        for (int i = 0; i < 7; ++i) tensors.push_back(torch::zeros(shapes[i], f32));
+    torch::Tensor block = host.to(torch::kCUDA);
+    ply_run(false, P, cols, tensors, block);
+    if (optimizer_ != nullptr) {  // a model that is being trained: the groups take the loaded tensors (and state)
+        for (int i = 0; i < 7; ++i) {
+            auto it = step_of.find(kGroupNames[i]);
+            param(i) = swap_param(*optimizer_, i, tensors[i], with_adam, it == step_of.end() ? 0 : it->second,
+                                  with_adam ? tensors[7 + i] : torch::Tensor(), with_adam ? tensors[14 + i] : torch::Tensor());
+        }
+    } else {
+        for (int i = 0; i < 7; ++i) param(i) = tensors[i].requires_grad_();
+    }
+    tensorsToVec();
+    active_sh_degree_ = max_sh_degree_;  // :967
+    exist_since_iter_ = torch::zeros({P}, f32.dtype(torch::kInt32));
+    max_radii2D_ = torch::zeros({P}, f32);
+    xyz_gradient_accum_ = torch::zeros({P, 1}, f32);
+    denom_ = torch::zeros({P, 1}, f32);
+}

@@ -132,6 +132,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         .def("prunePoints", [](GaussianModel& g, torch::Tensor mask) { g.prunePoints(mask); })
         .def("densifyAndPrune", &GaussianModel::densifyAndPrune)
         .def("addDensificationStats", [](GaussianModel& g, torch::Tensor v, torch::Tensor f) { g.addDensificationStats(v, f); })
+        .def("savePly", [](GaussianModel& g, std::string path, bool with_state) { g.savePly(path, with_state); })
+        .def("loadPly", [](GaussianModel& g, std::string path) { g.loadPly(path); })
         .def("percentDense", &GaussianModel::percentDense)
         .def("setPercentDense", &GaussianModel::setPercentDense)
         .def("adam_state", &model_adam_state)

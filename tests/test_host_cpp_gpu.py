@@ -366,3 +366,55 @@ def test_cpp_renderer_and_mapping_iteration():
     assert torch.equal(g.denom_, ours.stats.denom) and torch.equal(g.max_radii2D_, ours.stats.max_radii2D)
     ga, pa = g.xyz_gradient_accum_.cpu().numpy(), ours.stats.xyz_gradient_accum.cpu().numpy()
     assert np.abs(ga - pa).max() <= 2e-3 * np.abs(pa).max()
+
+
+def test_cpp_gaussian_model_ply_checkpoints(tmp_path):
+    """GaussianModel::savePly / loadPly in C++ against leg_slam_b200.ply_io (whose files are byte-identical to what the
+    reference's own tinyply writes, tests/test_ply_io.py): same bytes with and without the optimizer state, and a model
+    loaded from either file holds the tensors, the Adam moments and the step counts that went in."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from leg_slam_b200 import build_host, mapper as M, ply_io, synthetic
+    build_host.build()
+    from leg_slam_b200 import _L2
+    dev = torch.device("cuda:0")
+    sc = synthetic.make_scene(3001, seed=5, mean_scale=0.06, device=dev)
+    g = _cpp_model_from_scene(_L2, sc)
+    names = ("xyz_", "features_dc_", "features_rest_", "language_features_", "opacity_", "scaling_", "rotation_")
+    gen = torch.Generator().manual_seed(6)
+    for _ in range(2):
+        g.step([(torch.randn(getattr(g, n).shape, generator=gen) * 0.01).to(dev) for n in names])
+    # copies: the optimizer updates the model's tensors and moments in place further down
+    params = {k: getattr(g, n).detach().clone() for k, n in zip(M.PARAM_ORDER, names)}
+    m = {k: g.adam_state(i)[1].clone() for i, k in enumerate(M.PARAM_ORDER)}
+    v = {k: g.adam_state(i)[2].clone() for i, k in enumerate(M.PARAM_ORDER)}
+    a, b, c, d = (str(tmp_path / n) for n in ("cpp_state.ply", "py_state.ply", "cpp_plain.ply", "py_plain.ply"))
+    g.savePly(a, True)
+    ply_io.save_ply(b, params, m, v, {k: 2 for k in M.PARAM_ORDER})
+    g.savePly(c, False)
+    ply_io.save_ply(d, params)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    assert open(c, "rb").read() == open(d, "rb").read()
+    fresh = _L2.GaussianModel(3)
+    fresh.loadPly(c)  # no optimizer yet: plain leaves
+    for k, n in zip(M.PARAM_ORDER, names):
+        t = getattr(fresh, n)
+        assert torch.equal(t.detach(), params[k]) and t.requires_grad, k
+    assert fresh.active_sh_degree_ == 3 and fresh.denom_.shape == (3001, 1) and fresh.exist_since_iter_.shape == (3001,)
+    resumed = _cpp_model_from_scene(_L2, {k: torch.zeros_like(t) for k, t in sc.items() if k in M.PARAM_ORDER})
+    resumed.loadPly(b)  # written by the Python side, with the optimizer state
+    assert resumed.params_are_the_optimizers()
+    for i, (k, n) in enumerate(zip(M.PARAM_ORDER, names)):
+        st = resumed.adam_state(i)
+        assert torch.equal(getattr(resumed, n).detach(), params[k]) and st[0] == 2, k
+        assert torch.equal(st[1], m[k]) and torch.equal(st[2], v[k]), k
+    # both continue identically
+    grads = [(torch.randn(getattr(g, n).shape, generator=gen) * 0.01).to(dev) for n in names]
+    g.step([x.clone() for x in grads])
+    resumed.step([x.clone() for x in grads])
+    for n in names:
+        assert torch.equal(getattr(g, n).detach(), getattr(resumed, n).detach()), n
+    p2, m2, v2, steps2 = ply_io.load_ply(a, dev, 3)  # and the Python side reads the C++ file
+    assert all(torch.equal(p2[k], params[k]) and torch.equal(m2[k], m[k]) for k in M.PARAM_ORDER) and steps2["xyz"] == 2
+    with pytest.raises(RuntimeError, match="cannot open"):
+        fresh.loadPly(str(tmp_path / "missing.ply"))
