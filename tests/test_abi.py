@@ -79,6 +79,17 @@ def test_argument_validation_needs_no_gpu(built):
     assert L.lgs_dp_adam_shard(1, seg, lr, 1, 0, ptrs, ptrs, None, None, 0, 8, p, p, *common, 0, 0, None) == 1      # step < 1
     assert L.lgs_dp_adam_shard(1, seg, lr, 1, 0, ptrs, ptrs, None, None, 2, 8, p, p, *common, 1, 0, None) == 1      # shard not on 16 B
     assert L.lgs_dp_adam_shard(1, seg, lr, 1, 0, ptrs, ptrs, None, None, 4, 4, p, p, *common, 1, 0, None) == 0      # empty shard
+    # the operators beside the path: counts, null pointers and alignment are checked before any launch
+    assert L.lgs_scale_transform_mark_visible(-1, 1.0, p, p, p, p, p, p, 1, p, None) == 1
+    assert L.lgs_scale_transform_mark_visible(0, 1.0, None, None, None, None, None, None, 1, None, None) == 0
+    assert L.lgs_scale_transform_mark_visible(4, 1.0, p, p, p, p, p, p, 1, None, None) == 1                         # no counter
+    assert L.lgs_scale_transform_mark_visible(4, 1.0, p, ctypes.c_void_p(p.value + 4), p, p, p, p, 1, p, None) == 1  # rots off 16 B
+    assert L.lgs_inactive_geo_scratch_bytes(0) == 0 and L.lgs_inactive_geo_scratch_bytes(100) >= 100 * 25
+    assert L.lgs_inactive_geo_densify(-1, 8, 1.0, 1.0, 0.0, 0.0, 1.0, p, p, p, p, 64, p, p, p, p, None) == 1
+    assert L.lgs_inactive_geo_densify(4, 0, 1.0, 1.0, 0.0, 0.0, 1.0, p, p, p, p, 64, p, p, p, p, None) == 1          # width <= 0
+    assert L.lgs_inactive_geo_densify(4, 8, 1.0, 1.0, 0.0, 0.0, 1.0, p, p, p, p, 64, p, p, None, p, None) == 1       # no counter
+    assert L.lgs_inactive_geo_densify(4, 8, 1.0, 1.0, 0.0, 0.0, 1.0, p, p, p, None, 64, p, p, p, p, None) == 1       # no colours
+    assert L.lgs_inactive_geo_densify(4, 8, 1.0, 1.0, 0.0, 0.0, 1.0, ctypes.c_void_p(p.value + 4), p, p, p, 64, p, p, p, p, None) == 1
 
 
 def test_sass_is_sm100a_with_tma(built):
