@@ -10,6 +10,10 @@
   leg_slam_b200/_L2.so         : GaussianRasterizationSettings / GaussianRasterizerFunction / GaussianRasterizer
                                  (include/gaussian_rasterizer.h), LgsFusedAdam (include/lgs_adam.h), GaussianModel
                                  (include/gaussian_model.h) + the pybind module `_L2` for the tests
+  leg_slam_b200/liblgs_torch.so: the same libtorch layers (L1 functions, geometry operators, L2 rasterizer, LgsFusedAdam,
+                                 GaussianModel, GaussianRenderer + mapping-iteration functions) as a plain C++ library with
+                                 exported symbols and no pybind module: what a C++ consumer such as the reference's
+                                 gaussian_mapper links (tests/cpp/mapper_driver.cpp does)
 
     python -m leg_slam_b200.build_host [--force]
 """
@@ -26,6 +30,33 @@ HOST = os.path.join(PKG, "csrc", "host")
 LIB_HOST = os.path.join(PKG, "liblgs_host.so")
 LIB_C = os.path.join(PKG, "_C.so")
 LIB_L2 = os.path.join(PKG, "_L2.so")
+LIB_TORCH = os.path.join(PKG, "liblgs_torch.so")
+DRIVER_SRC = os.path.join(ROOT, "tests", "cpp", "mapper_driver.cpp")
+DRIVER_EXE = os.path.join(PKG, "build", "host", "mapper_driver")
+
+
+def build_mapper_driver(force=False, verbose=False):
+    """tests/cpp/mapper_driver.cpp: a plain C++ program (no Python in the process) on liblgs_torch.so, built here so that the
+    GPU box does not spend its time compiling libtorch headers.  Links libpython only because libtorch_python, which
+    <torch/extension.h> (include/rasterize_points.h, like the reference's) pulls in, needs its symbols."""
+    if not force and not _stale(DRIVER_EXE, [DRIVER_SRC, LIB_TORCH]):
+        return DRIVER_EXE
+    import torch  # noqa: F401
+    from torch.utils import cpp_extension as ce
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    os.makedirs(os.path.dirname(DRIVER_EXE), exist_ok=True)
+    pyver = "python%d.%d" % sys.version_info[:2]
+    cmd = ["g++", "-O1", "-std=c++17", "-D_GLIBCXX_USE_CXX11_ABI=1", DRIVER_SRC, "-I" + os.path.join(ROOT, "include"),
+           "-I" + os.path.join(cuda, "include"), "-I" + sysconfig.get_paths()["include"]] + ["-I" + p for p in ce.include_paths()]
+    cmd += ["-o", DRIVER_EXE, "-L" + PKG, "-llgs_torch", "-llgs"] + ["-L" + p for p in ce.library_paths()]
+    cmd += ["-L" + os.path.join(cuda, "lib64"), "-lc10", "-ltorch_cpu", "-ltorch", "-lc10_cuda", "-Wl,--no-as-needed", "-ltorch_cuda",
+            "-Wl,--as-needed", "-lcudart", "-L" + (sysconfig.get_config_var("LIBDIR") or "/usr/lib"), "-l" + pyver,
+            "-Wl,-rpath," + PKG]
+    cmd += ["-Wl,-rpath," + p for p in ce.library_paths()]
+    if verbose:
+        print("[lgs host]", " ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return DRIVER_EXE
 
 
 def _stale(target, deps):
@@ -88,6 +119,32 @@ def build(force=False, verbose=False):
                                                           "-lcudart"]
         cmd += ["-Wl,-rpath," + p for p in ce.library_paths()]
         run(cmd)
+    # the libtorch layers as a C++ library (default symbol visibility, no Python module in it)
+    srcs3 = [os.path.join(HOST, n) for n in ("rasterize_points.cpp", "geometry_ops.cpp", "gaussian_rasterizer.cpp", "fused_adam.cpp",
+                                             "gaussian_model.cpp", "gaussian_renderer.cpp")]
+    all_hdrs = hdrs + geo_hdrs + [os.path.join(inc, h) for h in ("gaussian_rasterizer.h", "lgs_adam.h", "gaussian_model.h",
+                                                                   "gaussian_renderer.h", "gaussian_keyframe.h")]
+    if force or _stale(LIB_TORCH, srcs3 + all_hdrs):
+        import torch  # noqa: F401
+        from torch.utils import cpp_extension as ce
+        cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+        common = ["g++", "-O2", "-std=c++17", "-fPIC", "-D_GLIBCXX_USE_CXX11_ABI=1", "-I" + inc, "-I" + os.path.join(cuda, "include"),
+                  "-I" + sysconfig.get_paths()["include"]] + ["-I" + p for p in ce.include_paths()]
+        objdir = os.path.join(PKG, "build", "host")
+        os.makedirs(objdir, exist_ok=True)
+        objs = [os.path.join(objdir, os.path.basename(x)[:-4] + ".lib.o") for x in srcs3]
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=len(srcs3)) as ex:
+            list(ex.map(lambda so: run(common + ["-c", so[0], "-o", so[1]]), zip(srcs3, objs)))
+        cmd = ["g++", "-shared"] + objs + ["-o", LIB_TORCH, "-L" + PKG, "-llgs", "-Wl,-rpath,$ORIGIN"]
+        # libtorch_cuda registers the CUDA backend from static initialisers: nothing references it by symbol, so it must be
+        # kept explicitly or a pure C++ process has no CUDA tensors (inside Python, torch has loaded it already)
+        cmd += ["-L" + p for p in ce.library_paths()] + ["-L" + os.path.join(cuda, "lib64"), "-lc10", "-ltorch_cpu", "-ltorch",
+                                                          "-lc10_cuda", "-Wl,--no-as-needed", "-ltorch_cuda", "-Wl,--as-needed",
+                                                          "-lcudart"]
+        cmd += ["-Wl,-rpath," + p for p in ce.library_paths()]
+        run(cmd)
+    build_mapper_driver(force, verbose)
     return LIB_HOST, LIB_C
 
 

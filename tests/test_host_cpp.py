@@ -253,3 +253,70 @@ def test_cpp_gaussian_model_settings_and_surgery_cpu(host_libs, oracle_mod):
     want_cov = torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], 1)
     assert torch.allclose(cov, want_cov, rtol=1e-5, atol=1e-6)
     assert torch.equal(g.getFeatures(), torch.cat([g.features_dc_, g.features_rest_], 1))
+
+
+def test_cpp_library_exports_the_reference_classes(host_libs):
+    """liblgs_torch.so -- the libtorch layers as a plain C++ library -- exports the reference's functions and classes by
+    their own (mangled) names, and the C++ mapper driver (tests/cpp/mapper_driver.cpp, no Python in the process) links
+    against it."""
+    from leg_slam_b200 import build_host
+    out = subprocess.run(["nm", "-D", "--defined-only", "-C", build_host.LIB_TORCH], capture_output=True, text=True).stdout
+    for sym in ("RasterizeGaussiansCUDA(", "RasterizeGaussiansBackwardCUDA(", "markVisible(", "transformPoints(", "distCUDA2(",
+                "scaleAndTransformThenMarkVisiblePoints(", "reprojectDepthPinhole(",
+                "monocularPinholeInactiveGeoDensifyBySearchingNeighborhoodKeypoints(", "GaussianRasterizerFunction::forward(",
+                "GaussianRasterizer::forward(", "LgsFusedAdam::step(", "GaussianModel::trainingSetup(",
+                "GaussianModel::densifyAndPrune(", "GaussianModel::increasePcd(", "GaussianModel::updateLearningRate(",
+                "GaussianModel::scaledTransformVisiblePointsOfKeyframe(", "GaussianModel::savePly(", "GaussianModel::loadPly(",
+                "GaussianRenderer::render(", "mappingIterationBackward(", "mappingIterationStep("):
+        assert sym in out, sym
+    assert "PyInit" not in out
+    exe = build_host.build_mapper_driver()
+    assert os.access(exe, os.X_OK)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1  # usage error: the program loads (every shared-library dependency resolves) and needs two paths
+
+
+@pytest.mark.gpu
+def test_cpp_mapper_driver_follows_the_python_mapper(host_libs, tmp_path):
+    """A C++ program on liblgs_torch.so that does what GaussianMapper::trainForOneIteration does with the reference's classes
+    (settings, render, loss, backward, statistics, optimizer step; reference src/gaussian_mapper.cpp:662-796), against the
+    Python mapper's fused path on the same scene, keyframe and learning-rate schedule."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import math
+    from leg_slam_b200 import build_host, mapper as M, synthetic
+    exe = build_host.build_mapper_driver()
+    dev = torch.device("cuda:0")
+    W, H, P, N_IT = 96, 64, 4000, 4
+    sc = synthetic.make_scene(P, seed=51, mean_scale=0.06, device=dev)
+    cam = synthetic.make_cameras(1, W, H, seed=51)[0].to(dev)
+    g = torch.Generator().manual_seed(52)
+    kf = M.Keyframe(cam, torch.rand(3, H, W, generator=g).to(dev), torch.randn(64, 37, 37, generator=g).to(dev),
+                    (torch.rand(1, H, W, generator=g) * 3).to(dev))
+    with open(tmp_path / "in.bin", "wb") as f:
+        np.array([P, W, H, N_IT, 37, 37], np.int32).tofile(f)
+        np.array([2.0 * math.atan(cam.tanfovx), 2.0 * math.atan(cam.tanfovy)], np.float32).tofile(f)
+        for t in ([sc[k] for k in M.PARAM_ORDER] + [cam.viewmatrix, cam.projmatrix, cam.campos, kf.gt_image, kf.gt_lf, kf.gt_depth]):
+            t.detach().contiguous().cpu().numpy().astype(np.float32).tofile(f)
+    r = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    with open(tmp_path / "out.bin", "rb") as fh:
+        losses = np.fromfile(fh, np.float32, N_IT)
+        xyz = np.fromfile(fh, np.float32, 3 * P).reshape(P, 3)
+        opacity = np.fromfile(fh, np.float32, P).reshape(P, 1)
+        denom = np.fromfile(fh, np.float32, P)
+        max_radii = np.fromfile(fh, np.float32, P)
+        lr_last = float(np.fromfile(fh, np.float32, 1)[0])
+    mp = M.Mapper(sc, sh_degree=3, track_densify_stats=True)
+    mp.set_position_lr_schedule(3.2e-4, 3.2e-6, 0.01, N_IT)
+    lrs = []
+    for it in range(N_IT):
+        lrs.append(mp.update_learning_rate(it))
+        l_py = float(mp.train_step([kf]))
+        assert abs(float(losses[it]) - l_py) <= 1e-4 * abs(l_py), (it, float(losses[it]), l_py)
+    assert abs(lr_last - lrs[-1]) <= 2e-7 * lrs[-1]
+    assert np.array_equal(denom, mp.stats.denom.cpu().numpy().reshape(-1))
+    assert np.array_equal(max_radii, mp.stats.max_radii2D.cpu().numpy())
+    for got, k, step in ((xyz, "xyz", sum(lrs)), (opacity, "opacity", N_IT * M.DEFAULT_LRS["opacity"])):
+        d = np.abs(got - mp.params[k].detach().cpu().numpy())
+        assert (d > 0.05 * step).mean() <= 3e-3, (k, float(d.max()), step)
