@@ -79,71 +79,51 @@ def build(force=False, verbose=False):
     if force or _stale(LIB_HOST, [src0] + hdrs):
         run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I" + inc, src0, "-o", LIB_HOST, "-L" + PKG, "-llgs",
              "-Wl,-rpath,$ORIGIN"])
-    srcs = [os.path.join(HOST, "rasterize_points.cpp"), os.path.join(HOST, "geometry_ops.cpp"), os.path.join(HOST, "ext.cpp")]
-    if force or _stale(LIB_C, srcs + hdrs + geo_hdrs):
-        import torch  # noqa: F401
-        from torch.utils import cpp_extension as ce
-        cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
-        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=_C",
-               "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=1", "-I" + inc,
-               "-I" + os.path.join(cuda, "include"), "-I" + sysconfig.get_paths()["include"]]
-        cmd += ["-I" + p for p in ce.include_paths()] + srcs + ["-o", LIB_C, "-L" + PKG, "-llgs", "-Wl,-rpath,$ORIGIN"]
-        cmd += ["-L" + p for p in ce.library_paths()] + ["-L" + os.path.join(cuda, "lib64"), "-lc10", "-ltorch_cpu",
-                                                          "-ltorch", "-ltorch_python", "-lc10_cuda", "-ltorch_cuda",
-                                                          "-lcudart"]
-        cmd += ["-Wl,-rpath," + p for p in ce.library_paths()]
-        run(cmd)
-    # L2 in C++ (include/gaussian_rasterizer.h): autograd node + module, with its own pybind module for the tests
-    srcs2 = [os.path.join(HOST, "gaussian_rasterizer.cpp"), os.path.join(HOST, "rasterize_points.cpp"),
-             os.path.join(HOST, "fused_adam.cpp"), os.path.join(HOST, "geometry_ops.cpp"), os.path.join(HOST, "gaussian_model.cpp"),
-             os.path.join(HOST, "gaussian_renderer.cpp"), os.path.join(HOST, "l2_ext.cpp")]
-    if force or _stale(LIB_L2, srcs2 + hdrs + geo_hdrs + [os.path.join(inc, "gaussian_rasterizer.h"), os.path.join(inc, "lgs_adam.h"),
-                                                          os.path.join(inc, "gaussian_model.h"), os.path.join(inc, "gaussian_renderer.h"),
-                                                          os.path.join(inc, "gaussian_keyframe.h")]):
-        import torch  # noqa: F401
-        from torch.utils import cpp_extension as ce
-        cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
-        common = ["g++", "-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-DTORCH_EXTENSION_NAME=_L2",
-                  "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=1", "-I" + inc,
-                  "-I" + os.path.join(cuda, "include"), "-I" + sysconfig.get_paths()["include"]]
-        common += ["-I" + p for p in ce.include_paths()]
-        objdir = os.path.join(PKG, "build", "host")
-        os.makedirs(objdir, exist_ok=True)
-        objs = [os.path.join(objdir, os.path.basename(x)[:-4] + ".l2.o") for x in srcs2]
-        from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(max_workers=len(srcs2)) as ex:  # libtorch-heavy translation units: ~1 min each
-            list(ex.map(lambda so: run(common + ["-c", so[0], "-o", so[1]]), zip(srcs2, objs)))
-        cmd = ["g++", "-shared"] + objs + ["-o", LIB_L2, "-L" + PKG, "-llgs", "-Wl,-rpath,$ORIGIN"]
-        cmd += ["-L" + p for p in ce.library_paths()] + ["-L" + os.path.join(cuda, "lib64"), "-lc10", "-ltorch_cpu",
-                                                          "-ltorch", "-ltorch_python", "-lc10_cuda", "-ltorch_cuda",
-                                                          "-lcudart"]
-        cmd += ["-Wl,-rpath," + p for p in ce.library_paths()]
-        run(cmd)
-    # the libtorch layers as a C++ library (default symbol visibility, no Python module in it)
-    srcs3 = [os.path.join(HOST, n) for n in ("rasterize_points.cpp", "geometry_ops.cpp", "gaussian_rasterizer.cpp", "fused_adam.cpp",
-                                             "gaussian_model.cpp", "gaussian_renderer.cpp")]
     all_hdrs = hdrs + geo_hdrs + [os.path.join(inc, h) for h in ("gaussian_rasterizer.h", "lgs_adam.h", "gaussian_model.h",
                                                                    "gaussian_renderer.h", "gaussian_keyframe.h")]
-    if force or _stale(LIB_TORCH, srcs3 + all_hdrs):
+    objdir = os.path.join(PKG, "build", "host")
+    os.makedirs(objdir, exist_ok=True)
+    from concurrent.futures import ThreadPoolExecutor
+
+    def torch_flags():
         import torch  # noqa: F401
         from torch.utils import cpp_extension as ce
         cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
-        common = ["g++", "-O2", "-std=c++17", "-fPIC", "-D_GLIBCXX_USE_CXX11_ABI=1", "-I" + inc, "-I" + os.path.join(cuda, "include"),
-                  "-I" + sysconfig.get_paths()["include"]] + ["-I" + p for p in ce.include_paths()]
-        objdir = os.path.join(PKG, "build", "host")
-        os.makedirs(objdir, exist_ok=True)
-        objs = [os.path.join(objdir, os.path.basename(x)[:-4] + ".lib.o") for x in srcs3]
-        from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(max_workers=len(srcs3)) as ex:
-            list(ex.map(lambda so: run(common + ["-c", so[0], "-o", so[1]]), zip(srcs3, objs)))
-        cmd = ["g++", "-shared"] + objs + ["-o", LIB_TORCH, "-L" + PKG, "-llgs", "-Wl,-rpath,$ORIGIN"]
-        # libtorch_cuda registers the CUDA backend from static initialisers: nothing references it by symbol, so it must be
-        # kept explicitly or a pure C++ process has no CUDA tensors (inside Python, torch has loaded it already)
-        cmd += ["-L" + p for p in ce.library_paths()] + ["-L" + os.path.join(cuda, "lib64"), "-lc10", "-ltorch_cpu", "-ltorch",
-                                                          "-lc10_cuda", "-Wl,--no-as-needed", "-ltorch_cuda", "-Wl,--as-needed",
-                                                          "-lcudart"]
-        cmd += ["-Wl,-rpath," + p for p in ce.library_paths()]
-        run(cmd)
+        incs = ["-I" + inc, "-I" + os.path.join(cuda, "include"), "-I" + sysconfig.get_paths()["include"]] + ["-I" + p for p in ce.include_paths()]
+        libdirs = ["-L" + p for p in ce.library_paths()] + ["-L" + os.path.join(cuda, "lib64")]
+        rpaths = ["-Wl,-rpath," + p for p in ce.library_paths()]
+        return incs, libdirs, rpaths
+
+    def target(lib, names, hdr_deps, cflags, suffix, libs):
+        """One shared library from libtorch-heavy translation units (~1 min each): objects in parallel, then the link."""
+        srcs = [os.path.join(HOST, n) for n in names]
+        if not (force or _stale(lib, srcs + hdr_deps)):
+            return
+        incs, libdirs, rpaths = torch_flags()
+        common = ["g++", "-O2", "-std=c++17", "-fPIC", "-D_GLIBCXX_USE_CXX11_ABI=1"] + cflags + incs
+        objs = [os.path.join(objdir, n[:-4] + suffix) for n in names]
+        with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
+            list(ex.map(lambda so: run(common + ["-c", so[0], "-o", so[1]]), zip(srcs, objs)))
+        run(["g++", "-shared"] + objs + ["-o", lib, "-L" + PKG, "-llgs", "-Wl,-rpath,$ORIGIN"] + libdirs + libs + rpaths)
+
+    py_libs = ["-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python", "-lc10_cuda", "-ltorch_cuda", "-lcudart"]
+    # libtorch_cuda registers the CUDA backend from static initialisers: nothing references it by symbol, so the C++ library
+    # keeps it explicitly, or a pure C++ process has no CUDA tensors (inside Python, torch has loaded it already)
+    cpp_libs = ["-lc10", "-ltorch_cpu", "-ltorch", "-lc10_cuda", "-Wl,--no-as-needed", "-ltorch_cuda", "-Wl,--as-needed", "-lcudart"]
+    jobs = [
+        # L1 (+ the geometry operators) and the pybind module `_C`
+        (LIB_C, ["rasterize_points.cpp", "geometry_ops.cpp", "ext.cpp"], hdrs + geo_hdrs,
+         ["-DTORCH_EXTENSION_NAME=_C", "-DTORCH_API_INCLUDE_EXTENSION_H"], ".c.o", py_libs),
+        # L2 in C++: autograd node + module, optimizer, model, renderer, with its own pybind module for the tests
+        (LIB_L2, ["gaussian_rasterizer.cpp", "rasterize_points.cpp", "fused_adam.cpp", "geometry_ops.cpp", "gaussian_model.cpp",
+                  "gaussian_renderer.cpp", "l2_ext.cpp"], all_hdrs,
+         ["-fvisibility=hidden", "-DTORCH_EXTENSION_NAME=_L2", "-DTORCH_API_INCLUDE_EXTENSION_H"], ".l2.o", py_libs),
+        # the libtorch layers as a C++ library (default symbol visibility, no Python module in it)
+        (LIB_TORCH, ["rasterize_points.cpp", "geometry_ops.cpp", "gaussian_rasterizer.cpp", "fused_adam.cpp", "gaussian_model.cpp",
+                     "gaussian_renderer.cpp"], all_hdrs, [], ".lib.o", cpp_libs),
+    ]
+    with ThreadPoolExecutor(max_workers=len(jobs)) as ex:  # the three targets side by side
+        list(ex.map(lambda j: target(*j), jobs))
     build_mapper_driver(force, verbose)
     return LIB_HOST, LIB_C
 
