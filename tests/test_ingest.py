@@ -168,6 +168,34 @@ def test_inactive_geo_restatement_cpu():
     np.testing.assert_allclose(col, [[12, 13, 14], [15, 16, 17], [13, 14, 15], [0, 1, 2]])
 
 
+def test_restatement_matches_reference_golden_cpu():
+    """The numpy restatement against outputs of the UNMODIFIED reference operators (tests/golden/geometry.npz, written on a
+    B200 by tests/golden/make_geometry_golden.py from oracle/_ref/ref_geometry.so): depth reprojection bit-exact, point
+    transform within 2 ulp-scale (the restatement evaluates in float64), the loop-closure selection / count / flags exact with
+    points and rotation rows within 1e-5, the inactive-geometry densification's selection exact (same rows, same colours)
+    with reprojected points within 1e-6 -- for fractional pixels and for integer pixels with distance ties."""
+    G = np.load(os.path.join(ROOT, "tests", "golden", "geometry.npz"))
+    pts = IR.reproject_depth_pinhole(G["rp_depth"], G["rp_mask"], G["rp_intr"], int(G["rp_width"]))
+    np.testing.assert_array_equal(pts, G["rp_points"])
+    np.testing.assert_allclose(IR.transform_points(G["rp_points"], G["tp_T"]), G["tp_out"], rtol=2e-6, atol=2e-6)
+    p2, r2, nt2, num = IR.scale_and_transform_then_mark_visible(G["lc_points"], G["lc_rots"], G["lc_not_transformed"], G["lc_unstable"],
+                                                               G["lc_T"], G["lc_view"], float(G["lc_scale"]))
+    assert num == int(G["lc_num"]) and 0 < num < G["lc_points"].shape[0]
+    np.testing.assert_array_equal(nt2, G["lc_out_not_transformed"])
+    np.testing.assert_allclose(p2, G["lc_out_points"], rtol=3e-6, atol=3e-6)
+    sel = G["lc_not_transformed"] & ~G["lc_out_not_transformed"]
+    assert sel.sum() == num and np.all(G["lc_out_rots"][sel][:, 3] == 0)          # the shipped (w, x, z, 0) rows
+    np.testing.assert_array_equal(r2[~sel], G["lc_out_rots"][~sel])
+    assert _quat_close(r2[sel], G["lc_out_rots"][sel], 1e-5)
+    for tag in ("ig", "igi"):
+        qp, qc = IR.inactive_geo_densify(G[f"{tag}_pixels"], G[f"{tag}_has3D"], G[f"{tag}_points"], G[f"{tag}_colors"],
+                                         float(G[f"{tag}_maxd"]), G[f"{tag}_intr"], int(G[f"{tag}_width"]))
+        assert qp.shape == G[f"{tag}_out_points"].shape and 0 < qp.shape[0] < G[f"{tag}_pixels"].shape[0], tag
+        np.testing.assert_array_equal(qc, G[f"{tag}_out_colors"])
+        np.testing.assert_allclose(qp, G[f"{tag}_out_points"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_array_equal(qp[:, 2], G[f"{tag}_out_points"][:, 2])  # borrowed depths: the same neighbours were chosen
+
+
 @pytest.fixture(scope="module")
 def ref_geo(dev):
     import build_ref
