@@ -320,3 +320,28 @@ def test_cpp_mapper_driver_follows_the_python_mapper(host_libs, tmp_path):
     for got, k, step in ((xyz, "xyz", sum(lrs)), (opacity, "opacity", N_IT * M.DEFAULT_LRS["opacity"])):
         d = np.abs(got - mp.params[k].detach().cpu().numpy())
         assert (d > 0.05 * step).mean() <= 3e-3, (k, float(d.max()), step)
+
+
+def test_public_headers_are_self_contained():
+    """Every header under include/ compiles on its own (what a maintainer who includes just one of them needs): the C ABI as
+    C and as C++, the libtorch-level headers against the pip libtorch."""
+    import sysconfig
+    from concurrent.futures import ThreadPoolExecutor
+    from torch.utils import cpp_extension as ce
+    inc = os.path.join(ROOT, "include")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    torch_inc = ["-I" + inc, "-I" + os.path.join(cuda, "include"), "-I" + sysconfig.get_paths()["include"]] + ["-I" + p for p in ce.include_paths()]
+    jobs = [["gcc", "-std=c11", "-fsyntax-only", "-x", "c", os.path.join(inc, "lgs.h")],
+            ["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", os.path.join(inc, "lgs.h")],
+            ["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", "-I" + inc, "-I" + os.path.join(cuda, "include"),
+             os.path.join(inc, "cuda_rasterizer", "rasterizer.h")]]
+    for h in ("rasterize_points.h", "operate_points.h", "stereo_vision.h", "spatial.h", "lgs_adam.h", "gaussian_rasterizer.h",
+              "gaussian_keyframe.h", "gaussian_model.h", "gaussian_renderer.h"):
+        jobs.append(["g++", "-std=c++17", "-fsyntax-only", "-D_GLIBCXX_USE_CXX11_ABI=1", "-x", "c++"] + torch_inc + [os.path.join(inc, h)])
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return cmd[-1], r.returncode, r.stderr[-1500:]
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        for name, rc, err in ex.map(run, jobs):
+            assert rc == 0, (name, err)
