@@ -60,6 +60,35 @@ class ExponLr:
         return float(f(delay) * log_lerp)
 
 
+class DensityControlParams(NamedTuple):
+    """The settings GaussianMapper's density control reads (reference src/gaussian_mapper.cpp:338-352; defaults
+    include/gaussian_parameters.h:68-75, the Replica configuration overrides them in cfg/gaussian_mapper/RGB-D/Replica/
+    replica_rgbd.yaml:69-74)."""
+    densification_interval: int = 100
+    opacity_reset_interval: int = 3000      # 0: never
+    densify_from_iter: int = 500
+    densify_until_iter: int = 15_000
+    densify_grad_threshold: float = 0.0002
+    densify_min_opacity: float = 0.005
+    prune_big_point_after_iter: int = 0
+    white_background: bool = False
+
+
+def density_control_actions(iteration: int, p: DensityControlParams):
+    """What trainForOneIteration does to the Gaussian set after the backward of iteration `iteration` (reference
+    src/gaussian_mapper.cpp:737-761) -> dict(update_stats, densify, size_threshold, reset_opacity).  Pure host logic."""
+    out = dict(update_stats=False, densify=False, size_threshold=0, reset_opacity=False)
+    if iteration < p.densify_until_iter:
+        out["update_stats"] = True
+        if iteration > p.densify_from_iter and iteration % p.densification_interval == 0:
+            out["densify"] = True
+            out["size_threshold"] = 20 if iteration > p.prune_big_point_after_iter else 0
+        if p.opacity_reset_interval and (iteration % p.opacity_reset_interval == 0 or
+                                         (p.white_background and iteration == p.densify_from_iter)):
+            out["reset_opacity"] = True
+    return out
+
+
 class Keyframe(NamedTuple):
     camera: Camera
     gt_image: torch.Tensor   # [3,H,W]
@@ -598,6 +627,21 @@ class Mapper:
 
     def set_sh_degree(self, sh: int):                    # GaussianModel::setShDegree, :105-107
         self.sh_degree = min(int(sh), self.max_sh_degree)
+
+    def density_control(self, iteration: int, p: DensityControlParams, cameras_extent: float, generator=None):
+        """The density-control block of trainForOneIteration for iteration `iteration` (reference
+        src/gaussian_mapper.cpp:737-761), after `train_step` (which has already accumulated the view's statistics when the
+        mapper tracks them): densifyAndPrune on the reference's cadence with its size threshold, then resetOpacity on its own.
+        As in the reference this runs BEFORE the iteration's optimizer step would (there the step then finds no gradients on
+        the rebuilt tensors); here `train_step` has stepped already, so call it between iterations.  Returns the actions
+        taken (`density_control_actions`) with the densification's `info` under "info"."""
+        act = density_control_actions(int(iteration), p)
+        if act["densify"]:
+            act["info"] = self.densify_and_prune(p.densify_grad_threshold, p.densify_min_opacity, cameras_extent,
+                                                 act["size_threshold"], generator=generator)
+        if act["reset_opacity"]:
+            self.reset_opacity()
+        return act
 
     def apply_scaled_transformation(self, s: float, T):
         """GaussianModel::applyScaledTransformation (reference src/gaussian_model.cpp:387-405; the map-wide correction after

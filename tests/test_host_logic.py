@@ -174,3 +174,45 @@ def test_mapper_per_iteration_settings():
         assert mp.sh_degree == want
     mp.set_sh_degree(7)
     assert mp.sh_degree == 3 and mp.max_sh_degree == 3
+
+
+def test_density_control_cadence_matches_reference_conditions():
+    """density_control_actions against the conditions of trainForOneIteration written out (reference
+    src/gaussian_mapper.cpp:737-761), over every iteration of a run, for the default and the Replica settings; and
+    Mapper.density_control calls densify_and_prune / reset_opacity exactly then, with the reference's arguments."""
+    from leg_slam_b200 import mapper as M
+    replica = M.DensityControlParams(densification_interval=100, opacity_reset_interval=0, densify_from_iter=600, densify_until_iter=15_000,
+                                     densify_grad_threshold=0.001, densify_min_opacity=0.02, prune_big_point_after_iter=30_000)
+    white = M.DensityControlParams(white_background=True)
+    for p in (M.DensityControlParams(), replica, white):
+        for it in list(range(0, 1300)) + list(range(2900, 3200)) + list(range(14_890, 15_110)):
+            a = M.density_control_actions(it, p)
+            active = it < p.densify_until_iter
+            densify = active and it > p.densify_from_iter and it % p.densification_interval == 0
+            reset = active and bool(p.opacity_reset_interval) and (it % p.opacity_reset_interval == 0 or
+                                                                   (p.white_background and it == p.densify_from_iter))
+            assert a == dict(update_stats=active, densify=densify, size_threshold=(20 if it > p.prune_big_point_after_iter else 0) if densify else 0,
+                             reset_opacity=reset), (it, p)
+    assert M.density_control_actions(700, replica)["densify"] and M.density_control_actions(700, replica)["size_threshold"] == 0
+    assert not M.density_control_actions(600, replica)["densify"] and not M.density_control_actions(15_000, replica)["update_stats"]
+    assert M.density_control_actions(3000, M.DensityControlParams()) == dict(update_stats=True, densify=True, size_threshold=20, reset_opacity=True)
+    assert M.density_control_actions(500, white)["reset_opacity"] and not M.density_control_actions(500, M.DensityControlParams())["reset_opacity"]
+
+    calls = []
+
+    class Recorder(M.Mapper):
+        def densify_and_prune(self, *a, **kw):
+            calls.append(("densify", a, kw))
+            return dict(new_P=1)
+
+        def reset_opacity(self):
+            calls.append(("reset",))
+    mp = Recorder(synthetic.make_scene(20, seed=1), sh_degree=3)
+    gen = torch.Generator()
+    assert mp.density_control(650, replica, 4.5) == dict(update_stats=True, densify=False, size_threshold=0, reset_opacity=False) and not calls
+    act = mp.density_control(700, replica, 4.5, generator=gen)
+    assert act["densify"] and act["info"] == dict(new_P=1)
+    assert calls == [("densify", (0.001, 0.02, 4.5, 0), dict(generator=gen))]
+    calls.clear()
+    mp.density_control(3000, M.DensityControlParams(), 2.0)
+    assert [c[0] for c in calls] == ["densify", "reset"] and calls[0][1] == (0.0002, 0.005, 2.0, 20)
