@@ -41,7 +41,9 @@ def _worker(rank, world, port, out):
         mp_ = _make_mapper(sc)
         assert mp_.world_size == world and mp_.rank == rank
         losses = []
-        for _ in range(2):
+        mp_.set_position_lr_schedule(3.2e-4, 3.2e-6, 0.01, 2)  # the per-iteration settings run on every replica alike
+        for it in range(2):
+            mp_.update_learning_rate(it)
             losses.append(float(mp_.train_step(win)))
         assert mp_.last_num_views == len(M.shard_views(K_VIEWS, rank, world))
         out[rank] = ({k: v.detach().clone() for k, v in mp_.params.items()}, losses)
@@ -84,7 +86,13 @@ def test_two_rank_data_parallel_equals_single_process_accumulation():
     sc, win = _window()
     torch.set_num_threads(1)
     single = _make_mapper(sc)
-    single_losses = [float(single.train_step(win)) for _ in range(2)]
+    single.set_position_lr_schedule(3.2e-4, 3.2e-6, 0.01, 2)
+    single_losses = []
+    for it in range(2):
+        lr = single.update_learning_rate(it)
+        assert single.optimizer.param_groups[0]["lr"] == lr
+        single_losses.append(float(single.train_step(win)))
+    assert abs(lr - 3.2e-5) < 1e-9  # half way down the log-linear schedule at step 1 of 2
 
     mgr = mp.Manager()
     out = mgr.dict()
