@@ -34,8 +34,24 @@ DEFAULT_LRS = dict(xyz=3.2e-4, features_dc=2.5e-3, features_rest=2.5e-3 / 20.0, 
 class ExponLr:
     """GaussianModel::exponLrFunc (reference src/gaussian_model.cpp:1143-1157) with the constants trainingSetup stores for it
     (:513-517: lr_init / lr_final already multiplied by spatial_lr_scale): log-linear interpolation from lr_init at step 0 to
-    lr_final at max_steps, times an optional sine-eased delay factor.  Evaluated in float32 like the reference (logf, expf,
-    sinf on float operands)."""
+    lr_final at max_steps, times an optional sine-eased delay factor.  Evaluated like the reference: float operands, float
+    products and sums, and the C library's own logf / expf / sinf (through ctypes -- numpy's float32 log / exp are a different
+    implementation and land one ulp away on some steps), so the rate is the same float the reference's compiled code returns
+    (tests/test_reference_model.py holds it to the unmodified class, step for step)."""
+
+    _libm = None
+
+    @classmethod
+    def _m(cls):
+        if cls._libm is None:
+            import ctypes
+            import ctypes.util
+            m = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+            for name in ("logf", "expf", "sinf"):
+                fn = getattr(m, name)
+                fn.restype, fn.argtypes = ctypes.c_float, [ctypes.c_float]
+            cls._libm = m
+        return cls._libm
 
     def __init__(self, lr_init, lr_final, lr_delay_mult=1.0, max_steps=1_000_000, lr_delay_steps=0):
         import numpy as np
@@ -45,18 +61,17 @@ class ExponLr:
         self.max_steps, self.lr_delay_steps = int(max_steps), int(lr_delay_steps)
 
     def __call__(self, step: int) -> float:
-        np = self._np
-        f = np.float32
+        f = self._np.float32
+        m = self._m()
         if step < 0 or (self.lr_init == 0 and self.lr_final == 0):
             return 0.0
         if self.lr_delay_steps > 0:
             x = min(max(f(step) / f(self.lr_delay_steps), f(0)), f(1))
-            delay = self.lr_delay_mult + (f(1) - self.lr_delay_mult) * np.sin(f(np.pi / 2) * x, dtype=np.float32)
+            delay = self.lr_delay_mult + (f(1) - self.lr_delay_mult) * f(m.sinf(f(1.57079632679489661923) * x))
         else:
             delay = f(1)
         t = min(max(f(step) / f(self.max_steps), f(0)), f(1))
-        log_lerp = np.exp(np.log(self.lr_init, dtype=np.float32) * (f(1) - t) + np.log(self.lr_final, dtype=np.float32) * t,
-                          dtype=np.float32)
+        log_lerp = f(m.expf(f(m.logf(self.lr_init)) * (f(1) - t) + f(m.logf(self.lr_final)) * t))
         return float(f(delay) * log_lerp)
 
 

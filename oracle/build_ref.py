@@ -312,6 +312,61 @@ def load_geometry():
     return mod
 
 
+MODEL_REF = "/root/reference"
+MODEL_MOD = "ref_model"
+MODEL_SO = os.path.join(OUT, MODEL_MOD + ".so")
+STUBS = os.path.join(HERE, "ref_stubs")
+
+
+def build_model(force=False, verbose=True):
+    """The UNMODIFIED reference GaussianModel (src/gaussian_model.cpp + src/gaussian_parameters.cpp, libtorch; tinyply.cpp for
+    savePly / loadPly) behind oracle/ref_model_wrap.cpp -> oracle/_ref/ref_model.so (python module `ref_model`, runs on CPU
+    tensors).  Eigen / OpenCV / Sophus are absent from this image: oracle/ref_stubs/ (first on the include path) holds type-only
+    stand-ins for the headers gaussian_model.h pulls in, and ref_model_prelude.h (force-included) re-points three names for a
+    driverless machine with libtorch 2.11: the literal torch::kCUDA in build_rotation, emptyCache(), the optimizer-state key.  The CUDA operators the class calls are supplied by the test as Python
+    callables (see the wrapper's header).  Pins SURVEY.md 8f rows 1-3 and a18's Adam formula by the reference itself."""
+    if os.path.exists(MODEL_SO) and not force:
+        return MODEL_SO
+    if not os.path.isdir(os.path.join(MODEL_REF, "src")):
+        raise RuntimeError("reference tree not present (GPU box?) and no prebuilt " + MODEL_SO)
+    os.makedirs(OUT, exist_ok=True)
+    objdir = os.path.join(OUT, "model_obj")
+    os.makedirs(objdir, exist_ok=True)
+    inc, lib = _torch_paths()
+    pyinc = sysconfig.get_paths()["include"]
+    common = ["g++", "-O2", "-std=c++17", "-fPIC", "-DLANGUAGE_FEATURES_DIM=64", "-D_GLIBCXX_USE_CXX11_ABI=1",
+              "-DTORCH_EXTENSION_NAME=" + MODEL_MOD, "-DTORCH_API_INCLUDE_EXTENSION_H",
+              "-include", os.path.join(STUBS, "ref_model_prelude.h"),
+              "-I" + STUBS, "-I" + MODEL_REF, "-I" + os.path.join(MODEL_REF, "include"), "-I/usr/local/cuda/include",
+              "-I" + pyinc] + ["-I" + p for p in inc]
+    srcs = [os.path.join(MODEL_REF, "src", "gaussian_model.cpp"), os.path.join(MODEL_REF, "src", "gaussian_parameters.cpp"),
+            os.path.join(MODEL_REF, "third_party", "tinyply", "tinyply.cpp"), os.path.join(HERE, "ref_model_wrap.cpp")]
+    objs = [os.path.join(objdir, os.path.basename(s) + ".o") for s in srcs]
+    cmds = [common + ["-c", s, "-o", o] for s, o in zip(srcs, objs)]
+
+    def run(cmd):
+        if verbose:
+            print("[build_ref]", " ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+
+    with ThreadPoolExecutor(max_workers=len(cmds)) as ex:
+        list(ex.map(run, cmds))
+    run(["g++", "-shared"] + objs + ["-o", MODEL_SO] + ["-L" + p for p in lib] +
+        ["-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch", "-ltorch_python"] + ["-Wl,-rpath," + p for p in lib])
+    return MODEL_SO
+
+
+def load_model():
+    import importlib.util
+    import torch  # noqa: F401
+    if not os.path.exists(MODEL_SO):
+        raise FileNotFoundError(MODEL_SO + " missing: run `python oracle/build_ref.py` where /root/reference exists")
+    spec = importlib.util.spec_from_file_location(MODEL_MOD, MODEL_SO)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def load():
     """Import the prebuilt module (after `import torch`)."""
     import importlib.util
@@ -331,4 +386,5 @@ if __name__ == "__main__":
     print(build_loss(force="--force" in sys.argv))
     print(build_ply(force="--force" in sys.argv))
     print(build_utils(force="--force" in sys.argv))
+    print(build_model(force="--force" in sys.argv))
     print(build_geometry(force="--force" in sys.argv))

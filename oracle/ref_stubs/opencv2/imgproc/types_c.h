@@ -1,0 +1,2 @@
+// TEST INFRASTRUCTURE -- stand-in, see ../opencv.hpp
+#pragma once
