@@ -6,11 +6,13 @@ resetOpacity :567-575 / replaceTensorToOptimizer :577-595, general_utils.h:25-53
 and the max_radii2D update of src/gaussian_mapper.cpp:739-742.  Runs on CPU or CUDA tensors.  Only tests/ may
 import it (the package never does).
 
-Parity partly pinned: the reference's GaussianModel cannot be compiled here (gaussian_model.h pulls in Sophus -> Eigen and
-OpenCV, neither exists in this image) and it ships no fixtures for this path, so the SEQUENCE of tensor operations below is a
-restatement checked by construction (same libtorch ops in the same order) and by its own invariants (tests/test_densify.py).
-Its numeric helpers -- inverse_sigmoid, build_rotation -- are held bit-identical to the unmodified reference header
-(include/general_utils.h compiled into oracle/_ref/ref_utils.so; tests/test_reference_utils.py).
+PINNED by the reference's own class (tests/test_reference_model.py, CPU): the UNMODIFIED src/gaussian_model.cpp is compiled
+into oracle/_ref/ref_model.so (oracle/build_ref.py build_model(); type-only stand-ins for the absent Eigen / OpenCV / Sophus
+headers, see oracle/ref_model_wrap.cpp) and runs on CPU tensors; every method of Model below is bit-identical to the
+reference's -- parameters, Adam moments, step counts, exist_since_iter and the statistics vectors -- including the split's
+normal draws (same seeded CPU generator).  Its numeric helpers -- inverse_sigmoid, build_rotation -- are also held
+bit-identical to the unmodified header on its own (include/general_utils.h in oracle/_ref/ref_utils.so;
+tests/test_reference_utils.py).
 """
 import torch
 

@@ -7,8 +7,9 @@ transpose(1,2).flatten(1) of f_dc / f_rest, zero normals) with tinyply's binary 
 transposed).  PINNED (tests/test_ply_io.py::test_restatement_pinned_by_the_reference_tinyply_cpu): the file written here is
 byte-identical to the one the reference's own tinyply (third_party/tinyply, compiled unmodified into oracle/_ref/ref_ply.so)
 writes for savePly's call sequence, and the reference's reader -- tinyply with loadPly's property requests and reshapes
-(gaussian_model.cpp:882-956) -- returns the same tensors.  What stays restated is the sequence of tinyply calls itself
-(oracle/ref_ply_wrap.cpp, cited line by line): GaussianModel cannot be compiled here (Eigen / OpenCV / Sophus)."""
+(gaussian_model.cpp:882-956) -- returns the same tensors.  Also held to GaussianModel::savePly ITSELF: the unmodified class
+(oracle/_ref/ref_model.so, CPU tensors) writes a byte-identical file and its loadPly parses the one written here
+(tests/test_reference_model.py::test_ply_restatement_equals_reference_model_save_and_load)."""
 import numpy as np
 
 

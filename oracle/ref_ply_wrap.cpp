@@ -1,8 +1,9 @@
 // TEST INFRASTRUCTURE -- C entry points around the reference's OWN .ply library (third_party/tinyply/tinyply.{h,cpp}, compiled
 // from where it lies by oracle/build_ref.py build_ply()) -> oracle/_ref/ref_ply.so (ctypes).  Oracle for SURVEY.md 8f row 3.
 //
-// GaussianModel::savePly / loadPly themselves (/root/reference/src/gaussian_model.cpp:854-1075) cannot be compiled here (the
-// class pulls in Eigen / OpenCV / Sophus), so the two functions below issue the SAME tinyply calls in the same order -- the
+// The two functions below issue the SAME tinyply calls as GaussianModel::savePly / loadPly
+// (/root/reference/src/gaussian_model.cpp:854-1075) in the same order, without the class (which needs stand-ins for Eigen /
+// OpenCV / Sophus to compile: that build is oracle/_ref/ref_model.so, tests/test_reference_model.py, CPU tensors only) -- the
 // byte format (header syntax, record packing) is then the reference's own code, the property sequence is restated from:
 //   savePly : add_properties_to_element("vertex", ...) for xyz, normals, f_dc_*, f_rest_*, lf_*, opacity, scale_*, rot_*
 //             (gaussian_model.cpp:992-1068), write(os, /*isBinary=*/true) (:1071)

@@ -4,7 +4,7 @@
 // names they use are re-pointed, after every libtorch header has been read (so libtorch itself is not affected):
 //
 //  1. torch::kCUDA -> torch::kCPU.  The class takes its device from its parameters (src/gaussian_model.cpp:37-41) and we ask
-//     for "cpu", but general_utils::build_rotation allocates with a literal torch::kCUDA (include/general_utils.h:32), so
+//     for "cpu", but general_utils::build_rotation allocates with a literal torch::kCUDA (include/general_utils.h:42), so
 //     densifyAndSplit would stop at its first statement here.  Same arithmetic, on the only device this container has.
 //  2. c10::cuda::CUDACachingAllocator::emptyCache() -- the closing statement of increasePcd and densifyAndPrune
 //     (src/gaussian_model.cpp:291,380,831) -- raises "Found no NVIDIA driver" on a driverless machine; it is routed to a
