@@ -320,7 +320,7 @@ STUBS = os.path.join(HERE, "ref_stubs")
 
 def build_model(force=False, verbose=True):
     """The UNMODIFIED reference GaussianModel (src/gaussian_model.cpp + src/gaussian_parameters.cpp, libtorch; tinyply.cpp for
-    savePly / loadPly) behind oracle/ref_model_wrap.cpp -> oracle/_ref/ref_model.so (python module `ref_model`, runs on CPU
+    savePly / loadPly), its autograd glue and renderer (src/gaussian_rasterizer.cpp, src/gaussian_renderer.cpp) behind oracle/ref_model_wrap.cpp -> oracle/_ref/ref_model.so (python module `ref_model`, runs on CPU
     tensors).  Eigen / OpenCV / Sophus are absent from this image: oracle/ref_stubs/ (first on the include path) holds type-only
     stand-ins for the headers gaussian_model.h pulls in, and ref_model_prelude.h (force-included) re-points three names for a
     driverless machine with libtorch 2.11: the literal torch::kCUDA in build_rotation, emptyCache(), the optimizer-state key.  The CUDA operators the class calls are supplied by the test as Python
@@ -340,6 +340,7 @@ def build_model(force=False, verbose=True):
               "-I" + STUBS, "-I" + MODEL_REF, "-I" + os.path.join(MODEL_REF, "include"), "-I/usr/local/cuda/include",
               "-I" + pyinc] + ["-I" + p for p in inc]
     srcs = [os.path.join(MODEL_REF, "src", "gaussian_model.cpp"), os.path.join(MODEL_REF, "src", "gaussian_parameters.cpp"),
+            os.path.join(MODEL_REF, "src", "gaussian_rasterizer.cpp"), os.path.join(MODEL_REF, "src", "gaussian_renderer.cpp"),
             os.path.join(MODEL_REF, "third_party", "tinyply", "tinyply.cpp"), os.path.join(HERE, "ref_model_wrap.cpp")]
     objs = [os.path.join(objdir, os.path.basename(s) + ".o") for s in srcs]
     cmds = [common + ["-c", s, "-o", o] for s, o in zip(srcs, objs)]

@@ -1,5 +1,5 @@
-// ref_model_wrap.cpp -- pybind entry points around the UNMODIFIED reference GaussianModel (TEST INFRASTRUCTURE,
-// oracle/_ref/ref_model.so, built by oracle/build_ref.py build_model()).
+// ref_model_wrap.cpp -- pybind entry points around the UNMODIFIED reference GaussianModel, GaussianRasterizer(Function) and
+// GaussianRenderer (TEST INFRASTRUCTURE, oracle/_ref/ref_model.so, built by oracle/build_ref.py build_model()).
 //
 // /root/reference/src/gaussian_model.cpp and src/gaussian_parameters.cpp are compiled from where they lie; nothing of them is
 // copied.  The class is libtorch code and runs on CPU tensors when its parameters say data_device != "cuda"
@@ -29,6 +29,8 @@
 #include <stdexcept>
 
 #include "include/gaussian_model.h"
+#include "include/gaussian_rasterizer.h"
+#include "include/gaussian_renderer.h"
 
 namespace py = pybind11;
 
@@ -36,6 +38,10 @@ namespace py = pybind11;
 static py::object* g_dist2 = nullptr;
 static py::object* g_transform = nullptr;
 static py::object* g_scale_transform = nullptr;
+
+static py::object* g_rasterize = nullptr;
+static py::object* g_rasterize_backward = nullptr;
+static py::object* g_mark_visible = nullptr;
 
 static void set_cb(py::object*& slot, py::object f) {
     if (slot) { delete slot; slot = nullptr; }
@@ -68,14 +74,64 @@ void scaleAndTransformThenMarkVisiblePoints(torch::Tensor& points, torch::Tensor
                                            viewmatrix, projmatrix, scale).cast<int>();
 }
 
+// include/rasterize_points.h:18-39 -- L1 of the boundary.  Under GaussianRasterizerFunction / GaussianRasterizer /
+// GaussianRenderer (src/gaussian_rasterizer.cpp, src/gaussian_renderer.cpp, compiled unmodified into this module) the CUDA
+// entry points are Python callables: tests/oracle_l1.py runs the CPU oracle behind them and records every argument, so that
+// what the reference's glue hands to L1 -- and what it does with the results -- can be compared with the package's glue
+// call for call.
+std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+RasterizeGaussiansCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors,
+                       const torch::Tensor& lang_feat, const torch::Tensor& opacity, const torch::Tensor& scales,
+                       const torch::Tensor& rotations, const float scale_modifier, const torch::Tensor& cov3D_precomp,
+                       const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx,
+                       const float tan_fovy, const int image_height, const int image_width, const torch::Tensor& sh,
+                       const int degree, const torch::Tensor& campos, const bool prefiltered, const bool include_lang_feat) {
+    if (!g_rasterize) throw std::runtime_error("ref_model: RasterizeGaussiansCUDA called and no callable set (set_rasterizer)");
+    py::gil_scoped_acquire gil;
+    py::tuple r = (*g_rasterize)(background, means3D, colors, lang_feat, opacity, scales, rotations, scale_modifier,
+                                 cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree,
+                                 campos, prefiltered, include_lang_feat);
+    auto T = [&](int i) { return r[i].cast<torch::Tensor>(); };
+    return std::make_tuple(r[0].cast<int>(), T(1), T(2), T(3), T(4), T(5), T(6), T(7));
+}
+
+// include/rasterize_points.h:41-66
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
+           torch::Tensor>
+RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& radii,
+                               const torch::Tensor& colors, const torch::Tensor& lang_feat, const torch::Tensor& scales,
+                               const torch::Tensor& rotations, const float scale_modifier, const torch::Tensor& cov3D_precomp,
+                               const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx,
+                               const float tan_fovy, const torch::Tensor& dL_dout_color, const torch::Tensor& dL_dout_lang_feat,
+                               const torch::Tensor& dL_dout_depth, const torch::Tensor& sh, const int degree,
+                               const torch::Tensor& campos, const torch::Tensor& geomBuffer, const int R,
+                               const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer,
+                               const bool include_lang_feat) {
+    if (!g_rasterize_backward) throw std::runtime_error("ref_model: RasterizeGaussiansBackwardCUDA called and no callable set");
+    py::gil_scoped_acquire gil;
+    py::tuple r = (*g_rasterize_backward)(background, means3D, radii, colors, lang_feat, scales, rotations, scale_modifier,
+                                          cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
+                                          dL_dout_lang_feat, dL_dout_depth, sh, degree, campos, geomBuffer, R, binningBuffer,
+                                          imageBuffer, include_lang_feat);
+    auto T = [&](int i) { return r[i].cast<torch::Tensor>(); };
+    return std::make_tuple(T(0), T(1), T(2), T(3), T(4), T(5), T(6), T(7), T(8));
+}
+
+// include/rasterize_points.h:68-71
+torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix, torch::Tensor& projmatrix) {
+    if (!g_mark_visible) throw std::runtime_error("ref_model: markVisible called and no callable set");
+    py::gil_scoped_acquire gil;
+    return (*g_mark_visible)(means3D, viewmatrix, projmatrix).cast<torch::Tensor>();
+}
+
 namespace {
 
 struct RefModel {
-    std::unique_ptr<GaussianModel> m;
+    std::shared_ptr<GaussianModel> m;
 
     explicit RefModel(int sh_degree) {
         GaussianModelParams p("", "", "", sh_degree, "images", -1.0f, false, /*data_device=*/"cpu", false);
-        m = std::make_unique<GaussianModel>(p);
+        m = std::make_shared<GaussianModel>(p);
     }
 
     // the seven leaves + exist_since_iter_ of an existing map (what createFromPcd / loadPly leave behind)
@@ -191,12 +247,68 @@ struct RefModel {
     }
 };
 
+static std::shared_ptr<GaussianKeyframe> make_keyframe(double FoVx, double FoVy, torch::Tensor view, torch::Tensor proj,
+                                                       torch::Tensor campos) {
+    auto kf = std::make_shared<GaussianKeyframe>();   // only the fields render() reads (src/gaussian_renderer.cpp:51-66)
+    kf->FoVx_ = (float)FoVx;
+    kf->FoVy_ = (float)FoVy;
+    kf->world_view_transform_ = view;
+    kf->full_proj_transform_ = proj;
+    kf->camera_center_ = campos;
+    return kf;
+}
+
+// GaussianRenderer::render (src/gaussian_renderer.cpp:24-160) on a RefModel
+static std::vector<torch::Tensor> ref_render(RefModel& model, double FoVx, double FoVy, torch::Tensor view, torch::Tensor proj,
+                                             torch::Tensor campos, int image_height, int image_width, bool convert_SHs,
+                                             bool compute_cov3D, torch::Tensor bg, torch::Tensor override_color,
+                                             double scaling_modifier, bool use_override_color, bool include_language_features) {
+    auto kf = make_keyframe(FoVx, FoVy, view, proj, campos);
+    GaussianPipelineParams pipe(convert_SHs, compute_cov3D);
+    auto r = GaussianRenderer::render(kf, image_height, image_width, model.m, pipe, bg, override_color, (float)scaling_modifier,
+                                      use_override_color, include_language_features);
+    return {std::get<0>(r), std::get<1>(r), std::get<2>(r), std::get<3>(r), std::get<4>(r), std::get<5>(r)};
+}
+
+// GaussianRasterizer::forward (src/gaussian_rasterizer.cpp:178-236) with its own settings object
+static std::vector<torch::Tensor> ref_rasterizer_forward(int image_height, int image_width, double tanfovx, double tanfovy,
+                                                         torch::Tensor bg, double scale_modifier, torch::Tensor view,
+                                                         torch::Tensor proj, int sh_degree, torch::Tensor campos, bool prefiltered,
+                                                         bool include_language_features, torch::Tensor means3D,
+                                                         torch::Tensor means2D, torch::Tensor opacities, bool has_shs,
+                                                         bool has_colors_precomp, bool has_lang_feat, bool has_scales,
+                                                         bool has_rotations, bool has_cov3D_precomp, torch::Tensor shs,
+                                                         torch::Tensor colors_precomp, torch::Tensor lang_feat,
+                                                         torch::Tensor scales, torch::Tensor rotations, torch::Tensor cov3D_precomp) {
+    GaussianRasterizationSettings rs(image_height, image_width, (float)tanfovx, (float)tanfovy, bg, (float)scale_modifier, view, proj,
+                                     sh_degree, campos, prefiltered, include_language_features);
+    GaussianRasterizer rasterizer(rs);
+    auto r = rasterizer.forward(means3D, means2D, opacities, has_shs, has_colors_precomp, has_lang_feat, has_scales, has_rotations,
+                                has_cov3D_precomp, shs, colors_precomp, lang_feat, scales, rotations, cov3D_precomp);
+    return {std::get<0>(r), std::get<1>(r), std::get<2>(r), std::get<3>(r)};
+}
+
+static torch::Tensor ref_mark_visible_gaussians(torch::Tensor view, torch::Tensor proj, torch::Tensor campos, torch::Tensor bg,
+                                                torch::Tensor positions) {
+    GaussianRasterizationSettings rs(1, 1, 1.0f, 1.0f, bg, 1.0f, view, proj, 0, campos, false, false);
+    GaussianRasterizer rasterizer(rs);
+    return rasterizer.markVisibleGaussians(positions);
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod) {
     mod.def("set_dist2", [](py::object f) { set_cb(g_dist2, f); });
     mod.def("set_transform_points", [](py::object f) { set_cb(g_transform, f); });
     mod.def("set_scale_and_transform", [](py::object f) { set_cb(g_scale_transform, f); });
+    mod.def("set_rasterizer", [](py::object fwd, py::object bwd, py::object mark) {
+        set_cb(g_rasterize, fwd);
+        set_cb(g_rasterize_backward, bwd);
+        set_cb(g_mark_visible, mark);
+    });
+    mod.def("render", &ref_render);
+    mod.def("rasterizer_forward", &ref_rasterizer_forward);
+    mod.def("mark_visible_gaussians", &ref_mark_visible_gaussians);
     py::class_<RefModel>(mod, "GaussianModel")
         .def(py::init<int>())
         .def("set_state", &RefModel::set_state)

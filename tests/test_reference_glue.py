@@ -1,0 +1,196 @@
+"""The reference's own glue above L1 -- GaussianRasterizerFunction, GaussianRasterizer::forward / markVisibleGaussians
+(src/gaussian_rasterizer.cpp:18-236) and GaussianRenderer::render (src/gaussian_renderer.cpp:24-160), compiled UNMODIFIED into
+oracle/_ref/ref_model.so -- against the package's twins (leg_slam_b200/rasterizer.py, renderer.py), on CPU.
+
+Both sides sit on the same L1: tests/oracle_l1.py runs the CPU oracle behind RasterizeGaussiansCUDA /
+RasterizeGaussiansBackwardCUDA / markVisible and records every call.  Held: the two glues make the SAME calls (every argument of
+the 20- and the 24-argument signatures, empty-tensor sentinels included), return the same tensors, and route the nine gradients
+to the same leaves."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", "oracle"))
+import build_ref  # noqa: E402
+import cases  # noqa: E402,F401  (sys.path)
+import oracle_l1  # noqa: E402
+from leg_slam_b200 import rasterizer as RZ, renderer as RD, synthetic  # noqa: E402
+
+P, W, H = 300, 48, 32
+NAMES = ("xyz", "features_dc", "features_rest", "lang_feat", "opacity", "scaling", "rotation")
+
+
+@pytest.fixture(scope="module")
+def RM():
+    try:
+        return build_ref.load_model()
+    except FileNotFoundError as ex:
+        pytest.skip(str(ex))
+
+
+@pytest.fixture()
+def both(RM, monkeypatch):
+    """(reference-side L1 log, package-side L1 log): fresh recorders under both glues."""
+    import oracle as O
+    a, b = oracle_l1.RecordingL1(), oracle_l1.RecordingL1()
+    RM.set_rasterizer(a.rasterize_gaussians, a.rasterize_gaussians_backward, a.mark_visible)
+    monkeypatch.setattr(RZ, "_C", b)
+    n = O.num_threads()
+    O.lib().omp_set_num_threads(1)   # the oracle's backward accumulates with `omp atomic`: one thread = one summation order
+    yield a, b
+    O.lib().omp_set_num_threads(n)
+    RM.set_rasterizer(None, None, None)
+
+
+def scene():
+    sc = synthetic.make_scene(P, seed=5, mean_scale=0.08)
+    cam = synthetic.make_cameras(1, W, H, seed=5)[0]
+    return sc, cam
+
+
+def weights(seed=3):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(3, H, W, generator=g), torch.randn(64, H, W, generator=g), torch.randn(1, H, W, generator=g)
+
+
+@pytest.mark.parametrize("convert_SHs,compute_cov3D,use_override,include_lf,active_deg,modifier,touch", [
+    (False, False, False, True, 3, 1.0, "all"),      # the mapper's configuration (every shipped cfg: both pipe flags false)
+    (False, False, False, False, 1, 1.0, "all"),     # no language features, a growing SH degree
+    (False, True, False, True, 3, 1.0, "all"),       # precomputed 3D covariance
+    (False, False, True, True, 3, 1.0, "all"),       # override colours (the query's heat-map render)
+    (True, False, False, True, 2, 1.0, "all"),       # SH -> RGB on the host side
+    (False, False, False, True, 3, 0.7, "all"),      # the viewer's scaling modifier
+    (False, False, False, True, 3, 1.0, "colour"),   # a loss that touches one output: the other upstream gradients are zeros
+])
+def test_render_makes_the_same_l1_calls_and_routes_the_same_gradients(RM, both, convert_SHs, compute_cov3D, use_override,
+                                                                      include_lf, active_deg, modifier, touch):
+    la, lb = both
+    sc, cam = scene()
+    bg = torch.tensor([0.1, 0.2, 0.3])
+    g = torch.Generator().manual_seed(11)
+    override = torch.rand(P, 3, generator=g)
+    wc, wl, wd = weights()
+    kv = RD.KeyframeView(cam)
+
+    def loss_of(img, lf, depth):
+        if touch == "colour":
+            return (img * wc).sum()
+        return (img * wc).sum() + (lf * wl).sum() + (depth * wd).sum()
+
+    # reference
+    ref = RM.GaussianModel(3)
+    ref.set_state([sc[k] for k in NAMES], torch.zeros(P, dtype=torch.int32), 1.0)
+    ref.set_sh_degree(active_deg)
+    ov_r = override.clone().requires_grad_() if use_override else torch.empty(0)
+    out_r = RM.render(ref, kv.FoVx_, kv.FoVy_, cam.viewmatrix, cam.projmatrix, cam.campos, H, W, convert_SHs, compute_cov3D, bg,
+                      ov_r, modifier, use_override, include_lf)
+    loss_of(*out_r[:3]).backward()
+    grads_r = [p.grad for p in ref.params()]
+
+    # the package's twin
+    params = {k: sc[k].detach().clone().requires_grad_() for k in NAMES}
+    pc = RD.GaussianModelView(params, sh_degree=3, active_sh_degree=active_deg)
+    ov_o = override.clone().requires_grad_() if use_override else None
+    out_o = RD.GaussianRenderer.render(kv, H, W, pc, RD.GaussianPipelineParams(convert_SHs, compute_cov3D), bg, ov_o, modifier,
+                                       use_override, include_lf)
+    loss_of(*out_o[:3]).backward()
+
+    exact = not convert_SHs and not compute_cov3D   # those two run a host-side formula first (eval_sh / L L^T): float rounding
+    assert oracle_l1.same_calls(la.calls, lb.calls, rtol=0.0 if exact else 2e-5)
+    assert [c[0] for c in la.calls] == ["rasterize_gaussians", "rasterize_gaussians_backward"]
+    fwd = la.calls[0][1]
+    # the sentinels: exactly one of sh / colours and of scales + rotations / cov3D reaches L1, the others are empty tensors
+    assert (fwd[15].numel() == 0) == (use_override or convert_SHs) and (fwd[2].numel() == 0) != (fwd[15].numel() == 0)
+    assert (fwd[8].numel() == 0) != compute_cov3D and (fwd[5].numel() == 0) == compute_cov3D == (fwd[6].numel() == 0)
+    assert (fwd[3].numel() == 0) != include_lf and fwd[19] == include_lf and fwd[16] == active_deg and fwd[18] is False
+
+    tol = 0.0 if exact else 2e-5
+    def close(x, y, what):
+        assert x.shape == y.shape and x.dtype == y.dtype, what
+        if tol == 0.0:
+            assert torch.equal(x, y), what
+        else:
+            assert float((x.detach() - y.detach()).abs().max()) <= tol * max(1e-12, float(y.detach().abs().max())), what
+
+    for i, n in enumerate(("image", "lf", "depth")):
+        close(out_r[i], out_o[i], n)
+    assert torch.equal(out_r[4], out_o[4]) and out_r[4].dtype == torch.bool and torch.equal(out_r[4], out_r[5] > 0)
+    assert torch.equal(out_r[5], out_o[5]) and out_r[5].dtype == torch.int32
+    assert 0 < int(out_r[4].sum()) < P
+    # the screen-space leaf receives dL_dmeans2D on both sides
+    assert out_r[3].shape == (P, 3) and not out_r[3].any() and not out_o[3].any()
+    close(out_r[3].grad, out_o[3].grad, "means2D grad")
+    assert out_r[3].grad.abs().sum() > 0
+    for k, gr in zip(NAMES, grads_r):
+        go = params[k].grad
+        used = not ((k in ("features_dc", "features_rest") and use_override) or (k == "lang_feat" and not include_lf))
+        if not used:
+            assert gr is None or not gr.any(), k
+            assert go is None or not go.any(), k
+            continue
+        assert gr is not None and go is not None, k
+        close(gr, go, k)
+    if use_override:
+        close(ov_r.grad, ov_o.grad, "override colour grad")
+        assert ov_r.grad.abs().sum() > 0
+    if active_deg < 3 and not use_override:   # coefficients above the active degree get exactly zero on both sides
+        n_act = (active_deg + 1) ** 2 - 1
+        assert not grads_r[2][:, n_act:].any() and not params["features_rest"].grad[:, n_act:].any()
+        assert grads_r[2][:, :n_act].any()
+
+
+def test_rasterizer_forward_validation_and_sentinels(RM, both):
+    """GaussianRasterizer::forward's two refusals (reference :198-207, same messages in the package) and, for a valid call, the
+    sentinel tensors it substitutes (:209-221)."""
+    la, lb = both
+    sc, cam = scene()
+    bg = torch.zeros(3)
+    e = torch.empty(0)
+    xyz, op = sc["xyz"], torch.sigmoid(sc["opacity"])
+    shs = torch.cat([sc["features_dc"], sc["features_rest"]], dim=1)
+    scales, rots = torch.exp(sc["scaling"]), torch.nn.functional.normalize(sc["rotation"])
+    cols = torch.rand(P, 3)
+    cov = RD.GaussianModelView({k: sc[k] for k in NAMES}).getCovarianceActivation()
+    rs_args = (H, W, cam.tanfovx, cam.tanfovy, bg, 1.0, cam.viewmatrix, cam.projmatrix, 3, cam.campos, False, False)
+    rs = RZ.GaussianRasterizationSettings(*rs_args)
+    ours = RZ.GaussianRasterizer(rs)
+    means2D = torch.zeros_like(xyz)
+    bad = [  # (has_shs, has_cols, has_scales, has_rots, has_cov) -> which message
+        ((False, False, True, True, False), "excatly one of either SHs or precomputed colors"),
+        ((True, True, True, True, False), "excatly one of either SHs or precomputed colors"),
+        ((True, False, False, False, False), "exactly one of either scale/rotation pair or precomputed 3D covariance"),
+        ((True, False, True, False, False), "exactly one of either scale/rotation pair or precomputed 3D covariance"),
+        ((True, False, True, True, True), "exactly one of either scale/rotation pair or precomputed 3D covariance"),
+        ((True, False, False, True, True), "exactly one of either scale/rotation pair or precomputed 3D covariance"),
+    ]
+    for (hs, hc, hsc, hr, hcov), msg in bad:
+        with pytest.raises(RuntimeError, match=msg):
+            RM.rasterizer_forward(*rs_args, xyz, means2D, op, hs, hc, False, hsc, hr, hcov, shs if hs else e, cols if hc else e, e,
+                                  scales if hsc else e, rots if hr else e, cov if hcov else e)
+        with pytest.raises(Exception, match=msg):
+            ours(xyz, means2D, op, shs=shs if hs else None, colors_precomp=cols if hc else None,
+                 scales=scales if hsc else None, rotations=rots if hr else None, cov3D_precomp=cov if hcov else None)
+    assert not la.calls and not lb.calls          # refused before L1 on both sides
+    for hs, hcov in ((True, False), (False, True)):
+        r = RM.rasterizer_forward(*rs_args, xyz, means2D, op, hs, not hs, False, not hcov, not hcov, hcov, shs if hs else e,
+                                  e if hs else cols, e, e if hcov else scales, e if hcov else rots, cov if hcov else e)
+        o = ours(xyz, means2D, op, shs=shs if hs else None, colors_precomp=None if hs else cols,
+                 scales=None if hcov else scales, rotations=None if hcov else rots, cov3D_precomp=cov if hcov else None)
+        assert len(r) == len(o) == 4 and all(torch.equal(x, y) for x, y in zip(r, o))
+    assert oracle_l1.same_calls(la.calls, lb.calls) and len(la.calls) == 2
+
+
+def test_mark_visible_gaussians(RM, both):
+    """GaussianRasterizer::markVisibleGaussians (reference :18-25): positions + the settings' two matrices go to L1's markVisible."""
+    la, lb = both
+    sc, cam = scene()
+    bg = torch.zeros(3)
+    r = RM.mark_visible_gaussians(cam.viewmatrix, cam.projmatrix, cam.campos, bg, sc["xyz"])
+    rs = RZ.GaussianRasterizationSettings(1, 1, 1.0, 1.0, bg, 1.0, cam.viewmatrix, cam.projmatrix, 0, cam.campos, False, False)
+    o = RZ.GaussianRasterizer(rs).markVisible(sc["xyz"])
+    assert r.dtype == torch.bool and torch.equal(r, o) and 0 < int(r.sum()) < P
+    assert oracle_l1.same_calls(la.calls, lb.calls) and [c[0] for c in la.calls] == ["mark_visible"]
