@@ -414,3 +414,76 @@ def test_ply_restatement_equals_reference_model_save_and_load(RM, tmp_path):
     assert [tuple(x.shape) for x in got[:3]] == [(P, 3), (P, 1, 3), (P, 15, 3)]
     assert torch.equal(got[2].detach(), t[2])
     assert ld.active_sh_degree() == 3
+
+
+def test_cpp_model_of_the_package_side_by_side_with_the_reference_class(RM):
+    """The package's C++ GaussianModel (include/gaussian_model.h, leg_slam_b200/_L2.so -- the reference's member names on
+    liblgs) next to the reference's class on the same CPU tensors, for everything of it that is plain libtorch: trainingSetup's
+    seven rates, updateLearningRate over a whole schedule (the same float at every step), the six setters, the SH-degree
+    bookkeeping, the activations, and the optimizer-state surgery of resetOpacity and prunePoints (what needs a kernel refuses
+    CPU tensors there: tests/test_host_cpp.py; it is held to the restatement on a B200: tests/test_host_cpp_gpu.py)."""
+    from leg_slam_b200 import build_host
+    build_host.build()
+    from leg_slam_b200 import _L2
+    n = 40
+    t, exist, g = make_params(n, seed=8)
+    ref = RM.GaussianModel(3)
+    ref.set_state(t, exist, 5.3)
+    ref.training_setup(**OPT)
+    ours = _L2.GaussianModel(3)
+    for name, x in zip(("xyz_", "features_dc_", "features_rest_", "language_features_", "opacity_", "scaling_", "rotation_"), t):
+        setattr(ours, name, x.clone().requires_grad_())
+    ours.exist_since_iter_ = exist.clone()
+    ours.max_radii2D_ = torch.zeros(n)
+    ours.spatial_lr_scale_ = 5.3
+    a = _L2.GaussianOptimizationParams()   # the defaults of include/gaussian_parameters.h = OPT
+    ours.trainingSetup(a)
+    lrs = lambda: [ours.learning_rate(i) for i in range(7)]  # noqa: E731
+    assert lrs() == ref.lrs() and ours.percentDense() == ref.percent_dense()
+    for s in list(range(0, 30)) + list(range(30, 32000, 61)) + [29999, 30000, 30001, -1]:
+        assert ours.updateLearningRate(s) == ref.update_learning_rate(s), s
+        assert lrs() == ref.lrs()
+    for ro, rr, v in ((ours.setPositionLearningRate, ref.set_position_learning_rate, 2e-4),
+                      (ours.setFeatureLearningRate, ref.set_feature_learning_rate, 3e-3),
+                      (ours.setLanguageFeatureLearningRate, ref.set_language_feature_learning_rate, 2e-3),
+                      (ours.setOpacityLearningRate, ref.set_opacity_learning_rate, 0.06),
+                      (ours.setScalingLearningRate, ref.set_scaling_learning_rate, 4e-3),
+                      (ours.setRotationLearningRate, ref.set_rotation_learning_rate, 1.5e-3)):
+        ro(v), rr(v)
+        assert lrs() == ref.lrs()
+    for _ in range(5):
+        ours.oneUpShDegree(), ref.one_up_sh_degree()
+        assert ours.active_sh_degree_ == ref.active_sh_degree()
+    for sh in (7, 1, 0, 3):
+        ours.setShDegree(sh), ref.set_sh_degree(sh)
+        assert ours.active_sh_degree_ == ref.active_sh_degree()
+    assert torch.equal(ours.getScalingActivation(), ref.get_scaling_activation())
+    assert torch.equal(ours.getRotationActivation(), ref.get_rotation_activation())
+    assert torch.equal(ours.getOpacityActivation(), ref.get_opacity_activation())
+    assert torch.equal(ours.getFeatures(), ref.get_features())
+    assert torch.equal(ours.getLanguageFeatures(), ref.get_language_features())
+    co, cr = ours.getCovarianceActivation(1).detach(), ref.get_covariance_activation(1).detach()
+    assert float((co - cr).abs().max()) <= 1e-6 * float(cr.abs().max())
+
+    def same_params():
+        names = ("xyz_", "features_dc_", "features_rest_", "language_features_", "opacity_", "scaling_", "rotation_")
+        for name, r in zip(names, ref.params()):
+            assert torch.equal(getattr(ours, name).detach(), r.detach()), name
+        assert ours.params_are_the_optimizers()
+        assert torch.equal(ours.exist_since_iter_, ref.exist_since_iter)
+        assert torch.equal(ours.denom_, ref.denom) and torch.equal(ours.xyz_gradient_accum_, ref.xyz_gradient_accum)
+        assert torch.equal(ours.max_radii2D_, ref.max_radii2D)
+
+    same_params()
+    # the reference's replaceTensorToOptimizer dereferences the optimizer's state entry of the tensor it replaces (:580-581),
+    # which exists only after a first Adam::step -- resetOpacity before any step is a null dereference there.  A step on zero
+    # gradients creates the entries and moves nothing (m = v = 0 -> update 0); the package's class needs no such entry.
+    ref.set_grads([torch.zeros_like(x) for x in t])
+    ref.step()
+    same_params()
+    ours.resetOpacity(), ref.reset_opacity()
+    same_params()
+    mask = torch.rand(n, generator=g) < 0.3
+    ours.prunePoints(mask), ref.prune_points(mask)
+    same_params()
+    assert ours.xyz_.shape[0] == n - int(mask.sum())
