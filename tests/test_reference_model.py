@@ -487,3 +487,52 @@ def test_cpp_model_of_the_package_side_by_side_with_the_reference_class(RM):
     ours.prunePoints(mask), ref.prune_points(mask)
     same_params()
     assert ours.xyz_.shape[0] == n - int(mask.sum())
+
+
+def test_restatements_match_the_reference_model_golden():
+    """tests/golden/model.npz -- inputs and outputs of the UNMODIFIED reference class (tests/golden/make_model_golden.py; stored
+    so that the pin survives where oracle/_ref/ref_model.so cannot be built): the C oracle's Adam on trainingSetup's rates
+    reproduces its two steps (1e-6), oracle/densify_ref.py reproduces addDensificationStats x 3 -> densifyAndPrune ->
+    resetOpacity bit for bit from the stored state, and the mapper's schedule returns the stored float at every step."""
+    import oracle as O
+    from conftest import golden
+    from leg_slam_b200 import mapper as M
+    G = golden("model")
+    for case in ("a", "b"):
+        lrs = G[f"{case}_lrs"]
+        for i, k in enumerate(DR.PARAMS):
+            p = G[f"{case}_init_{k}"].copy().reshape(-1)
+            m, v = np.zeros_like(p), np.zeros_like(p)
+            for s in range(2):
+                O.adam(p, G[f"{case}_grad{s}_{k}"].reshape(-1), m, v, float(lrs[i]), step=s + 1)
+            for got, want in ((p, G[f"{case}_stepped_p_{k}"]), (m, G[f"{case}_stepped_m_{k}"]), (v, G[f"{case}_stepped_v_{k}"])):
+                assert float(np.abs(got - want.reshape(-1)).max()) <= 1e-6 * float(np.abs(want).max()), (case, k)
+            assert int(G[f"{case}_stepped_step_{k}"]) == 2
+        t = torch.from_numpy
+        ours = DR.Model({k: t(G[f"{case}_stepped_p_{k}"]) for k in DR.PARAMS}, percent_dense=OPT["percent_dense"])
+        for k in DR.PARAMS:
+            ours.m[k], ours.v[k] = t(G[f"{case}_stepped_m_{k}"]).clone(), t(G[f"{case}_stepped_v_{k}"]).clone()
+        ours.exist_since_iter = t(G[f"{case}_stepped_exist"]).clone()
+        for vw in range(3):
+            ours.add_stats(t(G[f"{case}_view{vw}_radii"]), t(G[f"{case}_view{vw}_grad"]))
+        for got, key in ((ours.xyz_gradient_accum, "accum"), (ours.denom, "denom"), (ours.max_radii2D, "max_radii")):
+            assert torch.equal(got, t(G[f"{case}_stats_{key}"])), (case, key)
+        max_grad, min_opacity, extent, mss = G[f"{case}_args"]
+        ours.densify_and_prune(float(max_grad), float(min_opacity), float(extent), int(mss),
+                               seeded_normal01(int(G[f"{case}_normal_seed"])))
+        for k in DR.PARAMS:
+            assert torch.equal(ours.p[k], t(G[f"{case}_densified_p_{k}"])), (case, k)
+            assert torch.equal(ours.m[k], t(G[f"{case}_densified_m_{k}"])) and torch.equal(ours.v[k], t(G[f"{case}_densified_v_{k}"]))
+        assert ours.p["xyz"].shape[0] != G[f"{case}_stepped_p_xyz"].shape[0]
+        assert torch.equal(ours.exist_since_iter, t(G[f"{case}_densified_exist"]))
+        assert not ours.denom.any() and not G[f"{case}_densified_denom"].any()
+        ours.reset_opacity()
+        assert torch.equal(ours.p["opacity"], t(G[f"{case}_reset_p_opacity"]))
+        assert not ours.m["opacity"].any() and not G[f"{case}_reset_m_opacity"].any() and int(G[f"{case}_reset_step_opacity"]) == 2
+    f32 = lambda x: float(np.float32(x))  # noqa: E731
+    for i in range(3):
+        scale, max_steps = G[f"lr{i}_cfg"]
+        sched = M.ExponLr(f32(OPT["position_lr_init"]) * float(scale), f32(OPT["position_lr_final"]) * float(scale),
+                          f32(OPT["position_lr_delay_mult"]), int(max_steps))
+        got = np.array([sched(int(s)) for s in G[f"lr{i}_steps"]])
+        assert np.array_equal(got, G[f"lr{i}_values"]), i
