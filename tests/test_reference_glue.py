@@ -194,3 +194,69 @@ def test_mark_visible_gaussians(RM, both):
     o = RZ.GaussianRasterizer(rs).markVisible(sc["xyz"])
     assert r.dtype == torch.bool and torch.equal(r, o) and 0 < int(r.sum()) < P
     assert oracle_l1.same_calls(la.calls, lb.calls) and [c[0] for c in la.calls] == ["mark_visible"]
+
+
+def test_mapping_iterations_of_reference_classes_equal_mapper_train_step(RM, both):
+    """Whole mapping iterations assembled ONLY from unmodified reference code, in trainForOneIteration's order (reference
+    src/gaussian_mapper.cpp:662-796): GaussianModel::updateLearningRate -> GaussianRenderer::render (language features on) ->
+    loss_utils chained as :707-721 (oracle/_ref/ref_loss.so) -> backward through GaussianRasterizerFunction -> max_radii2D /
+    addDensificationStats -> the model's own libtorch Adam::step + zero_grad -- against Mapper.train_step's autograd path.
+    Both arms render through the CPU oracle (the reference arm via the recording L1, the mapper via tests/oracle_autograd.py),
+    so what is compared is everything AROUND the kernels: activations, argument routing, loss, gradient routing, optimizer."""
+    import oracle_autograd
+    from leg_slam_b200 import mapper as M
+    try:
+        ref_loss = build_ref.load_loss()
+    except FileNotFoundError as ex:
+        pytest.skip(str(ex))
+    la, _ = both
+    n_it = 3
+    sc, cam = scene()
+    g = torch.Generator().manual_seed(42)
+    bg = torch.zeros(3)
+    gt = dict(image=torch.rand(3, H, W, generator=g), lf=torch.randn(64, 37, 37, generator=g),
+              depth=torch.rand(1, H, W, generator=g) * 3)
+    mask = (torch.rand(1, H, W, generator=g) > 0.1).float().expand(3, H, W).contiguous()
+    kv = RD.KeyframeView(cam)
+
+    ref = RM.GaussianModel(3)
+    ref.set_state([sc[k] for k in NAMES], torch.zeros(P, dtype=torch.int32), 2.0)
+    ref.set_sh_degree(3)
+    ref.training_setup(position_lr_init=0.00016, position_lr_final=0.0000016, position_lr_delay_mult=0.01, position_lr_max_steps=n_it,
+                       feature_lr=0.0025, language_feature_lr=0.0015, opacity_lr=0.05, scaling_lr=0.005, rotation_lr=0.001,
+                       percent_dense=0.01)
+    mp = M.Mapper({k: sc[k] for k in NAMES}, lrs=dict(zip(M.PARAM_ORDER, ref.lrs())), sh_degree=3, fused=False, use_cuda_graph=False,
+                  optimizer_factory=lambda gr: torch.optim.Adam(gr, lr=0.0, eps=1e-15),
+                  render_fn=oracle_autograd.make_render_fn(bg))
+    f32 = lambda x: float(np.float32(x))  # noqa: E731
+    mp.set_position_lr_schedule(f32(0.00016), f32(0.0000016), f32(0.01), n_it, spatial_lr_scale=2.0)
+    kf = M.Keyframe(cam, gt["image"], gt["lf"], gt["depth"], mask)
+    xyz_lr_sum = 0.0
+    for it in range(n_it):
+        lr = ref.update_learning_rate(it)
+        assert mp.update_learning_rate(it) == lr
+        xyz_lr_sum += lr
+        image, lf, depth, viewspace, visible, radii = RM.render(ref, kv.FoVx_, kv.FoVy_, cam.viewmatrix, cam.projmatrix, cam.campos,
+                                                                H, W, False, False, bg, torch.empty(0), 1.0, False, True)
+        loss = ref_loss.mapping_loss(image, lf, depth, gt["image"], gt["lf"], gt["depth"], mask, 0.2)
+        loss.backward()
+        with torch.no_grad():
+            mr = ref.max_radii2D
+            mr[visible] = torch.max(mr[visible], radii[visible].to(mr.dtype))
+            ref.max_radii2D = mr
+            ref.add_densification_stats(viewspace.grad, visible)
+            ref.step()
+            ref.zero_grad()
+        l_ours = mp.train_step([kf])
+        assert abs(float(l_ours) - float(loss.detach())) <= 1e-5 * abs(float(loss.detach())), (it, float(l_ours), float(loss.detach()))
+    assert [c[0] for c in la.calls] == ["rasterize_gaussians", "rasterize_gaussians_backward"] * n_it
+    assert float(ref.denom.max()) == n_it and ref.xyz_gradient_accum.any()
+    for k, r, lr in zip(M.PARAM_ORDER, ref.params(), ref.lrs()):
+        # differences are measured against the size of the steps taken (Adam's first steps are sign-like: ~lr per element)
+        step = xyz_lr_sum if k == "xyz" else n_it * lr
+        d = (mp.params[k].detach() - r.detach()).abs()
+        moved = (r.detach() - sc[k]).abs()
+        assert float(moved.max()) > 0.5 * step / n_it, k               # the reference arm did train this tensor
+        assert float(d.max()) <= 1e-3 * step, (k, float(d.max()), step)   # measured: <= 1.6e-5 of the steps taken
+        st = ref.moments(M.PARAM_ORDER.index(k))
+        assert st[0] == n_it and mp.optimizer.state[mp.params[k]]["step"] == n_it
