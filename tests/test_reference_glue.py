@@ -260,3 +260,75 @@ def test_mapping_iterations_of_reference_classes_equal_mapper_train_step(RM, bot
         assert float(d.max()) <= 1e-3 * step, (k, float(d.max()), step)   # measured: <= 1.6e-5 of the steps taken
         st = ref.moments(M.PARAM_ORDER.index(k))
         assert st[0] == n_it and mp.optimizer.state[mp.params[k]]["step"] == n_it
+
+
+REF_PY_PKG = "/root/reference/eval/submodules/diff-gaussian-rasterization-legs-slam/diff_gaussian_rasterization_legs_slam"
+
+
+def _import_reference_python_wrapper(l1):
+    """The reference's own Python wrapper (eval/submodules/.../diff_gaussian_rasterization_legs_slam/__init__.py), imported
+    from where it lies with `l1` standing in for its compiled `_C` submodule."""
+    import importlib.util
+    import types
+    name = "ref_dgr_legs_slam"
+    for k in [k for k in sys.modules if k == name or k.startswith(name + ".")]:
+        del sys.modules[k]
+    c = types.ModuleType(name + "._C")
+    c.rasterize_gaussians, c.rasterize_gaussians_backward, c.mark_visible = (
+        l1.rasterize_gaussians, l1.rasterize_gaussians_backward, l1.mark_visible)
+    sys.modules[name + "._C"] = c
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF_PY_PKG, "__init__.py"),
+                                                  submodule_search_locations=[REF_PY_PKG])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_PY_PKG), reason="reference tree not present (it does not travel to the GPU box)")
+def test_python_wrapper_of_the_reference_makes_the_same_forward_calls(monkeypatch):
+    """The eval package's GaussianRasterizer (reference eval/submodules/.../__init__.py:159-210), imported unmodified, next to
+    leg_slam_b200.rasterizer.GaussianRasterizer on the same recording L1, the way the eval scripts use it (forward only, under
+    no_grad -- SURVEY.md 8b: its backward passes 22 of the 24 arguments): same `_C.rasterize_gaussians` arguments for every
+    input selection, same results, same refusals, same markVisible call."""
+    import oracle as O
+    la, lb = oracle_l1.RecordingL1(), oracle_l1.RecordingL1()
+    ref = _import_reference_python_wrapper(la)
+    monkeypatch.setattr(RZ, "_C", lb)
+    n = O.num_threads()
+    O.lib().omp_set_num_threads(1)
+    try:
+        sc, cam = scene()
+        bg = torch.tensor([0.2, 0.1, 0.0])
+        xyz, op = sc["xyz"], torch.sigmoid(sc["opacity"])
+        shs = torch.cat([sc["features_dc"], sc["features_rest"]], dim=1)
+        scales, rots = torch.exp(sc["scaling"]), torch.nn.functional.normalize(sc["rotation"])
+        cols = torch.rand(P, 3, generator=torch.Generator().manual_seed(1))
+        cov = RD.GaussianModelView({k: sc[k] for k in NAMES}).getCovarianceActivation()
+        means2D = torch.zeros_like(xyz)
+        assert ref.GaussianRasterizationSettings._fields == RZ.GaussianRasterizationSettings._fields
+        selections = [dict(shs=shs, lang_feats=sc["lang_feat"], scales=scales, rotations=rots),
+                      dict(shs=shs, scales=scales, rotations=rots),
+                      dict(colors_precomp=cols, lang_feats=sc["lang_feat"], scales=scales, rotations=rots),   # heat-map render
+                      dict(shs=shs, lang_feats=sc["lang_feat"], cov3D_precomp=cov)]
+        with torch.no_grad():
+            for sel in selections:
+                args = (H, W, cam.tanfovx, cam.tanfovy, bg, 1.0, cam.viewmatrix, cam.projmatrix, 3, cam.campos, False, "lang_feats" in sel)
+                r = ref.GaussianRasterizer(ref.GaussianRasterizationSettings(*args))(xyz, means2D, op, **sel)
+                o = RZ.GaussianRasterizer(RZ.GaussianRasterizationSettings(*args))(xyz, means2D, op, **sel)
+                assert len(r) == len(o) == 4 and all(torch.equal(x, y) for x, y in zip(r, o))
+            vr = ref.GaussianRasterizer(ref.GaussianRasterizationSettings(*args)).markVisible(xyz)
+            vo = RZ.GaussianRasterizer(RZ.GaussianRasterizationSettings(*args)).markVisible(xyz)
+            assert torch.equal(vr, vo)
+        assert oracle_l1.same_calls(la.calls, lb.calls)
+        assert [c[0] for c in la.calls] == ["rasterize_gaussians"] * len(selections) + ["mark_visible"]
+        for bad, msg in ((dict(scales=scales, rotations=rots), "excatly one of either SHs or precomputed colors"),
+                         (dict(shs=shs, colors_precomp=cols, scales=scales, rotations=rots), "excatly one of either SHs"),
+                         (dict(shs=shs, scales=scales), "exactly one of either scale/rotation pair or precomputed 3D covariance"),
+                         (dict(shs=shs, scales=scales, rotations=rots, cov3D_precomp=cov), "exactly one of either scale/rotation pair")):
+            for mod in (ref, RZ):
+                with pytest.raises(Exception, match=msg):
+                    mod.GaussianRasterizer(mod.GaussianRasterizationSettings(*args))(xyz, means2D, op, **bad)
+        assert len(la.calls) == len(lb.calls) == len(selections) + 1
+    finally:
+        O.lib().omp_set_num_threads(n)
