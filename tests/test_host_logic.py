@@ -1,5 +1,7 @@
 """CPU: host-side logic of the reference-shaped interface (no kernels run)."""
 import math
+import os
+import sys
 
 import numpy as np
 import pytest
@@ -216,3 +218,42 @@ def test_density_control_cadence_matches_reference_conditions():
     calls.clear()
     mp.density_control(3000, M.DensityControlParams(), 2.0)
     assert [c[0] for c in calls] == ["densify", "reset"] and calls[0][1] == (0.0002, 0.005, 2.0, 20)
+
+
+REF_EVAL = "/root/reference/eval"
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF_EVAL, "utils.py")), reason="reference tree not present")
+def test_synthetic_cameras_equal_the_reference_minicam(monkeypatch):
+    """The camera tensors every test and bench renders with (leg_slam_b200.synthetic.camera_from_pose) against the reference's
+    own Python camera -- eval/utils.py: get_world2view (:67-81), focal2fov (:83-84), MiniCam (:10-48: transposed view matrix,
+    projection from the FoV only, full_proj = view @ P^T, centre from the inverse), imported unmodified (its unrelated imports
+    -- clip, cv2, torchvision -- replaced by empty modules, `.cuda()` by the identity: there is no GPU here)."""
+    import importlib.util
+    import types
+    for name in ("clip", "cv2", "torchvision", "torchvision.transforms"):
+        if name not in sys.modules:
+            monkeypatch.setitem(sys.modules, name, types.ModuleType(name))
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    spec = importlib.util.spec_from_file_location("ref_eval_utils", os.path.join(REF_EVAL, "utils.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    for (W, H, fx, fy, seed) in ((640, 480, 320.0, 320.0, 5), (1296, 968, 1169.7, 1169.7, 6), (320, 240, 160.0, 171.5, 7)):
+        g = torch.Generator().manual_seed(seed)
+        c = torch.rand(3, generator=g, dtype=torch.float64) * 2 + 1
+        tgt = torch.rand(3, generator=g, dtype=torch.float64) * 4
+        R = synthetic.look_at(tuple(c.tolist()), tuple(tgt.tolist()))
+        cam = synthetic.camera_from_pose(R, c, W, H, fx, fy)
+        fovx, fovy = ref.focal2fov(fx, W), ref.focal2fov(fy, H)
+        mini = ref.MiniCam(W, H, fovx, fovy, ref.get_world2view(R.numpy(), c.numpy()))
+        assert cam.tanfovx == math.tan(fovx * 0.5) and cam.tanfovy == math.tan(fovy * 0.5)   # what eval/render.py:29-30 passes
+        # the projection has no pose in it: bit-identical
+        P_ours = synthetic.projection_matrix(0.01, 100.0, fovx, fovy)
+        assert torch.equal(P_ours, ref.MiniCam.get_projection_matrix(0.01, 100.0, fovx, fovy))
+        # the view matrix: R^T and -R^T c written out here, a 4x4 inverse in double there -- equal after rounding to float
+        # up to the last bit
+        for ours, theirs in ((cam.viewmatrix, mini.world_view_transform), (cam.projmatrix, mini.full_proj_transform),
+                             (cam.campos, mini.camera_center)):
+            assert ours.shape == theirs.shape and ours.dtype == theirs.dtype == torch.float32
+            assert float((ours - theirs).abs().max()) <= 1e-6 * max(1.0, float(theirs.abs().max()))
+        assert float((cam.campos.double() - c).abs().max()) <= 1e-6 * float(c.abs().max())
