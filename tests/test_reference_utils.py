@@ -78,3 +78,24 @@ def test_build_rotation_restatements_match_the_reference_header(ref_utils):
     # proper rotations
     eye = torch.eye(3, device=dev).expand(5000, 3, 3)
     assert float((ref @ ref.transpose(1, 2) - eye).abs().max()) <= 1e-5
+
+
+REF_SH_PY = "/root/reference/eval/sh_utils.py"
+
+
+@pytest.mark.skipif(not os.path.isfile(REF_SH_PY), reason="reference tree not present")
+def test_eval_sh_equals_the_reference_python_module():
+    """leg_slam_b200.renderer.eval_sh against the eval package's own eval_sh (reference eval/sh_utils.py:58-113), imported
+    unmodified: bit-identical at every degree; RGB2SH / SH2RGB of that module against the constant the package uses."""
+    import importlib.util
+    from leg_slam_b200 import renderer as RD
+    spec = importlib.util.spec_from_file_location("ref_eval_sh_utils", REF_SH_PY)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    g = torch.Generator().manual_seed(0)
+    sh = torch.randn(500, 3, 16, generator=g)
+    d = torch.nn.functional.normalize(torch.randn(500, 3, generator=g))
+    for deg in range(4):
+        assert torch.equal(ref.eval_sh(deg, sh, d), RD.eval_sh(deg, sh, d)), deg
+    x = torch.rand(100, 3, generator=g)
+    assert torch.equal(ref.RGB2SH(x), (x - 0.5) / RD.SH_C0) and torch.equal(ref.SH2RGB(x), x * RD.SH_C0 + 0.5)
