@@ -334,7 +334,7 @@ def build_model(force=False, verbose=True):
     os.makedirs(objdir, exist_ok=True)
     inc, lib = _torch_paths()
     pyinc = sysconfig.get_paths()["include"]
-    common = ["g++", "-O2", "-std=c++17", "-fPIC", "-DLANGUAGE_FEATURES_DIM=64", "-D_GLIBCXX_USE_CXX11_ABI=1",
+    common = ["g++", "-O1", "-std=c++17", "-fPIC", "-DLANGUAGE_FEATURES_DIM=64", "-D_GLIBCXX_USE_CXX11_ABI=1",
               "-DTORCH_EXTENSION_NAME=" + MODEL_MOD, "-DTORCH_API_INCLUDE_EXTENSION_H",
               "-include", os.path.join(STUBS, "ref_model_prelude.h"),
               "-I" + STUBS, "-I" + MODEL_REF, "-I" + os.path.join(MODEL_REF, "include"), "-I/usr/local/cuda/include",
