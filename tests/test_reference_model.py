@@ -536,3 +536,44 @@ def test_restatements_match_the_reference_model_golden():
                           f32(OPT["position_lr_delay_mult"]), int(max_steps))
         got = np.array([sched(int(s)) for s in G[f"lr{i}_steps"]])
         assert np.array_equal(got, G[f"lr{i}_values"]), i
+
+
+@pytest.mark.parametrize("what", ["nothing_selected", "everything_cloned", "everything_split", "everything_pruned", "unseen"])
+def test_densify_edge_cases_equal_reference_model(RM, what):
+    """The corners of densifyAndPrune (reference :729-832): no Gaussian over the gradient threshold (empty clone and split
+    sets), every Gaussian cloned, every Gaussian split, every Gaussian pruned (the model ends with zero rows), and statistics
+    of Gaussians no view has seen (0 / 0 -> nan -> 0, :811-812) -- the restatement follows the reference class through each."""
+    P = 64
+    ref, ours, g = make_pair(RM, P, seed=200)
+    accum, denom = torch.rand(P, 1, generator=g) * 4e-4 + 3e-4, torch.ones(P, 1)
+    args = dict(max_grad=2e-4, min_opacity=0.005, extent=4.0, mss=0)
+    if what == "nothing_selected":
+        args["max_grad"] = 1.0
+    elif what == "everything_cloned":
+        args["extent"] = 1e6            # every scale is under percent_dense * extent
+    elif what == "everything_split":
+        args["extent"] = 1e-6           # every scale is over it (and the world-size prune stays off: mss = 0)
+    elif what == "everything_pruned":
+        args["min_opacity"] = 1.1
+    elif what == "unseen":
+        denom = torch.zeros(P, 1)
+        accum = torch.zeros(P, 1)
+        denom[::3], accum[::3] = 2.0, 9e-4
+    for m in (ref, ours):
+        m.xyz_gradient_accum, m.denom = accum.clone(), denom.clone()
+    mr = torch.rand(P, generator=g) * 40
+    ref.max_radii2D = mr.clone()
+    ours.max_radii2D = mr.clone()
+    torch.manual_seed(17)
+    ref.densify_and_prune(args["max_grad"], args["min_opacity"], args["extent"], args["mss"])
+    ours.densify_and_prune(args["max_grad"], args["min_opacity"], args["extent"], args["mss"], seeded_normal01(17))
+    assert_same(ref, ours, 2)
+    n = ours.p["xyz"].shape[0]
+    if what == "everything_pruned":
+        assert n == 0
+    elif what == "nothing_selected":
+        assert n <= P
+    elif what == "everything_cloned":
+        assert n > P
+    elif what == "everything_split":
+        assert n > P and not torch.equal(ours.p["scaling"][:1], ours.p["scaling"][:1] * 0)
