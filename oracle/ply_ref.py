@@ -9,7 +9,8 @@ byte-identical to the one the reference's own tinyply (third_party/tinyply, comp
 writes for savePly's call sequence, and the reference's reader -- tinyply with loadPly's property requests and reshapes
 (gaussian_model.cpp:882-956) -- returns the same tensors.  Also held to GaussianModel::savePly ITSELF: the unmodified class
 (oracle/_ref/ref_model.so, CPU tensors) writes a byte-identical file and its loadPly parses the one written here
-(tests/test_reference_model.py::test_ply_restatement_equals_reference_model_save_and_load)."""
+(tests/test_reference_model.py::test_ply_restatement_equals_reference_model_save_and_load); read_ply is held to the reference's
+Python reader itself, imported unmodified (tests/test_reference_eval.py)."""
 import numpy as np
 
 
