@@ -27,6 +27,8 @@ NAMES = ("xyz", "features_dc", "features_rest", "lang_feat", "opacity", "scaling
 @pytest.fixture(scope="module")
 def RM():
     try:
+        if os.path.isdir(os.path.join(build_ref.MODEL_REF, "src")):
+            build_ref.build_model(verbose=False)     # no-op when oracle/_ref/ref_model.so exists
         return build_ref.load_model()
     except FileNotFoundError as ex:
         pytest.skip(str(ex))

@@ -28,6 +28,8 @@ OPT = dict(position_lr_init=0.00016, position_lr_final=0.0000016, position_lr_de
 @pytest.fixture(scope="module")
 def RM():
     try:
+        if os.path.isdir(os.path.join(build_ref.MODEL_REF, "src")):
+            build_ref.build_model(verbose=False)     # no-op when oracle/_ref/ref_model.so exists
         return build_ref.load_model()
     except FileNotFoundError as ex:
         pytest.skip(str(ex))
