@@ -1,6 +1,7 @@
 """Adaptive density control: the fused CUDA path (lgs_densify_*) against the torch
 restatement of the reference's densifyAndPrune sequence (oracle/densify_ref.py), plus the restatement's own
-invariants on CPU."""
+invariants on CPU.  The restatement itself is held, bit for bit, to the unmodified reference GaussianModel class running on CPU
+tensors (tests/test_reference_model.py; fixture tests/golden/model.npz)."""
 import os
 import sys
 
