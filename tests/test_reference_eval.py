@@ -174,3 +174,34 @@ def test_reference_python_render_makes_the_same_calls(ref_eval, monkeypatch, tmp
         assert 0 < int(r["visibility_filter"].sum()) < P and r["rendered_lf"].abs().sum() > 0
     finally:
         O.lib().omp_set_num_threads(n)
+
+
+def test_semantic_query_lines_of_the_reference_equal_the_oracle(monkeypatch):
+    """The semantic query as the reference computes it -- the statements of eval/find_objects_gaussians.py between "Compute
+    similarity between each Gaussian and text embedding" and the relevance normalisation (:164-175), and the per-pixel line
+    (:323) -- cut out of the file as they stand and executed on CPU tensors, against the C oracle's cosine (what the CUDA
+    kernels are held to at 2e-6, tests/test_gpu_parity.py::test_cosine_query) and the relevance formula."""
+    import textwrap
+    import oracle as O
+    import torch.nn.functional as F
+    src = open(os.path.join(REF_EVAL, "find_objects_gaussians.py")).read().splitlines()
+    a = next(i for i, ln in enumerate(src) if "Compute similarity between each Gaussian and text embedding" in ln)
+    b = next(i for i, ln in enumerate(src) if ln.strip().startswith("similarities = 1 - ("))
+    block = textwrap.dedent("\n".join(src[a:b + 1]))
+    assert "F.normalize(gaussian_features, dim=1)" in block and "torch.matmul" in block
+    pix = next(ln.strip() for ln in src if ln.strip().startswith("dist = F.cosine_similarity(rendered_lf, text_embed, dim=0)"))
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *x, **k: self)
+    feats, text = cases.cosine_case()                    # [P,64], [Q,64]
+    ns = dict(F=F, torch=torch, gaussian_features=feats, text_emb_compressed=text[0:1].clone())   # the first request (:167)
+    exec(block, ns)
+    sim0 = O.cosine(feats.numpy(), text[0:1].numpy())[:, 0].astype(np.float64)
+    want = 1 - (sim0 - sim0.min()) / (sim0.max() - sim0.min())
+    assert ns["similarities"].shape == (feats.shape[0], 1)    # text_embed[:, 0] of the [64,1,1] embedding is [64,1]
+    assert float(np.abs(ns["similarities"].numpy()[:, 0] - want).max()) <= 5e-6
+    # per pixel: text_embed is [64,1,1] after the block above (:167), rendered_lf a [64,H,W] feature image
+    H, W = 24, 40
+    lf_img = feats[:H * W].t().reshape(64, H, W).contiguous()
+    ns2 = dict(F=F, rendered_lf=lf_img, text_embed=ns["text_embed"])
+    exec(pix.replace(".detach()", ""), ns2)
+    want_pix = O.cosine(feats[:H * W].numpy(), text[0:1].numpy())[:, 0].reshape(H, W)
+    assert ns2["dist"].shape == (H, W) and float(np.abs(ns2["dist"].numpy() - want_pix).max()) <= 2e-6
