@@ -350,8 +350,26 @@ def build_model(force=False, verbose=True):
             print("[build_ref]", " ".join(cmd), flush=True)
         subprocess.check_call(cmd)
 
-    with ThreadPoolExecutor(max_workers=len(cmds)) as ex:
-        list(ex.map(run, cmds))
+    # The density-control block and the optimizer step of GaussianMapper::trainForOneIteration (src/gaussian_mapper.cpp:737-761,
+    # 793-797) cannot be compiled with their file (ORB-SLAM3, OpenCV, jsoncpp ...).  The wrapper runs those very lines inside a
+    # harness whose members carry the mapper's names: they are cut out of the file HERE, at build time, into two .inc files
+    # next to the objects (git-ignored), #included by the wrapper, and removed again after the compile.
+    mapper_src = open(os.path.join(MODEL_REF, "src", "gaussian_mapper.cpp")).read().splitlines()
+    a = next(i for i, ln in enumerate(mapper_src) if ln.strip() == "// Densification")
+    b = next(i for i in range(a, len(mapper_src)) if mapper_src[i].strip().startswith("auto iter_end_timing"))
+    c = next(i for i in range(b, len(mapper_src)) if mapper_src[i].strip() == "// Optimizer step")
+    incs = {"density_control_block.inc": mapper_src[a:b], "optimizer_step_block.inc": mapper_src[c:c + 5]}
+    assert "resetOpacity" in "\n".join(incs["density_control_block.inc"]) and "zero_grad" in "\n".join(incs["optimizer_step_block.inc"])
+    for name, lines in incs.items():
+        with open(os.path.join(objdir, name), "w") as f:
+            f.write("\n".join(lines) + "\n")
+    cmds = [cmd + ["-I" + objdir] for cmd in cmds]
+    try:
+        with ThreadPoolExecutor(max_workers=len(cmds)) as ex:
+            list(ex.map(run, cmds))
+    finally:
+        for name in incs:
+            os.remove(os.path.join(objdir, name))
     run(["g++", "-shared"] + objs + ["-o", MODEL_SO] + ["-L" + p for p in lib] +
         ["-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch", "-ltorch_python"] + ["-Wl,-rpath," + p for p in lib])
     return MODEL_SO

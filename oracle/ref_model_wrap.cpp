@@ -295,6 +295,38 @@ static torch::Tensor ref_mark_visible_gaussians(torch::Tensor view, torch::Tenso
     return rasterizer.markVisibleGaussians(positions);
 }
 
+// The density-control block and the optimizer step of GaussianMapper::trainForOneIteration, run as they stand
+// (src/gaussian_mapper.cpp:737-761 and 793-797, cut out of the file at build time by oracle/build_ref.py build_model() --
+// gaussian_mapper.cpp itself needs ORB-SLAM3 / OpenCV / jsoncpp).  The members below carry the names those lines use, with
+// the meaning include/gaussian_mapper.h and src/gaussian_mapper.cpp:338-352,1841-1854 give them; `gaussians_` is the
+// reference's own GaussianModel.
+struct RefDensityControl {
+    std::shared_ptr<GaussianModel> gaussians_;
+    GaussianOptimizationParams opt_params_;
+    GaussianModelParams model_params_;
+    struct Scene { float cameras_extent_ = 0.0f; } scene_storage_;
+    Scene* scene_ = &scene_storage_;
+    int prune_big_point_after_iter_ = 0;
+    float densify_min_opacity_ = 0.005f;
+    int iteration_ = 0;
+
+    int getIteration() { return iteration_; }
+    int opacityResetInterval() { return opt_params_.opacity_reset_interval_; }
+    float densifyGradThreshold() { return opt_params_.densify_grad_threshold_; }
+    int densifyInterval() { return opt_params_.densification_interval_; }
+
+    void run(int iteration, torch::Tensor viewspace_grad, torch::Tensor visibility_filter, torch::Tensor radii) {
+        iteration_ = iteration;
+        torch::Tensor viewspace_point_tensor = torch::zeros_like(viewspace_grad).requires_grad_();
+        viewspace_point_tensor.mutable_grad() = viewspace_grad;
+        {
+            torch::NoGradGuard no_grad;   // the block sits inside the no_grad scope opened at :729
+#include "density_control_block.inc"
+#include "optimizer_step_block.inc"
+        }
+    }
+};
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod) {
@@ -306,6 +338,29 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod) {
         set_cb(g_rasterize_backward, bwd);
         set_cb(g_mark_visible, mark);
     });
+    py::class_<RefDensityControl>(mod, "DensityControl")
+        .def(py::init([](RefModel& model, int iterations, int densification_interval, int opacity_reset_interval, int densify_from_iter,
+                         int densify_until_iter, double densify_grad_threshold, double densify_min_opacity,
+                         int prune_big_point_after_iter, bool white_background, double cameras_extent) {
+                 auto d = std::make_unique<RefDensityControl>();
+                 d->gaussians_ = model.m;
+                 d->opt_params_.iterations_ = iterations;
+                 d->opt_params_.densification_interval_ = densification_interval;
+                 d->opt_params_.opacity_reset_interval_ = opacity_reset_interval;
+                 d->opt_params_.densify_from_iter_ = densify_from_iter;
+                 d->opt_params_.densify_until_iter_ = densify_until_iter;
+                 d->opt_params_.densify_grad_threshold_ = (float)densify_grad_threshold;
+                 d->densify_min_opacity_ = (float)densify_min_opacity;
+                 d->prune_big_point_after_iter_ = prune_big_point_after_iter;
+                 d->model_params_.white_background_ = white_background;
+                 d->scene_storage_.cameras_extent_ = (float)cameras_extent;
+                 return d;
+             }),
+             py::arg("model"), py::arg("iterations"), py::arg("densification_interval"), py::arg("opacity_reset_interval"),
+             py::arg("densify_from_iter"), py::arg("densify_until_iter"), py::arg("densify_grad_threshold"),
+             py::arg("densify_min_opacity"), py::arg("prune_big_point_after_iter"), py::arg("white_background"),
+             py::arg("cameras_extent"))
+        .def("run", &RefDensityControl::run);
     mod.def("render", &ref_render);
     mod.def("rasterizer_forward", &ref_rasterizer_forward);
     mod.def("mark_visible_gaussians", &ref_mark_visible_gaussians);

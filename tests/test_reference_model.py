@@ -579,3 +579,84 @@ def test_densify_edge_cases_equal_reference_model(RM, what):
         assert n > P
     elif what == "everything_split":
         assert n > P and not torch.equal(ours.p["scaling"][:1], ours.p["scaling"][:1] * 0)
+
+
+def _adam_like_libtorch(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-15):
+    """torch::optim::Adam::step for one tensor, statement for statement (torch/csrc/api/src/optim/adam.cpp): in place."""
+    import math
+    bc1 = 1 - math.pow(beta1, step)
+    bc2 = 1 - math.pow(beta2, step)
+    m.mul_(beta1).add_(g, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+    p.addcdiv_(m, denom, value=-(lr / bc1))
+
+
+@pytest.mark.parametrize("white_background", [False, True])
+def test_density_control_lines_of_the_mapper_over_a_run(RM, white_background):
+    """The density-control block and the optimizer step of GaussianMapper::trainForOneIteration AS THEY STAND (reference
+    src/gaussian_mapper.cpp:737-761, 793-797, cut out of the file at build time and compiled into a harness that carries the
+    mapper's member names, oracle/ref_model_wrap.cpp RefDensityControl) drive the reference's own GaussianModel over a whole
+    run with gradients arriving every iteration.  Beside it, leg_slam_b200.mapper.density_control_actions decides what
+    oracle/densify_ref.py does to its model: the same statistics, the same densifications with the reference's size threshold,
+    the same opacity resets, and -- as in the reference -- the optimizer step after them, which skips every tensor a
+    densification or a reset has just replaced (it carries no gradient).  State bit-identical after every iteration."""
+    from leg_slam_b200 import mapper as M
+    P = 200
+    cfg = M.DensityControlParams(densification_interval=10, opacity_reset_interval=30, densify_from_iter=20, densify_until_iter=75,
+                                 densify_grad_threshold=2e-4, densify_min_opacity=0.05, prune_big_point_after_iter=40,
+                                 white_background=white_background)
+    n_iter, extent = 90, 4.0
+    ref, ours, g = make_pair(RM, P, seed=300, steps=2)
+    ref.zero_grad()
+    dc = RM.DensityControl(ref, iterations=n_iter, densification_interval=cfg.densification_interval,
+                           opacity_reset_interval=cfg.opacity_reset_interval, densify_from_iter=cfg.densify_from_iter,
+                           densify_until_iter=cfg.densify_until_iter, densify_grad_threshold=cfg.densify_grad_threshold,
+                           densify_min_opacity=cfg.densify_min_opacity, prune_big_point_after_iter=cfg.prune_big_point_after_iter,
+                           white_background=white_background, cameras_extent=extent)
+    steps = {k: 2 for k in DR.PARAMS}
+    lrs = ref.lrs()
+    seen = dict(densify=0, reset=0, big=0, stats=0)
+    for it in range(1, n_iter + 1):
+        n = ours.p["xyz"].shape[0]
+        assert n > 0
+        grads = [torch.randn(*ours.p[k].shape, generator=g) * 0.01 for k in DR.PARAMS]
+        radii = torch.randint(-5, 40, (n,), generator=g, dtype=torch.int32).clamp_min(0)
+        vs_grad = torch.randn(n, 3, generator=g) * 3e-4
+        visible = radii > 0
+        # the reference: backward has left gradients on the parameters; then its own lines
+        ref.set_grads(grads)
+        torch.manual_seed(1000 + it)
+        dc.run(it, vs_grad, visible, radii)
+        # the restatement under the mapper's decision function
+        act = M.density_control_actions(it, cfg)
+        stepped = set(DR.PARAMS)
+        if act["update_stats"]:
+            ours.add_stats(radii, vs_grad)
+            seen["stats"] += 1
+        if act["densify"]:
+            ours.densify_and_prune(cfg.densify_grad_threshold, cfg.densify_min_opacity, extent, act["size_threshold"],
+                                   seeded_normal01(1000 + it))
+            stepped = set()                      # all seven tensors were rebuilt: no gradient on them
+            seen["densify"] += 1
+            seen["big"] += act["size_threshold"] == 20
+        if act["reset_opacity"]:
+            ours.reset_opacity()
+            stepped.discard("opacity")
+            seen["reset"] += 1
+        if it < n_iter:                          # :793-797
+            for i, k in enumerate(DR.PARAMS):
+                if k in stepped:
+                    steps[k] += 1
+                    _adam_like_libtorch(ours.p[k], grads[i], ours.m[k], ours.v[k], steps[k], lrs[i])
+        for i, k in enumerate(DR.PARAMS):
+            assert torch.equal(ref.params()[i].detach(), ours.p[k]), (it, k)
+            st = ref.moments(i)
+            assert st[0] == steps[k], (it, k, st[0], steps[k])
+            assert torch.equal(st[1], ours.m[k]) and torch.equal(st[2], ours.v[k]), (it, k)
+        assert torch.equal(ref.exist_since_iter, ours.exist_since_iter)
+        for a, b in ((ref.xyz_gradient_accum, ours.xyz_gradient_accum), (ref.denom, ours.denom), (ref.max_radii2D, ours.max_radii2D)):
+            assert torch.equal(a, b), it
+    assert seen["stats"] == cfg.densify_until_iter - 1 and seen["densify"] == 5 and seen["big"] == 3
+    assert seen["reset"] == (3 if white_background else 2)      # 30, 60 (+ densify_from_iter = 20 on a white background)
+    assert ours.p["xyz"].shape[0] != P
