@@ -350,15 +350,19 @@ def build_model(force=False, verbose=True):
             print("[build_ref]", " ".join(cmd), flush=True)
         subprocess.check_call(cmd)
 
-    # The density-control block and the optimizer step of GaussianMapper::trainForOneIteration (src/gaussian_mapper.cpp:737-761,
-    # 793-797) cannot be compiled with their file (ORB-SLAM3, OpenCV, jsoncpp ...).  The wrapper runs those very lines inside a
-    # harness whose members carry the mapper's names: they are cut out of the file HERE, at build time, into two .inc files
+    # Render -> loss -> backward (:686-724), the density-control block (:737-761) and the optimizer step (:793-797) of
+    # GaussianMapper::trainForOneIteration (src/gaussian_mapper.cpp) cannot be compiled with their file (ORB-SLAM3, OpenCV, jsoncpp ...).  The wrapper runs those very lines inside a
+    # harness whose members carry the mapper's names: they are cut out of the file HERE, at build time, into three .inc files
     # next to the objects (git-ignored), #included by the wrapper, and removed again after the compile.
     mapper_src = open(os.path.join(MODEL_REF, "src", "gaussian_mapper.cpp")).read().splitlines()
     a = next(i for i, ln in enumerate(mapper_src) if ln.strip() == "// Densification")
     b = next(i for i in range(a, len(mapper_src)) if mapper_src[i].strip().startswith("auto iter_end_timing"))
     c = next(i for i in range(b, len(mapper_src)) if mapper_src[i].strip() == "// Optimizer step")
-    incs = {"density_control_block.inc": mapper_src[a:b], "optimizer_step_block.inc": mapper_src[c:c + 5]}
+    r0 = next(i for i, ln in enumerate(mapper_src) if ln.strip() == "// Render")
+    r1 = next(i for i in range(r0, len(mapper_src)) if mapper_src[i].strip() == "loss.backward();")
+    incs = {"density_control_block.inc": mapper_src[a:b], "optimizer_step_block.inc": mapper_src[c:c + 5],
+            "render_loss_backward_block.inc": mapper_src[r0:r1 + 1]}
+    assert r1 < a and "GaussianRenderer::render" in "\n".join(incs["render_loss_backward_block.inc"])
     assert "resetOpacity" in "\n".join(incs["density_control_block.inc"]) and "zero_grad" in "\n".join(incs["optimizer_step_block.inc"])
     for name, lines in incs.items():
         with open(os.path.join(objdir, name), "w") as f:

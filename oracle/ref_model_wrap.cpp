@@ -31,6 +31,7 @@
 #include "include/gaussian_model.h"
 #include "include/gaussian_rasterizer.h"
 #include "include/gaussian_renderer.h"
+#include "include/loss_utils.h"
 
 namespace py = pybind11;
 
@@ -315,6 +316,30 @@ struct RefDensityControl {
     float densifyGradThreshold() { return opt_params_.densify_grad_threshold_; }
     int densifyInterval() { return opt_params_.densification_interval_; }
 
+    GaussianPipelineParams pipe_params_;
+    torch::Tensor background_ = torch::zeros({3});
+    torch::Tensor override_color_ = torch::empty(0);
+    torch::DeviceType device_type_ = torch::kCPU;
+    float lambdaDssim() { return opt_params_.lambda_dssim_; }
+
+    // one iteration: render -> loss -> backward (:686-724), then, under no_grad as at :729, density control (:737-761) and the
+    // optimizer step (:793-797) -- all three pieces are the reference's lines; what lies between them in the file (timing,
+    // logging, keyframe recording) is left out.  Returns (loss, radii, visibility_filter).
+    std::vector<torch::Tensor> train_iteration(int iteration, double FoVx, double FoVy, torch::Tensor view, torch::Tensor proj,
+                                               torch::Tensor campos, torch::Tensor kf_language_features, int image_height,
+                                               int image_width, torch::Tensor gt_image, torch::Tensor gt_depth, torch::Tensor mask) {
+        iteration_ = iteration;
+        std::shared_ptr<GaussianKeyframe> viewpoint_cam = make_keyframe(FoVx, FoVy, view, proj, campos);
+        viewpoint_cam->language_features_ = kf_language_features;
+#include "render_loss_backward_block.inc"
+        {
+            torch::NoGradGuard no_grad;
+#include "density_control_block.inc"
+#include "optimizer_step_block.inc"
+        }
+        return {loss.detach(), radii, visibility_filter};
+    }
+
     void run(int iteration, torch::Tensor viewspace_grad, torch::Tensor visibility_filter, torch::Tensor radii) {
         iteration_ = iteration;
         torch::Tensor viewspace_point_tensor = torch::zeros_like(viewspace_grad).requires_grad_();
@@ -360,7 +385,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod) {
              py::arg("densify_from_iter"), py::arg("densify_until_iter"), py::arg("densify_grad_threshold"),
              py::arg("densify_min_opacity"), py::arg("prune_big_point_after_iter"), py::arg("white_background"),
              py::arg("cameras_extent"))
-        .def("run", &RefDensityControl::run);
+        .def("run", &RefDensityControl::run)
+        .def("train_iteration", &RefDensityControl::train_iteration, py::call_guard<py::gil_scoped_release>())   // loss.backward() inside
+        .def("set_lambda_dssim", [](RefDensityControl& d, double v) { d.opt_params_.lambda_dssim_ = (float)v; })
+        .def("set_background", [](RefDensityControl& d, torch::Tensor bg) { d.background_ = bg; });
     mod.def("render", &ref_render);
     mod.def("rasterizer_forward", &ref_rasterizer_forward);
     mod.def("mark_visible_gaussians", &ref_mark_visible_gaussians);

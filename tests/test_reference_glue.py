@@ -334,3 +334,56 @@ def test_python_wrapper_of_the_reference_makes_the_same_forward_calls(monkeypatc
         assert len(la.calls) == len(lb.calls) == len(selections) + 1
     finally:
         O.lib().omp_set_num_threads(n)
+
+
+def test_train_for_one_iteration_lines_equal_mapper_train_step(RM, both):
+    """The same comparison with the reference arm made of trainForOneIteration's OWN LINES: render -> loss -> backward
+    (src/gaussian_mapper.cpp:686-724), density control (:737-761; statistics only here, the Gaussian set stays) and the
+    optimizer step (:793-797), cut out of the file at build time and compiled as they stand (oracle/ref_model_wrap.cpp
+    RefDensityControl::train_iteration) around the reference's model, renderer, glue and loss_utils, over the recording L1."""
+    import oracle_autograd
+    from leg_slam_b200 import mapper as M
+    la, _ = both
+    n_it = 3
+    sc, cam = scene()
+    g = torch.Generator().manual_seed(43)
+    bg = torch.zeros(3)
+    gt = dict(image=torch.rand(3, H, W, generator=g), lf=torch.randn(64, 37, 37, generator=g),
+              depth=torch.rand(1, H, W, generator=g) * 3)
+    mask = (torch.rand(1, H, W, generator=g) > 0.1).float().expand(3, H, W).contiguous()
+    kv = RD.KeyframeView(cam)
+    ref = RM.GaussianModel(3)
+    ref.set_state([sc[k] for k in NAMES], torch.zeros(P, dtype=torch.int32), 2.0)
+    ref.set_sh_degree(3)
+    ref.training_setup(position_lr_init=0.00016, position_lr_final=0.0000016, position_lr_delay_mult=0.01, position_lr_max_steps=n_it,
+                       feature_lr=0.0025, language_feature_lr=0.0015, opacity_lr=0.05, scaling_lr=0.005, rotation_lr=0.001,
+                       percent_dense=0.01)
+    it_ref = RM.DensityControl(ref, iterations=1000, densification_interval=100, opacity_reset_interval=0, densify_from_iter=500,
+                               densify_until_iter=1000, densify_grad_threshold=2e-4, densify_min_opacity=0.005,
+                               prune_big_point_after_iter=0, white_background=False, cameras_extent=4.0)
+    it_ref.set_lambda_dssim(0.2)
+    it_ref.set_background(bg)
+    mp = M.Mapper({k: sc[k] for k in NAMES}, lrs=dict(zip(M.PARAM_ORDER, ref.lrs())), sh_degree=3, fused=False, use_cuda_graph=False,
+                  optimizer_factory=lambda gr: torch.optim.Adam(gr, lr=0.0, eps=1e-15),
+                  render_fn=oracle_autograd.make_render_fn(bg))
+    f32 = lambda x: float(np.float32(x))  # noqa: E731
+    mp.set_position_lr_schedule(f32(0.00016), f32(0.0000016), f32(0.01), n_it, spatial_lr_scale=2.0)
+    kf = M.Keyframe(cam, gt["image"], gt["lf"], gt["depth"], mask)
+    xyz_lr_sum = 0.0
+    for it in range(1, n_it + 1):
+        lr = ref.update_learning_rate(it)
+        assert mp.update_learning_rate(it) == lr
+        xyz_lr_sum += lr
+        loss, radii, visible = it_ref.train_iteration(it, kv.FoVx_, kv.FoVy_, cam.viewmatrix, cam.projmatrix, cam.campos, gt["lf"], H, W,
+                                                      gt["image"], gt["depth"], mask)
+        l_ours = mp.train_step([kf])
+        assert abs(float(l_ours) - float(loss)) <= 1e-5 * abs(float(loss)), (it, float(l_ours), float(loss))
+        assert torch.equal(visible, radii > 0) and 0 < int(visible.sum()) < P
+    assert [c[0] for c in la.calls] == ["rasterize_gaussians", "rasterize_gaussians_backward"] * n_it
+    assert float(ref.denom.max()) == n_it and ref.xyz_gradient_accum.any() and ref.max_radii2D.any()
+    for k, r, lr in zip(M.PARAM_ORDER, ref.params(), ref.lrs()):
+        step = xyz_lr_sum if k == "xyz" else n_it * lr
+        d = (mp.params[k].detach() - r.detach()).abs()
+        assert float((r.detach() - sc[k]).abs().max()) > 0.5 * step / n_it, k
+        assert float(d.max()) <= 1e-3 * step, (k, float(d.max()), step)
+        assert ref.moments(M.PARAM_ORDER.index(k))[0] == n_it and r.grad is None      # zero_grad(true) of :796
