@@ -1,8 +1,11 @@
 // ref_model_wrap.cpp -- pybind entry points around the UNMODIFIED reference GaussianModel, GaussianRasterizer(Function) and
 // GaussianRenderer (TEST INFRASTRUCTURE, oracle/_ref/ref_model.so, built by oracle/build_ref.py build_model()).
 //
-// /root/reference/src/gaussian_model.cpp and src/gaussian_parameters.cpp are compiled from where they lie; nothing of them is
-// copied.  The class is libtorch code and runs on CPU tensors when its parameters say data_device != "cuda"
+// /root/reference/src/gaussian_model.cpp, gaussian_parameters.cpp, gaussian_rasterizer.cpp and gaussian_renderer.cpp are compiled
+// from where they lie; nothing of them is copied into the repository.  Three passages of src/gaussian_mapper.cpp (a file that
+// needs ORB-SLAM3 / OpenCV / jsoncpp) -- render -> loss -> backward, density control, optimizer step of trainForOneIteration --
+// are #included as they stand from .inc files that build_model() cuts out at build time and removes after the compile
+// (RefDensityControl below).  The class is libtorch code and runs on CPU tensors when its parameters say data_device != "cuda"
 // (gaussian_model.cpp:37-41), so the reference's density control (addDensificationStats, densifyAndClone / Split / Prune,
 // densificationPostfix, prunePoints), its optimizer-state surgery (replaceTensorToOptimizer, resetOpacity), trainingSetup's
 // seven Adam groups with libtorch's own Adam::step, the learning-rate schedule (exponLrFunc), the activations, createFromPcd /
