@@ -104,6 +104,16 @@ def density_control_actions(iteration: int, p: DensityControlParams):
     return out
 
 
+def optimizer_step_groups(actions: dict):
+    """Which parameter groups the optimizer step at the END of trainForOneIteration (reference src/gaussian_mapper.cpp:793-797)
+    still moves after that iteration's density control (`density_control_actions`): a densification rebuilds all seven tensors
+    and a resetOpacity the opacity, the rebuilt tensors carry no gradient, and libtorch's Adam skips parameters without one.
+    -> tuple of names from PARAM_ORDER.  Pure host logic (held to the reference's own lines on CPU)."""
+    if actions.get("densify"):
+        return ()
+    return tuple(k for k in PARAM_ORDER if not (k == "opacity" and actions.get("reset_opacity")))
+
+
 class Keyframe(NamedTuple):
     camera: Camera
     gt_image: torch.Tensor   # [3,H,W]

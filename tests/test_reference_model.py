@@ -630,19 +630,20 @@ def test_density_control_lines_of_the_mapper_over_a_run(RM, white_background):
         dc.run(it, vs_grad, visible, radii)
         # the restatement under the mapper's decision function
         act = M.density_control_actions(it, cfg)
-        stepped = set(DR.PARAMS)
+        stepped = set(M.optimizer_step_groups(act))
+        assert set(M.PARAM_ORDER) == set(DR.PARAMS)
         if act["update_stats"]:
             ours.add_stats(radii, vs_grad)
             seen["stats"] += 1
         if act["densify"]:
             ours.densify_and_prune(cfg.densify_grad_threshold, cfg.densify_min_opacity, extent, act["size_threshold"],
                                    seeded_normal01(1000 + it))
-            stepped = set()                      # all seven tensors were rebuilt: no gradient on them
+            assert not stepped                   # all seven tensors were rebuilt: no gradient on them
             seen["densify"] += 1
             seen["big"] += act["size_threshold"] == 20
         if act["reset_opacity"]:
             ours.reset_opacity()
-            stepped.discard("opacity")
+            assert "opacity" not in stepped
             seen["reset"] += 1
         if it < n_iter:                          # :793-797
             for i, k in enumerate(DR.PARAMS):
