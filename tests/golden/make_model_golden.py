@@ -45,7 +45,7 @@ def state(ref, tag, out, only=NAMES, stats=True):
     out[f"{tag}_max_radii"] = ref.max_radii2D.numpy().copy()
 
 
-def main():
+def main(path=None):
     RM = build_ref.load_model()
     out = {}
     for case, max_screen_size in (("a", 0), ("b", 20)):
@@ -94,10 +94,10 @@ def main():
         out[f"lr{i}_cfg"] = np.array([scale, max_steps], np.float64)
         out[f"lr{i}_steps"] = steps
         out[f"lr{i}_values"] = np.array([ref.update_learning_rate(int(s)) for s in steps], np.float64)
-    path = os.path.join(HERE, "model.npz")
+    path = path or os.path.join(HERE, "model.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)

@@ -661,3 +661,19 @@ def test_density_control_lines_of_the_mapper_over_a_run(RM, white_background):
     assert seen["stats"] == cfg.densify_until_iter - 1 and seen["densify"] == 5 and seen["big"] == 3
     assert seen["reset"] == (3 if white_background else 2)      # 30, 60 (+ densify_from_iter = 20 on a white background)
     assert ours.p["xyz"].shape[0] != P
+
+
+def test_model_golden_is_what_its_generator_writes(RM, tmp_path):
+    """tests/golden/model.npz is reproducible: tests/golden/make_model_golden.py, run again on the compiled reference class,
+    writes the same arrays (so the committed fixture is the reference's output, not an edited one)."""
+    import importlib.util
+    from conftest import golden
+    spec = importlib.util.spec_from_file_location("make_model_golden", os.path.join(HERE, "golden", "make_model_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    out = str(tmp_path / "model.npz")
+    gen.main(out)
+    a, b = golden("model"), np.load(out)
+    assert sorted(a.files) == sorted(b.files) and len(a.files) > 200
+    for k in a.files:
+        assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
